@@ -1,0 +1,12 @@
+"""consistent_viterbi_b200 -- B200-native (sm_100a) hot path of consistent-viterbi.
+
+The package directory uses an underscore (Python cannot import a hyphenated
+name); it holds only what the hot path needs: csrc/ (CUDA kernels + the C ABI of
+include/cv_b200.h) and the host-side mirror of the reference's solver interface.
+"""
+from . import _lib
+from ._lib import CvError
+from .hmm import HMM
+from .viterbi import decode, decode_batch
+
+__all__ = ["HMM", "decode", "decode_batch", "CvError", "_lib"]

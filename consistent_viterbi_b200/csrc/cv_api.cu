@@ -1,0 +1,451 @@
+// cv_api.cu -- C ABI (include/cv_b200.h) over the sm_100a kernels.
+//
+// Host side of the drop-in boundary: model upload, workspace management, launch
+// logic and the branch-and-bound control loop of the constrained solver.  No
+// CPU compute fallback exists anywhere in this file: if CUDA is unavailable the
+// entry points return CV_ERR_CUDA.
+#include "../../include/cv_b200.h"
+
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "decode_small.cuh"
+#include "decode_large.cuh"
+#include "cp_kernels.cuh"
+#include "probe.cuh"
+
+using namespace cvb;
+
+// ---------------------------------------------------------------------------
+// errors, counters
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_timing{0};
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            int _c = (_e == cudaErrorMemoryAllocation) ? CV_ERR_OOM : CV_ERR_CUDA;             \
+            return fail(_c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                      \
+    } while (0)
+
+extern "C" const char *cv_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t cv_launch_count(void) { return g_launches.load(); }
+extern "C" void cv_set_timing(int on) { g_timing.store(on); }
+
+// ---------------------------------------------------------------------------
+// model handle
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return CV_OK;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        size_t want = need + need / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, need);
+            want = need;
+        }
+        if (e != cudaSuccess) { p = nullptr; return fail(CV_ERR_OOM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); }
+        bytes = want;
+        return CV_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct cv_hmm {
+    int device = 0, K = 0, Kp = 0, G = 0, D = 0, num_sms = 0;
+    int64_t M = 1;
+    // device model
+    double *dA = nullptr;    // [K][Kp]   small-K layout (Kp = 8*ceil(K/8)), pad = -inf
+    double *dBT = nullptr;   // [M][Kp]
+    double *dPi = nullptr;   // [Kp]
+    // large-K layout
+    int Kl = 0;              // K padded to a multiple of LARGE_BN
+    double *dAl = nullptr;   // [Kl][Kl]
+    double *dBTl = nullptr;  // [M][Kl]
+    // host copy (control logic of the CP solver)
+    std::vector<double> hA, hB, hPi;
+    // workspaces
+    DevBuf obs, seq_off, path, score, psi, order, keys_in, keys_out, vals_in, cub_tmp, delta_g, misc;
+    DevBuf cp_ws[12];
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    // CP debug state
+    int64_t cp_N = 0;
+    std::vector<double> cp_ub;
+    void *pinned_status = nullptr;
+};
+
+static int check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(CV_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device >= n) return fail(CV_ERR_ARG, "device %d out of range (%d devices)", device, n);
+    return CV_OK;
+}
+
+__global__ void build_layouts_kernel(const double *A, const double *Bm, const double *pi, int K, int64_t M, int Kp,
+                                     double *Ap, double *BT, double *Pip)
+{
+    const int64_t n1 = (int64_t)K * Kp, n2 = M * Kp;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n1 + n2 + Kp; e += stride) {
+        if (e < n1) {
+            int j = (int)(e / Kp), i = (int)(e % Kp);
+            Ap[e] = i < K ? A[(int64_t)j * K + i] : neg_inf();
+        } else if (e < n1 + n2) {
+            int64_t r = e - n1;
+            int64_t o = r / Kp; int i = (int)(r % Kp);
+            BT[r] = i < K ? Bm[(int64_t)i * M + o] : neg_inf();
+        } else {
+            int i = (int)(e - n1 - n2);
+            Pip[i] = i < K ? pi[i] : neg_inf();
+        }
+    }
+}
+
+extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *logA, const double *logB,
+                             const double *logPi, int device, cv_hmm **out)
+{
+    if (!out) return fail(CV_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (K <= 0 || K > 65535) return fail(CV_ERR_ARG, "K=%d out of range [1,65535]", K);
+    if (D <= 0 || !bdims || !logA || !logB || !logPi) return fail(CV_ERR_ARG, "NULL/empty model argument");
+    int64_t M = 1;
+    for (int d = 0; d < D; d++) {
+        if (bdims[d] == 0) return fail(CV_ERR_ARG, "bdims[%d] == 0", d);
+        M *= (int64_t)bdims[d];
+    }
+    // NaN / +inf would make the reference's argmax().unwrap() panic (or poison every sum): reject.
+    auto bad = [](const double *v, int64_t n) {
+        for (int64_t i = 0; i < n; i++) if (std::isnan(v[i]) || v[i] == std::numeric_limits<double>::infinity()) return true;
+        return false;
+    };
+    if (bad(logA, (int64_t)K * K) || bad(logB, (int64_t)K * M) || bad(logPi, K))
+        return fail(CV_ERR_NAN, "model contains NaN or +inf");
+    if (device < 0) {
+        int rc = check_device(0);
+        if (rc) return rc;
+        CUDA_TRY(cudaGetDevice(&device));
+    }
+    int rc = check_device(device);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+
+    cv_hmm *h = new cv_hmm();
+    h->device = device; h->K = K; h->D = D; h->M = M;
+    h->G = (K + TQ - 1) / TQ; h->Kp = h->G * TQ;
+    h->hA.assign(logA, logA + (size_t)K * K);
+    h->hB.assign(logB, logB + (size_t)K * M);
+    h->hPi.assign(logPi, logPi + K);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    CUDA_TRY(cudaMallocHost(&h->pinned_status, 64));
+
+    const int Kp = (K <= SMALL_K_MAX) ? h->Kp : ((K + LARGE_BN - 1) / LARGE_BN) * LARGE_BN;
+    if (K > SMALL_K_MAX) { h->Kl = Kp; }
+    double *tA = nullptr, *tB = nullptr, *tPi = nullptr;
+    CUDA_TRY(cudaMalloc(&tA, sizeof(double) * (size_t)K * K));
+    CUDA_TRY(cudaMalloc(&tB, sizeof(double) * (size_t)K * M));
+    CUDA_TRY(cudaMalloc(&tPi, sizeof(double) * (size_t)K));
+    CUDA_TRY(cudaMemcpy(tA, logA, sizeof(double) * (size_t)K * K, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(tB, logB, sizeof(double) * (size_t)K * M, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(tPi, logPi, sizeof(double) * (size_t)K, cudaMemcpyHostToDevice));
+    double *pA = nullptr, *pBT = nullptr, *pPi = nullptr;
+    CUDA_TRY(cudaMalloc(&pA, sizeof(double) * (size_t)K * Kp));
+    CUDA_TRY(cudaMalloc(&pBT, sizeof(double) * (size_t)M * Kp));
+    CUDA_TRY(cudaMalloc(&pPi, sizeof(double) * (size_t)Kp));
+    build_layouts_kernel<<<std::max(1, h->num_sms) * 4, 256>>>(tA, tB, tPi, K, M, Kp, pA, pBT, pPi);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(tA); cudaFree(tB); cudaFree(tPi);
+    if (K <= SMALL_K_MAX) { h->dA = pA; h->dBT = pBT; h->dPi = pPi; }
+    else { h->dAl = pA; h->dBTl = pBT; h->dPi = pPi; }
+    *out = h;
+    return CV_OK;
+}
+
+extern "C" void cv_hmm_destroy(cv_hmm *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl}) if (p) cudaFree(p);
+    for (DevBuf *b : {&h->obs, &h->seq_off, &h->path, &h->score, &h->psi, &h->order, &h->keys_in, &h->keys_out,
+                      &h->vals_in, &h->cub_tmp, &h->delta_g, &h->misc})
+        b->release();
+    for (auto &b : h->cp_ws) b.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->pinned_status) cudaFreeHost(h->pinned_status);
+    delete h;
+}
+
+extern "C" int cv_hmm_nstates(const cv_hmm *h) { return h ? h->K : 0; }
+extern "C" int64_t cv_hmm_nobs(const cv_hmm *h) { return h ? h->M : 0; }
+extern "C" double cv_last_kernel_ms(const cv_hmm *h) { return h ? h->last_ms : 0.0; }
+
+extern "C" void *cv_host_alloc(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void cv_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------
+// batched plain Viterbi
+// ---------------------------------------------------------------------------
+__global__ void seq_len_keys_kernel(const int64_t *seq_off, int64_t B, uint32_t *keys, uint32_t *vals, int *status)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t len = seq_off[b + 1] - seq_off[b];
+    if (len <= 0) *status = CV_ERR_EMPTY;          // reference: sequence.len()-1 underflow panic
+    keys[b] = (uint32_t)(len < 0 ? 0 : (len > 0xffffffffLL ? 0xffffffffLL : len));
+    vals[b] = (uint32_t)b;
+}
+
+#include "decode_large_host.inl"
+
+static int launch_decode_small(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, uint32_t *d_path,
+                               double *d_score, const uint32_t *d_order, unsigned int *d_counter, int *d_status,
+                               cudaStream_t st)
+{
+    const int G = h->G;
+    // sequences per tile: 64*S.  Prefer wide tiles (more warps per SM) but keep >= 2 tiles per SM.
+    int S = std::max(1, std::min(4, 16 / G));
+    while (S > 1 && (B + 64 * S - 1) / (64 * S) < 2 * (int64_t)h->num_sms) S--;
+    const int NS = 64 * S;
+    size_t smem = decode_small_smem_bytes(h->K, h->Kp, NS);
+    while (smem > 220 * 1024 && S > 1) { S--; smem = decode_small_smem_bytes(h->K, h->Kp, 64 * S); }
+    DecodeSmallParams p;
+    p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
+    p.psi = (uint8_t *)h->psi.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
+    p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S;
+    p.ntiles = (int)((B + 64 * S - 1) / (64 * S)); p.zero = 0;
+    auto kern = decode_small_kernel<CVB_CELL_VARIANT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = 32 * G * S;
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    occ = std::max(1, occ);
+    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * occ, p.ntiles);
+    kern<<<std::max(1, grid), threads, smem, st>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CV_OK;
+}
+
+extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
+                                   int64_t max_len, uint32_t *d_path, double *d_score, void *stream, int sync_status)
+{
+    if (!h) return fail(CV_ERR_ARG, "NULL model");
+    if (B < 0 || N < 0) return fail(CV_ERR_ARG, "negative size");
+    if (B == 0) return CV_OK;
+    if (!d_obs || !d_off || !d_path) return fail(CV_ERR_ARG, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    (void)max_len;
+
+    int rc;
+    if ((rc = h->order.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
+    if ((rc = h->keys_in.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
+    if ((rc = h->keys_out.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
+    if ((rc = h->vals_in.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
+    if ((rc = h->misc.ensure(256))) return rc;
+    unsigned int *d_counter = (unsigned int *)h->misc.p;
+    int *d_status = (int *)h->misc.p + 16;
+    CUDA_TRY(cudaMemsetAsync(h->misc.p, 0, 256, st));
+
+    // order sequences by length, longest first (stable radix sort => deterministic)
+    seq_len_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_off, B, (uint32_t *)h->keys_in.p,
+                                                                    (uint32_t *)h->vals_in.p, d_status);
+    g_launches++;
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)h->keys_in.p,
+                                                       (uint32_t *)h->keys_out.p, (uint32_t *)h->vals_in.p,
+                                                       (uint32_t *)h->order.p, (int)B, 0, 32, st));
+    if ((rc = h->cub_tmp.ensure(tmp_bytes))) return rc;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp.p, tmp_bytes, (uint32_t *)h->keys_in.p,
+                                                       (uint32_t *)h->keys_out.p, (uint32_t *)h->vals_in.p,
+                                                       (uint32_t *)h->order.p, (int)B, 0, 32, st));
+
+    const bool timing = g_timing.load() != 0;
+    if (h->K <= SMALL_K_MAX) {
+        if ((rc = h->psi.ensure((size_t)N * h->Kp))) return rc;
+        if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
+        if ((rc = launch_decode_small(h, d_obs, d_off, B, d_path, d_score, (const uint32_t *)h->order.p, d_counter,
+                                      d_status, st)))
+            return rc;
+        if (timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    } else {
+        if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
+        if ((rc = launch_decode_large(h, d_obs, d_off, B, N, d_path, d_score, (const uint32_t *)h->order.p,
+                                      (const uint32_t *)h->keys_out.p, d_counter, d_status, st)))
+            return rc;
+        if (timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    }
+    if (sync_status || timing) {
+        CUDA_TRY(cudaMemcpyAsync(h->pinned_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (timing) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            h->last_ms = ms;
+        }
+        const int s = *(int *)h->pinned_status;
+        if (s == CV_ERR_EMPTY) return fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)");
+        if (s == CV_ERR_ARG) return fail(CV_ERR_ARG, "observation index >= M (reference: ndarray index panic)");
+        if (s) return fail(s, "device status %d", s);
+    }
+    return CV_OK;
+}
+
+extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B,
+                               uint32_t *path_out, double *score_out)
+{
+    if (!h) return fail(CV_ERR_ARG, "NULL model");
+    if (B < 0) return fail(CV_ERR_ARG, "negative B");
+    if (B == 0) return CV_OK;
+    if (!obs_flat || !seq_off || !path_out) return fail(CV_ERR_ARG, "NULL buffer");
+    if (seq_off[0] != 0) return fail(CV_ERR_ARG, "seq_off[0] must be 0");
+    const int64_t N = seq_off[B];
+    int64_t max_len = 0;
+    for (int64_t b = 0; b < B; b++) {
+        const int64_t len = seq_off[b + 1] - seq_off[b];
+        if (len < 0) return fail(CV_ERR_ARG, "seq_off not monotone at %lld", (long long)b);
+        if (len == 0) return fail(CV_ERR_EMPTY, "sequence %lld is empty (reference: usize underflow panic)", (long long)b);
+        max_len = std::max(max_len, len);
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = h->obs.ensure(sizeof(uint32_t) * (size_t)N))) return rc;
+    if ((rc = h->seq_off.ensure(sizeof(int64_t) * (size_t)(B + 1)))) return rc;
+    if ((rc = h->path.ensure(sizeof(uint32_t) * (size_t)N))) return rc;
+    if ((rc = h->score.ensure(sizeof(double) * (size_t)B))) return rc;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->seq_off.p, seq_off, sizeof(int64_t) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->obs.p, obs_flat, sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
+    rc = cv_decode_batch_dev(h, (const uint32_t *)h->obs.p, (const int64_t *)h->seq_off.p, B, N, max_len,
+                             (uint32_t *)h->path.p, (double *)h->score.p, st, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(path_out, h->path.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+    if (score_out)
+        CUDA_TRY(cudaMemcpyAsync(score_out, h->score.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h->pinned_status, (int *)h->misc.p + 16, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (g_timing.load()) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms; else cudaGetLastError();
+    }
+    const int s = *(int *)h->pinned_status;
+    if (s == CV_ERR_ARG) return fail(CV_ERR_ARG, "observation index >= M (reference: ndarray index panic)");
+    if (s) return fail(s, "device status %d", s);
+    return CV_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 probe
+// ---------------------------------------------------------------------------
+extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_out, double *ms_out)
+{
+    int rc = check_device(device < 0 ? 0 : device);
+    if (rc) return rc;
+    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    const int threads = 384, blocks = prop.multiProcessorCount;
+    double *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * (size_t)threads * blocks));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int K = 45;
+    const size_t smem = (size_t)K * 48 * 8 + (size_t)K * (threads / 32) * 64 * 8;
+    double fp64_ops = 0.0;
+    for (int rep = 0; rep < 2; rep++) {   // rep 0 = warm-up
+        CUDA_TRY(cudaEventRecord(e0));
+        if (mode == 0) {
+            probe_fp64_kernel<0><<<blocks, threads>>>(d_out, iters, 1.0);
+            fp64_ops = 16.0 * iters * threads * blocks;
+        } else if (mode == 1) {
+            probe_fp64_kernel<1><<<blocks, threads>>>(d_out, iters, 1.0);
+            fp64_ops = 32.0 * iters * threads * blocks;
+        } else {
+            auto launch = [&](auto kern) -> cudaError_t {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                kern<<<blocks, threads, smem>>>(d_out, K, iters, 0, 1.0);
+                return cudaSuccess;
+            };
+            cudaError_t e = cudaSuccess;
+            switch (mode) {
+                case 2: e = launch(probe_tile_kernel<0>); break;
+                case 3: e = launch(probe_tile_kernel<1>); break;
+                case 4: e = launch(probe_tile_kernel<2>); break;
+                case 5: e = launch(probe_tile_kernel<3>); break;
+                default: return fail(CV_ERR_ARG, "unknown probe mode %d", mode);
+            }
+            CUDA_TRY(e);
+            fp64_ops = 2.0 * 16.0 * K * (double)iters * threads * blocks;   // DADD + DSETP per cell
+        }
+        g_launches++;
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaGetLastError());
+    }
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (ops_per_s_out) *ops_per_s_out = fp64_ops / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    return CV_OK;
+}
+
+#include "cp_host.inl"

@@ -1,0 +1,65 @@
+// probe.cuh -- FP64 issue-rate micro-benchmarks (roofline denominator) and the
+// decode inner loop run in isolation with each select-placement variant.
+#pragma once
+
+#include "common.cuh"
+
+namespace cvb {
+
+// mode 0: independent DADD chains; mode 1: DADD + DSETP (predicate OR-chained, no selects)
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) probe_fp64_kernel(double *out, int iters, double seed)
+{
+    constexpr int NCH = 16;
+    double acc[NCH];
+    bool pr = false;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) acc[c] = seed * (threadIdx.x + c);
+    const double inc = seed * 1e-3;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            if constexpr (MODE == 0) {
+                acc[c] += inc;
+            } else {
+                acc[c] += inc;
+                pr = pr || (acc[c] > seed);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) s += acc[c];
+    if (s == 12345.678 || (pr && seed == -1.0)) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// The real micro-tile on synthetic shared-memory operands (K predecessors, `iters` steps).
+template <int VARIANT>
+__global__ void __launch_bounds__(512, 1) probe_tile_kernel(double *out, int K, int iters, int zero, double seed)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Kp = ((K + 7) / 8) * 8;
+    const int NS = (blockDim.x / 32) * SEQ_PER_WARP;   // every warp its own 64 sequences here
+    double *sA = reinterpret_cast<double *>(smem_raw);
+    double *sD = sA + (size_t)K * Kp;
+    for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) sA[e] = -seed * ((e * 37) % 101);
+    for (int e = threadIdx.x; e < K * NS; e += blockDim.x) sD[e] = -seed * ((e * 53) % 89);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i0 = (w % (Kp / 8)) * TQ;
+    const int s0 = w * SEQ_PER_WARP + lane * TP;
+    double tot = 0.0; int ti = 0;
+    for (int it = 0; it < iters; it++) {
+        double best[TP][TQ]; int idx[TP][TQ];
+        maxplus_tile<VARIANT>(sD + s0, NS, sA + i0, Kp, K, best, idx, zero);
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) { tot += best[p][q]; ti += idx[p][q]; }
+        // perturb one operand so iterations are not hoisted
+        sD[(size_t)(it % K) * NS + s0] = tot * 1e-30;
+    }
+    if (tot == 12345.678 || ti == -7) out[blockIdx.x * blockDim.x + threadIdx.x] = tot + ti;
+}
+
+}  // namespace cvb

@@ -1,0 +1,122 @@
+/*
+ * cv_b200.h -- C ABI of the B200-native consistent-viterbi hot path.
+ *
+ * The reference (AlexandreDubray/consistent-viterbi) is one Rust binary with no
+ * FFI seam; this header is the seam a maintainer would bind from Rust (see
+ * INTEGRATION.md for the `extern "C"` block + build.rs).  Every entry point
+ * cites the reference interface it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - All probabilities are log10, zero probability = -inf, exactly as the
+ *     reference stores them (src/hmm/hmm.rs:192-205).
+ *   - logA  [K*K]  row-major, logA[from*K + to]   (hmm.rs:12-13, a[[from,to]])
+ *     logB  [K*M]  state-major, logB[state*M + o] (hmm.rs:14-15, b[state][obs]);
+ *                  o = the D-dimensional observation flattened row-major over
+ *                  bdims, M = prod(bdims)
+ *     logPi [K]                                   (hmm.rs:16-17)
+ *   - Every function returns CV_OK or a non-zero status; where the reference
+ *     would panic (unwrap/assert/index) the status says which panic.  The text
+ *     of the last error of the calling thread is cv_last_error().
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns CV_ERR_CUDA.
+ */
+#ifndef CV_B200_H
+#define CV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CV_OK          0
+#define CV_ERR_EMPTY   1  /* reference panics: empty sequence / empty super-sequence      */
+#define CV_ERR_NAN     2  /* reference panics: argmax().unwrap() on NaN (model has NaN/+inf) */
+#define CV_ERR_ARG     3  /* bad argument; observation >= M or comp id >= ncomp (index panic) */
+#define CV_ERR_ASSERT  4  /* reference assert!(obj > self.best_obj) fires (cp.rs:87)        */
+#define CV_ERR_CUDA    5  /* CUDA runtime error / no device                                */
+#define CV_ERR_OOM     6  /* device or host allocation failed                              */
+#define CV_ERR_UNSUPPORTED 7 /* shape outside what the kernels cover        */
+
+typedef struct cv_hmm cv_hmm;   /* device-resident model + its workspaces, one device */
+
+/* ---- model ---------------------------------------------------------------
+ * Replaces: struct HMM<D>{a,b,pi} (hmm.rs:10-18) as loaded by HMM::from_json
+ * (hmm.rs:242-245).  Uploads the model to `device` (-1 = current device),
+ * builds the padded/transposed device layouts the kernels read.  NaN or +inf
+ * entries are rejected with CV_ERR_NAN (the reference would panic later inside
+ * argmax). */
+int  cv_hmm_create(int K, int D, const uint64_t *bdims, const double *logA,
+                   const double *logB, const double *logPi, int device,
+                   cv_hmm **out);
+void cv_hmm_destroy(cv_hmm *h);
+int  cv_hmm_nstates(const cv_hmm *h);          /* HMM::nstates (hmm.rs:207-209) */
+int64_t cv_hmm_nobs(const cv_hmm *h);          /* M = prod(bdims)               */
+
+/* ---- plain Viterbi, batched ------------------------------------------------
+ * Replaces: B calls of viterbi::decode(sequence, hmm) -> Array1<usize>
+ * (src/viterbi_solver/viterbi.rs:5-32), association order (delta + a) + b,
+ * pi and the first observation ignored, lowest-index argmax.
+ *   obs_flat[N]   flattened observations of all sequences back to back
+ *   seq_off[B+1]  offsets into obs_flat / path_out (seq_off[0] = 0)
+ *   path_out[N]   decoded state of every element
+ *   score_out[B]  delta[T-1][end_state] of every sequence (may be NULL)
+ * HOST pointers (pinned memory gives full PCIe speed; see cv_host_alloc).
+ * An empty sequence returns CV_ERR_EMPTY (reference: usize underflow panic). */
+int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off,
+                    int64_t B, uint32_t *path_out, double *score_out);
+
+/* Same, with every buffer already resident on the model's device; enqueued on
+ * `stream` (a cudaStream_t, NULL = default stream) without host sync, except
+ * that the status word is read back when `sync_status` != 0. */
+int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs_flat, const int64_t *d_seq_off,
+                        int64_t B, int64_t N, int64_t max_len, uint32_t *d_path_out,
+                        double *d_score_out, void *stream, int sync_status);
+
+/* ---- constrained decode ----------------------------------------------------
+ * Replaces: CPSolver::new(&hmm, &super_seq) + Solver::solve + get_solution +
+ * get_objective + get_explored_nodes (src/viterbi_solver/cp.rs:20-152,
+ * src/viterbi_solver.rs:11-16), association order delta + (a + b), argmax on
+ * delta + a, clamp = row reset to {-inf.., 0.0 at the chosen state}.
+ *   obs[N]          flattened observation of each super-sequence element, in the
+ *                   (reordered) order SuperSequence holds them
+ *   is_seq_start[N] 1 iff MetaElements.t == 0 (viterbi_solver/utils.rs:11)
+ *   comp[N]         constraint_component of ACTIVE elements, -1 otherwise
+ *                   (is_constrained(), viterbi_solver/utils.rs:44-46)
+ *   ncomp           SuperSequence::number_constraints() (utils.rs:200-202)
+ *   max_nodes       0 = unlimited (reference); else stop opening nodes once
+ *                   explored == max_nodes
+ *   sol_out[N]      get_solution()      obj_out  get_objective()
+ *   explored_out    get_explored_nodes() steps_out forward sweep steps executed
+ * HOST pointers. */
+int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq_start,
+                const int32_t *comp, int64_t N, int32_t ncomp, uint64_t max_nodes,
+                uint64_t *sol_out, double *obj_out, uint64_t *explored_out,
+                uint64_t *steps_out);
+
+/* Debug/parity hooks for the CP path: after cv_cp_solve, copy out the final
+ * delta[N*K] / psi[N*K] state and the per-node upper bounds (first `cap` nodes). */
+int cv_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out);
+int cv_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *n_out);
+
+/* ---- plumbing --------------------------------------------------------------*/
+const char *cv_last_error(void);
+/* kernels launched by this library in this process (bench.py "gpu_launches") */
+uint64_t cv_launch_count(void);
+/* device time (ms, CUDA events on the library's stream) of the forward kernel(s)
+ * of the most recent cv_decode_batch / cv_decode_batch_dev / cv_cp_solve call
+ * when timing was enabled with cv_set_timing(1). */
+void   cv_set_timing(int on);
+double cv_last_kernel_ms(const cv_hmm *h);
+/* pinned host memory helpers */
+void *cv_host_alloc(uint64_t bytes);
+void  cv_host_free(void *p);
+/* FP64 issue-rate probe used as the ALU roofline denominator: runs `iters`
+ * dependent-free DADD (mode 0), DADD+DSETP pairs (mode 1) or the decode inner
+ * loop body (mode >= 2) on every SM and returns FP64 instructions per second. */
+int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_out, double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CV_B200_H */

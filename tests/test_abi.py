@@ -1,0 +1,62 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/cv_b200.h
+declares, and fails loudly (no CPU fallback) when no CUDA device exists."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import consistent_viterbi_b200 as cv
+from util import random_hmm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cv_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    L = cv._lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/cv_b200.h but not exported"
+    assert set(names) == set(cv._lib.SIGNATURES), "ctypes table out of sync with the header"
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    rng = np.random.default_rng(0)
+    A, B, pi = random_hmm(rng, 5, 4)
+    h = cv.HMM(A, B, pi)
+    with pytest.raises(cv.CvError) as e:
+        cv.decode([[0], [1], [2]], h)
+    assert e.value.code == cv._lib.ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "consistent_viterbi_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+def test_hmm_json_roundtrip(tmp_path):
+    rng = np.random.default_rng(3)
+    A, B, pi = random_hmm(rng, 4, 6)
+    h = cv.HMM(A, B.reshape(4, 3, 2), pi)
+    p = tmp_path / "hmm.json"
+    h.write(p)
+    txt = p.read_text()
+    assert txt.startswith('{"a":{"v":1,"dim":[4,4],"data":[') and "null" in txt
+    h2 = cv.HMM.from_json(p)
+    assert h2.a.tobytes() == h.a.tobytes() and h2.b.tobytes() == h.b.tobytes() and h2.pi.tobytes() == h.pi.tobytes()
+    assert h2.bdims == (3, 2)
+    assert list(h.flatten_obs([[1, 1], [2, 0]])) == [3, 4]

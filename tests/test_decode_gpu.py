@@ -1,0 +1,100 @@
+"""GPU parity tests (mode R1): cv_decode_batch through the C ABI against the C
+oracle, bit-exact on paths (u32) and scores (f64 bit patterns)."""
+import numpy as np
+import pytest
+
+import consistent_viterbi_b200 as cv
+from oracle import pyoracle as po
+from util import random_batch, random_hmm
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(A, B, pi, obs, off):
+    h = cv.HMM(A, B, pi)
+    paths, scores = cv.decode_batch(h, obs, off)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    bad = np.nonzero(paths != rp)[0]
+    assert bad.size == 0, f"{bad.size} path mismatches, first at {bad[:5]}"
+    assert scores.tobytes() == rs.tobytes()
+    h.close()
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 7, 8, 9, 12, 16, 18, 24, 31, 33, 45, 48, 57, 64])
+def test_small_k_random(K):
+    rng = np.random.default_rng(1000 + K)
+    M = int(rng.integers(1, 40))
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.2)
+    obs, off = random_batch(rng, 700, M, 1, 40)
+    _check(A, B, pi, obs, off)
+
+
+@pytest.mark.parametrize("K", [2, 5, 8, 13, 45])
+def test_small_k_ties_and_neg_inf(K):
+    """log-probs from a tiny dyadic set incl. -inf and +-0.0: exact ties everywhere, so the
+    lowest-index rule (ndarray-stats argmax) decides almost every backpointer."""
+    rng = np.random.default_rng(2000 + K)
+    M = 6
+    A, B, pi = random_hmm(rng, K, M, ties=True)
+    obs, off = random_batch(rng, 500, M, 1, 25)
+    _check(A, B, pi, obs, off)
+
+
+def test_edge_lengths_and_single_sequence():
+    rng = np.random.default_rng(5)
+    A, B, pi = random_hmm(rng, 45, 30)
+    for lens in ([1], [2], [1, 1, 1], [300], [1, 500, 2, 1, 77]):
+        off = np.zeros(len(lens) + 1, dtype=np.int64); off[1:] = np.cumsum(lens)
+        obs = rng.integers(0, 30, size=int(off[-1])).astype(np.uint32)
+        _check(A, B, pi, obs, off)
+    path = cv.decode([[3], [1], [2], [29]], cv.HMM(A, B, pi))
+    ref, _ = po.decode(A, B, np.array([3, 1, 2, 29], dtype=np.uint32))
+    assert path.dtype == np.uint64 and (path == ref).all()
+
+
+def test_all_neg_inf_emissions():
+    rng = np.random.default_rng(6)
+    A, B, pi = random_hmm(rng, 9, 4)
+    B[:] = -np.inf
+    obs, off = random_batch(rng, 70, 4, 1, 12)
+    _check(A, B, pi, obs, off)
+
+
+def test_errors_match_reference_panics():
+    rng = np.random.default_rng(8)
+    A, B, pi = random_hmm(rng, 6, 4)
+    h = cv.HMM(A, B, pi)
+    with pytest.raises(cv.CvError) as e:                      # empty sequence: usize underflow panic
+        cv.decode_batch(h, np.array([0, 1], dtype=np.uint32), np.array([0, 2, 2], dtype=np.int64))
+    assert e.value.code == cv._lib.ERR_EMPTY
+    with pytest.raises(cv.CvError) as e:                      # obs >= M: ndarray index panic
+        cv.decode_batch(h, np.array([0, 9, 1], dtype=np.uint32), np.array([0, 3], dtype=np.int64))
+    assert e.value.code == cv._lib.ERR_ARG
+    An = A.copy(); An[0, 0] = np.nan
+    with pytest.raises(cv.CvError) as e:
+        cv.HMM(An, B, pi).device_handle()
+    assert e.value.code == cv._lib.ERR_NAN
+
+
+def test_pos_shape_sample_and_properties():
+    """POS shape (K=45, V=20k), 20k sentences: oracle parity on the full sample plus
+    size-independent properties: batch == concatenation of singles; permuting the batch
+    permutes the output."""
+    rng = np.random.default_rng(3019)
+    K, M, Bn = 45, 20000, 20000
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.05, alpha=0.1)
+    lens = np.clip(np.rint(rng.gamma(2.5, 10.0, size=Bn)), 1, 200).astype(np.int64)
+    off = np.zeros(Bn + 1, dtype=np.int64); off[1:] = np.cumsum(lens)
+    obs = (rng.zipf(1.1, size=int(off[-1])) % M).astype(np.uint32)
+    h = cv.HMM(A, B, pi)
+    paths, scores = cv.decode_batch(h, obs, off)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    assert (paths == rp).all() and scores.tobytes() == rs.tobytes()
+    perm = rng.permutation(Bn)
+    off2 = np.zeros(Bn + 1, dtype=np.int64); off2[1:] = np.cumsum(lens[perm])
+    obs2 = np.concatenate([obs[off[b]:off[b + 1]] for b in perm])
+    p2, s2 = cv.decode_batch(h, obs2, off2)
+    assert s2.tobytes() == scores[perm].tobytes()
+    for k in (0, 1, Bn // 2, Bn - 1):
+        b = perm[k]
+        assert (p2[off2[k]:off2[k + 1]] == paths[off[b]:off[b + 1]]).all()

@@ -1,0 +1,147 @@
+"""CPU tests: the C oracle against (1) brute-force path enumeration and (2) the
+independent pure-Python restatement.  The reference ships no tests or golden
+vectors (parity unpinned), so these are the pins the oracle has."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import py_restatement as pr
+from oracle import pyoracle as po
+from util import random_hmm, random_superseq
+
+
+def _bits(x):
+    return np.asarray(x, dtype=np.float64).tobytes()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_r1_oracle_vs_restatement_and_bruteforce(seed):
+    rng = np.random.default_rng(100 + seed)
+    nbf = 0
+    for it in range(120):
+        K = int(rng.integers(1, 6)); M = int(rng.integers(1, 5)); T = int(rng.integers(1, 7))
+        A, B, pi = random_hmm(rng, K, M, ties=(it % 3 == 0))
+        obs = rng.integers(0, M, size=T).astype(np.uint32)
+        path, score = po.decode(A, B, obs)
+        h = pr.HMM(A, B, pi)
+        seq = [int(o) for o in obs]
+        p2, arr, bt = pr.decode(seq, h)
+        assert list(path) == p2
+        assert _bits(score) == _bits(arr[-1][p2[-1]])
+        d, ps = po.decode_trace(A, B, obs)
+        assert _bits(d) == _bits(arr)
+        assert (ps == np.array(bt)).all()
+        if K ** T <= 4096:
+            bf = pr.r1_bruteforce_best(seq, h)
+            assert bf == score                      # exact (fl(x+c) monotone in x)
+            if score > -math.inf:
+                assert pr.r1_path_score(p2, seq, h) == score
+            nbf += 1
+    assert nbf > 50
+
+
+def test_r1_edge_cases():
+    rng = np.random.default_rng(7)
+    A, B, pi = random_hmm(rng, 4, 3)
+    # T = 1 -> path [0], score 0.0 (viterbi.rs:6,24: argmax of an all-zero row)
+    path, score = po.decode(A, B, np.array([2], dtype=np.uint32))
+    assert list(path) == [0] and score == 0.0
+    # T = 0 -> reference panics (usize underflow)
+    with pytest.raises(po.OracleError) as e:
+        po.decode(A, B, np.zeros(0, dtype=np.uint32))
+    assert e.value.code == po.ERR_EMPTY
+    # all emissions -inf -> every delta -inf, psi stays 0, path all zeros
+    Binf = np.full_like(B, -np.inf)
+    path, score = po.decode(A, Binf, np.array([0, 1, 2, 1], dtype=np.uint32))
+    assert list(path) == [0, 0, 0, 0] and score == -np.inf
+    # K = 1
+    path, score = po.decode(np.array([[-0.5]]), np.array([[-1.0, -2.0]]), np.array([0, 1, 1], dtype=np.uint32))
+    assert list(path) == [0, 0, 0] and score == ((0.0 + -0.5) + -2.0 + -0.5) + -2.0
+    # observation out of range -> index panic
+    with pytest.raises(po.OracleError) as e:
+        po.decode(A, B, np.array([0, 3], dtype=np.uint32))
+    assert e.value.code == po.ERR_ARG
+
+
+def test_r1_batch_matches_single_and_threads():
+    rng = np.random.default_rng(11)
+    A, B, pi = random_hmm(rng, 7, 9)
+    lens = rng.integers(1, 30, size=200)
+    off = np.zeros(201, dtype=np.int64); off[1:] = np.cumsum(lens)
+    obs = rng.integers(0, 9, size=int(off[-1])).astype(np.uint32)
+    p1, s1 = po.decode_batch(A, B, obs, off, nthreads=1)
+    p4, s4 = po.decode_batch(A, B, obs, off, nthreads=4)
+    assert (p1 == p4).all() and _bits(s1) == _bits(s4)
+    for b in (0, 17, 199):
+        pb, sb = po.decode(A, B, obs[off[b]:off[b + 1]])
+        assert (pb == p1[off[b]:off[b + 1]]).all() and _bits(sb) == _bits(s1[b])
+
+
+def _elements(obs, start, comp):
+    els, tt = [], 0
+    for i in range(len(obs)):
+        if start[i]:
+            tt = 0
+        els.append(pr.Element(tt, int(obs[i]), int(comp[i]), comp[i] >= 0))
+        tt += 1
+    return els
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_r2_cp_oracle_vs_restatement(seed):
+    rng = np.random.default_rng(200 + seed)
+    nok = 0
+    for it in range(100):
+        K = int(rng.integers(1, 5)); M = int(rng.integers(1, 4))
+        A, B, pi = random_hmm(rng, K, M, ties=(it % 3 == 0), zero_frac=0.15)
+        obs, start, comp, ncomp = random_superseq(rng, int(rng.integers(1, 5)), M, int(rng.integers(0, 4)), 0.35)
+        s = pr.CPSolver(pr.HMM(A, B, pi), _elements(obs, start, comp), ncomp)
+        try:
+            s.solve(); perr = False
+        except AssertionError:
+            perr = True
+        try:
+            r = po.cp_solve(A, B, pi, obs, start, comp, ncomp, trace_nodes=4096, want_state=True); cerr = False
+        except po.OracleError as e:
+            assert e.code == po.ERR_ASSERT; cerr = True
+        assert perr == cerr
+        if perr:
+            continue
+        nok += 1
+        assert list(r["sol"]) == s.best_sol
+        assert _bits(r["obj"]) == _bits(s.best_obj)
+        assert r["explored"] == s.explored and r["steps"] == s.steps
+        assert _bits(s.ub_log) == _bits(r["ub"][: s.explored])
+        assert _bits(r["delta"]) == _bits(s.final_state[0])
+        assert (r["psi"] == np.array(s.final_state[1], dtype=np.uint64)).all()
+    assert nok > 60
+
+
+def test_r2_no_constraints_is_chain_viterbi():
+    """ncomp == 0: obj = max(delta[N-1]) (cp.rs:139-142); with a single sequence whose pi
+    row is all zero and T small the solution must be a best path of the chain score."""
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        K = int(rng.integers(2, 4)); M = 3; T = int(rng.integers(2, 6))
+        A, B, pi = random_hmm(rng, K, M, zero_frac=0.0)
+        obs = rng.integers(0, M, size=T).astype(np.uint32)
+        start = np.zeros(T, dtype=np.uint8); start[0] = 1
+        comp = np.full(T, -1, dtype=np.int32)
+        r = po.cp_solve(A, B, pi, obs, start, comp, 0)
+        els = _elements(obs, start, comp)
+        h = pr.HMM(A, B, pi)
+        sc = pr.r2_chain_score([int(x) for x in r["sol"]], els, h)
+        assert sc == r["obj"]
+        import itertools
+        best = max(pr.r2_chain_score(p, els, h) for p in itertools.product(range(K), repeat=T))
+        assert abs(best - r["obj"]) <= 1e-12 * max(1.0, abs(best))   # selection uses fl(d+a): ulp-level only
+
+
+def test_r2_max_nodes_budget():
+    rng = np.random.default_rng(9)
+    A, B, pi = random_hmm(rng, 4, 3, zero_frac=0.0)
+    obs, start, comp, ncomp = random_superseq(rng, 4, 3, 3, 0.4)
+    full = po.cp_solve(A, B, pi, obs, start, comp, ncomp)
+    cut = po.cp_solve(A, B, pi, obs, start, comp, ncomp, max_nodes=3)
+    assert cut["explored"] == min(3, full["explored"])
