@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -100,8 +101,8 @@ struct cv_hmm {
     DevBuf obs, seq_off, path, score, psi, order, keys_in, keys_out, vals_in, cub_tmp, delta_g, misc;
     DevBuf cp_ws[12];
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double last_ms = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    double last_ms = 0.0, last_bt_ms = 0.0;   // forward kernel / backtrace kernel
     // CP debug state
     int64_t cp_N = 0;
     std::vector<double> cp_ub;
@@ -181,6 +182,7 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&h->ev0));
     CUDA_TRY(cudaEventCreate(&h->ev1));
+    CUDA_TRY(cudaEventCreate(&h->ev2));
     CUDA_TRY(cudaMallocHost(&h->pinned_status, 64));
 
     const int Kp = (K <= SMALL_K_MAX) ? h->Kp : ((K + LARGE_BN - 1) / LARGE_BN) * LARGE_BN;
@@ -219,6 +221,7 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
     for (auto &b : h->cp_ws) b.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->pinned_status) cudaFreeHost(h->pinned_status);
     delete h;
@@ -227,6 +230,7 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
 extern "C" int cv_hmm_nstates(const cv_hmm *h) { return h ? h->K : 0; }
 extern "C" int64_t cv_hmm_nobs(const cv_hmm *h) { return h ? h->M : 0; }
 extern "C" double cv_last_kernel_ms(const cv_hmm *h) { return h ? h->last_ms : 0.0; }
+extern "C" double cv_last_backtrace_ms(const cv_hmm *h) { return h ? h->last_bt_ms : 0.0; }
 
 extern "C" void *cv_host_alloc(uint64_t bytes)
 {
@@ -251,34 +255,89 @@ __global__ void seq_len_keys_kernel(const int64_t *seq_off, int64_t B, uint32_t 
 
 #include "decode_large_host.inl"
 
-static int launch_decode_small(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, uint32_t *d_path,
-                               double *d_score, const uint32_t *d_order, unsigned int *d_counter, int *d_status,
-                               cudaStream_t st)
+static int g_small_cfg = -1;   // test/bench override of the small-K launch shape (see cv_set_small_config)
+
+// longest length of every tile of NS sequences (lengths are sorted descending)
+__global__ void tile_tmax_kernel(const uint32_t *sorted_len, int ntiles, int NS, long long *tmax)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles) tmax[t] = (long long)sorted_len[(size_t)t * NS];
+}
+
+static int launch_decode_small(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
+                               uint32_t *d_path, double *d_score, const uint32_t *d_order,
+                               const uint32_t *d_sorted_len, unsigned int *d_counter, int *d_status, int64_t max_len,
+                               cudaStream_t st, bool timing)
 {
     const int G = h->G;
-    // sequences per tile: 64*S.  Prefer wide tiles (more warps per SM) but keep >= 2 tiles per SM.
-    int S = std::max(1, std::min(4, 16 / G));
-    while (S > 1 && (B + 64 * S - 1) / (64 * S) < 2 * (int64_t)h->num_sms) S--;
-    const int NS = 64 * S;
-    size_t smem = decode_small_smem_bytes(h->K, h->Kp, NS);
+    // Launch shape: S sequence groups of 64 per CTA, and which register budget (kernel instantiation) to use.
+    int S = 1, variant = 2;
+    if (g_small_cfg >= 0) { S = std::max(1, std::min(4, g_small_cfg / 10)); variant = std::max(1, g_small_cfg % 10); }
+    while (S > 1 && (B + 64 * S - 1) / (64 * S) < 4 * (int64_t)h->num_sms) S--;
+    size_t smem = decode_small_smem_bytes(h->K, h->Kp, 64 * S);
     while (smem > 220 * 1024 && S > 1) { S--; smem = decode_small_smem_bytes(h->K, h->Kp, 64 * S); }
+    const int NS = 64 * S;
+    const int threads = 32 * G * S;
+    if (variant == 3 && threads > 256) variant = 2;
+    if (variant == 2 && threads > 384) variant = 1;
+    if (threads > 512) return fail(CV_ERR_UNSUPPORTED, "small-K launch shape needs %d threads", threads);
+    const int64_t ntiles64 = (B + NS - 1) / NS;
+    if (ntiles64 > 0x7fffffffLL) return fail(CV_ERR_UNSUPPORTED, "batch too large");
+    const int ntiles = (int)ntiles64;
+    int rc;
+    if (max_len <= 0) {   // not supplied: read the longest length back (one sync)
+        uint32_t L = 0;
+        CUDA_TRY(cudaMemcpyAsync(&L, d_sorted_len, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        max_len = L;
+    }
+    // history slabs: sum over tiles of NS * Tmax(tile) <= N + NS * max_len because lengths are sorted
+    const size_t hist_elems = ((size_t)N + (size_t)NS * (size_t)max_len) * (size_t)h->K;
+    if ((rc = h->psi.ensure(hist_elems * sizeof(double)))) return rc;
+    DevBuf &b_tmax = h->cp_ws[0], &b_base = h->cp_ws[1], &b_tmp = h->cp_ws[3];
+    if ((rc = b_tmax.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
+    if ((rc = b_base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
+    tile_tmax_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_sorted_len, ntiles, NS, (long long *)b_tmax.p);
+    g_launches++;
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (long long *)b_tmax.p, (long long *)b_base.p, ntiles, st));
+    if ((rc = b_tmp.ensure(tmp_bytes))) return rc;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(b_tmp.p, tmp_bytes, (long long *)b_tmax.p, (long long *)b_base.p, ntiles, st));
+
     DecodeSmallParams p;
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
-    p.psi = (uint8_t *)h->psi.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
-    p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S;
-    p.ntiles = (int)((B + 64 * S - 1) / (64 * S)); p.zero = 0;
-    auto kern = decode_small_kernel<CVB_CELL_VARIANT>;
+    p.tile_base = (const long long *)b_base.p;
+    p.hist = (double *)h->psi.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
+    p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.ntiles = ntiles;
+    void (*kern)(DecodeSmallParams) = variant == 1 ? decode_small_fwd_kernel<512, 1>
+                                    : variant == 2 ? decode_small_fwd_kernel<384, 2> : decode_small_fwd_kernel<256, 3>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = 32 * G * S;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     occ = std::max(1, occ);
-    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * occ, p.ntiles);
+    const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * occ, ntiles);
+    if (getenv("CV_DEBUG"))
+        fprintf(stderr, "[cv] decode_small: K=%d G=%d S=%d variant=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
+                h->K, G, S, variant, threads, smem, occ, grid, ntiles);
+    if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     kern<<<std::max(1, grid), threads, smem, st>>>(p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    if (timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    // end state + backtrace with lazy backpointers: 8 lanes per sequence, 32 sequences per 256-thread block pass
+    const size_t smem_bt = (size_t)h->K * h->Kp * 8;
+    CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
+    const int64_t npass = ((int64_t)ntiles * NS + 31) / 32;
+    const int grid_bt = (int)std::max<int64_t>(1, std::min<int64_t>(npass, (int64_t)h->num_sms * 8));
+    backtrace_small_kernel<<<grid_bt, 256, smem_bt, st>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (timing) CUDA_TRY(cudaEventRecord(h->ev2, st));
     return CV_OK;
 }
+
+extern "C" void cv_set_small_config(int cfg) { g_small_cfg = cfg; }
 
 extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
                                    int64_t max_len, uint32_t *d_path, double *d_score, void *stream, int sync_status)
@@ -289,7 +348,6 @@ extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64
     if (!d_obs || !d_off || !d_path) return fail(CV_ERR_ARG, "NULL buffer");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    (void)max_len;
 
     int rc;
     if ((rc = h->order.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
@@ -316,18 +374,15 @@ extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64
 
     const bool timing = g_timing.load() != 0;
     if (h->K <= SMALL_K_MAX) {
-        if ((rc = h->psi.ensure((size_t)N * h->Kp))) return rc;
-        if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
-        if ((rc = launch_decode_small(h, d_obs, d_off, B, d_path, d_score, (const uint32_t *)h->order.p, d_counter,
-                                      d_status, st)))
+        if ((rc = launch_decode_small(h, d_obs, d_off, B, N, d_path, d_score, (const uint32_t *)h->order.p,
+                                      (const uint32_t *)h->keys_out.p, d_counter, d_status, max_len, st, timing)))
             return rc;
-        if (timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
     } else {
         if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
         if ((rc = launch_decode_large(h, d_obs, d_off, B, N, d_path, d_score, (const uint32_t *)h->order.p,
-                                      (const uint32_t *)h->keys_out.p, d_counter, d_status, st)))
+                                      (const uint32_t *)h->keys_out.p, d_counter, d_status, max_len, st)))
             return rc;
-        if (timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
+        if (timing) { CUDA_TRY(cudaEventRecord(h->ev1, st)); CUDA_TRY(cudaEventRecord(h->ev2, st)); }
     }
     if (sync_status || timing) {
         CUDA_TRY(cudaMemcpyAsync(h->pinned_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -336,6 +391,8 @@ extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64
             float ms = 0.f;
             CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
             h->last_ms = ms;
+            CUDA_TRY(cudaEventElapsedTime(&ms, h->ev1, h->ev2));
+            h->last_bt_ms = ms;
         }
         const int s = *(int *)h->pinned_status;
         if (s == CV_ERR_EMPTY) return fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)");
@@ -381,6 +438,7 @@ extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_
     if (g_timing.load()) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms; else cudaGetLastError();
+        if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->last_bt_ms = ms; else cudaGetLastError();
     }
     const int s = *(int *)h->pinned_status;
     if (s == CV_ERR_ARG) return fail(CV_ERR_ARG, "observation index >= M (reference: ndarray index panic)");
@@ -407,7 +465,7 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
     const int K = 45;
-    const size_t smem = (size_t)K * 48 * 8 + (size_t)K * (threads / 32) * 64 * 8;
+    const size_t smem = (size_t)K * 48 * 8 + (size_t)K * ((threads / 32 + 5) / 6) * 64 * 8;
     double fp64_ops = 0.0;
     for (int rep = 0; rep < 2; rep++) {   // rep 0 = warm-up
         CUDA_TRY(cudaEventRecord(e0));
@@ -430,10 +488,19 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
                 case 3: e = launch(probe_tile_kernel<1>); break;
                 case 4: e = launch(probe_tile_kernel<2>); break;
                 case 5: e = launch(probe_tile_kernel<3>); break;
+                case 6:
+                    e = cudaFuncSetAttribute(probe_tile_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e == cudaSuccess) probe_tile_val_kernel<<<blocks, threads, smem>>>(d_out, K, iters, 1.0);
+                    break;
+                case 7: probe_mix_kernel<1, 1><<<blocks, threads>>>(d_out, iters, 1.0); break;
+                case 8: probe_mix_kernel<1, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
+                case 9: probe_mix_kernel<0, 3><<<blocks, threads>>>(d_out, iters, 1.0); break;
+                case 10: probe_mix_kernel<1, 0><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 default: return fail(CV_ERR_ARG, "unknown probe mode %d", mode);
             }
             CUDA_TRY(e);
             fp64_ops = 2.0 * 16.0 * K * (double)iters * threads * blocks;   // DADD + DSETP per cell
+            if (mode >= 7) fp64_ops = 8.0 * (double)iters * threads * blocks;   // DADD count (8 chains) per iteration
         }
         g_launches++;
         CUDA_TRY(cudaEventRecord(e1));

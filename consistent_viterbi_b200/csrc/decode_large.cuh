@@ -1,3 +1,248 @@
-// decode_large.cuh -- batched plain Viterbi (mode R1) for K > 64 (tiled logA). Placeholder until implemented.
+// decode_large.cuh -- batched plain Viterbi (mode R1) for K > 64: logA tiled
+// through shared memory (reference: viterbi::decode, src/viterbi_solver/viterbi.rs:5-32).
+//
+// One time step of 64 sequences is a max-plus "GEMM"
+//     delta_t[b][i] = max_j ( delta_{t-1}[b][j] + logA[j][i] )   (+ logB[i][o_t(b)])
+// that no longer fits one SM's shared memory (logA alone is 8 MB at K = 1024), so
+// the step is cut into work items (t, rb, cb): row block rb = 64 sequences (sorted
+// by length), column block cb = 128 target states.  A persistent grid (one CTA
+// per SM) claims items from a global counter in (t, rb, cb) order; item (t, rb, *)
+// may start once all NCB items of (t-1, rb, *) have published their delta slice
+// (per-row-block completion counter, release/acquire).  Items are claimed only by
+// running CTAs and depend only on lower-numbered items, so the scheme cannot
+// deadlock and keeps all 148 SMs busy without clusters or grid-wide barriers.
+//
+// Inside an item, one producer thread streams 16-row chunks of logA[:, cb] (16 KB) and
+// of delta_{t-1}[rb] (8 KB) from L2 into a 4-stage shared-memory ring with TMA
+// bulk copies (cp.async.bulk + mbarrier full/empty pairs); 16 warps each
+// own 8 target states x 64 sequences and run the same 2x8 register micro-tile as
+// the small-K kernel.  delta is kept in HBM/L2 as [2][Kl][Bpad] (state-major,
+// sequence fastest) so both the chunk loads and the slice stores are contiguous.
 #pragma once
+
 #include "common.cuh"
+
+namespace cvb {
+
+constexpr int LG_BM = 64;        // sequences per row block
+constexpr int LG_BK = 16;        // predecessor rows per pipeline stage
+constexpr int LG_STAGES = 4;
+constexpr int LG_CONSUMER_WARPS = LARGE_BN / TQ;               // 16
+constexpr int LG_THREADS = 32 * LG_CONSUMER_WARPS;             // producer = lane 0 of warp 0
+constexpr int LG_STAGE_A = LG_BK * LARGE_BN;                   // doubles
+constexpr int LG_STAGE_D = LG_BK * LG_BM;                      // doubles
+constexpr size_t LG_SMEM_BYTES = (size_t)LG_STAGES * (LG_STAGE_A + LG_STAGE_D) * 8 + 256;
+
+struct DecodeLargeParams {
+    const double *A;          // [Kl][Kl] logA padded with -inf
+    const double *BT;         // [M][Kl]
+    const uint32_t *obs;      // [N]
+    const int64_t *seq_off;   // [B+1]
+    const uint32_t *order;    // [B] longest first
+    const uint32_t *sorted_len;  // [B] lengths in that order
+    uint32_t *path;           // [N]
+    double *score;            // [B] or nullptr
+    double *delta;            // [2][Kl][Bpad]
+    void *psi;                // [N][Kl] u8 (Kl <= 256) or u16
+    const long long *step_start; // [Tmax+1] first item id of step t (index t, t >= 1); [Tmax] = total
+    unsigned long long *item_counter;
+    unsigned int *done;       // [NRB] completed items per row block
+    int *status;
+    int64_t M, B, Bpad;
+    int K, Kl, NCB, NRB, Tmax, psi16, zero;
+};
+
+template <int VARIANT>
+__device__ __forceinline__ void maxplus_accum(const double *__restrict__ dcol, int ldd,
+                                              const double *__restrict__ arow, int lda, int nj, int jbase,
+                                              double (&best)[TP][TQ], int (&idx)[TP][TQ], int zero)
+{
+#pragma unroll 2
+    for (int jj = 0; jj < nj; jj++) {
+        const double2 d = *reinterpret_cast<const double2 *>(dcol + jj * ldd);
+        const double2 a01 = *reinterpret_cast<const double2 *>(arow + jj * lda);
+        const double2 a23 = *reinterpret_cast<const double2 *>(arow + jj * lda + 2);
+        const double2 a45 = *reinterpret_cast<const double2 *>(arow + jj * lda + 4);
+        const double2 a67 = *reinterpret_cast<const double2 *>(arow + jj * lda + 6);
+        const double a[TQ] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+        const double dd[TP] = {d.x, d.y};
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) cell<VARIANT>(dd[p], a[q], best[p][q], idx[p][q], jbase + jj, zero);
+    }
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const DecodeLargeParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sA = reinterpret_cast<double *>(smem_raw);                       // [STAGES][BK][128]
+    double *sD = sA + (size_t)LG_STAGES * LG_STAGE_A;                        // [STAGES][BK][64]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sD + (size_t)LG_STAGES * LG_STAGE_D);
+    uint64_t *empty = full + LG_STAGES;
+    long long *sItem = reinterpret_cast<long long *>(empty + LG_STAGES);    // [0]=item, [1]=t, [2]=rb, [3]=cb
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int Kl = p.Kl, K = p.K;
+    const int nchunks = (K + LG_BK - 1) / LG_BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < LG_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LG_CONSUMER_WARPS); }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long total_items = p.step_start[p.Tmax];
+    uint32_t chunk_ctr = 0;   // chunks pushed (producer) / consumed (consumers) so far; same sequence in every warp
+
+    for (;;) {
+        // ---- claim the next work item ----
+        if (tid == 0) {
+            const long long n = (long long)atomicAdd(p.item_counter, 1ULL);
+            long long t = 0, rb = 0, cb = 0;
+            if (n < total_items) {
+                int lo = 1, hi = p.Tmax - 1;          // largest t with step_start[t] <= n
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (p.step_start[mid] <= n) lo = mid; else hi = mid - 1;
+                }
+                t = lo;
+                const long long r = n - p.step_start[t];
+                rb = r / p.NCB; cb = r % p.NCB;
+            }
+            sItem[0] = n; sItem[1] = t; sItem[2] = rb; sItem[3] = cb;
+        }
+        __syncthreads();
+        const long long item = sItem[0];
+        const int t = (int)sItem[1], rb = (int)sItem[2], cb = (int)sItem[3];
+        if (item >= total_items) break;
+
+        const double *dsrc = p.delta + (size_t)((t - 1) & 1) * Kl * p.Bpad + (size_t)rb * LG_BM;
+        const double *asrc = p.A + (size_t)cb * LARGE_BN;
+
+        // The producer is lane 0 of warp 0: it waits for the dependency, then keeps the TMA ring
+        // LG_STAGES-1 chunks ahead of the consumers (itself included).
+        auto issue_chunk = [&](int c) {
+            const uint32_t g = chunk_ctr + c;
+            const int s = g % LG_STAGES;
+            if (g >= LG_STAGES) mbar_wait(empty + s, ((g / LG_STAGES) - 1) & 1);
+            mbar_expect_tx(full + s, (uint32_t)((LG_STAGE_A + LG_STAGE_D) * 8));
+            double *dstA = sA + (size_t)s * LG_STAGE_A;
+            double *dstD = sD + (size_t)s * LG_STAGE_D;
+            const int j0 = c * LG_BK;
+#pragma unroll 4
+            for (int jj = 0; jj < LG_BK; jj++) {
+                tma_bulk_g2s(dstA + jj * LARGE_BN, asrc + (size_t)(j0 + jj) * Kl, LARGE_BN * 8, full + s);
+                tma_bulk_g2s(dstD + jj * LG_BM, dsrc + (size_t)(j0 + jj) * p.Bpad, LG_BM * 8, full + s);
+            }
+        };
+        if (tid == 0) {
+            // wait until step t-1 of this row block is fully published (step 1 reads the zeroed buffer)
+            const unsigned int need = (unsigned int)(t - 1) * (unsigned int)p.NCB;
+            while (ld_acquire_u32(p.done + rb) < need) { __nanosleep(64); }
+            asm volatile("fence.proxy.async;" ::: "memory");
+            for (int c = 0; c < LG_STAGES - 1 && c < nchunks; c++) issue_chunk(c);
+        }
+        __syncwarp();
+        {
+            // =================== consumer warps ===================
+            const int i0 = cb * LARGE_BN + w * TQ;        // global target state of q = 0
+            const int r0 = rb * LG_BM + lane * TP;        // sorted rank of p = 0
+            double best[TP][TQ]; int idx[TP][TQ];
+#pragma unroll
+            for (int q = 0; q < TP; q++)
+#pragma unroll
+                for (int k = 0; k < TQ; k++) { best[q][k] = neg_inf(); idx[q][k] = 0; }
+
+            for (int c = 0; c < nchunks; c++) {
+                if (tid == 0 && c + LG_STAGES - 1 < nchunks) issue_chunk(c + LG_STAGES - 1);
+                __syncwarp();
+                const uint32_t g = chunk_ctr + c;
+                const int s = g % LG_STAGES;
+                mbar_wait(full + s, (g / LG_STAGES) & 1);
+                const int nj = min(LG_BK, K - c * LG_BK);
+                maxplus_accum<VARIANT>(sD + (size_t)s * LG_STAGE_D + lane * TP, LG_BM,
+                                       sA + (size_t)s * LG_STAGE_A + w * TQ, LARGE_BN, nj, c * LG_BK, best, idx,
+                                       p.zero);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + s);
+            }
+            chunk_ctr += nchunks;
+
+            // ---- epilogue: emission, -inf rule, delta slice + backpointers ----
+            double *dnext = p.delta + (size_t)(t & 1) * Kl * p.Bpad;
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                const int r = r0 + q;
+                if (r >= p.B) continue;
+                const int len = (int)p.sorted_len[r];
+                if (t >= len) continue;
+                const uint32_t b = p.order[r];
+                const int64_t pos = p.seq_off[b] + t;
+                uint32_t o = p.obs[pos];
+                if ((int64_t)o >= p.M) { *p.status = 3; o = 0; }
+                const double *em = p.BT + (size_t)o * Kl + i0;
+                uint32_t pk[TQ];
+#pragma unroll
+                for (int k = 0; k < TQ; k++) {
+                    const double e = __ldg(em + k);
+                    double v = best[q][k] + e;                      // (delta + a) + b   viterbi.rs:17
+                    int ix = idx[q][k];
+                    if (!(e > neg_inf())) { v = neg_inf(); ix = 0; }   // viterbi.rs:19-21
+                    if (i0 + k < K) dnext[(size_t)(i0 + k) * p.Bpad + r] = v;
+                    pk[k] = (uint32_t)ix;
+                }
+                if (p.psi16) {
+                    uint4 v4 = make_uint4(pk[0] | (pk[1] << 16), pk[2] | (pk[3] << 16), pk[4] | (pk[5] << 16),
+                                          pk[6] | (pk[7] << 16));
+                    __stcs(reinterpret_cast<uint4 *>((uint16_t *)p.psi + (size_t)pos * Kl + i0), v4);
+                } else {
+                    uint2 v2 = make_uint2(pk[0] | (pk[1] << 8) | (pk[2] << 16) | (pk[3] << 24),
+                                          pk[4] | (pk[5] << 8) | (pk[6] << 16) | (pk[7] << 24));
+                    __stcs(reinterpret_cast<uint2 *>((uint8_t *)p.psi + (size_t)pos * Kl + i0), v2);
+                }
+            }
+            __threadfence();   // publish this thread's delta slice before the item is counted done
+        }
+        __syncthreads();
+        if (tid == 0) atomicAdd(p.done + rb, 1u);   // release: all consumers fenced before the barrier
+    }
+}
+
+// End state (viterbi.rs:24) and backtrace (viterbi.rs:25-30), one thread per sequence.
+__global__ void backtrace_large_kernel(const DecodeLargeParams p)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.B) return;
+    const int len = (int)p.sorted_len[r];
+    const uint32_t b = p.order[r];
+    const int64_t off = p.seq_off[b];
+    const double *fin = p.delta + (size_t)((len - 1) & 1) * p.Kl * p.Bpad + r;
+    double bv = __ldcg(fin); uint32_t cur = 0;
+    for (int i = 1; i < p.K; i++) {
+        const double v = __ldcg(fin + (size_t)i * p.Bpad);
+        if (v > bv) { bv = v; cur = (uint32_t)i; }
+    }
+    if (p.score) p.score[b] = bv;
+    p.path[off + len - 1] = cur;
+    for (int t = len - 1; t >= 1; t--) {
+        const size_t e = (size_t)(off + t) * p.Kl + cur;
+        cur = p.psi16 ? (uint32_t)__ldcg((const uint16_t *)p.psi + e) : (uint32_t)__ldcg((const uint8_t *)p.psi + e);
+        p.path[off + t - 1] = cur;
+    }
+}
+
+}  // namespace cvb

@@ -2,21 +2,40 @@
 //
 // Replaces B calls of viterbi::decode (reference src/viterbi_solver/viterbi.rs:5-32).
 //
-// Mapping (B200): one persistent CTA per SM pulls tiles of NS = 64*S sequences
-// (sequences are pre-sorted by length, longest first, so a tile runs in lock
-// step with little idle tail).  logA (K x Kp f64) is staged once per CTA into
-// shared memory with a TMA bulk copy; delta lives in shared memory, double
-// buffered, laid out [state j][sequence slot] so that
-//   - a lane owns TP=2 adjacent sequences  -> one conflict-free LDS.128 per j
-//   - a warp owns TQ=8 adjacent target states -> four broadcast LDS.128 per j
-// giving 16 max-plus cells per thread per predecessor j from 5 shared loads
-// (shared-memory crossbar at ~50 % when the FP64 pipe is saturated).
-// Warps = G state groups (G = ceil(K/8)) x S sequence groups.
-// Per step a thread adds the emission (viterbi.rs:17: (delta + a) + b), forces
-// psi = 0 / delta = -inf where the emission is -inf (viterbi.rs:12,19-21), writes
-// 8 backpointers as one 8-byte store and 16 delta values to the other buffer.
-// The backtrace (viterbi.rs:24-30) runs fused at the end of the tile, one thread
-// per sequence, while the tile's psi rows are still in L2.
+// Two kernels:
+//
+// 1. decode_small_fwd_kernel -- forward max-plus recurrence, VALUE ONLY.
+//    sm_100a has neither a 64-bit select nor DMNMX, so tracking (value, argmax)
+//    per cell costs DADD + DSETP + 3 selects and is bound by the ALU pipe (ncu:
+//    alu 74 %, fp64 49 %).  The forward pass therefore keeps only the running
+//    maximum (DADD + DSETP + 2 FSEL) and writes every delta row to HBM ("delta
+//    history").  The backpointer psi[t][s] = first-argmax_j fl(delta[t-1][j] +
+//    logA[j][s]) is a pure function of the stored row, so the backtrace recomputes
+//    it only for the one state per step on the decoded path (K cells, not K*K).
+//
+//    Mapping: persistent CTAs pull tiles of NS = 64*S sequences (pre-sorted by
+//    length, longest first, so a tile runs in lock step).  Shared memory holds
+//      sA  [K][Kp]      logA, staged once per CTA by a TMA bulk copy
+//      sD  [2][K][NS]   delta, double buffered, [state][sequence slot]
+//      sEm [NS][Kp+2]   this step's emission rows logB^T[o_t(s)][.], fetched by TMA
+//                       bulk copies (one 8*Kp-byte row per sequence, L2 resident)
+//    A lane owns TP=2 adjacent sequences (one conflict-free LDS.128 per j), a warp
+//    owns TQ=8 adjacent target states (four broadcast LDS.128 per j): 16 cells per
+//    thread per predecessor from 5 shared loads.  Warps = G state groups
+//    (G = ceil(K/8)) x S sequence groups.  After the j loop the thread adds the
+//    emission ((delta + a) + b, viterbi.rs:17; an emission of -inf gives -inf,
+//    viterbi.rs:19-21) and stores 8 x double2 into the other buffer; after the
+//    step barrier one thread writes the whole [K][NS] slab to the history with a
+//    single TMA bulk store.  No per-thread global loads or stores remain in the
+//    step loop except the observation prefetch of the producer warp.
+//
+//    History layout: slab (tile, t) at hist + (tile_base[tile] + t) * K * NS,
+//    tile_base = exclusive scan of the tiles' longest lengths.
+//
+// 2. backtrace_small_kernel -- end state (viterbi.rs:24) and backtrace
+//    (viterbi.rs:25-30) with lazy psi; 8 lanes per sequence split the K
+//    predecessors and reduce (value, index) with shuffles; a warp holds 4 adjacent
+//    sequences so each 32-byte sector of a slab row is read by one instruction.
 #pragma once
 
 #include "common.cuh"
@@ -29,49 +48,121 @@ struct DecodeSmallParams {
     const uint32_t *obs;     // [N]
     const int64_t *seq_off;  // [B+1]
     const uint32_t *order;   // [B] sequence ids, longest first
-    uint8_t *psi;            // [N][Kp]   backpointers
+    const long long *tile_base;  // [ntiles] first slab of each tile
+    double *hist;            // delta history slabs, [K][NS] each
     uint32_t *path;          // [N]
     double *score;           // [B] or nullptr
     unsigned int *tile_counter;
     int *status;             // 0 ok, else CV_ERR_*
     int64_t M, B;
-    int K, Kp, G, S, ntiles, zero;
+    int K, Kp, G, S, ntiles;
 };
 
-// dynamic smem: [ A: K*Kp f64 ][ delta: 2*K*NS f64 ][ off: NS i64 ][ len: NS i32 ][ seq: NS u32 ][ mbar ][ tile ]
+__host__ __device__ inline int em_pitch(int Kp) { return Kp + 2; }   // doubles; bank-conflict-free row pitch
+
+// dynamic smem: [A][delta x2][em][off i64][len i32][mbarA, mbarEm][tile]
 __host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS)
 {
-    return (size_t)K * Kp * 8 + (size_t)2 * K * NS * 8 + (size_t)NS * (8 + 4 + 4) + 16 + 16;
+    return (size_t)K * Kp * 8 + (size_t)2 * K * NS * 8 + (size_t)NS * em_pitch(Kp) * 8 + (size_t)NS * (8 + 4) + 32 + 16;
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(512, 1) decode_small_kernel(const DecodeSmallParams p)
+// value-only TP x TQ micro-tile: best[p][q] = max_j ( dcol[j*ldd + p] + arow[j*lda + q] )
+// (strict > keeps the first maximum's bits, e.g. the sign of a zero, as the reference does).
+__device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol, int ldd,
+                                                 const double *__restrict__ arow, int lda, int nj,
+                                                 double (&best)[TP][TQ])
+{
+#pragma unroll 2
+    for (int j = 0; j < nj; j++) {
+        const double2 d = *reinterpret_cast<const double2 *>(dcol + (size_t)j * ldd);
+        const double2 a01 = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda);
+        const double2 a23 = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2);
+        const double2 a45 = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 4);
+        const double2 a67 = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 6);
+        const double a[TQ] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+        const double dd[TP] = {d.x, d.y};
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) {
+                const double v = dd[p] + a[q];
+                best[p][q] = v > best[p][q] ? v : best[p][q];
+            }
+    }
+}
+
+__device__ __forceinline__ void tma_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// MAXT/MINB only set the register budget (launch bounds).
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = p.K, Kp = p.Kp, NS = 64 * p.S;
+    const int K = p.K, Kp = p.Kp, NS = 64 * p.S, EP = em_pitch(Kp);
     double *sA = reinterpret_cast<double *>(smem_raw);
     double *sD = sA + (size_t)K * Kp;
-    int64_t *sOff = reinterpret_cast<int64_t *>(sD + (size_t)2 * K * NS);
+    double *sEm = sD + (size_t)2 * K * NS;
+    int64_t *sOff = reinterpret_cast<int64_t *>(sEm + (size_t)NS * EP);
     int *sLen = reinterpret_cast<int *>(sOff + NS);
-    uint32_t *sSeq = reinterpret_cast<uint32_t *>(sLen + NS);
-    uint64_t *sBar = reinterpret_cast<uint64_t *>(sSeq + NS);
-    int *sTile = reinterpret_cast<int *>(sBar + 2);
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(sLen + NS);   // [0] logA, [1] emissions
+    int *sTile = reinterpret_cast<int *>(sBar + 4);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = w % p.G, sg = w / p.G;
     const int i0 = g * TQ;
     const int s0 = sg * SEQ_PER_WARP + lane * TP;
+    const uint32_t slab_bytes = (uint32_t)((size_t)K * NS * 8);
+    const uint32_t row_bytes = (uint32_t)(Kp * 8);
 
     // ---- stage logA once per CTA (TMA bulk copy, UBLKCP) ----
     if (tid == 0) {
         mbar_init(sBar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_init(sBar + 1, 1);
+        fence_proxy_async_smem();
         const uint32_t bytes = (uint32_t)((size_t)K * Kp * 8);
         mbar_expect_tx(sBar, bytes);
         tma_bulk_g2s(sA, p.A, bytes, sBar);
     }
     __syncthreads();
     mbar_wait(sBar, 0);
+    uint32_t em_phase = 0;
+
+    // producer (warp 0): fetch the emission rows of step t for every sequence still running.
+    // Lane l serves slots l, l+32, ...; `o_cur` holds obs[off + t] of those slots.
+    auto issue_emissions = [&](int t, const uint32_t (&o_cur)[8]) {
+        int nact = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int s = lane + 32 * k;
+            if (s < NS && t < sLen[s]) nact++;
+        }
+        const int total = __reduce_add_sync(0xffffffffu, nact);
+        if (lane == 0) mbar_expect_tx(sBar + 1, (uint32_t)total * row_bytes);   // arrive + expected bytes (0 is fine)
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int s = lane + 32 * k;
+            if (s < NS && t < sLen[s]) {
+                uint32_t o = o_cur[k];
+                if ((int64_t)o >= p.M) { *p.status = 3; o = 0; }   // index panic in the reference
+                tma_bulk_g2s(sEm + (size_t)s * EP, p.BT + (size_t)o * Kp, row_bytes, sBar + 1);
+            }
+        }
+    };
 
     for (;;) {
         if (tid == 0) *sTile = (int)atomicAdd(p.tile_counter, 1u);
@@ -82,89 +173,195 @@ __global__ void __launch_bounds__(512, 1) decode_small_kernel(const DecodeSmallP
         // ---- tile set-up: sequence slots, delta(0) = 0.0 (viterbi.rs:6) ----
         for (int s = tid; s < NS; s += blockDim.x) {
             const int64_t r = (int64_t)tile * NS + s;
-            int64_t off = 0; int len = 0; uint32_t b = 0;
+            int64_t off = 0; int len = 0;
             if (r < p.B) {
-                b = p.order[r];
+                const uint32_t b = p.order[r];
                 off = p.seq_off[b];
                 len = (int)(p.seq_off[b + 1] - off);
             }
-            sOff[s] = off; sLen[s] = len; sSeq[s] = b;
+            sOff[s] = off; sLen[s] = len;
         }
         for (int e = tid; e < K * NS; e += blockDim.x) sD[e] = 0.0;
+        fence_proxy_async_smem();
         __syncthreads();
 
         const int Tmax = sLen[0];   // slot 0 holds the longest sequence of the tile
-        int len_p[TP]; int64_t off_p[TP];
-#pragma unroll
-        for (int q = 0; q < TP; q++) { len_p[q] = sLen[s0 + q]; off_p[q] = sOff[s0 + q]; }
-        const bool warp_has_work = __any_sync(0xffffffffu, len_p[0] > 1 || len_p[1] > 1);
+        double *slab = p.hist + (size_t)p.tile_base[tile] * K * NS;
+        if (tid == 0) tma_bulk_s2g(slab, sD, slab_bytes);   // history slab 0 = delta(0)
 
-        uint32_t o_next[TP];
+        uint32_t o_nxt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                // producer: obs of the NEXT step to fetch
+        if (w == 0) {
+            uint32_t o1[8];
 #pragma unroll
-        for (int q = 0; q < TP; q++) o_next[q] = (1 < len_p[q]) ? __ldg(p.obs + off_p[q] + 1) : 0u;
+            for (int k = 0; k < 8; k++) {
+                const int s = lane + 32 * k;
+                const bool in = s < NS;
+                o1[k] = (in && 1 < sLen[s]) ? __ldg(p.obs + sOff[s] + 1) : 0u;
+                o_nxt[k] = (in && 2 < sLen[s]) ? __ldg(p.obs + sOff[s] + 2) : 0u;
+            }
+            if (Tmax > 1) issue_emissions(1, o1);
+        }
 
         for (int t = 1; t < Tmax; t++) {
-            const bool act0 = t < len_p[0], act1 = t < len_p[1];
-            const bool act[TP] = {act0, act1};
-            if (warp_has_work && __any_sync(0xffffffffu, act0 || act1)) {
-                // emission rows for this step (issued before the j loop, used after it)
-                double em[TP][TQ];
+            double best[TP][TQ];
 #pragma unroll
-                for (int q = 0; q < TP; q++) {
-                    uint32_t o = o_next[q];
-                    if (act[q] && (int64_t)o >= p.M) { *p.status = 3; o = 0; }   // index panic in the reference
-                    const double2 *src = reinterpret_cast<const double2 *>(p.BT + (size_t)o * Kp + i0);
+            for (int q = 0; q < TP; q++)
 #pragma unroll
-                    for (int k = 0; k < TQ / 2; k++) {
-                        double2 v = act[q] ? __ldg(src + k) : make_double2(0.0, 0.0);
-                        em[q][2 * k] = v.x; em[q][2 * k + 1] = v.y;
-                    }
-                    o_next[q] = (t + 1 < len_p[q]) ? __ldg(p.obs + off_p[q] + t + 1) : 0u;
-                }
+                for (int k = 0; k < TQ; k++) best[q][k] = neg_inf();
+            const double *dcur = sD + (size_t)((t - 1) & 1) * K * NS + s0;
+            maxplus_tile_val(dcur, NS, sA + i0, Kp, K, best);
 
-                double best[TP][TQ]; int idx[TP][TQ];
-                const double *dcur = sD + (size_t)((t - 1) & 1) * K * NS + s0;
-                maxplus_tile<VARIANT>(dcur, NS, sA + i0, Kp, K, best, idx, p.zero);
-
-                double *dnext = sD + (size_t)(t & 1) * K * NS + s0;
+            mbar_wait(sBar + 1, em_phase);      // emission rows of step t have landed
+            em_phase ^= 1;
+            double *dnext = sD + (size_t)(t & 1) * K * NS + s0;
+            const double *e0 = sEm + (size_t)s0 * EP + i0, *e1 = e0 + EP;
 #pragma unroll
-                for (int q = 0; q < TP; q++) {
-                    if (!act[q]) continue;
-                    uint32_t pk[2] = {0u, 0u};
-#pragma unroll
-                    for (int k = 0; k < TQ; k++) {
-                        double v = best[q][k] + em[q][k];            // (delta + a) + b   viterbi.rs:17
-                        int ix = idx[q][k];
-                        if (!(em[q][k] > neg_inf())) { v = neg_inf(); ix = 0; }   // viterbi.rs:19-21
-                        if (i0 + k < K) dnext[(size_t)(i0 + k) * NS + q] = v;
-                        pk[k >> 2] |= (uint32_t)ix << (8 * (k & 3));
-                    }
-                    *reinterpret_cast<uint2 *>(p.psi + (size_t)(off_p[q] + t) * Kp + i0) = make_uint2(pk[0], pk[1]);
-                }
+            for (int k = 0; k < TQ / 2; k++) {
+                const double2 x0 = *reinterpret_cast<const double2 *>(e0 + 2 * k);
+                const double2 x1 = *reinterpret_cast<const double2 *>(e1 + 2 * k);
+                // (delta + a) + b (viterbi.rs:17).  Sequences that already ended compute garbage in their
+                // own column only; their last row is already in the history.
+                if (i0 + 2 * k < K)
+                    *reinterpret_cast<double2 *>(dnext + (size_t)(i0 + 2 * k) * NS) =
+                        make_double2(best[0][2 * k] + x0.x, best[1][2 * k] + x1.x);
+                if (i0 + 2 * k + 1 < K)
+                    *reinterpret_cast<double2 *>(dnext + (size_t)(i0 + 2 * k + 1) * NS) =
+                        make_double2(best[0][2 * k + 1] + x0.y, best[1][2 * k + 1] + x1.y);
             }
+            fence_proxy_async_smem();           // make this thread's delta writes visible to the TMA store
+            if (tid == 0) tma_store_wait_read_all();   // slab t-1 has left the buffer step t+1 will overwrite
             __syncthreads();
-        }
-
-        // ---- end state (viterbi.rs:24) + backtrace (viterbi.rs:25-30), one thread per sequence ----
-        if (tid < NS) {
-            const int len = sLen[tid];
-            if (len > 0) {
-                const int64_t off = sOff[tid];
-                const double *fin = sD + (size_t)((len - 1) & 1) * K * NS + tid;
-                double bv = fin[0]; uint32_t cur = 0;
-                for (int i = 1; i < K; i++) {
-                    const double v = fin[(size_t)i * NS];
-                    if (v > bv) { bv = v; cur = (uint32_t)i; }
-                }
-                if (p.score) p.score[sSeq[tid]] = bv;
-                p.path[off + len - 1] = cur;
-                for (int t = len - 1; t >= 1; t--) {
-                    cur = __ldcg(p.psi + (size_t)(off + t) * Kp + cur);
-                    p.path[off + t - 1] = cur;
+            if (tid == 0) tma_bulk_s2g(slab + (size_t)t * K * NS, sD + (size_t)(t & 1) * K * NS, slab_bytes);
+            if (w == 0 && t + 1 < Tmax) {
+                issue_emissions(t + 1, o_nxt);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int s = lane + 32 * k;
+                    o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? __ldg(p.obs + sOff[s] + t + 2) : 0u;
                 }
             }
         }
+        if (tid == 0) tma_store_wait_read_all();   // last slab read out before the buffers are reused
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// End state + backtrace with lazy backpointers: 8 lanes per sequence.
+//
+// Why no emission lookup is needed: the reference leaves psi[t][s] = 0 when b[s][o_t] = -inf
+// (viterbi.rs:7,19-21) and otherwise stores argmax_j(delta[t-1][j] + a[j][s]).  If delta[t][s] > -inf the
+// emission was finite and the argmax is recomputed here.  If delta[t][s] = -inf then either the emission was
+// -inf (psi = 0) or every candidate was -inf (argmax of an all -inf vector = 0): psi = 0 both ways.
+// ---------------------------------------------------------------------------
+constexpr int BT_LANES = 8;                         // lanes per sequence: a warp covers 4 adjacent sequences
+constexpr int BT_SLOTS = SMALL_K_MAX / BT_LANES;    // predecessors per lane (j = sub + 8*k)
+
+// (value, index) argmax over an 8-lane group: strictly greater value wins, equal values keep the lower
+// index -- the order ndarray-stats argmax visits them (viterbi.rs:16,24).
+__device__ __forceinline__ void group_argmax(double &v, int &ix)
+{
+#pragma unroll
+    for (int d = BT_LANES / 2; d >= 1; d >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, d, BT_LANES);
+        const int oi = __shfl_xor_sync(0xffffffffu, ix, d, BT_LANES);
+        if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+    }
+}
+
+// column s of one slab, predecessors j = sub + 8*k
+__device__ __forceinline__ void load_slab_col(const double *slab_col, int NS, int sub, int K, bool on,
+                                              double (&v)[BT_SLOTS])
+{
+#pragma unroll
+    for (int k = 0; k < BT_SLOTS; k++) {
+        const int j = sub + BT_LANES * k;
+        v[k] = (on && j < K) ? __ldcs(slab_col + (size_t)j * NS) : neg_inf();
+    }
+}
+
+__global__ void __launch_bounds__(256) backtrace_small_kernel(const DecodeSmallParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K, Kp = p.Kp, NS = 64 * p.S;
+    double *sAT = reinterpret_cast<double *>(smem_raw);     // sAT[s*Kp + j] = logA[j][s]
+    for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) {
+        const int j = e / Kp, s = e % Kp;
+        if (s < K) sAT[(size_t)s * Kp + j] = p.A[e];
+    }
+    __syncthreads();
+
+    const int sub = threadIdx.x % BT_LANES;
+    const int gpb = blockDim.x / BT_LANES;                   // sequences per block pass
+    const size_t sl = (size_t)K * NS;
+    const int64_t npass = ((int64_t)p.ntiles * NS + gpb - 1) / gpb;
+    for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+        // ranks are contiguous inside a pass: a warp holds 4 adjacent sequences of one tile, so each
+        // 32-byte sector of a slab row is consumed by one load instruction
+        const int64_t r = pass * gpb + threadIdx.x / BT_LANES;
+        const int tile = (int)(r / NS), s = (int)(r % NS);
+        const bool valid = r < p.B;
+        const uint32_t b = valid ? p.order[r] : 0u;
+        const int64_t off = valid ? p.seq_off[b] : 0;
+        const int len = valid ? (int)(p.seq_off[b + 1] - off) : 0;
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        const double *col = p.hist + (size_t)(valid ? p.tile_base[tile] : 0) * sl + s;   // column s of slab 0
+
+        double rv[BT_SLOTS], n1[BT_SLOTS], n2[BT_SLOTS];
+        load_slab_col(col + (size_t)(len - 1) * sl, NS, sub, K, valid, rv);               // delta[len-1][.]
+        // rows maxlen-2 and maxlen-3 in flight for the first two iterations
+        load_slab_col(col + (size_t)(maxlen - 2) * sl, NS, sub, K, valid && maxlen - 2 >= 0 && maxlen - 1 < len, n1);
+        load_slab_col(col + (size_t)(maxlen - 3) * sl, NS, sub, K, valid && maxlen - 3 >= 0 && maxlen - 2 < len, n2);
+
+        // end state: argmax of the last row (viterbi.rs:24)
+        double bv = neg_inf(); int cur = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < BT_SLOTS; k++) {
+            const int j = sub + BT_LANES * k;
+            if (j < K && (cur == 0x7fffffff || rv[k] > bv)) { bv = rv[k]; cur = j; }
+        }
+        group_argmax(bv, cur);
+        if (valid && sub == 0) {
+            if (p.score) p.score[b] = bv;
+            p.path[off + len - 1] = (uint32_t)cur;
+        }
+        double dcur = bv;                                     // delta[tt][cur]
+        // walk back (viterbi.rs:27-30): psi[tt][cur] recomputed from delta row tt-1 (held in n1)
+        for (int tt = maxlen - 1; tt >= 1; tt--) {
+            const bool act = valid && tt < len;
+            double n3[BT_SLOTS];                              // row tt-3, needed two iterations from now
+            load_slab_col(col + (size_t)(tt - 3) * sl, NS, sub, K, valid && tt - 3 >= 0 && tt - 2 < len, n3);
+            double mv = neg_inf(), msel = neg_inf(); int mi = 0x7fffffff;
+            const double *at = sAT + (size_t)(act ? cur : 0) * Kp;
+#pragma unroll
+            for (int k = 0; k < BT_SLOTS; k++) {
+                const int j = sub + BT_LANES * k;
+                if (j < K) {
+                    const double v = n1[k] + at[j];                                       // viterbi.rs:15
+                    if (mi == 0x7fffffff || v > mv) { mv = v; mi = j; msel = n1[k]; }
+                }
+            }
+            // reduce (value, index) and carry delta[tt-1][index] along
+            {
+#pragma unroll
+                for (int d = BT_LANES / 2; d >= 1; d >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, mv, d, BT_LANES);
+                    const int oi = __shfl_xor_sync(0xffffffffu, mi, d, BT_LANES);
+                    const double os = __shfl_xor_sync(0xffffffffu, msel, d, BT_LANES);
+                    if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; msel = os; }
+                }
+            }
+            // delta[tt-1][0], needed when psi = 0 is forced
+            const double d0 = __shfl_sync(0xffffffffu, n1[0], 0, BT_LANES);
+            if (act) {
+                const bool live = dcur > neg_inf();          // else psi = 0 (see header comment)
+                cur = live ? mi : 0;
+                dcur = live ? msel : d0;
+                if (sub == 0) p.path[off + tt - 1] = (uint32_t)cur;
+            }
+#pragma unroll
+            for (int k = 0; k < BT_SLOTS; k++) { n1[k] = n2[k]; n2[k] = n3[k]; }
+        }
     }
 }
 

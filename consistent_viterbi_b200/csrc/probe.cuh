@@ -3,6 +3,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "decode_small.cuh"
 
 namespace cvb {
 
@@ -39,15 +40,16 @@ __global__ void __launch_bounds__(512, 1) probe_tile_kernel(double *out, int K, 
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Kp = ((K + 7) / 8) * 8;
-    const int NS = (blockDim.x / 32) * SEQ_PER_WARP;   // every warp its own 64 sequences here
+    const int G = Kp / 8;
+    const int NS = ((blockDim.x / 32 + G - 1) / G) * SEQ_PER_WARP;   // warps = G state groups x sequence groups
     double *sA = reinterpret_cast<double *>(smem_raw);
     double *sD = sA + (size_t)K * Kp;
     for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) sA[e] = -seed * ((e * 37) % 101);
     for (int e = threadIdx.x; e < K * NS; e += blockDim.x) sD[e] = -seed * ((e * 53) % 89);
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int i0 = (w % (Kp / 8)) * TQ;
-    const int s0 = w * SEQ_PER_WARP + lane * TP;
+    const int i0 = (w % G) * TQ;
+    const int s0 = (w / G) * SEQ_PER_WARP + lane * TP;
     double tot = 0.0; int ti = 0;
     for (int it = 0; it < iters; it++) {
         double best[TP][TQ]; int idx[TP][TQ];
@@ -57,9 +59,69 @@ __global__ void __launch_bounds__(512, 1) probe_tile_kernel(double *out, int K, 
 #pragma unroll
             for (int q = 0; q < TQ; q++) { tot += best[p][q]; ti += idx[p][q]; }
         // perturb one operand so iterations are not hoisted
-        sD[(size_t)(it % K) * NS + s0] = tot * 1e-30;
+        if (i0 == 0) sD[(size_t)(it % K) * NS + s0] = tot * 1e-30;
     }
     if (tot == 12345.678 || ti == -7) out[blockIdx.x * blockDim.x + threadIdx.x] = tot + ti;
+}
+
+
+// value-only micro-tile (the forward kernel's inner loop) in isolation
+__global__ void __launch_bounds__(512, 1) probe_tile_val_kernel(double *out, int K, int iters, double seed)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Kp = ((K + 7) / 8) * 8;
+    const int G = Kp / 8;
+    const int NS = ((blockDim.x / 32 + G - 1) / G) * SEQ_PER_WARP;
+    double *sA = reinterpret_cast<double *>(smem_raw);
+    double *sD = sA + (size_t)K * Kp;
+    for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) sA[e] = -seed * ((e * 37) % 101);
+    for (int e = threadIdx.x; e < K * NS; e += blockDim.x) sD[e] = -seed * ((e * 53) % 89);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i0 = (w % G) * TQ;
+    const int s0 = (w / G) * SEQ_PER_WARP + lane * TP;
+    double tot = 0.0;
+    for (int it = 0; it < iters; it++) {
+        double best[TP][TQ];
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) best[p][q] = neg_inf();
+        maxplus_tile_val(sD + s0, NS, sA + i0, Kp, K, best);
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) tot += best[p][q];
+        if (i0 == 0) sD[(size_t)(it % K) * NS + s0] = tot * 1e-30;
+    }
+    if (tot == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = tot;
+}
+
+// dispatch-port test: NF independent FFMA per DADD (ND = 0 -> FFMA only)
+template <int ND, int NF>
+__global__ void __launch_bounds__(512, 1) probe_mix_kernel(double *out, int iters, double seed)
+{
+    constexpr int NCH = 8;
+    double acc[NCH]; float facc[NCH * (NF > 0 ? NF : 1)];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) acc[c] = seed * (threadIdx.x + c);
+#pragma unroll
+    for (int c = 0; c < NCH * (NF > 0 ? NF : 1); c++) facc[c] = (float)seed * (threadIdx.x + c);
+    const double inc = seed * 1e-3; const float finc = (float)seed * 1e-3f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            if (ND) acc[c] += inc;
+#pragma unroll
+            for (int f = 0; f < NF; f++) facc[c * NF + f] = fmaf(facc[c * NF + f], finc, finc);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) s += acc[c];
+#pragma unroll
+    for (int c = 0; c < NCH * (NF > 0 ? NF : 1); c++) s += facc[c];
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 }  // namespace cvb

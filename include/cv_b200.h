@@ -107,7 +107,11 @@ uint64_t cv_launch_count(void);
  * of the most recent cv_decode_batch / cv_decode_batch_dev / cv_cp_solve call
  * when timing was enabled with cv_set_timing(1). */
 void   cv_set_timing(int on);
-double cv_last_kernel_ms(const cv_hmm *h);
+double cv_last_kernel_ms(const cv_hmm *h);     /* forward (dominant) kernel */
+double cv_last_backtrace_ms(const cv_hmm *h);  /* end-state + backtrace kernel */
+/* tuning hook: force the small-K launch shape, cfg = 10*S + MINB (S sequence groups of 64 per CTA,
+ * MINB co-resident CTAs per SM); -1 = automatic. */
+void   cv_set_small_config(int cfg);
 /* pinned host memory helpers */
 void *cv_host_alloc(uint64_t bytes);
 void  cv_host_free(void *p);

@@ -29,6 +29,24 @@ def test_small_k_random(K):
     _check(A, B, pi, obs, off)
 
 
+@pytest.mark.parametrize("K,Bn,tmax", [(65, 300, 20), (100, 130, 30), (128, 64, 40), (129, 200, 12), (200, 70, 25),
+                                       (256, 65, 10), (257, 40, 10), (300, 100, 8)])
+def test_large_k_random(K, Bn, tmax):
+    """K > 64: tiled logA kernel (work items (t, row block, column block), TMA ring)."""
+    rng = np.random.default_rng(3000 + K)
+    M = int(rng.integers(2, 30))
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.3)
+    obs, off = random_batch(rng, Bn, M, 1, tmax)
+    _check(A, B, pi, obs, off)
+
+
+def test_large_k_ties():
+    rng = np.random.default_rng(3100)
+    A, B, pi = random_hmm(rng, 150, 5, ties=True)
+    obs, off = random_batch(rng, 150, 5, 1, 15)
+    _check(A, B, pi, obs, off)
+
+
 @pytest.mark.parametrize("K", [2, 5, 8, 13, 45])
 def test_small_k_ties_and_neg_inf(K):
     """log-probs from a tiny dyadic set incl. -inf and +-0.0: exact ties everywhere, so the

@@ -14,7 +14,7 @@ from util import random_hmm
 
 L = cv._lib.lib()
 out = {}
-for mode, iters in [(0, 20000), (1, 20000), (2, 300), (3, 300), (4, 300), (5, 300)]:
+for mode, iters in [(0, 20000), (1, 20000), (2, 300), (6, 300), (10, 20000), (7, 20000), (8, 20000), (9, 20000)]:
     ops, ms = C.c_double(), C.c_double()
     cv._lib.check(L.cv_probe_fp64(0, mode, iters, C.byref(ops), C.byref(ms)))
     out[f"probe_mode{mode}"] = {"fp64_ops_per_s": ops.value, "ms": ms.value}
@@ -30,12 +30,17 @@ obs = (rng.zipf(1.1, size=int(off[-1])) % M).astype(np.uint32)
 cells = float(((lens - 1) * K * K).sum())
 h = cv.HMM(A, B, pi)
 L.cv_set_timing(1)
-for it in range(4):
-    t0 = time.perf_counter()
-    paths, scores = cv.decode_batch(h, obs, off)
-    t1 = time.perf_counter()
-    kms = L.cv_last_kernel_ms(h.device_handle())
-    print(f"POS B={Bn} cells={cells:.3e} e2e {1e3*(t1-t0):.2f} ms  kernel {kms:.3f} ms  -> {cells/kms/1e-3:.3e} cells/s", flush=True)
-out["pos"] = {"B": Bn, "cells": cells, "kernel_ms": kms, "cells_per_s": cells / (kms * 1e-3)}
+res = {}
+for cfg in [int(c) for c in os.environ.get("CFGS", "-1,11,13,21,12").split(",")]:
+    L.cv_set_small_config(cfg)
+    for it in range(3):
+        t0 = time.perf_counter()
+        paths, scores = cv.decode_batch(h, obs, off)
+        t1 = time.perf_counter()
+        kms = L.cv_last_kernel_ms(h.device_handle())
+        bms = L.cv_last_backtrace_ms(h.device_handle())
+    print(f"cfg {cfg:3d} POS B={Bn} cells={cells:.3e} e2e {1e3*(t1-t0):.2f} ms  fwd {kms:.3f} ms bt {bms:.3f} ms -> fwd {cells/kms/1e-3:.3e} total {cells/(kms+bms)/1e-3:.3e} cells/s", flush=True)
+    res[cfg] = kms
+out["pos"] = {"B": Bn, "cells": cells, "kernel_ms": res}
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/probe.json", "w"), indent=1)
