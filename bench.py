@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- Viterbi cells/s of the B200 hot path, one JSON line (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pos|large|ar|cp] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json
+configs[2], the POS-tagging shape (K=45 tags, 20k vocab, 1M sentences, avg T=25): the batched, sharding
+configuration the metric "cells/s at 1/2/4/8 B200" is quoted on (configs[1], datasets/ar, is 60 sequences /
+1.5e7 cells, latency bound and unshardable -- it is run as `--workload ar` and reported under "other").
+N > 1: launched by torchrun, one rank per GPU, every rank decodes its own shard of 1M sentences (weak
+scaling, no data-path collective), max-over-ranks timing.
+
+value    cells/s with inputs resident in HBM (cv_decode_batch_dev on torch's current stream)
+e2e      cells/s through the C ABI call a user makes (cv_decode_batch, pinned HOST buffers, H2D + D2H inside)
+roofline dominant kernel (forward recurrence) vs the FP64 issue peak measured in the same run, plus HBM view
+cpu_baseline  the C oracle (port of the reference loops) on this box's cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "viterbi_cells_per_s"
+UNIT = "cells/s"
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic workloads, seeded
+# ----------------------------------------------------------------------------------------------
+def _log_dirichlet_rows(rng, n, m, alpha, zero_frac):
+    # gamma draws normalised per row = Dirichlet(alpha); chunked to bound memory
+    out = np.empty((n, m), dtype=np.float64)
+    for r0 in range(0, n, 64):
+        r1 = min(n, r0 + 64)
+        g = rng.standard_gamma(alpha, size=(r1 - r0, m))
+        g[g == 0.0] = np.finfo(np.float64).tiny
+        p = g / g.sum(axis=1, keepdims=True)
+        p[rng.random((r1 - r0, m)) < zero_frac] = 0.0
+        with np.errstate(divide="ignore"):
+            out[r0:r1] = np.log10(p)
+    return out
+
+
+def make_hmm(seed, K, M, alpha, zero_frac):
+    rng = np.random.default_rng(seed)
+    A = _log_dirichlet_rows(rng, K, K, alpha, zero_frac)
+    B = _log_dirichlet_rows(rng, K, M, alpha, zero_frac)
+    pi = _log_dirichlet_rows(rng, 1, K, alpha, zero_frac)[0]
+    return A, B, pi
+
+
+def workload_pos(rank, nseq):
+    """K=45, V=20000, T = clamp(round(Gamma(2.5, 10)), 1, 200), Zipf(1.1) word ids; seed 3019 (+rank)."""
+    K, M = 45, 20000
+    A, B, pi = make_hmm(3019, K, M, 0.1, 0.05)
+    rng = np.random.default_rng(3019 + 1000 * (rank + 1))
+    lens = np.clip(np.rint(rng.gamma(2.5, 10.0, size=nseq)), 1, 200).astype(np.int64)
+    off = np.zeros(nseq + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    obs = (rng.zipf(1.1, size=int(off[-1])) % M).astype(np.uint32)
+    cells = float(((lens - 1) * K * K).sum())
+    return dict(name="pos_K45_V20k", K=K, M=M, A=A, B=B, pi=pi, obs=obs, off=off, cells=cells,
+                steps=float((lens - 1).sum()), desc=f"POS shape K=45 V=20000 B={nseq} avgT=25 (configs[2])")
+
+
+def workload_large(rank, nseq, T, K=1024, M=4096):
+    A, B, pi = make_hmm(3019, K, M, 0.05, 0.0)
+    rng = np.random.default_rng(3019 + 1000 * (rank + 1))
+    off = np.arange(nseq + 1, dtype=np.int64) * T
+    obs = rng.integers(0, M, size=nseq * T).astype(np.uint32)
+    cells = float(nseq) * (T - 1) * K * K
+    return dict(name=f"large_K{K}", K=K, M=M, A=A, B=B, pi=pi, obs=obs, off=off, cells=cells,
+                steps=float(nseq) * (T - 1), desc=f"large-state K={K} M={M} T={T} B={nseq} (configs[3])")
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi fields via NVML) during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self.stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline: the C oracle (port of the reference loops), bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_baseline(wl, budget_s=12.0, threads=None):
+    from oracle import pyoracle as po
+
+    threads = threads or (os.cpu_count() or 1)
+    off, obs, K = wl["off"], wl["obs"], wl["K"]
+    B = len(off) - 1
+
+    def run(nb):
+        o = off[: nb + 1]
+        t0 = time.perf_counter()
+        po.decode_batch(wl["A"], wl["B"], obs[: o[-1]], o, nthreads=threads)
+        dt = time.perf_counter() - t0
+        return float(((np.diff(o) - 1) * K * K).sum()), dt
+
+    nb = max(1, min(B, 64 if K > 64 else 2000))
+    if K > 64:
+        # one long sequence already costs seconds on the CPU: bound T as well
+        T = int(off[1] - off[0])
+        Tc = min(T, 64)
+        o = np.arange(min(B, threads) + 1, dtype=np.int64) * Tc
+        ob = np.concatenate([obs[off[b]: off[b] + Tc] for b in range(len(o) - 1)])
+        t0 = time.perf_counter()
+        po.decode_batch(wl["A"], wl["B"], ob, o, nthreads=threads)
+        dt = time.perf_counter() - t0
+        cells = float(len(o) - 1) * (Tc - 1) * K * K
+        return {"value": cells / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{len(o) - 1} sequences x first {Tc} steps of the workload, {dt:.1f} s, C oracle (port of "
+                          f"viterbi.rs:5-32), {threads} OpenMP threads"}
+    cells, dt = run(nb)
+    rate = cells / max(dt, 1e-6)
+    nb2 = int(max(nb, min(B, nb * budget_s / max(dt, 1e-3))))
+    cells, dt = run(nb2)
+    return {"value": cells / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {nb2} sequences of the workload, {dt:.1f} s, C oracle (port of viterbi.rs:5-32), "
+                      f"{threads} OpenMP threads"}
+
+
+# ----------------------------------------------------------------------------------------------
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pos", choices=["pos", "large"])
+    ap.add_argument("--nseq", type=int, default=0, help="sequences per GPU (0 = the config's size)")
+    ap.add_argument("--seqlen", type=int, default=0, help="T for --workload large (0 = 4096)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def build_workload(args, rank):
+    if args.workload == "pos":
+        return workload_pos(rank, args.nseq or 1_000_000)
+    return workload_large(rank, args.nseq or 4096, args.seqlen or 4096)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm (C oracle port; the Rust binary cannot be
+    built here) with all host threads, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+
+    wl = build_workload(args, 0)
+    threads = os.cpu_count() or 1
+    K, off, obs = wl["K"], wl["off"], wl["obs"]
+    if K > 64:
+        Tc, nb = 32, min(len(off) - 1, threads)
+        o = np.arange(nb + 1, dtype=np.int64) * Tc
+        ob = np.concatenate([obs[off[b]: off[b] + Tc] for b in range(nb)])
+        sample = f"{nb} sequences x first {Tc} steps per step"
+    else:
+        nb = min(len(off) - 1, 20000)
+        o = off[: nb + 1]
+        ob = obs[: o[-1]]
+        sample = f"first {nb} sequences per step"
+    cells = float(((np.diff(o) - 1) * K * K).sum())
+    for _ in range(args.warmup):
+        po.decode_batch(wl["A"], wl["B"], ob, o, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        po.decode_batch(wl["A"], wl["B"], ob, o, nthreads=threads)
+    dt = time.perf_counter() - t0
+    v = cells * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "desc": wl["desc"]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample + f", C oracle (port of viterbi.rs:5-32), {threads} OpenMP threads"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import consistent_viterbi_b200 as cv
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = cv._lib.lib()
+    wl = build_workload(args, rank)
+    hmm = cv.HMM(wl["A"], wl["B"], wl["pi"])
+    h = hmm.device_handle(local)
+    obs_np, off_np = wl["obs"], wl["off"]
+    B, N = len(off_np) - 1, int(off_np[-1])
+    max_len = int(np.diff(off_np).max())
+
+    # ---- FP64 issue peak of this GPU, measured now (roofline denominator) ----
+    ops, ms = C.c_double(), C.c_double()
+    cv._lib.check(L.cv_probe_fp64(local, 0, 20000, C.byref(ops), C.byref(ms)))
+    peak_dadd = ops.value
+    cv._lib.check(L.cv_probe_fp64(local, 1, 20000, C.byref(ops), C.byref(ms)))
+    peak_mix = ops.value
+
+    # ---- device-resident inputs ----
+    d_obs = torch.from_numpy(obs_np.view(np.int32)).cuda()
+    d_off = torch.from_numpy(off_np).cuda()
+    d_path = torch.empty(N, dtype=torch.int32, device="cuda")
+    d_score = torch.empty(B, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step_dev(timing=False):
+        rc = L.cv_decode_batch_dev(h, d_obs.data_ptr(), d_off.data_ptr(), B, N, max_len, d_path.data_ptr(),
+                                   d_score.data_ptr(), stream.cuda_stream, 0)
+        cv._lib.check(rc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    launches0 = L.cv_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_dev()
+        e1.record(stream)
+        barrier()
+    launches = L.cv_launch_count() - launches0
+    dev_ms = e0.elapsed_time(e1)
+
+    # ---- dominant-kernel duration: CUDA events on the launching stream around the forward kernel ----
+    L.cv_set_timing(1)
+    fwd_ms, bt_ms = [], []
+    for _ in range(max(3, min(args.steps, 5))):
+        rc = L.cv_decode_batch_dev(h, d_obs.data_ptr(), d_off.data_ptr(), B, N, max_len, d_path.data_ptr(),
+                                   d_score.data_ptr(), stream.cuda_stream, 1)
+        cv._lib.check(rc)
+        fwd_ms.append(L.cv_last_kernel_ms(h))
+        bt_ms.append(L.cv_last_backtrace_ms(h))
+    L.cv_set_timing(0)
+    fwd = float(np.mean(fwd_ms))
+
+    # ---- end to end through the C ABI with pinned host buffers ----
+    def pinned(arr):
+        p = L.cv_host_alloc(arr.nbytes)
+        assert p, "cv_host_alloc failed"
+        buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(arr.nbytes,))
+        buf[:] = arr.view(np.uint8).reshape(-1)
+        return p, buf
+    p_obs, _ = pinned(obs_np)
+    p_off, _ = pinned(off_np)
+    p_path = L.cv_host_alloc(4 * N)
+    p_score = L.cv_host_alloc(8 * B)
+
+    def step_e2e():
+        cv._lib.check(L.cv_decode_batch(h, p_obs, p_off, B, p_path, p_score))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 5))
+    for _ in range(n_e2e):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    # check the end-to-end result against the device-resident one
+    host_paths = np.ctypeslib.as_array(C.cast(p_path, C.POINTER(C.c_uint32)), shape=(N,))
+    assert (host_paths == d_path.cpu().numpy().view(np.uint32)).all(), "e2e and device-resident paths differ"
+
+    # ---- reduce over ranks ----
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    total_cells = allsum(wl["cells"])
+    dev_ms = allmax(dev_ms)
+    e2e_s = allmax(e2e_s)
+    launches = int(allsum(float(launches)))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        K = wl["K"]
+        # algorithmic HBM bytes per step of one sequence (DESIGN.md "Roofline"): obs u32 + logB^T row +
+        # delta-history row written by the forward kernel and read back by the backtrace + path u32
+        if K <= 64:
+            bytes_per_step = 4 + 8 * K + 8 * K + 8 * K + 4
+        else:
+            w = 1 if ((K + 127) // 128) * 128 <= 256 else 2
+            bytes_per_step = 4 + 8 * K + w * K + w + 4
+        fp64_ops = 2.0 * wl["cells"]                      # 1 DADD + 1 compare per cell
+        achieved_alu = fp64_ops / (fwd * 1e-3)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl["name"])
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": total_cells * args.steps / (dev_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "desc": wl["desc"], "per_gpu_sequences": B, "per_gpu_elements": N,
+                       "sharding": f"{world} x independent shards, no data-path collective",
+                       "l2": "inputs + delta history per step >> 126 MB L2 (no flush needed)"},
+            "e2e": {"value": total_cells / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(obs_np.nbytes + off_np.nbytes),
+                    "d2h_bytes_per_step": int(4 * N + 8 * B), "ms_per_step": 1e3 * e2e_s,
+                    "api": "cv_decode_batch (C ABI, pinned host buffers)"},
+            "gpu_launches": launches,
+            "clocks": clk.summary(),
+            "roofline": {
+                "bound": "fp64_alu", "kernel": "decode_small_fwd_kernel" if K <= 64 else "decode_large_kernel",
+                "achieved": achieved_alu / 1e12, "peak": peak_mix / 1e12, "unit": "TFLOP/s(fp64 add+compare)",
+                "frac": achieved_alu / peak_mix, "traffic": traffic,
+                "peak_source": "measured in this run: DADD+DSETP issue rate over all SMs (cv_probe_fp64 mode 1); "
+                               f"DADD alone {peak_dadd / 1e12:.2f}",
+                "kernel_ms": fwd, "backtrace_ms": float(np.mean(bt_ms)),
+                "hbm": {"achieved": wl["steps"] * bytes_per_step / ((fwd + float(np.mean(bt_ms))) * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "bytes_per_step": bytes_per_step,
+                        "frac": wl["steps"] * bytes_per_step / ((fwd + float(np.mean(bt_ms))) * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            },
+        }
+        if not args.no_cpu and world >= 1:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    for p in (p_obs, p_off, p_path, p_score):
+        L.cv_host_free(p)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""Constrained decode: mirror of the reference's `Solver` trait (src/viterbi_solver.rs:11-16) and
+`CPSolver` (src/viterbi_solver/cp.rs:8-152) over the C ABI entry cv_cp_solve.  GPU only."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .hmm import HMM
+from .superseq import SuperSequence
+
+
+def cp_solve_arrays(hmm: HMM, obs, is_seq_start, comp, ncomp, max_nodes: int = 0, device: int = -1,
+                    want_state: bool = False, want_ub: int = 0):
+    """cv_cp_solve on raw arrays.  Returns dict(sol u64[N], obj, explored, steps[, delta, psi, ub])."""
+    obs = np.ascontiguousarray(obs, dtype=np.uint32)
+    start = np.ascontiguousarray(is_seq_start, dtype=np.uint8)
+    comp = np.ascontiguousarray(comp, dtype=np.int32)
+    N = obs.shape[0]
+    sol = np.zeros(max(N, 1), dtype=np.uint64)
+    obj = C.c_double(0.0)
+    explored, steps = C.c_uint64(0), C.c_uint64(0)
+    L = _lib.lib()
+    h = hmm.device_handle(device)
+    rc = L.cv_cp_solve(h, obs.ctypes.data, start.ctypes.data, comp.ctypes.data, N, int(ncomp), int(max_nodes),
+                       sol.ctypes.data, C.byref(obj), C.byref(explored), C.byref(steps))
+    _lib.check(rc)
+    out = dict(sol=sol[:N], obj=obj.value, explored=explored.value, steps=steps.value)
+    if want_state:
+        K = hmm.nstates()
+        delta = np.zeros((N, K), dtype=np.float64)
+        psi = np.zeros((N, K), dtype=np.uint64)
+        _lib.check(L.cv_cp_last_state(h, delta.ctypes.data, psi.ctypes.data))
+        out["delta"], out["psi"] = delta, psi
+    if want_ub:
+        ub = np.zeros(want_ub, dtype=np.float64)
+        n = C.c_uint64(0)
+        _lib.check(L.cv_cp_last_ub(h, ub.ctypes.data, want_ub, C.byref(n)))
+        out["ub"] = ub[: min(want_ub, n.value)]
+    return out
+
+
+class Solver:
+    """trait Solver (viterbi_solver.rs:11-16)."""
+
+    def solve(self):
+        raise NotImplementedError
+
+    def get_solution(self):
+        raise NotImplementedError
+
+    def get_objective(self):
+        raise NotImplementedError
+
+    def get_name(self):
+        raise NotImplementedError
+
+
+class CPSolver(Solver):
+    """CPSolver::new(&hmm, &super_seq) (cp.rs:20); solve / get_solution / get_objective / get_name /
+    get_explored_nodes keep the reference's names and meaning."""
+
+    def __init__(self, hmm: HMM, sequence: SuperSequence, device: int = -1, max_nodes: int = 0):
+        self.hmm, self.sequence, self.device, self.max_nodes = hmm, sequence, device, max_nodes
+        self.best_obj = -np.inf                                      # cp.rs:29
+        self.best_sol = np.zeros(len(sequence), dtype=np.uint64)
+        self.explored_nodes = 0
+        self.sweep_steps = 0
+
+    def solve(self):                                                # cp.rs:133-143
+        obs, start, comp, ncomp = self.sequence.solver_inputs()
+        r = cp_solve_arrays(self.hmm, obs, start, comp, ncomp, self.max_nodes, self.device)
+        self.best_sol, self.best_obj = r["sol"], r["obj"]
+        self.explored_nodes, self.sweep_steps = r["explored"], r["steps"]
+
+    def get_solution(self):                                         # cp.rs:145-147
+        return self.best_sol
+
+    def get_objective(self):                                        # cp.rs:149
+        return self.best_obj
+
+    def get_name(self):                                             # cp.rs:151
+        return "cp"
+
+    def get_explored_nodes(self):                                   # cp.rs:128
+        return self.explored_nodes

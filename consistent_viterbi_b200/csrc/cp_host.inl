@@ -1,9 +1,283 @@
-// host control loop of the constrained solver (included by cv_api.cu)
-extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *, const uint8_t *, const int32_t *, int64_t, int32_t, uint64_t,
-                           uint64_t *, double *, uint64_t *, uint64_t *)
+// cp_host.inl -- host control loop of the constrained solver (included by cv_api.cu).
+//
+// Mirrors CPSolver::{new, solve, solve_r, backtrack} (reference src/viterbi_solver/cp.rs:20-30,
+// 85-143): the recursion over components and states, the pruning test `ub > best_obj` and the
+// explored-node counter run here on the host exactly as in the reference; every array operation
+// (sweeps, fix-ups, bound terms, their ordered sum, the backtrack) is a kernel of cp_kernels.cuh.
+// Nothing here computes Viterbi values on the CPU.
+
+namespace {
+
+struct CpRun {
+    cv_hmm *h;
+    CpParams p;
+    cudaStream_t st;
+    int32_t ncomp;
+    uint64_t max_nodes, explored = 0, steps = 0;
+    double best_obj = -std::numeric_limits<double>::infinity();
+    std::vector<int64_t> cons_off;               // positions of component c: cons_pos[cons_off[c] .. cons_off[c+1])
+    int64_t *d_cons_pos = nullptr;               // all components back to back = term order of cp.rs:104-116
+    int32_t *d_term_comp = nullptr;
+    std::vector<int64_t> seg_off;                // sweep segments of depth c: [seg_off[c], seg_off[c+1])
+    std::vector<uint64_t> seg_steps;             // rows swept per node of depth c
+    int64_t *d_seg_from = nullptr; int32_t *d_seg_len = nullptr;
+    double *d_terms = nullptr, *d_ub = nullptr; int *d_end = nullptr; unsigned int *d_counter = nullptr;
+    psi_t *d_F = nullptr; int *d_entry = nullptr; uint64_t *d_sol = nullptr;
+    double *h_ub = nullptr;                      // pinned
+    int err = CV_OK;
+    size_t smem;
+};
+
+int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
 {
-    (void)h;
-    return fail(CV_ERR_UNSUPPORTED, "cv_cp_solve not built yet");
+    if (nseg <= 0) return CV_OK;
+    CpSweepArgs a;
+    a.seg_from = r.d_seg_from + seg_begin; a.seg_len = r.d_seg_len + seg_begin;
+    a.nseg = (int)nseg; a.ntiles = (int)((nseg + 63) / 64); a.node = node; a.init_mode = init_mode;
+    a.tile_counter = r.d_counter;
+    CUDA_TRY(cudaMemsetAsync(r.d_counter, 0, sizeof(unsigned int), r.st));
+    const int grid = std::min(a.ntiles, r.h->num_sms * 2);
+    cp_sweep_kernel<<<grid, 32 * r.p.G, r.smem, r.st>>>(r.p, a);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CV_OK;
 }
-extern "C" int cv_cp_last_state(cv_hmm *, double *, uint64_t *) { return fail(CV_ERR_UNSUPPORTED, "not built yet"); }
-extern "C" int cv_cp_last_ub(cv_hmm *, double *, uint64_t, uint64_t *) { return fail(CV_ERR_UNSUPPORTED, "not built yet"); }
+
+// cp.rs:85-93
+int cp_backtrack(CpRun &r, double obj)
+{
+    if (!(obj > r.best_obj)) return fail(CV_ERR_ASSERT, "assert!(obj > self.best_obj) would fire (cp.rs:87)");
+    r.best_obj = obj;
+    const int nchunks = (int)((r.p.N + CP_BT_CHUNK - 1) / CP_BT_CHUNK);
+    double *d_obj = r.d_ub + 1;
+    cp_last_row_kernel<<<1, 32, 0, r.st>>>(r.p, d_obj, r.d_end);
+    const int64_t nmap = (int64_t)nchunks * r.p.K;
+    cp_bt_maps_kernel<<<(unsigned)((nmap + 127) / 128), 128, 0, r.st>>>(r.p, nchunks, r.d_F);
+    cp_bt_chain_kernel<<<1, 32, 0, r.st>>>(r.p, nchunks, r.d_F, r.d_end, r.d_entry);
+    cp_bt_fill_kernel<<<(nchunks + 127) / 128, 128, 0, r.st>>>(r.p, nchunks, r.d_entry, r.d_sol);
+    g_launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    return CV_OK;
+}
+
+// cp.rs:95-126
+int cp_solve_r(CpRun &r, int32_t comp)
+{
+    const int K = r.p.K;
+    const int64_t npos = r.cons_off[comp + 1] - r.cons_off[comp];
+    const int nterms = (int)r.cons_off[comp + 1];
+    for (int state = 0; state < K; state++) {
+        if (r.max_nodes && r.explored >= r.max_nodes) break;            // builder-added, deterministic budget
+        r.explored++;                                                    // cp.rs:97
+        cp_set_choice_kernel<<<1, 1, 0, r.st>>>(r.p.choice, comp, state);   // cp.rs:98
+        g_launches++;
+        int rc = cp_sweep(r, r.seg_off[comp], npos, state, 0);          // cp.rs:99-102, phases A + B
+        if (rc) return rc;
+        r.steps += r.seg_steps[comp];
+        if (npos > 0) {
+            cp_fixup_kernel<<<(unsigned)((npos + 127) / 128), 128, 0, r.st>>>(r.p, r.d_cons_pos + r.cons_off[comp],
+                                                                              (int)npos, comp, state);
+            g_launches++;
+        }
+        if (nterms > 0) {
+            cp_terms_kernel<<<(nterms + 255) / 256, 256, 0, r.st>>>(r.p, r.d_cons_pos, r.d_term_comp, nterms, r.d_terms);
+            g_launches++;
+        }
+        cp_sum_kernel<<<1, 256, 0, r.st>>>(r.d_terms, nterms, r.d_ub);   // cp.rs:103-116
+        g_launches++;
+        CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, sizeof(double), cudaMemcpyDeviceToHost, r.st));
+        CUDA_TRY(cudaStreamSynchronize(r.st));
+        const double ub = *r.h_ub;
+        if (r.h->cp_ub.size() < (1u << 20)) r.h->cp_ub.push_back(ub);
+        if (std::isnan(ub)) return fail(CV_ERR_NAN, "NaN upper bound");
+        if (ub > r.best_obj) {                                           // cp.rs:117
+            if (comp + 1 < r.ncomp) {                                    // cp.rs:118-119
+                if ((rc = cp_solve_r(r, comp + 1))) return rc;
+            } else {
+                if ((rc = cp_backtrack(r, ub))) return rc;               // cp.rs:121
+            }
+        }
+    }
+    cp_set_choice_kernel<<<1, 1, 0, r.st>>>(r.p.choice, comp, -1);      // cp.rs:125
+    g_launches++;
+    return CV_OK;
+}
+
+template <class T>
+int upload(DevBuf &b, const std::vector<T> &v, T **out, cudaStream_t st)
+{
+    int rc = b.ensure(std::max<size_t>(sizeof(T) * v.size(), 16));
+    if (rc) return rc;
+    if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
+    *out = (T *)b.p;
+    return CV_OK;
+}
+
+}  // namespace
+
+extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq_start, const int32_t *comp, int64_t N,
+                           int32_t ncomp, uint64_t max_nodes, uint64_t *sol_out, double *obj_out,
+                           uint64_t *explored_out, uint64_t *steps_out)
+{
+    if (!h) return fail(CV_ERR_ARG, "NULL model");
+    if (N <= 0) return fail(CV_ERR_EMPTY, "empty super-sequence (reference: array.row(len-1) panics)");
+    if (!obs || !is_seq_start || !comp || !sol_out) return fail(CV_ERR_ARG, "NULL buffer");
+    if (ncomp < 0) return fail(CV_ERR_ARG, "ncomp < 0");
+    if (h->K > SMALL_K_MAX) return fail(CV_ERR_UNSUPPORTED, "cv_cp_solve covers K <= %d (K = %d)", SMALL_K_MAX, h->K);
+    for (int64_t t = 0; t < N; t++) {
+        if ((int64_t)obs[t] >= h->M) return fail(CV_ERR_ARG, "observation index >= M at %lld (reference: ndarray index panic)", (long long)t);
+        if (comp[t] >= ncomp) return fail(CV_ERR_ARG, "component id %d >= ncomp %d at %lld (reference: constraints[ucomp] index panic, cp.rs:25)", comp[t], ncomp, (long long)t);
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int K = h->K;
+    h->cp_ub.clear();
+    h->cp_N = 0;
+
+    CpRun r;
+    r.h = h; r.st = st; r.ncomp = ncomp; r.max_nodes = max_nodes;
+    r.smem = cp_sweep_smem_bytes(K, h->Kp);
+
+    // ---- CPSolver::new (cp.rs:20-30): positions of every component, ascending ----
+    std::vector<std::vector<int64_t>> cons((size_t)ncomp);
+    for (int64_t t = 0; t < N; t++) if (comp[t] >= 0) cons[comp[t]].push_back(t);
+    std::vector<int64_t> cons_pos; std::vector<int32_t> term_comp;
+    r.cons_off.assign((size_t)ncomp + 1, 0);
+    for (int32_t c = 0; c < ncomp; c++) {
+        r.cons_off[c] = (int64_t)cons_pos.size();
+        for (int64_t t : cons[c]) { cons_pos.push_back(t); term_comp.push_back(c); }
+    }
+    r.cons_off[ncomp] = (int64_t)cons_pos.size();
+    if (cons_pos.size() > 0x7fffffffULL) return fail(CV_ERR_UNSUPPORTED, "too many clamped positions");
+
+    // ---- sweep segments ----
+    // depth c (components 0..c assigned): one sweep per position of c, running to the next position whose
+    // component is <= c (cp.rs:48); segment 0 of the list is the init_viterbi prefix (cp.rs:63-83).
+    std::vector<int64_t> seg_from; std::vector<int32_t> seg_len;
+    int64_t prefix = 0;
+    while (prefix < N && comp[prefix] < 0) prefix++;                 // rows 0 .. prefix-1 are swept by init_viterbi
+    seg_from.push_back(0); seg_len.push_back((int32_t)std::max<int64_t>(prefix - 1, 0));
+    r.seg_off.assign((size_t)ncomp + 1, 1);
+    r.seg_steps.assign((size_t)std::max(ncomp, 1), 0);
+    {
+        std::vector<int64_t> next_fixed((size_t)N + 1);
+        for (int32_t c = 0; c < ncomp; c++) {
+            r.seg_off[c] = (int64_t)seg_from.size();
+            int64_t nf = N;
+            for (int64_t t = N - 1; t >= 0; t--) { next_fixed[t] = nf; if (comp[t] >= 0 && comp[t] <= c) nf = t; }
+            std::vector<std::pair<int64_t, int64_t>> segs;           // (len, from)
+            for (int64_t pos : cons[c]) {
+                const int64_t len = next_fixed[pos] - pos - 1;
+                if (len > 0x7fffffffLL) return fail(CV_ERR_UNSUPPORTED, "segment too long");
+                segs.emplace_back(len, pos);
+                r.seg_steps[c] += (uint64_t)len;
+            }
+            std::stable_sort(segs.begin(), segs.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
+            for (auto &s : segs) { seg_from.push_back(s.second); seg_len.push_back((int32_t)s.first); }
+        }
+        r.seg_off[ncomp] = (int64_t)seg_from.size();
+    }
+
+    // ---- device state ----
+    DevBuf *b = h->cpb;
+    int rc;
+    if ((rc = b[0].ensure(sizeof(double) * (size_t)N * K))) return rc;
+    if ((rc = b[1].ensure(sizeof(psi_t) * (size_t)N * K))) return rc;
+    CUDA_TRY(cudaMemsetAsync(b[0].p, 0, sizeof(double) * (size_t)N * K, st));     // Array2::from_elem(.., 0.0) cp.rs:134
+    CUDA_TRY(cudaMemsetAsync(b[1].p, 0, sizeof(psi_t) * (size_t)N * K, st));      // bt = 0                    cp.rs:135
+    if ((rc = b[2].ensure(sizeof(uint32_t) * (size_t)N))) return rc;
+    if ((rc = b[3].ensure((size_t)N))) return rc;
+    if ((rc = b[4].ensure(sizeof(int32_t) * (size_t)N))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(b[2].p, obs, sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b[3].p, is_seq_start, (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b[4].p, comp, sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> choice0((size_t)std::max(ncomp, 1), -1);
+    int32_t *d_choice = nullptr;
+    if ((rc = upload(b[5], choice0, &d_choice, st))) return rc;
+    if ((rc = upload(b[6], seg_from, &r.d_seg_from, st))) return rc;
+    if ((rc = upload(b[7], seg_len, &r.d_seg_len, st))) return rc;
+    if ((rc = upload(b[8], cons_pos, &r.d_cons_pos, st))) return rc;
+    if ((rc = upload(b[9], term_comp, &r.d_term_comp, st))) return rc;
+    if ((rc = b[10].ensure(sizeof(double) * (cons_pos.size() + 8) + 256))) return rc;
+    r.d_terms = (double *)b[10].p + 4; r.d_ub = (double *)b[10].p;                 // [0] ub, [1] obj
+    r.d_end = (int *)((double *)b[10].p + 2); r.d_counter = (unsigned int *)((double *)b[10].p + 3);
+    const int nchunks = (int)((N + CP_BT_CHUNK - 1) / CP_BT_CHUNK);
+    if ((rc = b[11].ensure((size_t)nchunks * K + 64))) return rc;
+    if ((rc = b[12].ensure(sizeof(int) * (size_t)nchunks + 64))) return rc;
+    if ((rc = b[13].ensure(sizeof(uint64_t) * (size_t)N))) return rc;
+    r.d_F = (psi_t *)b[11].p; r.d_entry = (int *)b[12].p; r.d_sol = (uint64_t *)b[13].p;
+    CUDA_TRY(cudaMemsetAsync(r.d_sol, 0, sizeof(uint64_t) * (size_t)N, st));       // best_sol = 0 (cp.rs:29)
+    r.h_ub = (double *)h->pinned_status + 1;
+
+    CpParams &p = r.p;
+    p.A = h->dA; p.BT = h->dBT; p.Pi = h->dPi;
+    p.obs = (const uint32_t *)b[2].p; p.start = (const uint8_t *)b[3].p; p.comp = (const int32_t *)b[4].p;
+    p.delta = (double *)b[0].p; p.psi = (psi_t *)b[1].p; p.choice = d_choice;
+    p.N = N; p.M = h->M; p.K = K; p.Kp = h->Kp; p.G = h->G;
+    CUDA_TRY(cudaFuncSetAttribute(cp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem));
+
+    const bool timing = g_timing.load() != 0;
+    if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
+    // ---- init_viterbi (cp.rs:63-83) ----
+    if (prefix >= 1) {
+        cp_row0_kernel<<<1, 64, 0, st>>>(p);
+        g_launches++;
+        if (prefix > 1) {
+            if ((rc = cp_sweep(r, 0, 1, 0, 1))) return rc;
+            r.steps += (uint64_t)(prefix - 1);
+        }
+    }
+    // ---- solve (cp.rs:137-142) ----
+    if (ncomp > 0) {
+        rc = cp_solve_r(r, 0);
+    } else {
+        double *d_obj = r.d_ub + 1;
+        cp_last_row_kernel<<<1, 32, 0, st>>>(p, d_obj, r.d_end);
+        g_launches++;
+        CUDA_TRY(cudaMemcpyAsync(r.h_ub, d_obj, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        rc = cp_backtrack(r, *r.h_ub);
+    }
+    if (timing) {
+        CUDA_TRY(cudaEventRecord(h->ev1, st));
+        CUDA_TRY(cudaEventRecord(h->ev2, st));
+    }
+    h->cp_N = N;
+    CUDA_TRY(cudaMemcpyAsync(sol_out, r.d_sol, sizeof(uint64_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (timing) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms; else cudaGetLastError();
+        h->last_bt_ms = 0.0;
+    }
+    if (obj_out) *obj_out = r.best_obj;
+    if (explored_out) *explored_out = r.explored;
+    if (steps_out) *steps_out = r.steps;
+    return rc;
+}
+
+extern "C" int cv_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out)
+{
+    if (!h || h->cp_N <= 0) return fail(CV_ERR_ARG, "no constrained solve has run on this model");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->cp_N * h->K;
+    if (delta_out) CUDA_TRY(cudaMemcpy(delta_out, h->cpb[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (psi_out) {
+        uint64_t *tmp = nullptr;
+        CUDA_TRY(cudaMalloc(&tmp, sizeof(uint64_t) * n));
+        cp_widen_psi_kernel<<<(unsigned)((n + 255) / 256), 256>>>((const psi_t *)h->cpb[1].p, (int64_t)n, tmp);
+        g_launches++;
+        CUDA_TRY(cudaMemcpy(psi_out, tmp, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+        cudaFree(tmp);
+    }
+    return CV_OK;
+}
+
+extern "C" int cv_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *n_out)
+{
+    if (!h) return fail(CV_ERR_ARG, "NULL model");
+    const uint64_t n = std::min<uint64_t>(cap, h->cp_ub.size());
+    if (ub_out) for (uint64_t i = 0; i < n; i++) ub_out[i] = h->cp_ub[i];
+    if (n_out) *n_out = h->cp_ub.size();
+    return CV_OK;
+}

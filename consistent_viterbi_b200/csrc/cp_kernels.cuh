@@ -1,3 +1,291 @@
-// cp_kernels.cuh -- device kernels of the constrained (CPSolver) path. Placeholder until implemented.
+// cp_kernels.cuh -- device kernels of the constrained decode (mode R2).
+//
+// Replaces the inner loops of CPSolver (reference src/viterbi_solver/cp.rs:32-126):
+// viterbi_from / init_viterbi sweeps, the backpointer fix-ups of viterbi_from, the
+// upper-bound terms of solve_r and backtrack.  The branch-and-bound control flow
+// stays on the host (cp_host.inl) exactly as the reference's recursion.
+//
+// Persistent device state, as in the reference (cp.rs:134-135): delta f64 [N][K]
+// (init 0.0) and psi [N][K] (init 0), never restored between nodes.
+//
+// One B&B node (comp, state) = the reference's sequential viterbi_from calls for
+// every position of the component, executed as parallel phases with bit-identical
+// result: (A) reset the clamped rows, (B) sweep every clamp-to-next-
+// fixed-position segment concurrently, (C1/C2) backpointer fix-ups, (D) bound terms
+// gathered in parallel and summed serially in the reference's order.
+//
+// Sweep kernel mapping = the small-K decode mapping with "sequence" := segment:
+// tiles of 64 segments (sorted by length) run in lock step, a lane owns 2 segments,
+// a warp 8 target states, logA in shared memory, delta double-buffered in shared
+// memory as [state][slot].  Arithmetic is the reference's R2 order (cp.rs:49-58):
+//   psi = first-argmax_j fl(delta[t-1][j] + tr_j),  tr_j = a[j][s]  (pi[s] if el.t == 0)
+//   delta[t][s] = fl(delta[t-1][psi] + fl(tr_psi + b[s][o_t]))
+// so the cell keeps (value, index) -- the index IS state here, unlike mode R1.
 #pragma once
+
 #include "common.cuh"
+
+namespace cvb {
+
+typedef uint8_t psi_t;   // K <= 64 on this path
+
+struct CpParams {
+    const double *A;          // [K][Kp] padded -inf
+    const double *BT;         // [M][Kp]
+    const double *Pi;         // [Kp]
+    const uint32_t *obs;      // [N]
+    const uint8_t *start;     // [N] el.t == 0
+    const int32_t *comp;      // [N] active component or -1
+    double *delta;            // [N][K]
+    psi_t *psi;               // [N][K]
+    int32_t *choice;          // [ncomp] cstr_choices, -1 = None
+    int64_t N, M;
+    int K, Kp, G;
+};
+
+struct CpSweepArgs {
+    const int64_t *seg_from;  // [nseg] start row of each sweep, longest sweep first
+    const int32_t *seg_len;   // [nseg] number of rows swept after seg_from
+    int nseg, ntiles;
+    int node;                 // clamped state (ignored when init_mode)
+    int init_mode;            // 1: rows start from delta[seg_from] as stored (init_viterbi prefix)
+    unsigned int *tile_counter;
+};
+
+__host__ __device__ inline size_t cp_sweep_smem_bytes(int K, int Kp)
+{
+    return (size_t)K * Kp * 8 + (size_t)2 * K * 64 * 8 + (size_t)Kp * 8 + 64 * (8 + 4) + 16;
+}
+
+// delta[0][i] = fl(pi[i] + b[i][o_0])   (init_probs, hmm.rs:215-218; cp.rs:66-68)
+__global__ void cp_row0_kernel(const CpParams p)
+{
+    const int i = threadIdx.x;
+    if (i < p.K) p.delta[i] = p.Pi[i] + p.BT[(size_t)p.obs[0] * p.Kp + i];
+}
+
+__global__ void __launch_bounds__(256, 2) cp_sweep_kernel(const CpParams p, const CpSweepArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = p.K, Kp = p.Kp, NS = 64;
+    double *sA = reinterpret_cast<double *>(smem_raw);
+    double *sD = sA + (size_t)K * Kp;
+    double *sPi = sD + (size_t)2 * K * NS;
+    int64_t *sFrom = reinterpret_cast<int64_t *>(sPi + Kp);
+    int *sLen = reinterpret_cast<int *>(sFrom + NS);
+    int *sTile = sLen + NS;
+
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const int i0 = g * TQ;
+    const int s0 = lane * TP;
+    for (int e = tid; e < K * Kp; e += blockDim.x) sA[e] = p.A[e];
+    for (int e = tid; e < Kp; e += blockDim.x) sPi[e] = p.Pi[e];
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) *sTile = (int)atomicAdd(a.tile_counter, 1u);
+        __syncthreads();
+        const int tile = *sTile;
+        if (tile >= a.ntiles) break;
+
+        for (int s = tid; s < NS; s += blockDim.x) {
+            const int r = tile * NS + s;
+            sFrom[s] = r < a.nseg ? a.seg_from[r] : 0;
+            sLen[s] = r < a.nseg ? a.seg_len[r] : -1;       // -1: empty slot
+        }
+        __syncthreads();
+        // phase A: the clamped row (cp.rs:33-34), or the stored row for the init prefix
+        for (int e = tid; e < K * NS; e += blockDim.x) {
+            const int j = e / NS, s = e % NS;
+            double v = (j == a.node) ? 0.0 : neg_inf();
+            if (sLen[s] >= 0) {
+                if (a.init_mode) v = p.delta[(size_t)sFrom[s] * K + j];
+                else p.delta[(size_t)sFrom[s] * K + j] = v;
+            }
+            sD[e] = v;
+        }
+        __syncthreads();
+
+        const int Tmax = sLen[0];
+        int len_p[TP]; int64_t from_p[TP];
+#pragma unroll
+        for (int q = 0; q < TP; q++) { len_p[q] = sLen[s0 + q]; from_p[q] = sFrom[s0 + q]; }
+
+        // phase B: rows from+1 .. from+len (cp.rs:47-60 / cp.rs:70-78)
+        for (int k = 1; k <= Tmax; k++) {
+            const bool act[TP] = {k <= len_p[0], k <= len_p[1]};
+            uint32_t o[TP] = {0u, 0u}; bool st[TP] = {false, false};
+#pragma unroll
+            for (int q = 0; q < TP; q++)
+                if (act[q]) { o[q] = p.obs[from_p[q] + k]; st[q] = p.start[from_p[q] + k] != 0; }
+            const double *dcur = sD + (size_t)((k - 1) & 1) * K * NS + s0;
+            double best[TP][TQ]; int idx[TP][TQ];
+            const bool any_start = __any_sync(0xffffffffu, st[0] || st[1]);
+            if (!any_start) {
+                maxplus_tile<0>(dcur, NS, sA + i0, Kp, K, best, idx, 0);
+            } else {
+                // some segment crosses a sequence boundary at this row: its candidates are
+                // delta[t-1][j] + pi[s] (viterbi_solver/utils.rs:32-38), per lane
+#pragma unroll
+                for (int q = 0; q < TP; q++)
+#pragma unroll
+                    for (int c = 0; c < TQ; c++) { best[q][c] = neg_inf(); idx[q][c] = 0; }
+                for (int j = 0; j < K; j++) {
+                    const double2 d = *reinterpret_cast<const double2 *>(dcur + (size_t)j * NS);
+                    const double dd[TP] = {d.x, d.y};
+#pragma unroll
+                    for (int q = 0; q < TP; q++)
+#pragma unroll
+                        for (int c = 0; c < TQ; c++) {
+                            const double tr = st[q] ? sPi[i0 + c] : sA[(size_t)j * Kp + i0 + c];
+                            const double v = dd[q] + tr;
+                            if (v > best[q][c]) { best[q][c] = v; idx[q][c] = j; }
+                        }
+                }
+            }
+            double *dnext = sD + (size_t)(k & 1) * K * NS + s0;
+            const double *dold = sD + (size_t)((k - 1) & 1) * K * NS + s0;
+#pragma unroll
+            for (int q = 0; q < TP; q++) {
+                if (!act[q]) continue;
+                const int64_t t = from_p[q] + k;
+                const double *em = p.BT + (size_t)o[q] * Kp + i0;
+#pragma unroll
+                for (int c = 0; c < TQ; c++) {
+                    const int i = i0 + c;
+                    if (i < K) {
+                        const int ix = idx[q][c];
+                        const double tr = st[q] ? sPi[i] : sA[(size_t)ix * Kp + i];
+                        const double arc = tr + __ldg(em + c);                 // arc_p: a + b (utils.rs:24-30)
+                        const double v = dold[(size_t)ix * NS + q] + arc;      // delta + (a + b)  cp.rs:55
+                        dnext[(size_t)i * NS + q] = v;
+                        p.delta[(size_t)t * K + i] = v;
+                        p.psi[(size_t)t * K + i] = (psi_t)ix;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Phases C1 + C2 for the positions of the component just assigned (cp.rs:35-45).
+//  C2: psi[pos][state] = first-argmax_j fl(delta[pos-1][j] + tr_j(state))          (pos != 0)
+//  C1: psi[pos+1][choice[comp[pos+1]]] = state when pos+1 is fixed.  If pos+1 belongs to the same component
+//      the reference overwrites that very entry in the next viterbi_from call (C2 of pos+1), so it is skipped.
+__global__ void cp_fixup_kernel(const CpParams p, const int64_t *pos_list, int npos, int comp, int state)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npos) return;
+    const int64_t pos = pos_list[k];
+    const int K = p.K, Kp = p.Kp;
+    if (pos != 0) {
+        const double *prev = p.delta + (size_t)(pos - 1) * K;
+        const bool st = p.start[pos] != 0;
+        double bv = 0.0; int bi = 0;
+        for (int j = 0; j < K; j++) {
+            const double v = prev[j] + (st ? p.Pi[state] : p.A[(size_t)j * Kp + state]);
+            if (j == 0 || v > bv) { bv = v; bi = j; }
+        }
+        p.psi[(size_t)pos * K + state] = (psi_t)bi;
+    }
+    if (pos + 1 < p.N) {
+        const int c1 = p.comp[pos + 1];
+        if (c1 >= 0 && c1 < comp) p.psi[(size_t)(pos + 1) * K + p.choice[c1]] = (psi_t)state;
+    }
+}
+
+// Phase D: one bound term per clamped position of components 0..comp, in the reference's order
+// (cid ascending, position ascending; cp.rs:104-116).  term_pos[k] / term_comp[k] give position and component.
+__global__ void cp_terms_kernel(const CpParams p, const int64_t *term_pos, const int32_t *term_comp, int nterms,
+                                double *terms)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nterms) return;
+    const int64_t t = term_pos[k];
+    const int st = p.choice[term_comp[k]];
+    const int K = p.K, Kp = p.Kp;
+    const double b = p.BT[(size_t)p.obs[t] * Kp + st];
+    double term;
+    if (t == 0) {
+        term = p.Pi[st] + b;                                   // sequence[0].arc_p(hmm, 0, state), el.t == 0
+    } else {
+        const int sf = p.psi[(size_t)t * K + st];
+        const double arc = (p.start[t] ? p.Pi[st] : p.A[(size_t)sf * Kp + st]) + b;
+        term = p.delta[(size_t)(t - 1) * K + sf] + arc;
+    }
+    terms[k] = term;
+}
+
+// ub = ((0.0 + term_0) + term_1) + ...  exactly in order (cp.rs:103,109,114).  One thread adds; the block
+// stages the terms through shared memory so the adds are the only dependent chain.
+__global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, double *ub_out)
+{
+    __shared__ double buf[2048];
+    double ub = 0.0;
+    for (int base = 0; base < nterms; base += 2048) {
+        const int n = min(2048, nterms - base);
+        for (int e = threadIdx.x; e < n; e += blockDim.x) buf[e] = terms[base + e];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll 8
+            for (int e = 0; e < n; e++) ub += buf[e];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *ub_out = ub;
+}
+
+// obj = max(delta[N-1][.]) for the no-constraint case (cp.rs:139-141) and cur = argmax (cp.rs:86)
+__global__ void cp_last_row_kernel(const CpParams p, double *obj_out, int *end_out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double *row = p.delta + (size_t)(p.N - 1) * p.K;
+    double bv = row[0]; int bi = 0;
+    for (int j = 1; j < p.K; j++) if (row[j] > bv) { bv = row[j]; bi = j; }
+    *obj_out = bv; *end_out = bi;
+}
+
+// ---- backtrack (cp.rs:85-93) as a composition of backpointer maps -------------------------------
+// The chain sol[t] = cur; cur = psi[t][cur] is cut into chunks of CP_BT_CHUNK rows.  (1) for every chunk
+// and every possible state at the chunk's last row, walk the chunk: F[chunk][e] = state entering the
+// previous chunk; (2) one thread chains the chunks; (3) every chunk replays its walk from its known
+// entry state and writes sol.  Integer-exact, N*K lookups instead of N dependent ones.
+constexpr int CP_BT_CHUNK = 256;
+
+__global__ void cp_bt_maps_kernel(const CpParams p, int nchunks, psi_t *F)
+{
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)nchunks * p.K) return;
+    const int c = (int)(gid / p.K); int cur = (int)(gid % p.K);
+    const int64_t hi = min((int64_t)(c + 1) * CP_BT_CHUNK, p.N) - 1, lo = (int64_t)c * CP_BT_CHUNK;
+    for (int64_t t = hi; t >= lo; t--) cur = p.psi[(size_t)t * p.K + cur];
+    F[gid] = (psi_t)cur;
+}
+
+__global__ void cp_bt_chain_kernel(const CpParams p, int nchunks, const psi_t *F, const int *end_state, int *entry)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int cur = *end_state;
+    for (int c = nchunks - 1; c >= 0; c--) { entry[c] = cur; cur = F[(size_t)c * p.K + cur]; }
+}
+
+__global__ void cp_bt_fill_kernel(const CpParams p, int nchunks, const int *entry, uint64_t *sol)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    int cur = entry[c];
+    const int64_t hi = min((int64_t)(c + 1) * CP_BT_CHUNK, p.N) - 1, lo = (int64_t)c * CP_BT_CHUNK;
+    for (int64_t t = hi; t >= lo; t--) { sol[t] = (uint64_t)cur; cur = p.psi[(size_t)t * p.K + cur]; }
+}
+
+__global__ void cp_set_choice_kernel(int32_t *choice, int comp, int value) { choice[comp] = value; }
+
+// psi widened to u64 for the parity hook (cv_cp_last_state)
+__global__ void cp_widen_psi_kernel(const psi_t *psi, int64_t n, uint64_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = psi[i];
+}
+
+}  // namespace cvb

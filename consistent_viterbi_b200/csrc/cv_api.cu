@@ -99,7 +99,8 @@ struct cv_hmm {
     std::vector<double> hA, hB, hPi;
     // workspaces
     DevBuf obs, seq_off, path, score, psi, order, keys_in, keys_out, vals_in, cub_tmp, delta_g, misc;
-    DevBuf cp_ws[12];
+    DevBuf cp_ws[12];   // scratch of the decode launchers
+    DevBuf cpb[16];     // constrained-solver state (kept after cv_cp_solve for the parity hooks)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     double last_ms = 0.0, last_bt_ms = 0.0;   // forward kernel / backtrace kernel
@@ -219,6 +220,7 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
                       &h->vals_in, &h->cub_tmp, &h->delta_g, &h->misc})
         b->release();
     for (auto &b : h->cp_ws) b.release();
+    for (auto &b : h->cpb) b.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
