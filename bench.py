@@ -255,6 +255,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = cv._lib.lib()
+    if os.environ.get("CV_CHUNKS"):
+        L.cv_set_chunks(int(os.environ["CV_CHUNKS"]))
+    if os.environ.get("CV_SMALL_CFG"):
+        L.cv_set_small_config(int(os.environ["CV_SMALL_CFG"]))
     wl = build_workload(args, rank)
     hmm = cv.HMM(wl["A"], wl["B"], wl["pi"])
     h = hmm.device_handle(local)

@@ -98,8 +98,15 @@ struct cv_hmm {
     // host copy (control logic of the CP solver)
     std::vector<double> hA, hB, hPi;
     // workspaces
-    DevBuf obs, seq_off, path, score, psi, order, keys_in, keys_out, vals_in, cub_tmp, delta_g, misc;
-    DevBuf cp_ws[12];   // scratch of the decode launchers
+    DevBuf obs, seq_off, path, score;   // device copies of the host-API buffers
+    // decode workspaces: two sets so that consecutive chunks of a batch overlap (forward of chunk k+1 with the
+    // backtrace / copies of chunk k) on two internal streams
+    struct DecodeWs {
+        DevBuf order, keys_in, keys_out, vals_in, cub_tmp, hist, tmax, base, misc, lg_arr, lg_start, lg_done, delta_g;
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+    } ws[2];
+    cudaEvent_t ev_fork = nullptr;
     DevBuf cpb[16];     // constrained-solver state (kept after cv_cp_solve for the parity hooks)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -185,6 +192,11 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     CUDA_TRY(cudaEventCreate(&h->ev1));
     CUDA_TRY(cudaEventCreate(&h->ev2));
     CUDA_TRY(cudaMallocHost(&h->pinned_status, 64));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (auto &w : h->ws) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    }
 
     const int Kp = (K <= SMALL_K_MAX) ? h->Kp : ((K + LARGE_BN - 1) / LARGE_BN) * LARGE_BN;
     if (K > SMALL_K_MAX) { h->Kl = Kp; }
@@ -216,10 +228,15 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl}) if (p) cudaFree(p);
-    for (DevBuf *b : {&h->obs, &h->seq_off, &h->path, &h->score, &h->psi, &h->order, &h->keys_in, &h->keys_out,
-                      &h->vals_in, &h->cub_tmp, &h->delta_g, &h->misc})
-        b->release();
-    for (auto &b : h->cp_ws) b.release();
+    for (DevBuf *b : {&h->obs, &h->seq_off, &h->path, &h->score}) b->release();
+    for (auto &w : h->ws) {
+        for (DevBuf *b : {&w.order, &w.keys_in, &w.keys_out, &w.vals_in, &w.cub_tmp, &w.hist, &w.tmax, &w.base, &w.misc,
+                          &w.lg_arr, &w.lg_start, &w.lg_done, &w.delta_g})
+            b->release();
+        if (w.st) cudaStreamDestroy(w.st);
+        if (w.done) cudaEventDestroy(w.done);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (auto &b : h->cpb) b.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -255,10 +272,6 @@ __global__ void seq_len_keys_kernel(const int64_t *seq_off, int64_t B, uint32_t 
     vals[b] = (uint32_t)b;
 }
 
-#include "decode_large_host.inl"
-
-static int g_small_cfg = -1;   // test/bench override of the small-K launch shape (see cv_set_small_config)
-
 // longest length of every tile of NS sequences (lengths are sorted descending)
 __global__ void tile_tmax_kernel(const uint32_t *sorted_len, int ntiles, int NS, long long *tmax)
 {
@@ -266,14 +279,20 @@ __global__ void tile_tmax_kernel(const uint32_t *sorted_len, int ntiles, int NS,
     if (t < ntiles) tmax[t] = (long long)sorted_len[(size_t)t * NS];
 }
 
-static int launch_decode_small(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
-                               uint32_t *d_path, double *d_score, const uint32_t *d_order,
-                               const uint32_t *d_sorted_len, unsigned int *d_counter, int *d_status, int64_t max_len,
-                               cudaStream_t st, bool timing)
+typedef cv_hmm::DecodeWs DecodeWs;
+static int g_small_cfg = -1;   // test/bench override of the small-K launch shape (see cv_set_small_config)
+static int g_chunks = -1;      // test/bench override of the chunk count (see cv_set_chunks)
+
+#include "decode_large_host.inl"
+
+static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int64_t *d_off, int64_t B,
+                               int64_t N, uint32_t *d_path, double *d_score, unsigned int *d_counter, int *d_status,
+                               int64_t max_len, cudaStream_t st, bool timing)
 {
     const int G = h->G;
+    const uint32_t *d_order = (const uint32_t *)w.order.p, *d_sorted_len = (const uint32_t *)w.keys_out.p;
     // Launch shape: S sequence groups of 64 per CTA, and which register budget (kernel instantiation) to use.
-    int S = 1, variant = 2;
+    int S = 1, variant = 1;
     if (g_small_cfg >= 0) { S = std::max(1, std::min(4, g_small_cfg / 10)); variant = std::max(1, g_small_cfg % 10); }
     while (S > 1 && (B + 64 * S - 1) / (64 * S) < 4 * (int64_t)h->num_sms) S--;
     size_t smem = decode_small_smem_bytes(h->K, h->Kp, 64 * S);
@@ -295,21 +314,20 @@ static int launch_decode_small(cv_hmm *h, const uint32_t *d_obs, const int64_t *
     }
     // history slabs: sum over tiles of NS * Tmax(tile) <= N + NS * max_len because lengths are sorted
     const size_t hist_elems = ((size_t)N + (size_t)NS * (size_t)max_len) * (size_t)h->K;
-    if ((rc = h->psi.ensure(hist_elems * sizeof(double)))) return rc;
-    DevBuf &b_tmax = h->cp_ws[0], &b_base = h->cp_ws[1], &b_tmp = h->cp_ws[3];
-    if ((rc = b_tmax.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
-    if ((rc = b_base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
-    tile_tmax_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_sorted_len, ntiles, NS, (long long *)b_tmax.p);
+    if ((rc = w.hist.ensure(hist_elems * sizeof(double)))) return rc;
+    if ((rc = w.tmax.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
+    if ((rc = w.base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
+    tile_tmax_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_sorted_len, ntiles, NS, (long long *)w.tmax.p);
     g_launches++;
     size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (long long *)b_tmax.p, (long long *)b_base.p, ntiles, st));
-    if ((rc = b_tmp.ensure(tmp_bytes))) return rc;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(b_tmp.p, tmp_bytes, (long long *)b_tmax.p, (long long *)b_base.p, ntiles, st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (long long *)w.tmax.p, (long long *)w.base.p, ntiles, st));
+    if ((rc = w.cub_tmp.ensure(tmp_bytes))) return rc;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(w.cub_tmp.p, tmp_bytes, (long long *)w.tmax.p, (long long *)w.base.p, ntiles, st));
 
     DecodeSmallParams p;
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
-    p.tile_base = (const long long *)b_base.p;
-    p.hist = (double *)h->psi.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
+    p.tile_base = (const long long *)w.base.p;
+    p.hist = (double *)w.hist.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
     p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.ntiles = ntiles;
     void (*kern)(DecodeSmallParams) = variant == 1 ? decode_small_fwd_kernel<512, 1>
                                     : variant == 2 ? decode_small_fwd_kernel<384, 2> : decode_small_fwd_kernel<256, 3>;
@@ -327,12 +345,12 @@ static int launch_decode_small(cv_hmm *h, const uint32_t *d_obs, const int64_t *
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
-    // end state + backtrace with lazy backpointers: 8 lanes per sequence, 32 sequences per 256-thread block pass
-    const size_t smem_bt = (size_t)h->K * h->Kp * 8;
+    // end state + backtrace with lazy backpointers: one thread per sequence
+    const size_t smem_bt = (size_t)h->K * (h->K | 1) * 8;
     CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
-    const int64_t npass = ((int64_t)ntiles * NS + 31) / 32;
-    const int grid_bt = (int)std::max<int64_t>(1, std::min<int64_t>(npass, (int64_t)h->num_sms * 8));
-    backtrace_small_kernel<<<grid_bt, 256, smem_bt, st>>>(p);
+    const int64_t nblk = ((int64_t)ntiles * NS + 127) / 128;
+    const int grid_bt = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, (int64_t)h->num_sms * 12));
+    backtrace_small_kernel<<<grid_bt, 128, smem_bt, st>>>(p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (timing) CUDA_TRY(cudaEventRecord(h->ev2, st));
@@ -340,6 +358,64 @@ static int launch_decode_small(cv_hmm *h, const uint32_t *d_obs, const int64_t *
 }
 
 extern "C" void cv_set_small_config(int cfg) { g_small_cfg = cfg; }
+extern "C" void cv_set_chunks(int n) { g_chunks = n; }
+
+// One chunk of sequences [0, B) of d_off (offsets are absolute into d_obs / d_path): order by length,
+// forward, backtrace; everything enqueued on `st` with workspace set `w`.
+static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
+                        int64_t max_len, uint32_t *d_path, double *d_score, cudaStream_t st, bool timing)
+{
+    int rc;
+    if (B > 0x7fffffffLL) return fail(CV_ERR_UNSUPPORTED, "more than 2^31 sequences in one chunk");
+    if ((rc = w.order.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
+    if ((rc = w.keys_in.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
+    if ((rc = w.keys_out.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
+    if ((rc = w.vals_in.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
+    if ((rc = w.misc.ensure(256))) return rc;
+    unsigned int *d_counter = (unsigned int *)w.misc.p;
+    int *d_status = (int *)w.misc.p + 16;
+    CUDA_TRY(cudaMemsetAsync(w.misc.p, 0, 256, st));
+    // order sequences by length, longest first (stable radix sort => deterministic)
+    seq_len_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_off, B, (uint32_t *)w.keys_in.p,
+                                                                    (uint32_t *)w.vals_in.p, d_status);
+    g_launches++;
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)w.keys_in.p,
+                                                       (uint32_t *)w.keys_out.p, (uint32_t *)w.vals_in.p,
+                                                       (uint32_t *)w.order.p, (int)B, 0, 32, st));
+    if ((rc = w.cub_tmp.ensure(tmp_bytes))) return rc;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p,
+                                                       (uint32_t *)w.keys_out.p, (uint32_t *)w.vals_in.p,
+                                                       (uint32_t *)w.order.p, (int)B, 0, 32, st));
+    if (h->K <= SMALL_K_MAX)
+        return launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, st, timing);
+    if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
+    if ((rc = launch_decode_large(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, st))) return rc;
+    if (timing) { CUDA_TRY(cudaEventRecord(h->ev1, st)); CUDA_TRY(cudaEventRecord(h->ev2, st)); }
+    return CV_OK;
+}
+
+static int chunk_count(const cv_hmm *h, int64_t B, bool timing, bool host_buffers)
+{
+    if (timing || h->K > SMALL_K_MAX) return 1;          // kernel timing wants one launch for the whole batch
+    if (g_chunks > 0) return (int)std::min<int64_t>(g_chunks, std::max<int64_t>(B, 1));
+    // >= ~6 tiles per resident CTA per chunk keeps the dynamic tile scheduler balanced.  Host buffers: many
+    // chunks so that H2D / D2H copies hide behind the kernels; device buffers: two (backtrace of one chunk
+    // overlaps the forward pass of the other; measured best on B200)
+    const int64_t per_chunk = (int64_t)h->num_sms * 2 * 6 * 64;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 8 : 2, B / per_chunk));
+}
+
+static int report_status(const int *status_words, int n)
+{
+    for (int i = 0; i < n; i++) {
+        const int s = status_words[i];
+        if (s == CV_ERR_EMPTY) return fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)");
+        if (s == CV_ERR_ARG) return fail(CV_ERR_ARG, "observation index >= M (reference: ndarray index panic)");
+        if (s) return fail(s, "device status %d", s);
+    }
+    return CV_OK;
+}
 
 extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
                                    int64_t max_len, uint32_t *d_path, double *d_score, void *stream, int sync_status)
@@ -349,46 +425,35 @@ extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64
     if (B == 0) return CV_OK;
     if (!d_obs || !d_off || !d_path) return fail(CV_ERR_ARG, "NULL buffer");
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)stream;
-
-    int rc;
-    if ((rc = h->order.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
-    if ((rc = h->keys_in.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
-    if ((rc = h->keys_out.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
-    if ((rc = h->vals_in.ensure(sizeof(uint32_t) * (size_t)B))) return rc;
-    if ((rc = h->misc.ensure(256))) return rc;
-    unsigned int *d_counter = (unsigned int *)h->misc.p;
-    int *d_status = (int *)h->misc.p + 16;
-    CUDA_TRY(cudaMemsetAsync(h->misc.p, 0, 256, st));
-
-    // order sequences by length, longest first (stable radix sort => deterministic)
-    seq_len_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_off, B, (uint32_t *)h->keys_in.p,
-                                                                    (uint32_t *)h->vals_in.p, d_status);
-    g_launches++;
-    size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)h->keys_in.p,
-                                                       (uint32_t *)h->keys_out.p, (uint32_t *)h->vals_in.p,
-                                                       (uint32_t *)h->order.p, (int)B, 0, 32, st));
-    if ((rc = h->cub_tmp.ensure(tmp_bytes))) return rc;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp.p, tmp_bytes, (uint32_t *)h->keys_in.p,
-                                                       (uint32_t *)h->keys_out.p, (uint32_t *)h->vals_in.p,
-                                                       (uint32_t *)h->order.p, (int)B, 0, 32, st));
-
+    cudaStream_t user = (cudaStream_t)stream;
     const bool timing = g_timing.load() != 0;
-    if (h->K <= SMALL_K_MAX) {
-        if ((rc = launch_decode_small(h, d_obs, d_off, B, N, d_path, d_score, (const uint32_t *)h->order.p,
-                                      (const uint32_t *)h->keys_out.p, d_counter, d_status, max_len, st, timing)))
-            return rc;
+    const int nch = chunk_count(h, B, timing, false);
+    int rc;
+    if (nch == 1) {
+        if ((rc = decode_chunk(h, h->ws[0], d_obs, d_off, B, N, max_len, d_path, d_score, user, timing))) return rc;
     } else {
-        if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
-        if ((rc = launch_decode_large(h, d_obs, d_off, B, N, d_path, d_score, (const uint32_t *)h->order.p,
-                                      (const uint32_t *)h->keys_out.p, d_counter, d_status, max_len, st)))
-            return rc;
-        if (timing) { CUDA_TRY(cudaEventRecord(h->ev1, st)); CUDA_TRY(cudaEventRecord(h->ev2, st)); }
+        // fork: chunk k runs on internal stream k % 2 so that backtrace(k) overlaps forward(k+1)
+        if (max_len <= 0) return fail(CV_ERR_ARG, "max_len is required for the chunked device path");
+        CUDA_TRY(cudaEventRecord(h->ev_fork, user));
+        for (int k = 0; k < 2; k++) CUDA_TRY(cudaStreamWaitEvent(h->ws[k].st, h->ev_fork, 0));
+        for (int k = 0; k < nch; k++) {
+            const int64_t b0 = B * k / nch, b1 = B * (k + 1) / nch;
+            DecodeWs &w = h->ws[k & 1];
+            if ((rc = decode_chunk(h, w, d_obs, d_off + b0, b1 - b0, N, max_len, d_path,
+                                   d_score ? d_score + b0 : nullptr, w.st, false)))
+                return rc;
+        }
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaEventRecord(h->ws[k].done, h->ws[k].st));
+            CUDA_TRY(cudaStreamWaitEvent(user, h->ws[k].done, 0));
+        }
     }
     if (sync_status || timing) {
-        CUDA_TRY(cudaMemcpyAsync(h->pinned_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        int *hs = (int *)h->pinned_status + 8;
+        for (int k = 0; k < 2; k++)
+            if (h->ws[k].misc.p) CUDA_TRY(cudaMemcpyAsync(hs + k, (int *)h->ws[k].misc.p + 16, sizeof(int), cudaMemcpyDeviceToHost, user));
+            else hs[k] = 0;
+        CUDA_TRY(cudaStreamSynchronize(user));
         if (timing) {
             float ms = 0.f;
             CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -396,10 +461,7 @@ extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64
             CUDA_TRY(cudaEventElapsedTime(&ms, h->ev1, h->ev2));
             h->last_bt_ms = ms;
         }
-        const int s = *(int *)h->pinned_status;
-        if (s == CV_ERR_EMPTY) return fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)");
-        if (s == CV_ERR_ARG) return fail(CV_ERR_ARG, "observation index >= M (reference: ndarray index panic)");
-        if (s) return fail(s, "device status %d", s);
+        return report_status(hs, 2);
     }
     return CV_OK;
 }
@@ -413,39 +475,55 @@ extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_
     if (!obs_flat || !seq_off || !path_out) return fail(CV_ERR_ARG, "NULL buffer");
     if (seq_off[0] != 0) return fail(CV_ERR_ARG, "seq_off[0] must be 0");
     const int64_t N = seq_off[B];
-    int64_t max_len = 0;
-    for (int64_t b = 0; b < B; b++) {
-        const int64_t len = seq_off[b + 1] - seq_off[b];
-        if (len < 0) return fail(CV_ERR_ARG, "seq_off not monotone at %lld", (long long)b);
-        if (len == 0) return fail(CV_ERR_EMPTY, "sequence %lld is empty (reference: usize underflow panic)", (long long)b);
-        max_len = std::max(max_len, len);
-    }
     CUDA_TRY(cudaSetDevice(h->device));
     int rc;
     if ((rc = h->obs.ensure(sizeof(uint32_t) * (size_t)N))) return rc;
     if ((rc = h->seq_off.ensure(sizeof(int64_t) * (size_t)(B + 1)))) return rc;
     if ((rc = h->path.ensure(sizeof(uint32_t) * (size_t)N))) return rc;
     if ((rc = h->score.ensure(sizeof(double) * (size_t)B))) return rc;
-    cudaStream_t st = h->stream;
-    CUDA_TRY(cudaMemcpyAsync(h->seq_off.p, seq_off, sizeof(int64_t) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(h->obs.p, obs_flat, sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
-    rc = cv_decode_batch_dev(h, (const uint32_t *)h->obs.p, (const int64_t *)h->seq_off.p, B, N, max_len,
-                             (uint32_t *)h->path.p, (double *)h->score.p, st, 0);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(path_out, h->path.p, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
-    if (score_out)
-        CUDA_TRY(cudaMemcpyAsync(score_out, h->score.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(h->pinned_status, (int *)h->misc.p + 16, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (g_timing.load()) {
+    uint32_t *d_obs = (uint32_t *)h->obs.p, *d_path = (uint32_t *)h->path.p;
+    int64_t *d_off = (int64_t *)h->seq_off.p;
+    double *d_score = (double *)h->score.p;
+    const bool timing = g_timing.load() != 0;
+    const int nch = chunk_count(h, B, timing, true);
+    // Chunk k: H2D of its observations -> order/forward/backtrace -> D2H of its paths, on stream k % 2, so the
+    // copies of one chunk overlap the kernels of its neighbours.  Offsets are validated while the first copy flies.
+    for (int k = 0; k < nch; k++) {
+        const int64_t b0 = B * k / nch, b1 = B * (k + 1) / nch;
+        int64_t max_len = 0;
+        for (int64_t b = b0; b < b1; b++) {
+            const int64_t len = seq_off[b + 1] - seq_off[b];
+            if (len < 0) return fail(CV_ERR_ARG, "seq_off not monotone at %lld", (long long)b);
+            if (len == 0) return fail(CV_ERR_EMPTY, "sequence %lld is empty (reference: usize underflow panic)", (long long)b);
+            max_len = std::max(max_len, len);
+        }
+        DecodeWs &w = h->ws[k & 1];
+        cudaStream_t st = nch == 1 ? h->stream : w.st;
+        const int64_t e0 = seq_off[b0], e1 = seq_off[b1];
+        CUDA_TRY(cudaMemcpyAsync(d_off + b0, seq_off + b0, sizeof(int64_t) * (size_t)(b1 - b0 + 1), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_obs + e0, obs_flat + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, st));
+        if ((rc = decode_chunk(h, w, d_obs, d_off + b0, b1 - b0, e1 - e0, max_len, d_path, d_score + b0, st, timing))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(path_out + e0, d_path + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, st));
+        if (score_out)
+            CUDA_TRY(cudaMemcpyAsync(score_out + b0, d_score + b0, sizeof(double) * (size_t)(b1 - b0), cudaMemcpyDeviceToHost, st));
+    }
+    int *hs = (int *)h->pinned_status + 8;
+    hs[0] = hs[1] = 0;
+    if (nch == 1) {
+        CUDA_TRY(cudaMemcpyAsync(hs, (int *)h->ws[0].misc.p + 16, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    } else {
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaMemcpyAsync(hs + k, (int *)h->ws[k].misc.p + 16, sizeof(int), cudaMemcpyDeviceToHost, h->ws[k].st));
+            CUDA_TRY(cudaStreamSynchronize(h->ws[k].st));
+        }
+    }
+    if (timing) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms; else cudaGetLastError();
         if (cudaEventElapsedTime(&ms, h->ev1, h->ev2) == cudaSuccess) h->last_bt_ms = ms; else cudaGetLastError();
     }
-    const int s = *(int *)h->pinned_status;
-    if (s == CV_ERR_ARG) return fail(CV_ERR_ARG, "observation index >= M (reference: ndarray index panic)");
-    if (s) return fail(s, "device status %d", s);
-    return CV_OK;
+    return report_status(hs, 2);
 }
 
 // ---------------------------------------------------------------------------

@@ -17,11 +17,11 @@ __global__ void step_items_kernel(const uint32_t *sorted_len, int NRB, int NCB, 
     arr[t] = n;
 }
 
-static int launch_decode_large(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
-                               uint32_t *d_path, double *d_score, const uint32_t *d_order,
-                               const uint32_t *d_sorted_len, unsigned int *d_counter, int *d_status, int64_t max_len,
+static int launch_decode_large(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
+                               uint32_t *d_path, double *d_score, unsigned int *d_counter, int *d_status, int64_t max_len,
                                cudaStream_t st)
 {
+    const uint32_t *d_order = (const uint32_t *)w.order.p, *d_sorted_len = (const uint32_t *)w.keys_out.p;
     const int Kl = h->Kl, NCB = Kl / LARGE_BN;
     const int64_t NRB = (B + LG_BM - 1) / LG_BM, Bpad = NRB * LG_BM;
     if (NRB > 0x7fffffffLL) return fail(CV_ERR_UNSUPPORTED, "batch too large");
@@ -35,14 +35,14 @@ static int launch_decode_large(cv_hmm *h, const uint32_t *d_obs, const int64_t *
     if (max_len > 0x7ffffff0LL) return fail(CV_ERR_UNSUPPORTED, "sequence too long");
     const int Tmax = (int)max_len;
     const int psi16 = Kl > 256 ? 1 : 0;
-    if ((rc = h->psi.ensure((size_t)N * Kl * (psi16 ? 2 : 1)))) return rc;
-    if ((rc = h->delta_g.ensure((size_t)2 * Kl * Bpad * sizeof(double)))) return rc;
-    DevBuf &b_arr = h->cp_ws[0], &b_start = h->cp_ws[1], &b_done = h->cp_ws[2], &b_tmp = h->cp_ws[3];
+    if ((rc = w.hist.ensure((size_t)N * Kl * (psi16 ? 2 : 1)))) return rc;
+    if ((rc = w.delta_g.ensure((size_t)2 * Kl * Bpad * sizeof(double)))) return rc;
+    DevBuf &b_arr = w.lg_arr, &b_start = w.lg_start, &b_done = w.lg_done, &b_tmp = w.cub_tmp;
     if ((rc = b_arr.ensure(sizeof(long long) * (size_t)(Tmax + 2)))) return rc;
     if ((rc = b_start.ensure(sizeof(long long) * (size_t)(Tmax + 2)))) return rc;
     if ((rc = b_done.ensure(sizeof(unsigned int) * (size_t)NRB))) return rc;
     CUDA_TRY(cudaMemsetAsync(b_done.p, 0, sizeof(unsigned int) * (size_t)NRB, st));
-    CUDA_TRY(cudaMemsetAsync(h->delta_g.p, 0, (size_t)Kl * Bpad * sizeof(double), st));   // delta(0) = 0.0 (viterbi.rs:6)
+    CUDA_TRY(cudaMemsetAsync(w.delta_g.p, 0, (size_t)Kl * Bpad * sizeof(double), st));   // delta(0) = 0.0 (viterbi.rs:6)
 
     step_items_kernel<<<(Tmax + 1 + 255) / 256, 256, 0, st>>>(d_sorted_len, (int)NRB, NCB, Tmax, (long long *)b_arr.p);
     g_launches++;
@@ -53,7 +53,7 @@ static int launch_decode_large(cv_hmm *h, const uint32_t *d_obs, const int64_t *
 
     DecodeLargeParams p;
     p.A = h->dAl; p.BT = h->dBTl; p.obs = d_obs; p.seq_off = d_off; p.order = d_order; p.sorted_len = d_sorted_len;
-    p.path = d_path; p.score = d_score; p.delta = (double *)h->delta_g.p; p.psi = h->psi.p;
+    p.path = d_path; p.score = d_score; p.delta = (double *)w.delta_g.p; p.psi = w.hist.p;
     p.step_start = (const long long *)b_start.p; p.item_counter = (unsigned long long *)d_counter;
     p.done = (unsigned int *)b_done.p; p.status = d_status;
     p.M = h->M; p.B = B; p.Bpad = Bpad; p.K = h->K; p.Kl = Kl; p.NCB = NCB; p.NRB = (int)NRB; p.Tmax = Tmax;

@@ -33,9 +33,9 @@
 //    tile_base = exclusive scan of the tiles' longest lengths.
 //
 // 2. backtrace_small_kernel -- end state (viterbi.rs:24) and backtrace
-//    (viterbi.rs:25-30) with lazy psi; 8 lanes per sequence split the K
-//    predecessors and reduce (value, index) with shuffles; a warp holds 4 adjacent
-//    sequences so each 32-byte sector of a slab row is read by one instruction.
+//    (viterbi.rs:25-30) with lazy psi; one thread per sequence, a warp holds 32
+//    adjacent sequences of a tile so every slab-row read is a coalesced 256-byte
+//    run; rows are prefetched in chunks of 16 predecessors ahead of the reduce.
 #pragma once
 
 #include "common.cuh"
@@ -247,120 +247,88 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 }
 
 // ---------------------------------------------------------------------------
-// End state + backtrace with lazy backpointers: 8 lanes per sequence.
+// End state + backtrace with lazy backpointers: one thread per sequence.
 //
 // Why no emission lookup is needed: the reference leaves psi[t][s] = 0 when b[s][o_t] = -inf
 // (viterbi.rs:7,19-21) and otherwise stores argmax_j(delta[t-1][j] + a[j][s]).  If delta[t][s] > -inf the
 // emission was finite and the argmax is recomputed here.  If delta[t][s] = -inf then either the emission was
 // -inf (psi = 0) or every candidate was -inf (argmax of an all -inf vector = 0): psi = 0 both ways.
 // ---------------------------------------------------------------------------
-constexpr int BT_LANES = 8;                         // lanes per sequence: a warp covers 4 adjacent sequences
-constexpr int BT_SLOTS = SMALL_K_MAX / BT_LANES;    // predecessors per lane (j = sub + 8*k)
+constexpr int BT_CHUNK = 16;   // predecessors per prefetch chunk
 
-// (value, index) argmax over an 8-lane group: strictly greater value wins, equal values keep the lower
-// index -- the order ndarray-stats argmax visits them (viterbi.rs:16,24).
-__device__ __forceinline__ void group_argmax(double &v, int &ix)
-{
-#pragma unroll
-    for (int d = BT_LANES / 2; d >= 1; d >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, v, d, BT_LANES);
-        const int oi = __shfl_xor_sync(0xffffffffu, ix, d, BT_LANES);
-        if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
-    }
-}
-
-// column s of one slab, predecessors j = sub + 8*k
-__device__ __forceinline__ void load_slab_col(const double *slab_col, int NS, int sub, int K, bool on,
-                                              double (&v)[BT_SLOTS])
-{
-#pragma unroll
-    for (int k = 0; k < BT_SLOTS; k++) {
-        const int j = sub + BT_LANES * k;
-        v[k] = (on && j < K) ? __ldcs(slab_col + (size_t)j * NS) : neg_inf();
-    }
-}
-
-__global__ void __launch_bounds__(256) backtrace_small_kernel(const DecodeSmallParams p)
+// One thread per sequence; the 32 lanes of a warp hold 32 adjacent sequences of one tile, so the loads of
+// predecessor j are one coalesced 256-byte run of the slab row.  Rows do not depend on the decoded path, so
+// the next chunk of 16 predecessors is always in flight while the current one is reduced; the only dependent
+// chain per step is 16 x (DADD, DSETP, select) x ceil(K/16).
+__global__ void __launch_bounds__(128) backtrace_small_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, Kp = p.Kp, NS = 64 * p.S;
-    double *sAT = reinterpret_cast<double *>(smem_raw);     // sAT[s*Kp + j] = logA[j][s]
+    const int ATP = K | 1;                                   // odd pitch: rows of different states spread over banks
+    double *sAT = reinterpret_cast<double *>(smem_raw);     // sAT[s*ATP + j] = logA[j][s]
     for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) {
         const int j = e / Kp, s = e % Kp;
-        if (s < K) sAT[(size_t)s * Kp + j] = p.A[e];
+        if (s < K) sAT[(size_t)s * ATP + j] = p.A[e];
     }
     __syncthreads();
 
-    const int sub = threadIdx.x % BT_LANES;
-    const int gpb = blockDim.x / BT_LANES;                   // sequences per block pass
     const size_t sl = (size_t)K * NS;
-    const int64_t npass = ((int64_t)p.ntiles * NS + gpb - 1) / gpb;
-    for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x) {
-        // ranks are contiguous inside a pass: a warp holds 4 adjacent sequences of one tile, so each
-        // 32-byte sector of a slab row is consumed by one load instruction
-        const int64_t r = pass * gpb + threadIdx.x / BT_LANES;
+    const int nchunk = (K + BT_CHUNK - 1) / BT_CHUNK;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total = (int64_t)p.ntiles * NS;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += nthreads) {
+        if (r >= p.B) continue;
         const int tile = (int)(r / NS), s = (int)(r % NS);
-        const bool valid = r < p.B;
-        const uint32_t b = valid ? p.order[r] : 0u;
-        const int64_t off = valid ? p.seq_off[b] : 0;
-        const int len = valid ? (int)(p.seq_off[b + 1] - off) : 0;
-        const int maxlen = __reduce_max_sync(0xffffffffu, len);
-        const double *col = p.hist + (size_t)(valid ? p.tile_base[tile] : 0) * sl + s;   // column s of slab 0
-
-        double rv[BT_SLOTS], n1[BT_SLOTS], n2[BT_SLOTS];
-        load_slab_col(col + (size_t)(len - 1) * sl, NS, sub, K, valid, rv);               // delta[len-1][.]
-        // rows maxlen-2 and maxlen-3 in flight for the first two iterations
-        load_slab_col(col + (size_t)(maxlen - 2) * sl, NS, sub, K, valid && maxlen - 2 >= 0 && maxlen - 1 < len, n1);
-        load_slab_col(col + (size_t)(maxlen - 3) * sl, NS, sub, K, valid && maxlen - 3 >= 0 && maxlen - 2 < len, n2);
+        const uint32_t b = p.order[r];
+        const int64_t off = p.seq_off[b];
+        const int len = (int)(p.seq_off[b + 1] - off);
+        const double *col = p.hist + (size_t)p.tile_base[tile] * sl + s;   // column s of slab 0
 
         // end state: argmax of the last row (viterbi.rs:24)
-        double bv = neg_inf(); int cur = 0x7fffffff;
-#pragma unroll
-        for (int k = 0; k < BT_SLOTS; k++) {
-            const int j = sub + BT_LANES * k;
-            if (j < K && (cur == 0x7fffffff || rv[k] > bv)) { bv = rv[k]; cur = j; }
+        const double *row = col + (size_t)(len - 1) * sl;
+        double bv = __ldcs(row); int cur = 0;
+        for (int j = 1; j < K; j++) {
+            const double v = __ldcs(row + (size_t)j * NS);
+            if (v > bv) { bv = v; cur = j; }
         }
-        group_argmax(bv, cur);
-        if (valid && sub == 0) {
-            if (p.score) p.score[b] = bv;
-            p.path[off + len - 1] = (uint32_t)cur;
-        }
+        if (p.score) p.score[b] = bv;
+        p.path[off + len - 1] = (uint32_t)cur;
+        if (len == 1) continue;
+
+        // walk back (viterbi.rs:27-30) over the flat stream of (step, chunk) pairs
         double dcur = bv;                                     // delta[tt][cur]
-        // walk back (viterbi.rs:27-30): psi[tt][cur] recomputed from delta row tt-1 (held in n1)
-        for (int tt = maxlen - 1; tt >= 1; tt--) {
-            const bool act = valid && tt < len;
-            double n3[BT_SLOTS];                              // row tt-3, needed two iterations from now
-            load_slab_col(col + (size_t)(tt - 3) * sl, NS, sub, K, valid && tt - 3 >= 0 && tt - 2 < len, n3);
-            double mv = neg_inf(), msel = neg_inf(); int mi = 0x7fffffff;
-            const double *at = sAT + (size_t)(act ? cur : 0) * Kp;
+        double nx[BT_CHUNK];
+        const int64_t nq = (int64_t)(len - 1) * nchunk;
+        auto load_chunk = [&](int64_t q, double (&dst)[BT_CHUNK]) {
+            const int tt = len - 1 - (int)(q / nchunk), c = (int)(q % nchunk);
+            const double *prow = col + (size_t)(tt - 1) * sl + (size_t)c * BT_CHUNK * NS;
 #pragma unroll
-            for (int k = 0; k < BT_SLOTS; k++) {
-                const int j = sub + BT_LANES * k;
-                if (j < K) {
-                    const double v = n1[k] + at[j];                                       // viterbi.rs:15
-                    if (mi == 0x7fffffff || v > mv) { mv = v; mi = j; msel = n1[k]; }
+            for (int k = 0; k < BT_CHUNK; k++) dst[k] = (c * BT_CHUNK + k < K) ? __ldcs(prow + (size_t)k * NS) : neg_inf();
+        };
+        load_chunk(0, nx);
+        double mv = neg_inf(); int mi = 0;
+        for (int64_t q = 0; q < nq; q++) {
+            double cu[BT_CHUNK];
+#pragma unroll
+            for (int k = 0; k < BT_CHUNK; k++) cu[k] = nx[k];
+            if (q + 1 < nq) load_chunk(q + 1, nx);
+            const int tt = len - 1 - (int)(q / nchunk), c = (int)(q % nchunk);
+            const double *at = sAT + (size_t)cur * ATP + c * BT_CHUNK;
+            if (c == 0) { mv = cu[0] + at[0]; mi = 0; }                    // viterbi.rs:15-16: first candidate
+#pragma unroll
+            for (int k = 0; k < BT_CHUNK; k++) {
+                const int j = c * BT_CHUNK + k;
+                if (j < K && j > 0) {
+                    const double v = cu[k] + at[k];
+                    if (v > mv) { mv = v; mi = j; }
                 }
             }
-            // reduce (value, index) and carry delta[tt-1][index] along
-            {
-#pragma unroll
-                for (int d = BT_LANES / 2; d >= 1; d >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, mv, d, BT_LANES);
-                    const int oi = __shfl_xor_sync(0xffffffffu, mi, d, BT_LANES);
-                    const double os = __shfl_xor_sync(0xffffffffu, msel, d, BT_LANES);
-                    if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; msel = os; }
-                }
+            if (c == nchunk - 1) {
+                // psi = 0 when delta[tt][cur] = -inf (emission -inf or all candidates -inf; see header comment)
+                cur = (dcur > neg_inf()) ? mi : 0;
+                dcur = __ldcg(col + (size_t)(tt - 1) * sl + (size_t)cur * NS);   // delta[tt-1][cur]
+                p.path[off + tt - 1] = (uint32_t)cur;
             }
-            // delta[tt-1][0], needed when psi = 0 is forced
-            const double d0 = __shfl_sync(0xffffffffu, n1[0], 0, BT_LANES);
-            if (act) {
-                const bool live = dcur > neg_inf();          // else psi = 0 (see header comment)
-                cur = live ? mi : 0;
-                dcur = live ? msel : d0;
-                if (sub == 0) p.path[off + tt - 1] = (uint32_t)cur;
-            }
-#pragma unroll
-            for (int k = 0; k < BT_SLOTS; k++) { n1[k] = n2[k]; n2[k] = n3[k]; }
         }
     }
 }

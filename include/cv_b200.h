@@ -112,6 +112,8 @@ double cv_last_backtrace_ms(const cv_hmm *h);  /* end-state + backtrace kernel *
 /* tuning hook: force the small-K launch shape, cfg = 10*S + MINB (S sequence groups of 64 per CTA,
  * MINB co-resident CTAs per SM); -1 = automatic. */
 void   cv_set_small_config(int cfg);
+/* tuning hook: number of chunks a batch is cut into (chunks overlap on two internal streams); -1 = automatic */
+void   cv_set_chunks(int n);
 /* pinned host memory helpers */
 void *cv_host_alloc(uint64_t bytes);
 void  cv_host_free(void *p);
