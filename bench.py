@@ -83,6 +83,41 @@ def workload_large(rank, nseq, T, K=1024, M=4096):
                 steps=float(nseq) * (T - 1), desc=f"large-state K={K} M={M} T={T} B={nseq} (configs[3])")
 
 
+def workload_ar():
+    """BASELINE configs[1]: datasets/ar houses A/B/C as committed fixtures (tests/golden/ar_house_*.npz, made by
+    tools/make_golden.py from the reference's CSVs; the reference has no preprocessing of its own)."""
+    out = []
+    for hname in "ABC":
+        z = np.load(os.path.join(ROOT, "tests", "golden", f"ar_house_{hname}.npz"))
+        K = int(z["n_activities"])
+        off = z["seq_off"]
+        out.append(dict(name=f"ar_house_{hname}", K=K, M=int(z["n_sensors"]), A=z["logA"], B=z["logB"], pi=z["logPi"],
+                        obs=z["obs"], off=off, cells=float(((np.diff(off) - 1) * K * K).sum()), golden=z["paths"]))
+    return out
+
+
+def workload_cp(kind):
+    """Constrained decode inputs.  trucks: BASELINE configs[0] stand-in (real datasets/trucks is absent): D=2
+    bdims [16,8], K=12, 200 sequences T~U[50,400], control tags on ~10 % of the positions over 4 tag values,
+    prop=1.  heavy: configs[4]: K=16, M=64, 64 sequences x T=10000, 4 components, 20 % of positions clamped."""
+    rng = np.random.default_rng(3019)
+    if kind == "trucks":
+        K, M, nseq, ncomp, pact, tlo, thi = 12, 128, 200, 4, 0.10, 50, 400
+        A, B, pi = make_hmm(3019, K, M, 0.5, 0.2)
+    else:
+        K, M, nseq, ncomp, pact, tlo, thi = 16, 64, 64, 4, 0.20, 10000, 10000
+        A, B, pi = make_hmm(3019, K, M, 0.5, 0.0)
+    lens = rng.integers(tlo, thi + 1, size=nseq)
+    N = int(lens.sum())
+    start = np.zeros(N, dtype=np.uint8)
+    start[np.concatenate([[0], np.cumsum(lens)[:-1]])] = 1
+    obs = rng.integers(0, M, size=N).astype(np.uint32)
+    comp = np.full(N, -1, dtype=np.int32)
+    mask = rng.random(N) < pact
+    comp[mask] = rng.integers(0, ncomp, size=int(mask.sum()))
+    return dict(name=f"cp_{kind}", K=K, M=M, A=A, B=B, pi=pi, obs=obs, start=start, comp=comp, ncomp=ncomp, N=N)
+
+
 # ----------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi fields via NVML) during the timed region
 # ----------------------------------------------------------------------------------------------
@@ -177,6 +212,50 @@ def cpu_baseline(wl, budget_s=12.0, threads=None):
 
 
 # ----------------------------------------------------------------------------------------------
+def run_other(cv, L, device):
+    """Short, bounded runs of the other BASELINE configs (reported under "other"; parity for each is in tests/)."""
+    from oracle import pyoracle as po
+    other = {}
+    # configs[1]: datasets/ar, full data set, batched decode (three models, 60 day-sequences in total)
+    ar, t_gpu, t_cpu, cells = workload_ar(), 0.0, 0.0, 0.0
+    for w in ar:
+        hm = cv.HMM(w["A"], w["B"], w["pi"])
+        cv.decode_batch(hm, w["obs"], w["off"], device=device)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            paths, _ = cv.decode_batch(hm, w["obs"], w["off"], device=device)
+        t_gpu += (time.perf_counter() - t0) / 5
+        assert (paths == w["golden"]).all()
+        t0 = time.perf_counter()
+        po.decode_batch(w["A"], w["B"], w["obs"], w["off"], nthreads=os.cpu_count() or 1)
+        t_cpu += time.perf_counter() - t0
+        cells += w["cells"]
+        hm.close()
+    other["ar_full_dataset"] = {"cells": cells, "e2e_ms": 1e3 * t_gpu, "e2e_cells_per_s": cells / t_gpu,
+                                "cpu_port_cells_per_s": cells / t_cpu,
+                                "note": "60 sequences, 1.5e7 cells: latency bound (serial in t), paths equal the golden fixture"}
+    # configs[0] stand-in and configs[4]: constrained decode with a node budget
+    for kind, budget in (("trucks", 300), ("heavy", 40)):
+        w = workload_cp(kind)
+        hm = cv.HMM(w["A"], w["B"], w["pi"])
+        cv.cp_solve_arrays(hm, w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=3, device=device)
+        t0 = time.perf_counter()
+        r = cv.cp_solve_arrays(hm, w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=budget, device=device)
+        dt = time.perf_counter() - t0
+        cpu_budget = max(2, budget // 10)
+        t0 = time.perf_counter()
+        rc = po.cp_solve(w["A"], w["B"], w["pi"], w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=cpu_budget)
+        dtc = time.perf_counter() - t0
+        K = w["K"]
+        other[w["name"]] = {"N": w["N"], "K": K, "nodes": int(r["explored"]), "sweep_steps": int(r["steps"]),
+                            "cells": float(r["steps"]) * K * K, "e2e_ms": 1e3 * dt,
+                            "e2e_cells_per_s": float(r["steps"]) * K * K / dt, "ms_per_node": 1e3 * dt / max(1, r["explored"]),
+                            "cpu_port_cells_per_s": float(rc["steps"]) * K * K / dtc, "cpu_nodes": int(rc["explored"]),
+                            "note": "node budget (max_nodes) applied identically in oracle and GPU path"}
+        hm.close()
+    return other
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +266,7 @@ def parse():
     ap.add_argument("--nseq", type=int, default=0, help="sequences per GPU (0 = the config's size)")
     ap.add_argument("--seqlen", type=int, default=0, help="T for --workload large (0 = 4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other configs")
     return ap.parse_args()
 
 
@@ -414,6 +494,11 @@ def main():
         }
         if not args.no_cpu and world >= 1:
             line["cpu_baseline"] = cpu_baseline(wl)
+        if not args.no_other and world == 1 and args.workload == "pos":
+            try:
+                line["other"] = run_other(cv, L, local)
+            except Exception as e:  # the headline numbers stand on their own
+                line["other"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     for p in (p_obs, p_off, p_path, p_score):
         L.cv_host_free(p)

@@ -36,8 +36,12 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
     a.nseg = (int)nseg; a.ntiles = (int)((nseg + 63) / 64); a.node = node; a.init_mode = init_mode;
     a.tile_counter = r.d_counter;
     CUDA_TRY(cudaMemsetAsync(r.d_counter, 0, sizeof(unsigned int), r.st));
-    const int grid = std::min(a.ntiles, r.h->num_sms * 2);
-    cp_sweep_kernel<<<grid, 32 * r.p.G, r.smem, r.st>>>(r.p, a);
+    // one warp per segment (latency-oriented); the lock-step tile kernel only pays off with very many segments
+    const size_t smem_c = (size_t)r.p.K * r.p.Kp * 8 + (r.p.bt_in_smem ? (size_t)r.p.M * r.p.Kp * 8 : 0) +
+                          (size_t)CPW_WARPS * 16 * r.p.Kp;
+    const int grid = (int)std::min<int64_t>((nseg + CPW_WARPS - 1) / CPW_WARPS, (int64_t)r.h->num_sms * 8);
+    if (r.p.K <= 32) cp_sweep_chain_kernel<1><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
+    else cp_sweep_chain_kernel<2><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CV_OK;
@@ -214,6 +218,12 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     p.obs = (const uint32_t *)b[2].p; p.start = (const uint8_t *)b[3].p; p.comp = (const int32_t *)b[4].p;
     p.delta = (double *)b[0].p; p.psi = (psi_t *)b[1].p; p.choice = d_choice;
     p.N = N; p.M = h->M; p.K = K; p.Kp = h->Kp; p.G = h->G;
+    p.bt_in_smem = ((size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
+    {
+        const size_t smem_c = (size_t)K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) + (size_t)CPW_WARPS * 16 * h->Kp;
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    }
     CUDA_TRY(cudaFuncSetAttribute(cp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem));
 
     const bool timing = g_timing.load() != 0;

@@ -24,6 +24,8 @@
 #pragma once
 
 #include "common.cuh"
+#include "chain_warp.cuh"
+#include "decode_chain.cuh"
 
 namespace cvb {
 
@@ -41,6 +43,7 @@ struct CpParams {
     int32_t *choice;          // [ncomp] cstr_choices, -1 = None
     int64_t N, M;
     int K, Kp, G;
+    int bt_in_smem;           // logB^T staged in shared memory by the warp-per-segment sweep
 };
 
 struct CpSweepArgs {
@@ -169,6 +172,105 @@ __global__ void __launch_bounds__(256, 2) cp_sweep_kernel(const CpParams p, cons
     }
 }
 
+
+// ---- sweeps, one warp per segment (latency-oriented; see chain_warp.cuh) -----------------------------
+// Same arithmetic and the same phases A + B as cp_sweep_kernel; segments are claimed longest first.
+constexpr int CPW_WARPS = 4;
+
+template <int NSL>
+__global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const CpParams p, const CpSweepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K, Kp = p.Kp;
+    double *sA = reinterpret_cast<double *>(smem_raw);
+    double *sBT = sA + (size_t)K * Kp;
+    const size_t nbt = p.bt_in_smem ? (size_t)p.M * Kp : 0;
+    const int lane = threadIdx.x & 31;
+    for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) sA[e] = p.A[e];
+    for (size_t e = threadIdx.x; e < nbt; e += blockDim.x) sBT[e] = p.BT[e];
+    __syncthreads();
+    const double *bt = p.bt_in_smem ? sBT : p.BT;
+    const bool pf = !p.bt_in_smem;
+    double *sdw = sBT + nbt + (size_t)(threadIdx.x >> 5) * 2 * Kp;       // this warp's delta rows [2][Kp]
+
+    double pi_i[NSL]; int col[NSL];
+#pragma unroll
+    for (int s = 0; s < NSL; s++) { col[s] = min(lane + 32 * s, Kp - 1); pi_i[s] = p.Pi[col[s]]; }
+
+    for (;;) {
+        unsigned int r = 0;
+        if (lane == 0) r = atomicAdd(a.tile_counter, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if ((int)r >= a.nseg) break;
+        const int64_t from = a.seg_from[r];
+        const int len = a.seg_len[r];
+
+        double d[NSL];
+#pragma unroll
+        for (int s = 0; s < NSL; s++) {
+            const int i = lane + 32 * s;
+            if (a.init_mode) {
+                d[s] = (i < K) ? p.delta[(size_t)from * K + i] : neg_inf();
+            } else {
+                d[s] = (i == a.node) ? 0.0 : neg_inf();                          // cp.rs:33-34
+                if (i < K) p.delta[(size_t)from * K + i] = d[s];
+            }
+            if (i < Kp) { sdw[i] = (i < K) ? d[s] : neg_inf(); sdw[Kp + i] = neg_inf(); }
+        }
+        __syncwarp();
+        auto load_meta = [&](int k, uint32_t &o, bool &st) {
+            o = 0u; st = false;
+            if (k <= len) { o = __ldg(p.obs + from + k); st = __ldg(p.start + from + k) != 0; }
+        };
+        // rings: oq[q] / sq[q] = observation / sequence-start flag of row from + 2 + q
+        uint32_t o1, oq[CHAIN_PF + 1]; bool st1, sq[CHAIN_PF + 1];
+        load_meta(1, o1, st1);
+#pragma unroll
+        for (int q = 0; q <= CHAIN_PF; q++) load_meta(2 + q, oq[q], sq[q]);
+        double e_next[NSL];
+#pragma unroll
+        for (int s = 0; s < NSL; s++) e_next[s] = bt[(size_t)o1 * Kp + col[s]];
+        if (pf) {
+#pragma unroll
+            for (int q = 0; q < CHAIN_PF; q++) prefetch_l1(p.BT + (size_t)oq[q] * Kp + col[0]);
+        }
+
+        for (int k = 1; k <= len; k++) {                                          // cp.rs:47-60 / 70-78
+            const int64_t t = from + k;
+            const bool st = st1;
+            double e[NSL];
+#pragma unroll
+            for (int s = 0; s < NSL; s++) { e[s] = e_next[s]; e_next[s] = bt[(size_t)oq[0] * Kp + col[s]]; }
+            if (pf) prefetch_l1(p.BT + (size_t)oq[CHAIN_PF] * Kp + col[0]);
+            st1 = sq[0];
+#pragma unroll
+            for (int q = 0; q < CHAIN_PF; q++) { oq[q] = oq[q + 1]; sq[q] = sq[q + 1]; }
+            load_meta(k + 2 + CHAIN_PF, oq[CHAIN_PF], sq[CHAIN_PF]);
+            double best[NSL]; int idx[NSL];
+            const double *sdo = sdw + ((k - 1) & 1) * Kp;
+            chain_scan<NSL>(sdo, sA, Kp, K, lane, st, pi_i, best, idx);           // argmax on delta + tr
+            double v[NSL];
+#pragma unroll
+            for (int s = 0; s < NSL; s++) {
+                const double tr = st ? pi_i[s] : sA[(size_t)idx[s] * Kp + col[s]];
+                const double arc = tr + e[s];                                     // arc_p (utils.rs:24-30)
+                v[s] = sdo[idx[s]] + arc;                                         // delta + (a + b)  cp.rs:55
+            }
+#pragma unroll
+            for (int s = 0; s < NSL; s++) {
+                const int i = lane + 32 * s;
+                if (i < K) {
+                    p.delta[(size_t)t * K + i] = v[s];
+                    p.psi[(size_t)t * K + i] = (psi_t)idx[s];
+                }
+                d[s] = (i < K) ? v[s] : neg_inf();
+                if (i < K) sdw[(k & 1) * Kp + i] = v[s];
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // Phases C1 + C2 for the positions of the component just assigned (cp.rs:35-45).
 //  C2: psi[pos][state] = first-argmax_j fl(delta[pos-1][j] + tr_j(state))          (pos != 0)
 //  C1: psi[pos+1][choice[comp[pos+1]]] = state when pos+1 is fixed.  If pos+1 belongs to the same component
@@ -217,19 +319,33 @@ __global__ void cp_terms_kernel(const CpParams p, const int64_t *term_pos, const
     terms[k] = term;
 }
 
-// ub = ((0.0 + term_0) + term_1) + ...  exactly in order (cp.rs:103,109,114).  One thread adds; the block
-// stages the terms through shared memory so the adds are the only dependent chain.
+// ub = ((0.0 + term_0) + term_1) + ...  exactly in order (cp.rs:103,109,114).  The order is part of the result,
+// so one thread performs the adds; the rest of the block streams the terms through a double-buffered shared
+// memory stage and the adder keeps 16 terms in registers ahead of the dependent DADD chain (8 clk per term).
 __global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, double *ub_out)
 {
-    __shared__ double buf[2048];
+    constexpr int CH = 4096;
+    __shared__ double buf[2][CH];
     double ub = 0.0;
-    for (int base = 0; base < nterms; base += 2048) {
-        const int n = min(2048, nterms - base);
-        for (int e = threadIdx.x; e < n; e += blockDim.x) buf[e] = terms[base + e];
-        __syncthreads();
+    const int nchunks = (nterms + CH - 1) / CH;
+    for (int e = threadIdx.x; e < min(CH, nterms); e += blockDim.x) buf[0][e] = terms[e];
+    __syncthreads();
+    for (int c = 0; c < nchunks; c++) {
+        const int n = min(CH, nterms - c * CH);
         if (threadIdx.x == 0) {
-#pragma unroll 8
-            for (int e = 0; e < n; e++) ub += buf[e];
+            const double *b = buf[c & 1];
+            int e = 0;
+            for (; e + 16 <= n; e += 16) {
+                double x[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = b[e + k];
+#pragma unroll
+                for (int k = 0; k < 16; k++) ub += x[k];
+            }
+            for (; e < n; e++) ub += b[e];
+        } else if (c + 1 < nchunks) {
+            const int base = (c + 1) * CH, m = min(CH, nterms - base);
+            for (int e = threadIdx.x - 1; e < m; e += blockDim.x - 1) buf[(c + 1) & 1][e] = terms[base + e];
         }
         __syncthreads();
     }

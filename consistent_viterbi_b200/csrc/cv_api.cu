@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "decode_small.cuh"
+#include "decode_chain.cuh"
 #include "decode_large.cuh"
 #include "cp_kernels.cuh"
 #include "probe.cuh"
@@ -282,6 +283,7 @@ __global__ void tile_tmax_kernel(const uint32_t *sorted_len, int ntiles, int NS,
 typedef cv_hmm::DecodeWs DecodeWs;
 static int g_small_cfg = -1;   // test/bench override of the small-K launch shape (see cv_set_small_config)
 static int g_chunks = -1;      // test/bench override of the chunk count (see cv_set_chunks)
+static long long g_chain_max_b = -1;   // batches up to this size use the warp-per-sequence kernel (-1: 8192)
 
 #include "decode_large_host.inl"
 
@@ -359,6 +361,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
 
 extern "C" void cv_set_small_config(int cfg) { g_small_cfg = cfg; }
 extern "C" void cv_set_chunks(int n) { g_chunks = n; }
+extern "C" void cv_set_chain_max_batch(long long b) { g_chain_max_b = b; }
 
 // One chunk of sequences [0, B) of d_off (offsets are absolute into d_obs / d_path): order by length,
 // forward, backtrace; everything enqueued on `st` with workspace set `w`.
@@ -387,6 +390,30 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p,
                                                        (uint32_t *)w.keys_out.p, (uint32_t *)w.vals_in.p,
                                                        (uint32_t *)w.order.p, (int)B, 0, 32, st));
+    if (h->K <= SMALL_K_MAX && (g_chain_max_b < 0 ? B <= 8192 : B <= g_chain_max_b)) {
+        // few sequences: one warp per sequence (latency-oriented), backpointers as u8 rows
+        if ((rc = w.hist.ensure((size_t)N * h->Kp + 64))) return rc;
+        DecodeChainParams p;
+        p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = (const uint32_t *)w.order.p;
+        p.psi = (uint8_t *)w.hist.p; p.path = d_path; p.score = d_score; p.counter = d_counter; p.status = d_status;
+        p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp;
+        p.bt_in_smem = ((size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
+        const size_t smem = (size_t)h->K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) +
+                            (size_t)DC_WARPS * (16 * h->Kp + 32 * h->Kp + 128);
+        const int grid = (int)std::min<int64_t>((B + DC_WARPS - 1) / DC_WARPS, (int64_t)h->num_sms * 8);
+        if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
+        if (h->K <= 32) {
+            CUDA_TRY(cudaFuncSetAttribute(decode_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_chain_kernel<1><<<grid, 32 * DC_WARPS, smem, st>>>(p);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(decode_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            decode_chain_kernel<2><<<grid, 32 * DC_WARPS, smem, st>>>(p);
+        }
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (timing) { CUDA_TRY(cudaEventRecord(h->ev1, st)); CUDA_TRY(cudaEventRecord(h->ev2, st)); }
+        return CV_OK;
+    }
     if (h->K <= SMALL_K_MAX)
         return launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, st, timing);
     if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
@@ -576,6 +603,20 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
                 case 8: probe_mix_kernel<1, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 case 9: probe_mix_kernel<0, 3><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 case 10: probe_mix_kernel<1, 0><<<blocks, threads>>>(d_out, iters, 1.0); break;
+                case 11: case 12: case 13: {
+                    long long *d_cyc = nullptr, h_cyc = 0;
+                    CUDA_TRY(cudaMalloc(&d_cyc, sizeof(long long)));
+                    if (mode == 11) probe_latency_kernel<0><<<1, 32>>>(d_out, iters, 1.0, d_cyc);
+                    else if (mode == 12) probe_latency_kernel<1><<<1, 32>>>(d_out, iters, 1.0, d_cyc);
+                    else probe_latency_kernel<2><<<1, 32>>>(d_out, iters, 1.0, d_cyc);
+                    CUDA_TRY(cudaMemcpy(&h_cyc, d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
+                    cudaFree(d_cyc);
+                    if (ms_out) *ms_out = (double)h_cyc / (16.0 * iters);      // cycles per dependent op
+                    if (ops_per_s_out) *ops_per_s_out = (double)h_cyc / (16.0 * iters);
+                    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+                    g_launches++;
+                    return CV_OK;
+                }
                 default: return fail(CV_ERR_ARG, "unknown probe mode %d", mode);
             }
             CUDA_TRY(e);

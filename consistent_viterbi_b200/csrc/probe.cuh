@@ -124,4 +124,25 @@ __global__ void __launch_bounds__(512, 1) probe_mix_kernel(double *out, int iter
     if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// dependent-chain latency probe: one warp, `iters` x 16 dependent ops; mode 0 DADD, 1 DSETP+FSEL (max), 2 SHFL+DADD
+template <int MODE>
+__global__ void probe_latency_kernel(double *out, int iters, double seed, long long *cycles)
+{
+    double acc = seed * (threadIdx.x + 1), best = -seed;
+    const double inc = seed * 1e-3;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (MODE == 0) acc += inc;
+            else if (MODE == 1) { const double v = inc * (k + it); best = v > best ? v : best; }
+            else { acc = __shfl_sync(0xffffffffu, acc, (threadIdx.x + 1) & 31) + inc; }
+        }
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (acc + best == 12345.678) out[threadIdx.x] = acc;
+}
+
 }  // namespace cvb

@@ -114,6 +114,9 @@ double cv_last_backtrace_ms(const cv_hmm *h);  /* end-state + backtrace kernel *
 void   cv_set_small_config(int cfg);
 /* tuning hook: number of chunks a batch is cut into (chunks overlap on two internal streams); -1 = automatic */
 void   cv_set_chunks(int n);
+/* tuning hook: batches of at most b sequences (K <= 64) use the warp-per-sequence kernel; -1 = default (8192),
+ * 0 = always the tile kernel */
+void   cv_set_chain_max_batch(long long b);
 /* pinned host memory helpers */
 void *cv_host_alloc(uint64_t bytes);
 void  cv_host_free(void *p);

@@ -11,12 +11,20 @@ pytestmark = pytest.mark.gpu
 
 
 def _check(A, B, pi, obs, off):
+    """Both K <= 64 kernels are exercised: the warp-per-sequence kernel (default for small batches) and the
+    lock-step tile kernel (forced with cv_set_chain_max_batch(0))."""
     h = cv.HMM(A, B, pi)
-    paths, scores = cv.decode_batch(h, obs, off)
     rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
-    bad = np.nonzero(paths != rp)[0]
-    assert bad.size == 0, f"{bad.size} path mismatches, first at {bad[:5]}"
-    assert scores.tobytes() == rs.tobytes()
+    L = cv._lib.lib()
+    try:
+        for chain_max in (-1, 0):
+            L.cv_set_chain_max_batch(chain_max)
+            paths, scores = cv.decode_batch(h, obs, off)
+            bad = np.nonzero(paths != rp)[0]
+            assert bad.size == 0, f"chain_max={chain_max}: {bad.size} path mismatches, first at {bad[:5]}"
+            assert scores.tobytes() == rs.tobytes(), f"chain_max={chain_max}: scores differ"
+    finally:
+        L.cv_set_chain_max_batch(-1)
     h.close()
 
 

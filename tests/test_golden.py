@@ -68,10 +68,16 @@ def test_oracle_matches_golden_ar(house):
 @pytest.mark.gpu
 def test_gpu_matches_golden_r1():
     import consistent_viterbi_b200 as cv
+    L = cv._lib.lib()
     for c in _r1_cases():
         h = cv.HMM(c["A"], c["B"], c["pi"])
-        p, s = cv.decode_batch(h, c["obs"], c["off"])
-        assert (p == c["paths"]).all() and _bits(s) == _bits(c["scores"])
+        try:
+            for chain_max in (-1, 0):           # warp-per-sequence kernel, then the tile kernel
+                L.cv_set_chain_max_batch(chain_max)
+                p, s = cv.decode_batch(h, c["obs"], c["off"])
+                assert (p == c["paths"]).all() and _bits(s) == _bits(c["scores"])
+        finally:
+            L.cv_set_chain_max_batch(-1)
         h.close()
 
 
