@@ -140,7 +140,6 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
 
     CpRun r;
     r.h = h; r.st = st; r.ncomp = ncomp; r.max_nodes = max_nodes;
-    r.smem = cp_sweep_smem_bytes(K, h->Kp);
 
     // ---- CPSolver::new (cp.rs:20-30): positions of every component, ascending ----
     std::vector<std::vector<int64_t>> cons((size_t)ncomp);
@@ -224,7 +223,6 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     }
-    CUDA_TRY(cudaFuncSetAttribute(cp_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem));
 
     const bool timing = g_timing.load() != 0;
     if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));

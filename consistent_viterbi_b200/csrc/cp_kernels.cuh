@@ -14,10 +14,9 @@
 // fixed-position segment concurrently, (C1/C2) backpointer fix-ups, (D) bound terms
 // gathered in parallel and summed serially in the reference's order.
 //
-// Sweep kernel mapping = the small-K decode mapping with "sequence" := segment:
-// tiles of 64 segments (sorted by length) run in lock step, a lane owns 2 segments,
-// a warp 8 target states, logA in shared memory, delta double-buffered in shared
-// memory as [state][slot].  Arithmetic is the reference's R2 order (cp.rs:49-58):
+// Sweep kernel mapping: one warp per segment, lanes = target states (chain_warp.cuh) -- a node's
+// segments are many but short and the longest one bounds the node's latency, so the per-step
+// latency matters more than lane efficiency.  Arithmetic is the reference's R2 order (cp.rs:49-58):
 //   psi = first-argmax_j fl(delta[t-1][j] + tr_j),  tr_j = a[j][s]  (pi[s] if el.t == 0)
 //   delta[t][s] = fl(delta[t-1][psi] + fl(tr_psi + b[s][o_t]))
 // so the cell keeps (value, index) -- the index IS state here, unlike mode R1.
@@ -67,114 +66,8 @@ __global__ void cp_row0_kernel(const CpParams p)
     if (i < p.K) p.delta[i] = p.Pi[i] + p.BT[(size_t)p.obs[0] * p.Kp + i];
 }
 
-__global__ void __launch_bounds__(256, 2) cp_sweep_kernel(const CpParams p, const CpSweepArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = p.K, Kp = p.Kp, NS = 64;
-    double *sA = reinterpret_cast<double *>(smem_raw);
-    double *sD = sA + (size_t)K * Kp;
-    double *sPi = sD + (size_t)2 * K * NS;
-    int64_t *sFrom = reinterpret_cast<int64_t *>(sPi + Kp);
-    int *sLen = reinterpret_cast<int *>(sFrom + NS);
-    int *sTile = sLen + NS;
-
-    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
-    const int i0 = g * TQ;
-    const int s0 = lane * TP;
-    for (int e = tid; e < K * Kp; e += blockDim.x) sA[e] = p.A[e];
-    for (int e = tid; e < Kp; e += blockDim.x) sPi[e] = p.Pi[e];
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) *sTile = (int)atomicAdd(a.tile_counter, 1u);
-        __syncthreads();
-        const int tile = *sTile;
-        if (tile >= a.ntiles) break;
-
-        for (int s = tid; s < NS; s += blockDim.x) {
-            const int r = tile * NS + s;
-            sFrom[s] = r < a.nseg ? a.seg_from[r] : 0;
-            sLen[s] = r < a.nseg ? a.seg_len[r] : -1;       // -1: empty slot
-        }
-        __syncthreads();
-        // phase A: the clamped row (cp.rs:33-34), or the stored row for the init prefix
-        for (int e = tid; e < K * NS; e += blockDim.x) {
-            const int j = e / NS, s = e % NS;
-            double v = (j == a.node) ? 0.0 : neg_inf();
-            if (sLen[s] >= 0) {
-                if (a.init_mode) v = p.delta[(size_t)sFrom[s] * K + j];
-                else p.delta[(size_t)sFrom[s] * K + j] = v;
-            }
-            sD[e] = v;
-        }
-        __syncthreads();
-
-        const int Tmax = sLen[0];
-        int len_p[TP]; int64_t from_p[TP];
-#pragma unroll
-        for (int q = 0; q < TP; q++) { len_p[q] = sLen[s0 + q]; from_p[q] = sFrom[s0 + q]; }
-
-        // phase B: rows from+1 .. from+len (cp.rs:47-60 / cp.rs:70-78)
-        for (int k = 1; k <= Tmax; k++) {
-            const bool act[TP] = {k <= len_p[0], k <= len_p[1]};
-            uint32_t o[TP] = {0u, 0u}; bool st[TP] = {false, false};
-#pragma unroll
-            for (int q = 0; q < TP; q++)
-                if (act[q]) { o[q] = p.obs[from_p[q] + k]; st[q] = p.start[from_p[q] + k] != 0; }
-            const double *dcur = sD + (size_t)((k - 1) & 1) * K * NS + s0;
-            double best[TP][TQ]; int idx[TP][TQ];
-            const bool any_start = __any_sync(0xffffffffu, st[0] || st[1]);
-            if (!any_start) {
-                maxplus_tile<0>(dcur, NS, sA + i0, Kp, K, best, idx, 0);
-            } else {
-                // some segment crosses a sequence boundary at this row: its candidates are
-                // delta[t-1][j] + pi[s] (viterbi_solver/utils.rs:32-38), per lane
-#pragma unroll
-                for (int q = 0; q < TP; q++)
-#pragma unroll
-                    for (int c = 0; c < TQ; c++) { best[q][c] = neg_inf(); idx[q][c] = 0; }
-                for (int j = 0; j < K; j++) {
-                    const double2 d = *reinterpret_cast<const double2 *>(dcur + (size_t)j * NS);
-                    const double dd[TP] = {d.x, d.y};
-#pragma unroll
-                    for (int q = 0; q < TP; q++)
-#pragma unroll
-                        for (int c = 0; c < TQ; c++) {
-                            const double tr = st[q] ? sPi[i0 + c] : sA[(size_t)j * Kp + i0 + c];
-                            const double v = dd[q] + tr;
-                            if (v > best[q][c]) { best[q][c] = v; idx[q][c] = j; }
-                        }
-                }
-            }
-            double *dnext = sD + (size_t)(k & 1) * K * NS + s0;
-            const double *dold = sD + (size_t)((k - 1) & 1) * K * NS + s0;
-#pragma unroll
-            for (int q = 0; q < TP; q++) {
-                if (!act[q]) continue;
-                const int64_t t = from_p[q] + k;
-                const double *em = p.BT + (size_t)o[q] * Kp + i0;
-#pragma unroll
-                for (int c = 0; c < TQ; c++) {
-                    const int i = i0 + c;
-                    if (i < K) {
-                        const int ix = idx[q][c];
-                        const double tr = st[q] ? sPi[i] : sA[(size_t)ix * Kp + i];
-                        const double arc = tr + __ldg(em + c);                 // arc_p: a + b (utils.rs:24-30)
-                        const double v = dold[(size_t)ix * NS + q] + arc;      // delta + (a + b)  cp.rs:55
-                        dnext[(size_t)i * NS + q] = v;
-                        p.delta[(size_t)t * K + i] = v;
-                        p.psi[(size_t)t * K + i] = (psi_t)ix;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-
 // ---- sweeps, one warp per segment (latency-oriented; see chain_warp.cuh) -----------------------------
-// Same arithmetic and the same phases A + B as cp_sweep_kernel; segments are claimed longest first.
+// Phases A (reset row) + B (sweep); segments are claimed longest first from a global counter.
 constexpr int CPW_WARPS = 4;
 
 template <int NSL>
@@ -324,7 +217,7 @@ __global__ void cp_terms_kernel(const CpParams p, const int64_t *term_pos, const
 // memory stage and the adder keeps 16 terms in registers ahead of the dependent DADD chain (8 clk per term).
 __global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, double *ub_out)
 {
-    constexpr int CH = 4096;
+    constexpr int CH = 2048;
     __shared__ double buf[2][CH];
     double ub = 0.0;
     const int nchunks = (nterms + CH - 1) / CH;

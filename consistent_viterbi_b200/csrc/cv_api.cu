@@ -86,7 +86,7 @@ struct DevBuf {
 };
 
 struct cv_hmm {
-    int device = 0, K = 0, Kp = 0, G = 0, D = 0, num_sms = 0;
+    int device = 0, K = 0, Kp = 0, G = 0, D = 0, num_sms = 0, TQT = 8;
     int64_t M = 1;
     // device model
     double *dA = nullptr;    // [K][Kp]   small-K layout (Kp = 8*ceil(K/8)), pad = -inf
@@ -181,7 +181,29 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
 
     cv_hmm *h = new cv_hmm();
     h->device = device; h->K = K; h->D = D; h->M = M;
-    h->G = (K + TQ - 1) / TQ; h->Kp = h->G * TQ;
+    // tile shape of the forward kernel: TQT target states per warp, G = ceil(K/TQT) state groups.  Pick the
+    // shape with the least padded work among those whose warps per CTA (G*S, S in {1,2,4}) divide by 4.
+    {
+        double best_eff = -1.0; int best_tq = 8;
+        for (int tq : {8, 12}) {
+            const int g = (K + tq - 1) / tq;
+            double eff = 0.0;
+            for (int s : {1, 2, 4}) {
+                if (g * s * 32 > 512) continue;
+                const int w = g * s;
+                const double bal = (double)w / (4.0 * ((w + 3) / 4));
+                // wide CTAs (one per SM) lose to the per-step barrier: mild penalty so that S = 1 wins ties
+                eff = std::max(eff, bal * (s == 1 ? 1.0 : 0.93) * (double)K / (g * tq));
+            }
+            if (eff > best_eff + 1e-9) { best_eff = eff; best_tq = tq; }
+        }
+        // measured on B200 (POS shape): TQ = 8 with two 6-warp CTAs per SM beats the balanced TQ = 12 shape
+        // (12 vs 8 resident warps), so 8 stays the default; CV_TQ=12 / CV_TQ=auto select the alternatives
+        const char *e = getenv("CV_TQ");
+        h->TQT = (e && !strcmp(e, "auto")) ? best_tq : (e && atoi(e) == 12) ? 12 : 8;
+    }
+    h->G = (K + h->TQT - 1) / h->TQT;
+    h->Kp = ((std::max(h->G * h->TQT, K) + 7) / 8) * 8;
     h->hA.assign(logA, logA + (size_t)K * K);
     h->hB.assign(logB, logB + (size_t)K * M);
     h->hPi.assign(logPi, logPi + K);
@@ -331,8 +353,10 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     p.tile_base = (const long long *)w.base.p;
     p.hist = (double *)w.hist.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
     p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.ntiles = ntiles;
-    void (*kern)(DecodeSmallParams) = variant == 1 ? decode_small_fwd_kernel<512, 1>
-                                    : variant == 2 ? decode_small_fwd_kernel<384, 2> : decode_small_fwd_kernel<256, 3>;
+    void (*kern)(DecodeSmallParams);
+    if (h->TQT == 12) kern = variant == 1 ? decode_small_fwd_kernel<12, 512, 1> : decode_small_fwd_kernel<12, 256, 2>;
+    else kern = variant == 1 ? decode_small_fwd_kernel<8, 512, 1>
+              : variant == 2 ? decode_small_fwd_kernel<8, 384, 2> : decode_small_fwd_kernel<8, 256, 3>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int occ = 1;
@@ -340,8 +364,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     occ = std::max(1, occ);
     const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * occ, ntiles);
     if (getenv("CV_DEBUG"))
-        fprintf(stderr, "[cv] decode_small: K=%d G=%d S=%d variant=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
-                h->K, G, S, variant, threads, smem, occ, grid, ntiles);
+        fprintf(stderr, "[cv] decode_small: K=%d TQ=%d G=%d S=%d variant=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
+                h->K, h->TQT, G, S, variant, threads, smem, occ, grid, ntiles);
     if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     kern<<<std::max(1, grid), threads, smem, st>>>(p);
     g_launches++;
@@ -565,7 +589,8 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
     CUDA_TRY(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-    const int threads = 384, blocks = prop.multiProcessorCount;
+    int threads = 384; if (const char *e = getenv("CV_PROBE_THREADS")) threads = atoi(e);
+    const int blocks = prop.multiProcessorCount;
     double *d_out = nullptr;
     CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * (size_t)threads * blocks));
     cudaEvent_t e0, e1;
@@ -589,20 +614,33 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
                 kern<<<blocks, threads, smem>>>(d_out, K, iters, 0, 1.0);
                 return cudaSuccess;
             };
+            auto launch_val = [&](auto kern) -> cudaError_t {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                kern<<<blocks, threads, smem>>>(d_out, K, iters, 1.0);
+                return cudaSuccess;
+            };
             cudaError_t e = cudaSuccess;
             switch (mode) {
                 case 2: e = launch(probe_tile_kernel<0>); break;
                 case 3: e = launch(probe_tile_kernel<1>); break;
                 case 4: e = launch(probe_tile_kernel<2>); break;
                 case 5: e = launch(probe_tile_kernel<3>); break;
-                case 6:
-                    e = cudaFuncSetAttribute(probe_tile_val_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (e == cudaSuccess) probe_tile_val_kernel<<<blocks, threads, smem>>>(d_out, K, iters, 1.0);
-                    break;
+                case 6: e = launch_val(probe_tile_val_kernel<2>); break;
+                case 20: e = launch_val(probe_tile_val_kernel<3>); break;
+                case 21: e = launch_val(probe_tile_val_kernel<4>); break;
+                case 22: e = launch_val(probe_tile_val_kernel<5>); break;
+                case 23: e = launch_val(probe_tile_val_kernel<9>); break;
                 case 7: probe_mix_kernel<1, 1><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 case 8: probe_mix_kernel<1, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 case 9: probe_mix_kernel<0, 3><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 case 10: probe_mix_kernel<1, 0><<<blocks, threads>>>(d_out, iters, 1.0); break;
+                case 17: probe_tile_val_reg_kernel<<<blocks, threads>>>(d_out, K, iters, 1.0); break;
+                case 18: probe_tile_val_var_kernel<1><<<blocks, threads>>>(d_out, K, iters, 1.0); break;
+                case 19: probe_tile_val_var_kernel<2><<<blocks, threads>>>(d_out, K, iters, 1.0); break;
+                case 14: probe_mix_alu_kernel<1, 1><<<blocks, threads>>>(d_out, iters, 1.0); break;
+                case 15: probe_mix_alu_kernel<1, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
+                case 16: probe_mix_alu_kernel<0, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 case 11: case 12: case 13: {
                     long long *d_cyc = nullptr, h_cyc = 0;
                     CUDA_TRY(cudaMalloc(&d_cyc, sizeof(long long)));
@@ -622,6 +660,7 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
             CUDA_TRY(e);
             fp64_ops = 2.0 * 16.0 * K * (double)iters * threads * blocks;   // DADD + DSETP per cell
             if (mode >= 7) fp64_ops = 8.0 * (double)iters * threads * blocks;   // DADD count (8 chains) per iteration
+            if (mode >= 17) fp64_ops = 2.0 * 16.0 * K * (double)iters * threads * blocks;
         }
         g_launches++;
         CUDA_TRY(cudaEventRecord(e1));

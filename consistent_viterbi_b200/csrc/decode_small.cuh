@@ -68,23 +68,25 @@ __host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS)
 
 // value-only TP x TQ micro-tile: best[p][q] = max_j ( dcol[j*ldd + p] + arow[j*lda + q] )
 // (strict > keeps the first maximum's bits, e.g. the sign of a zero, as the reference does).
+template <int TQT, int UNR = 2>
 __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol, int ldd,
                                                  const double *__restrict__ arow, int lda, int nj,
-                                                 double (&best)[TP][TQ])
+                                                 double (&best)[TP][TQT])
 {
-#pragma unroll 2
+#pragma unroll UNR
     for (int j = 0; j < nj; j++) {
         const double2 d = *reinterpret_cast<const double2 *>(dcol + (size_t)j * ldd);
-        const double2 a01 = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda);
-        const double2 a23 = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2);
-        const double2 a45 = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 4);
-        const double2 a67 = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 6);
-        const double a[TQ] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+        double a[TQT];
+#pragma unroll
+        for (int q = 0; q < TQT / 2; q++) {
+            const double2 aa = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2 * q);
+            a[2 * q] = aa.x; a[2 * q + 1] = aa.y;
+        }
         const double dd[TP] = {d.x, d.y};
 #pragma unroll
         for (int p = 0; p < TP; p++)
 #pragma unroll
-            for (int q = 0; q < TQ; q++) {
+            for (int q = 0; q < TQT; q++) {
                 const double v = dd[p] + a[q];
                 best[p][q] = v > best[p][q] ? v : best[p][q];
             }
@@ -107,8 +109,10 @@ __device__ __forceinline__ void fence_proxy_async_smem()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// MAXT/MINB only set the register budget (launch bounds).
-template <int MAXT, int MINB>
+// TQT = target states per thread (8 or 12; a warp owns TQT adjacent states); MAXT/MINB only set the register
+// budget (launch bounds).  The host picks TQT and S so that a CTA has a multiple of 4 warps: warps map to the
+// four SM sub-partitions by warp id, and with the per-step barrier an uneven split leaves sub-partitions idle.
+template <int TQT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = w % p.G, sg = w / p.G;
-    const int i0 = g * TQ;
+    const int i0 = g * TQT;
     const int s0 = sg * SEQ_PER_WARP + lane * TP;
     const uint32_t slab_bytes = (uint32_t)((size_t)K * NS * 8);
     const uint32_t row_bytes = (uint32_t)(Kp * 8);
@@ -203,20 +207,20 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         }
 
         for (int t = 1; t < Tmax; t++) {
-            double best[TP][TQ];
+            double best[TP][TQT];
 #pragma unroll
             for (int q = 0; q < TP; q++)
 #pragma unroll
-                for (int k = 0; k < TQ; k++) best[q][k] = neg_inf();
+                for (int k = 0; k < TQT; k++) best[q][k] = neg_inf();
             const double *dcur = sD + (size_t)((t - 1) & 1) * K * NS + s0;
-            maxplus_tile_val(dcur, NS, sA + i0, Kp, K, best);
+            maxplus_tile_val<TQT, 2>(dcur, NS, sA + i0, Kp, K, best);
 
             mbar_wait(sBar + 1, em_phase);      // emission rows of step t have landed
             em_phase ^= 1;
             double *dnext = sD + (size_t)(t & 1) * K * NS + s0;
             const double *e0 = sEm + (size_t)s0 * EP + i0, *e1 = e0 + EP;
 #pragma unroll
-            for (int k = 0; k < TQ / 2; k++) {
+            for (int k = 0; k < TQT / 2; k++) {
                 const double2 x0 = *reinterpret_cast<const double2 *>(e0 + 2 * k);
                 const double2 x1 = *reinterpret_cast<const double2 *>(e1 + 2 * k);
                 // (delta + a) + b (viterbi.rs:17).  Sequences that already ended compute garbage in their

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(512, 1) probe_tile_kernel(double *out, int K, 
 
 
 // value-only micro-tile (the forward kernel's inner loop) in isolation
+template <int UNR>
 __global__ void __launch_bounds__(512, 1) probe_tile_val_kernel(double *out, int K, int iters, double seed)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -87,12 +88,111 @@ __global__ void __launch_bounds__(512, 1) probe_tile_val_kernel(double *out, int
         for (int p = 0; p < TP; p++)
 #pragma unroll
             for (int q = 0; q < TQ; q++) best[p][q] = neg_inf();
-        maxplus_tile_val(sD + s0, NS, sA + i0, Kp, K, best);
+        maxplus_tile_val<TQ, UNR>(sD + s0, NS, sA + i0, Kp, K, best);
 #pragma unroll
         for (int p = 0; p < TP; p++)
 #pragma unroll
             for (int q = 0; q < TQ; q++) tot += best[p][q];
         if (i0 == 0) sD[(size_t)(it % K) * NS + s0] = tot * 1e-30;
+    }
+    if (tot == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = tot;
+}
+
+
+// value-only micro-tile with operands in REGISTERS (no shared loads): compute-only ceiling of the inner loop
+__global__ void __launch_bounds__(512, 1) probe_tile_val_reg_kernel(double *out, int K, int iters, double seed)
+{
+    double a[TQ], d[TP];
+#pragma unroll
+    for (int q = 0; q < TQ; q++) a[q] = -seed * ((threadIdx.x * 7 + q * 3) % 11);
+#pragma unroll
+    for (int p = 0; p < TP; p++) d[p] = -seed * ((threadIdx.x * 5 + p) % 13);
+    double tot = 0.0;
+    for (int it = 0; it < iters; it++) {
+        double best[TP][TQ];
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) best[p][q] = neg_inf();
+#pragma unroll 2
+        for (int j = 0; j < K; j++) {
+#pragma unroll
+            for (int p = 0; p < TP; p++)
+#pragma unroll
+                for (int q = 0; q < TQ; q++) {
+                    const double v = d[p] + a[q];
+                    best[p][q] = v > best[p][q] ? v : best[p][q];
+                }
+#pragma unroll
+            for (int q = 0; q < TQ; q++) a[q] = a[q] * 1.0000001;     // keep the adds from being hoisted (8 DMUL per 16 cells)
+        }
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) tot += best[p][q];
+    }
+    if (tot == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = tot;
+}
+
+
+// compute-only ceiling, variants of instruction ordering (VAR 0: as the kernel; 1: adds of predecessor j+1 issued
+// before the compare/selects of j (explicit software pipelining); 2: unroll 4)
+template <int VAR>
+__global__ void __launch_bounds__(512, 1) probe_tile_val_var_kernel(double *out, int K, int iters, double seed)
+{
+    double a[TQ], d[TP];
+#pragma unroll
+    for (int q = 0; q < TQ; q++) a[q] = -seed * ((threadIdx.x * 7 + q * 3) % 11);
+#pragma unroll
+    for (int p = 0; p < TP; p++) d[p] = -seed * ((threadIdx.x * 5 + p) % 13);
+    double tot = 0.0;
+    for (int it = 0; it < iters; it++) {
+        double best[TP][TQ];
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) best[p][q] = neg_inf();
+        if (VAR == 1) {
+            double v[TP][TQ];
+#pragma unroll
+            for (int p = 0; p < TP; p++)
+#pragma unroll
+                for (int q = 0; q < TQ; q++) v[p][q] = d[p] + a[q];
+#pragma unroll 2
+            for (int j = 0; j < K; j++) {
+#pragma unroll
+                for (int q = 0; q < TQ; q++) a[q] = a[q] * 1.0000001;
+                double vn[TP][TQ];
+#pragma unroll
+                for (int p = 0; p < TP; p++)
+#pragma unroll
+                    for (int q = 0; q < TQ; q++) {
+                        vn[p][q] = d[p] + a[q];                                  // next predecessor's add ...
+                        best[p][q] = v[p][q] > best[p][q] ? v[p][q] : best[p][q];   // ... next to this one's select
+                    }
+#pragma unroll
+                for (int p = 0; p < TP; p++)
+#pragma unroll
+                    for (int q = 0; q < TQ; q++) v[p][q] = vn[p][q];
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < K; j++) {
+#pragma unroll
+                for (int p = 0; p < TP; p++)
+#pragma unroll
+                    for (int q = 0; q < TQ; q++) {
+                        const double v = d[p] + a[q];
+                        best[p][q] = v > best[p][q] ? v : best[p][q];
+                    }
+#pragma unroll
+                for (int q = 0; q < TQ; q++) a[q] = a[q] * 1.0000001;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < TP; p++)
+#pragma unroll
+            for (int q = 0; q < TQ; q++) tot += best[p][q];
     }
     if (tot == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = tot;
 }
@@ -124,6 +224,35 @@ __global__ void __launch_bounds__(512, 1) probe_mix_kernel(double *out, int iter
     if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+
+// dispatch-port test 2: NI independent integer ALU ops (LOP3/IADD3 class) per DADD; ND = 0 -> ALU only
+template <int ND, int NI>
+__global__ void __launch_bounds__(512, 1) probe_mix_alu_kernel(double *out, int iters, double seed)
+{
+    constexpr int NCH = 8;
+    double acc[NCH]; unsigned iacc[NCH * (NI > 0 ? NI : 1)];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) acc[c] = seed * (threadIdx.x + c);
+#pragma unroll
+    for (int c = 0; c < NCH * (NI > 0 ? NI : 1); c++) iacc[c] = threadIdx.x * 2654435761u + c;
+    const double inc = seed * 1e-3; const unsigned m = (unsigned)(seed * 12345.0) | 1u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            if (ND) acc[c] += inc;
+#pragma unroll
+            for (int f = 0; f < NI; f++) iacc[c * NI + f] = (iacc[c * NI + f] ^ m) + (iacc[c * NI + f] >> 3);   // LOP3 + SHF/IADD
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) s += acc[c];
+    unsigned si = 0;
+#pragma unroll
+    for (int c = 0; c < NCH * (NI > 0 ? NI : 1); c++) si += iacc[c];
+    if (s == 12345.678 || si == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = s + si;
+}
 
 // dependent-chain latency probe: one warp, `iters` x 16 dependent ops; mode 0 DADD, 1 DSETP+FSEL (max), 2 SHFL+DADD
 template <int MODE>
