@@ -95,6 +95,7 @@ struct cv_hmm {
     // large-K layout
     int Kl = 0;              // K padded to a multiple of LARGE_BN
     double *dAl = nullptr;   // [Kl][Kl]
+    double *dATl = nullptr;  // [Kl][Kl] transposed (lazy-psi backtrace)
     double *dBTl = nullptr;  // [M][Kl]
     // host copy (control logic of the CP solver)
     std::vector<double> hA, hB, hPi;
@@ -132,14 +133,14 @@ static int check_device(int device)
 }
 
 __global__ void build_layouts_kernel(const double *A, const double *Bm, const double *pi, int K, int64_t M, int Kp,
-                                     double *Ap, double *BT, double *Pip)
+                                     int rowsA, double *Ap, double *BT, double *Pip)
 {
-    const int64_t n1 = (int64_t)K * Kp, n2 = M * Kp;
+    const int64_t n1 = (int64_t)rowsA * Kp, n2 = M * Kp;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n1 + n2 + Kp; e += stride) {
         if (e < n1) {
             int j = (int)(e / Kp), i = (int)(e % Kp);
-            Ap[e] = i < K ? A[(int64_t)j * K + i] : neg_inf();
+            Ap[e] = (i < K && j < K) ? A[(int64_t)j * K + i] : neg_inf();
         } else if (e < n1 + n2) {
             int64_t r = e - n1;
             int64_t o = r / Kp; int i = (int)(r % Kp);
@@ -149,6 +150,17 @@ __global__ void build_layouts_kernel(const double *A, const double *Bm, const do
             Pip[i] = i < K ? pi[i] : neg_inf();
         }
     }
+}
+
+__global__ void transpose_kernel(const double *in, double *out, int n)
+{
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8)
+        if (by + r < n && bx + threadIdx.x < n) tile[r][threadIdx.x] = in[(size_t)(by + r) * n + bx + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8)
+        if (bx + r < n && by + threadIdx.x < n) out[(size_t)(bx + r) * n + by + threadIdx.x] = tile[threadIdx.x][r];
 }
 
 extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *logA, const double *logB,
@@ -231,16 +243,24 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     CUDA_TRY(cudaMemcpy(tB, logB, sizeof(double) * (size_t)K * M, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(tPi, logPi, sizeof(double) * (size_t)K, cudaMemcpyHostToDevice));
     double *pA = nullptr, *pBT = nullptr, *pPi = nullptr;
-    CUDA_TRY(cudaMalloc(&pA, sizeof(double) * (size_t)K * Kp));
+    const int rowsA = (K <= SMALL_K_MAX) ? K : Kp;   // the large-K TMA ring reads whole 16-row chunks
+    CUDA_TRY(cudaMalloc(&pA, sizeof(double) * (size_t)rowsA * Kp));
     CUDA_TRY(cudaMalloc(&pBT, sizeof(double) * (size_t)M * Kp));
     CUDA_TRY(cudaMalloc(&pPi, sizeof(double) * (size_t)Kp));
-    build_layouts_kernel<<<std::max(1, h->num_sms) * 4, 256>>>(tA, tB, tPi, K, M, Kp, pA, pBT, pPi);
+    build_layouts_kernel<<<std::max(1, h->num_sms) * 4, 256>>>(tA, tB, tPi, K, M, Kp, rowsA, pA, pBT, pPi);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
     cudaFree(tA); cudaFree(tB); cudaFree(tPi);
     if (K <= SMALL_K_MAX) { h->dA = pA; h->dBT = pBT; h->dPi = pPi; }
-    else { h->dAl = pA; h->dBTl = pBT; h->dPi = pPi; }
+    else {
+        h->dAl = pA; h->dBTl = pBT; h->dPi = pPi;
+        CUDA_TRY(cudaMalloc(&h->dATl, sizeof(double) * (size_t)Kp * Kp));
+        transpose_kernel<<<dim3((Kp + 31) / 32, (Kp + 31) / 32), dim3(32, 8)>>>(pA, h->dATl, Kp);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
     *out = h;
     return CV_OK;
 }
@@ -250,7 +270,7 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl}) if (p) cudaFree(p);
+    for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl, h->dATl}) if (p) cudaFree(p);
     for (DevBuf *b : {&h->obs, &h->seq_off, &h->path, &h->score}) b->release();
     for (auto &w : h->ws) {
         for (DevBuf *b : {&w.order, &w.keys_in, &w.keys_out, &w.vals_in, &w.cub_tmp, &w.hist, &w.tmax, &w.base, &w.misc,

@@ -15,9 +15,13 @@
 // Inside an item, one producer thread streams 16-row chunks of logA[:, cb] (16 KB) and
 // of delta_{t-1}[rb] (8 KB) from L2 into a 4-stage shared-memory ring with TMA
 // bulk copies (cp.async.bulk + mbarrier full/empty pairs); 16 warps each
-// own 8 target states x 64 sequences and run the same 2x8 register micro-tile as
-// the small-K kernel.  delta is kept in HBM/L2 as [2][Kl][Bpad] (state-major,
-// sequence fastest) so both the chunk loads and the slice stores are contiguous.
+// own 8 target states x 64 sequences and run the same value-only 2x8 register
+// micro-tile as the small-K kernel.  Every delta row is kept: the history is
+// [t][Kl][Bpad] f64 (state-major, sequence fastest), so the chunk loads of step t-1
+// and the slice stores of step t are contiguous, and the backtrace recomputes the
+// backpointer of the one path state per step from the stored row (lazy psi, see
+// decode_small.cuh).  When the history of the whole batch does not fit in HBM the
+// host runs the batch in groups of row blocks.
 #pragma once
 
 #include "common.cuh"
@@ -42,20 +46,20 @@ struct DecodeLargeParams {
     const uint32_t *sorted_len;  // [B] lengths in that order
     uint32_t *path;           // [N]
     double *score;            // [B] or nullptr
-    double *delta;            // [2][Kl][Bpad]
-    void *psi;                // [N][Kl] u8 (Kl <= 256) or u16
+    double *hist;             // [Tmax][Kl][Bpad] delta history of this group of row blocks
+    const double *AT;         // [Kl][Kl] logA transposed (backtrace)
     const long long *step_start; // [Tmax+1] first item id of step t (index t, t >= 1); [Tmax] = total
     unsigned long long *item_counter;
     unsigned int *done;       // [NRB] completed items per row block
     int *status;
     int64_t M, B, Bpad;
-    int K, Kl, NCB, NRB, Tmax, psi16, zero;
+    int64_t rank0;            // sorted rank of the group's first sequence
+    int K, Kl, NCB, NRB, Tmax;
 };
 
-template <int VARIANT>
-__device__ __forceinline__ void maxplus_accum(const double *__restrict__ dcol, int ldd,
-                                              const double *__restrict__ arow, int lda, int nj, int jbase,
-                                              double (&best)[TP][TQ], int (&idx)[TP][TQ], int zero)
+__device__ __forceinline__ void maxplus_accum_val(const double *__restrict__ dcol, int ldd,
+                                                  const double *__restrict__ arow, int lda, int nj,
+                                                  double (&best)[TP][TQ])
 {
 #pragma unroll 2
     for (int jj = 0; jj < nj; jj++) {
@@ -69,7 +73,10 @@ __device__ __forceinline__ void maxplus_accum(const double *__restrict__ dcol, i
 #pragma unroll
         for (int p = 0; p < TP; p++)
 #pragma unroll
-            for (int q = 0; q < TQ; q++) cell<VARIANT>(dd[p], a[q], best[p][q], idx[p][q], jbase + jj, zero);
+            for (int q = 0; q < TQ; q++) {
+                const double v = dd[p] + a[q];
+                best[p][q] = v > best[p][q] ? v : best[p][q];
+            }
     }
 }
 
@@ -85,7 +92,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int VARIANT>
 __global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const DecodeLargeParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -130,7 +136,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const Decod
         const int t = (int)sItem[1], rb = (int)sItem[2], cb = (int)sItem[3];
         if (item >= total_items) break;
 
-        const double *dsrc = p.delta + (size_t)((t - 1) & 1) * Kl * p.Bpad + (size_t)rb * LG_BM;
+        const size_t slab = (size_t)Kl * p.Bpad;
+        const double *dsrc = p.hist + (size_t)(t - 1) * slab + (size_t)rb * LG_BM;
         const double *asrc = p.A + (size_t)cb * LARGE_BN;
 
         // The producer is lane 0 of warp 0: it waits for the dependency, then keeps the TMA ring
@@ -160,12 +167,12 @@ __global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const Decod
         {
             // =================== consumer warps ===================
             const int i0 = cb * LARGE_BN + w * TQ;        // global target state of q = 0
-            const int r0 = rb * LG_BM + lane * TP;        // sorted rank of p = 0
-            double best[TP][TQ]; int idx[TP][TQ];
+            const int r0 = rb * LG_BM + lane * TP;        // column (rank inside the group) of p = 0
+            double best[TP][TQ];
 #pragma unroll
             for (int q = 0; q < TP; q++)
 #pragma unroll
-                for (int k = 0; k < TQ; k++) { best[q][k] = neg_inf(); idx[q][k] = 0; }
+                for (int k = 0; k < TQ; k++) best[q][k] = neg_inf();
 
             for (int c = 0; c < nchunks; c++) {
                 if (tid == 0 && c + LG_STAGES - 1 < nchunks) issue_chunk(c + LG_STAGES - 1);
@@ -174,46 +181,30 @@ __global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const Decod
                 const int s = g % LG_STAGES;
                 mbar_wait(full + s, (g / LG_STAGES) & 1);
                 const int nj = min(LG_BK, K - c * LG_BK);
-                maxplus_accum<VARIANT>(sD + (size_t)s * LG_STAGE_D + lane * TP, LG_BM,
-                                       sA + (size_t)s * LG_STAGE_A + w * TQ, LARGE_BN, nj, c * LG_BK, best, idx,
-                                       p.zero);
+                maxplus_accum_val(sD + (size_t)s * LG_STAGE_D + lane * TP, LG_BM,
+                                  sA + (size_t)s * LG_STAGE_A + w * TQ, LARGE_BN, nj, best);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + s);
             }
             chunk_ctr += nchunks;
 
-            // ---- epilogue: emission, -inf rule, delta slice + backpointers ----
-            double *dnext = p.delta + (size_t)(t & 1) * Kl * p.Bpad;
+            // ---- epilogue: emission ((delta + a) + b, viterbi.rs:17; -inf emission => -inf) and the slice of slab t ----
+            double *dnext = p.hist + (size_t)t * slab;
 #pragma unroll
             for (int q = 0; q < TP; q++) {
                 const int r = r0 + q;
-                if (r >= p.B) continue;
-                const int len = (int)p.sorted_len[r];
+                const int64_t rg = p.rank0 + r;
+                if (rg >= p.B) continue;
+                const int len = (int)p.sorted_len[rg];
                 if (t >= len) continue;
-                const uint32_t b = p.order[r];
+                const uint32_t b = p.order[rg];
                 const int64_t pos = p.seq_off[b] + t;
                 uint32_t o = p.obs[pos];
                 if ((int64_t)o >= p.M) { *p.status = 3; o = 0; }
                 const double *em = p.BT + (size_t)o * Kl + i0;
-                uint32_t pk[TQ];
 #pragma unroll
-                for (int k = 0; k < TQ; k++) {
-                    const double e = __ldg(em + k);
-                    double v = best[q][k] + e;                      // (delta + a) + b   viterbi.rs:17
-                    int ix = idx[q][k];
-                    if (!(e > neg_inf())) { v = neg_inf(); ix = 0; }   // viterbi.rs:19-21
-                    if (i0 + k < K) dnext[(size_t)(i0 + k) * p.Bpad + r] = v;
-                    pk[k] = (uint32_t)ix;
-                }
-                if (p.psi16) {
-                    uint4 v4 = make_uint4(pk[0] | (pk[1] << 16), pk[2] | (pk[3] << 16), pk[4] | (pk[5] << 16),
-                                          pk[6] | (pk[7] << 16));
-                    __stcs(reinterpret_cast<uint4 *>((uint16_t *)p.psi + (size_t)pos * Kl + i0), v4);
-                } else {
-                    uint2 v2 = make_uint2(pk[0] | (pk[1] << 8) | (pk[2] << 16) | (pk[3] << 24),
-                                          pk[4] | (pk[5] << 8) | (pk[6] << 16) | (pk[7] << 24));
-                    __stcs(reinterpret_cast<uint2 *>((uint8_t *)p.psi + (size_t)pos * Kl + i0), v2);
-                }
+                for (int k = 0; k < TQ; k++)
+                    if (i0 + k < K) dnext[(size_t)(i0 + k) * p.Bpad + r] = best[q][k] + __ldg(em + k);
             }
             __threadfence();   // publish this thread's delta slice before the item is counted done
         }
@@ -222,26 +213,65 @@ __global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const Decod
     }
 }
 
-// End state (viterbi.rs:24) and backtrace (viterbi.rs:25-30), one thread per sequence.
-__global__ void backtrace_large_kernel(const DecodeLargeParams p)
+// End state (viterbi.rs:24) and backtrace (viterbi.rs:25-30) with lazy backpointers, 8 lanes per sequence:
+// lane `sub` scans predecessors j = sub, sub+8, ... of the current path state (delta row from the history,
+// logA column from the transposed copy, both 64-byte runs per sequence), then the 8 lanes reduce
+// (value, index) -- strictly greater value, else lower index.  psi = 0 whenever delta[t][cur] = -inf
+// (emission -inf or all candidates -inf; see decode_small.cuh).
+__global__ void __launch_bounds__(256) backtrace_large_kernel(const DecodeLargeParams p)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.B) return;
-    const int len = (int)p.sorted_len[r];
-    const uint32_t b = p.order[r];
-    const int64_t off = p.seq_off[b];
-    const double *fin = p.delta + (size_t)((len - 1) & 1) * p.Kl * p.Bpad + r;
-    double bv = __ldcg(fin); uint32_t cur = 0;
-    for (int i = 1; i < p.K; i++) {
-        const double v = __ldcg(fin + (size_t)i * p.Bpad);
-        if (v > bv) { bv = v; cur = (uint32_t)i; }
+    constexpr int L = 8;
+    const int sub = threadIdx.x % L;
+    const int64_t gi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L;      // column inside the group
+    const int64_t rg = p.rank0 + gi;
+    const bool valid = gi < (int64_t)p.NRB * LG_BM && rg < p.B;
+    const int len = valid ? (int)p.sorted_len[rg] : 0;
+    const uint32_t b = valid ? p.order[rg] : 0u;
+    const int64_t off = valid ? p.seq_off[b] : 0;
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    const size_t slab = (size_t)p.Kl * p.Bpad;
+    const double *col = p.hist + gi;
+    auto reduce = [&](double &v, int &ix) {
+#pragma unroll
+        for (int d = L / 2; d >= 1; d >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, d, L);
+            const int oi = __shfl_xor_sync(0xffffffffu, ix, d, L);
+            if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+        }
+    };
+    // end state
+    double bv = neg_inf(); int cur = 0x7fffffff;
+    if (valid) {
+        const double *row = col + (size_t)(len - 1) * slab;
+        for (int j = sub; j < p.K; j += L) {
+            const double v = __ldcs(row + (size_t)j * p.Bpad);
+            if (cur == 0x7fffffff || v > bv) { bv = v; cur = j; }
+        }
     }
-    if (p.score) p.score[b] = bv;
-    p.path[off + len - 1] = cur;
-    for (int t = len - 1; t >= 1; t--) {
-        const size_t e = (size_t)(off + t) * p.Kl + cur;
-        cur = p.psi16 ? (uint32_t)__ldcg((const uint16_t *)p.psi + e) : (uint32_t)__ldcg((const uint8_t *)p.psi + e);
-        p.path[off + t - 1] = cur;
+    reduce(bv, cur);
+    if (valid && sub == 0) {
+        if (p.score) p.score[b] = bv;
+        p.path[off + len - 1] = (uint32_t)cur;
+    }
+    double dcur = bv;
+    for (int tt = maxlen - 1; tt >= 1; tt--) {
+        const bool act = valid && tt < len;
+        double mv = neg_inf(); int mi = 0x7fffffff;
+        if (act && dcur > neg_inf()) {
+            const double *row = col + (size_t)(tt - 1) * slab;
+            const double *at = p.AT + (size_t)cur * p.Kl;
+#pragma unroll 4
+            for (int j = sub; j < p.K; j += L) {
+                const double v = __ldcs(row + (size_t)j * p.Bpad) + __ldg(at + j);
+                if (mi == 0x7fffffff || v > mv) { mv = v; mi = j; }
+            }
+        }
+        reduce(mv, mi);
+        if (act) {
+            cur = (dcur > neg_inf()) ? mi : 0;
+            dcur = __ldcg(col + (size_t)(tt - 1) * slab + (size_t)cur * p.Bpad);
+            if (sub == 0) p.path[off + tt - 1] = (uint32_t)cur;
+        }
     }
 }
 

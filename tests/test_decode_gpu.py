@@ -48,6 +48,17 @@ def test_large_k_random(K, Bn, tmax):
     _check(A, B, pi, obs, off)
 
 
+def test_large_k_batch_groups(monkeypatch):
+    """The delta history of a large-K batch is processed in groups of row blocks when it does not fit in HBM;
+    force groups of one and two row blocks."""
+    rng = np.random.default_rng(3200)
+    A, B, pi = random_hmm(rng, 140, 9, zero_frac=0.3)
+    obs, off = random_batch(rng, 300, 9, 1, 14)
+    for rb in ("1", "2"):
+        monkeypatch.setenv("CV_LARGE_GROUP_RB", rb)
+        _check(A, B, pi, obs, off)
+
+
 def test_large_k_ties():
     rng = np.random.default_rng(3100)
     A, B, pi = random_hmm(rng, 150, 5, ties=True)
