@@ -6,6 +6,8 @@
 // (sweeps, fix-ups, bound terms, their ordered sum, the backtrack) is a kernel of cp_kernels.cuh.
 // Nothing here computes Viterbi values on the CPU.
 
+static int g_sum_parallel_min = 4096;
+
 namespace {
 
 struct CpRun {
@@ -87,7 +89,9 @@ int cp_solve_r(CpRun &r, int32_t comp)
             cp_terms_kernel<<<(nterms + 255) / 256, 256, 0, r.st>>>(r.p, r.d_cons_pos, r.d_term_comp, nterms, r.d_terms);
             g_launches++;
         }
-        cp_sum_kernel<<<1, 256, 0, r.st>>>(r.d_terms, nterms, r.d_ub);   // cp.rs:103-116
+        // cp.rs:103-116: the exact-order sum (parallel binade scan for long lists, plain loop for short ones)
+        if (nterms >= g_sum_parallel_min) cp_sum_exact_kernel<<<1, QS_THREADS, 0, r.st>>>(r.d_terms, nterms, r.d_ub);
+        else cp_sum_kernel<<<1, 256, 0, r.st>>>(r.d_terms, nterms, r.d_ub);
         g_launches++;
         CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, sizeof(double), cudaMemcpyDeviceToHost, r.st));
         CUDA_TRY(cudaStreamSynchronize(r.st));
@@ -287,5 +291,23 @@ extern "C" int cv_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *
     const uint64_t n = std::min<uint64_t>(cap, h->cp_ub.size());
     if (ub_out) for (uint64_t i = 0; i < n; i++) ub_out[i] = h->cp_ub[i];
     if (n_out) *n_out = h->cp_ub.size();
+    return CV_OK;
+}
+
+// Debug/parity hook: the ordered sum of `n` host values with the serial (mode 0) or the parallel (mode 1) kernel.
+extern "C" int cv_debug_ordered_sum(const double *values, int64_t n, int mode, double *out)
+{
+    int rc = check_device(0);
+    if (rc) return rc;
+    if (n < 0 || n > 0x7fffffffLL || !out) return fail(CV_ERR_ARG, "bad argument");
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)(n + 1)));
+    if (n) CUDA_TRY(cudaMemcpy(d + 1, values, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    if (mode == 1) cp_sum_exact_kernel<<<1, QS_THREADS>>>(d + 1, (int)n, d);
+    else cp_sum_kernel<<<1, 256>>>(d + 1, (int)n, d);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, d, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d);
     return CV_OK;
 }

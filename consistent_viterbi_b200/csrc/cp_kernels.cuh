@@ -245,6 +245,166 @@ __global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nt
     if (threadIdx.x == 0) *ub_out = ub;
 }
 
+
+// ---- exact-order sum, parallel ------------------------------------------------------------------------
+// ub = ((0.0 + x_0) + x_1) + ... with one IEEE round-to-nearest-even per add is a serial recurrence, but while
+// the running sum s stays inside one binade [2^e, 2^(e+1)) (ulp u = 2^(e-52)) and every term is <= 0, each add
+// is an INTEGER update of Q = |s| / u:  Q' = Q + I + [phi > 1/2], where |x| / u = I + phi, and on an exact tie
+// (phi = 1/2) the increment is decided by the parity of Q + I (ties-to-even).  A term is therefore a function
+// Q -> Q + (Q even ? a0 : a1); such functions are closed under composition, so a parallel scan yields every
+// partial sum of the binade exactly.  The scan runs over windows of 8192 terms; at the first add whose result
+// leaves the binade (Q' >= 2^53) that single add is done in floating point and the next binade starts.
+// Bit-identical to the serial loop (checked against it on the GPU and against a Python model); inputs with a
+// positive term, a NaN or a subnormal running sum take the serial loop instead.
+struct QFn { unsigned long long a0, a1; };
+constexpr unsigned long long QSAT = 1ULL << 60;
+
+__device__ __forceinline__ QFn qfn_compose(const QFn a, const QFn b)    // a first, then b
+{
+    QFn r;
+    r.a0 = a.a0 + ((a.a0 & 1ULL) == 0 ? b.a0 : b.a1);
+    r.a1 = a.a1 + (((1ULL + a.a1) & 1ULL) == 0 ? b.a0 : b.a1);
+    r.a0 = min(r.a0, QSAT); r.a1 = min(r.a1, QSAT);
+    return r;
+}
+__device__ __forceinline__ unsigned long long qfn_apply(const QFn f, unsigned long long Q)
+{
+    return min(Q + ((Q & 1ULL) == 0 ? f.a0 : f.a1), QSAT * 2);
+}
+// term x <= 0 (finite) seen from binade e
+__device__ __forceinline__ QFn qfn_elem(double x, int e)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    const int ef = (int)((b >> 52) & 0x7ff);
+    unsigned long long M = b & ((1ULL << 52) - 1);
+    int E = -1074;
+    if (ef) { M |= 1ULL << 52; E = ef - 1075; }
+    QFn r; r.a0 = r.a1 = 0;
+    if (M == 0) return r;
+    const int sh = E - (e - 52);
+    if (sh >= 0) { r.a0 = r.a1 = (sh > 6) ? QSAT : (M << sh); return r; }
+    const int n = -sh;
+    if (n >= 64) return r;
+    const unsigned long long I = M >> n, F = M & ((1ULL << n) - 1), half = 1ULL << (n - 1);
+    if (F != half) { r.a0 = r.a1 = I + (F > half ? 1ULL : 0ULL); return r; }
+    r.a0 = I + (I & 1ULL); r.a1 = I + ((I + 1ULL) & 1ULL);
+    return r;
+}
+
+constexpr int QS_THREADS = 1024, QS_EPT = 8;
+
+__global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *terms, int nterms, double *ub_out)
+{
+    __shared__ double s_sh; __shared__ int pos_sh, cross_sh, mode_sh;
+    __shared__ unsigned long long qbefore_sh, qend_sh;
+    __shared__ QFn warp_agg[QS_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    // pre-check: serial fallback for positive / NaN terms; -inf terms make the sum -inf
+    if (tid == 0) mode_sh = 0;
+    __syncthreads();
+    int flag = 0;
+    for (int k = tid; k < nterms; k += QS_THREADS) {
+        const double x = terms[k];
+        if (!(x <= 0.0)) flag |= 1;                 // positive or NaN
+        else if (x == neg_inf()) flag |= 2;
+    }
+    if (flag) atomicOr(&mode_sh, flag);
+    __syncthreads();
+    const int mode = mode_sh;
+    if (mode & 1) {                                 // reference loop, one thread
+        if (tid == 0) { double ub = 0.0; for (int k = 0; k < nterms; k++) ub += terms[k]; *ub_out = ub; }
+        return;
+    }
+    if (mode & 2) { if (tid == 0) *ub_out = neg_inf(); return; }
+
+    if (tid == 0) {
+        double s = 0.0; int pos = 0;
+        while (pos < nterms && s == 0.0) { s = s + terms[pos]; pos++; }      // 0.0 + x is exact
+        s_sh = s; pos_sh = pos;
+    }
+    for (;;) {
+        __syncthreads();
+        const double s = s_sh; const int pos = pos_sh;
+        if (pos >= nterms) break;
+        const unsigned long long sb = (unsigned long long)__double_as_longlong(s);
+        const int ef = (int)((sb >> 52) & 0x7ff);
+        if (ef == 0) {                              // subnormal running sum: finish with the reference loop
+            if (tid == 0) { double ub = s; for (int k = pos; k < nterms; k++) ub += terms[k]; s_sh = ub; pos_sh = nterms; }
+            continue;
+        }
+        const int e = ef - 1023;
+        const unsigned long long Q0 = (sb & ((1ULL << 52) - 1)) | (1ULL << 52);
+        const int W = min(nterms - pos, QS_THREADS * QS_EPT);
+        if (tid == 0) cross_sh = 0x7fffffff;
+        // local composition of this thread's contiguous terms
+        QFn el[QS_EPT]; QFn f; f.a0 = f.a1 = 0;
+        const int base = pos + tid * QS_EPT;
+#pragma unroll
+        for (int k = 0; k < QS_EPT; k++) {
+            el[k].a0 = el[k].a1 = 0;
+            if (tid * QS_EPT + k < W) el[k] = qfn_elem(terms[base + k], e);
+            f = qfn_compose(f, el[k]);
+        }
+        // block-wide exclusive scan of the composed functions
+        QFn inc = f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            QFn o;
+            o.a0 = __shfl_up_sync(0xffffffffu, inc.a0, d);
+            o.a1 = __shfl_up_sync(0xffffffffu, inc.a1, d);
+            if (lane >= d) inc = qfn_compose(o, inc);
+        }
+        if (lane == 31) warp_agg[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            QFn a = warp_agg[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                QFn o;
+                o.a0 = __shfl_up_sync(0xffffffffu, a.a0, d);
+                o.a1 = __shfl_up_sync(0xffffffffu, a.a1, d);
+                if (lane >= d) a = qfn_compose(o, a);
+            }
+            warp_agg[lane] = a;                     // inclusive over warps
+        }
+        __syncthreads();
+        QFn pre; pre.a0 = pre.a1 = 0;               // everything before this thread
+        if (w > 0) pre = warp_agg[w - 1];
+        {
+            QFn ex;                                  // exclusive within the warp
+            ex.a0 = __shfl_up_sync(0xffffffffu, inc.a0, 1);
+            ex.a1 = __shfl_up_sync(0xffffffffu, inc.a1, 1);
+            if (lane > 0) pre = qfn_compose(pre, ex);
+        }
+        unsigned long long Q = qfn_apply(pre, Q0);
+        // walk own terms, look for the first add that leaves the binade
+        int my_cross = 0x7fffffff; unsigned long long q_at_cross = 0;
+#pragma unroll
+        for (int k = 0; k < QS_EPT; k++) {
+            if (tid * QS_EPT + k < W && my_cross == 0x7fffffff) {
+                const unsigned long long Qn = qfn_apply(el[k], Q);
+                if (Qn >= (1ULL << 53)) { my_cross = base + k; q_at_cross = Q; }
+                else Q = Qn;
+            }
+        }
+        if (my_cross != 0x7fffffff) atomicMin(&cross_sh, my_cross);
+        if (tid == (W - 1) / QS_EPT) qend_sh = Q;   // the thread owning the last term of the window
+        __syncthreads();
+        const int cross = cross_sh;
+        if (cross != 0x7fffffff && my_cross == cross) qbefore_sh = q_at_cross;
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long Qf = (cross == 0x7fffffff) ? qend_sh : qbefore_sh;
+            const unsigned long long bits = (1ULL << 63) | ((unsigned long long)(e + 1023) << 52) | (Qf & ((1ULL << 52) - 1));
+            double sk = __longlong_as_double((long long)bits);               // -Qf * 2^(e-52), exact
+            if (cross == 0x7fffffff) { s_sh = sk; pos_sh = pos + W; }
+            else { s_sh = sk + terms[cross]; pos_sh = cross + 1; }          // the one add that changes binade
+        }
+    }
+    if (tid == 0) *ub_out = s_sh;
+}
+
 // obj = max(delta[N-1][.]) for the no-constraint case (cp.rs:139-141) and cur = argmax (cp.rs:86)
 __global__ void cp_last_row_kernel(const CpParams p, double *obj_out, int *end_out)
 {

@@ -99,6 +99,10 @@ int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq_start,
 int cv_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out);
 int cv_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *n_out);
 
+/* Debug/parity hook for the bound sum of solve_r (cp.rs:103-116): ((0.0 + v[0]) + v[1]) + ... of n host values,
+ * mode 0 = one-thread loop, mode 1 = the parallel exact-order kernel; both must agree bit for bit. */
+int cv_debug_ordered_sum(const double *values, int64_t n, int mode, double *out);
+
 /* ---- plumbing --------------------------------------------------------------*/
 const char *cv_last_error(void);
 /* kernels launched by this library in this process (bench.py "gpu_launches") */
