@@ -82,6 +82,37 @@ __device__ __forceinline__ void chain_scan(const double *__restrict__ sd, const 
     }
 }
 
+
+// Register-resident variant for K <= 32 (one state per lane): the lane's logA column acol[j] = logA[j][lane]
+// (-inf for j >= K) stays in registers for the whole kernel, so a predecessor costs half a broadcast LDS.128
+// plus DADD / DSETP / 3 selects.  KQ = 2*ceil(K/8) predecessors per range, fully unrolled; sd[j] = -inf, j >= K.
+template <int KQ>
+__device__ __forceinline__ void chain_scan_reg(const double *__restrict__ sd, const double (&acol)[4 * KQ],
+                                               double &best, int &idx)
+{
+    double b[4]; int ix[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { b[r] = neg_inf(); ix[r] = r * KQ; }
+#pragma unroll
+    for (int jj = 0; jj < KQ; jj += 2) {
+        double2 dj[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) dj[r] = *reinterpret_cast<const double2 *>(sd + r * KQ + jj);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int j = r * KQ + jj;
+            const double v0 = dj[r].x + acol[j];
+            if (v0 > b[r]) { b[r] = v0; ix[r] = j; }
+            const double v1 = dj[r].y + acol[j + 1];
+            if (v1 > b[r]) { b[r] = v1; ix[r] = j + 1; }
+        }
+    }
+    best = b[0]; idx = ix[0];
+#pragma unroll
+    for (int r = 1; r < 4; r++)
+        if (b[r] > best) { best = b[r]; idx = ix[r]; }
+}
+
 // (value, index) argmax across the warp's owned states: strictly greater value, else lower index.
 __device__ __forceinline__ void warp_argmax(double &v, int &ix)
 {

@@ -42,8 +42,16 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
     const size_t smem_c = (size_t)r.p.K * r.p.Kp * 8 + (r.p.bt_in_smem ? (size_t)r.p.M * r.p.Kp * 8 : 0) +
                           (size_t)CPW_WARPS * 16 * r.p.Kp;
     const int grid = (int)std::min<int64_t>((nseg + CPW_WARPS - 1) / CPW_WARPS, (int64_t)r.h->num_sms * 8);
-    if (r.p.K <= 32) cp_sweep_chain_kernel<1><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
-    else cp_sweep_chain_kernel<2><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
+    const bool regs = r.p.Kp == 8 * ((r.p.K + 7) / 8);       // register-resident logA column needs Kp = 4 * KQ
+    switch (regs ? (r.p.K + 7) / 8 : 9) {
+        case 1: cp_sweep_chain_kernel<1, 2><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;
+        case 2: cp_sweep_chain_kernel<1, 4><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;
+        case 3: cp_sweep_chain_kernel<1, 6><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;
+        case 4: cp_sweep_chain_kernel<1, 8><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;
+        default:
+            if (r.p.K <= 32) cp_sweep_chain_kernel<1, 0><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
+            else cp_sweep_chain_kernel<2, 0><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CV_OK;
@@ -224,8 +232,12 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     p.bt_in_smem = ((size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
     {
         const size_t smem_c = (size_t)K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) + (size_t)CPW_WARPS * 16 * h->Kp;
-        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     }
 
     const bool timing = g_timing.load() != 0;

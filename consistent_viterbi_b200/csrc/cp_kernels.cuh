@@ -70,7 +70,7 @@ __global__ void cp_row0_kernel(const CpParams p)
 // Phases A (reset row) + B (sweep); segments are claimed longest first from a global counter.
 constexpr int CPW_WARPS = 4;
 
-template <int NSL>
+template <int NSL, int KQ>
 __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const CpParams p, const CpSweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -89,6 +89,11 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
     double pi_i[NSL]; int col[NSL];
 #pragma unroll
     for (int s = 0; s < NSL; s++) { col[s] = min(lane + 32 * s, Kp - 1); pi_i[s] = p.Pi[col[s]]; }
+    double acol[KQ > 0 ? 4 * KQ : 1];
+    if (KQ > 0) {
+#pragma unroll
+        for (int j = 0; j < 4 * KQ; j++) acol[j] = (j < K && lane < Kp) ? sA[(size_t)j * Kp + lane] : neg_inf();
+    }
 
     for (;;) {
         unsigned int r = 0;
@@ -141,7 +146,8 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
             load_meta(k + 2 + CHAIN_PF, oq[CHAIN_PF], sq[CHAIN_PF]);
             double best[NSL]; int idx[NSL];
             const double *sdo = sdw + ((k - 1) & 1) * Kp;
-            chain_scan<NSL>(sdo, sA, Kp, K, lane, st, pi_i, best, idx);           // argmax on delta + tr
+            if (KQ > 0 && !st) chain_scan_reg<(KQ > 0 ? KQ : 2)>(sdo, reinterpret_cast<const double (&)[4 * (KQ > 0 ? KQ : 2)]>(acol), best[0], idx[0]);
+            else chain_scan<NSL>(sdo, sA, Kp, K, lane, st, pi_i, best, idx);      // argmax on delta + tr
             double v[NSL];
 #pragma unroll
             for (int s = 0; s < NSL; s++) {

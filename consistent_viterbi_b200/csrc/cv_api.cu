@@ -446,13 +446,20 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
                             (size_t)DC_WARPS * (16 * h->Kp + 32 * h->Kp + 128);
         const int grid = (int)std::min<int64_t>((B + DC_WARPS - 1) / DC_WARPS, (int64_t)h->num_sms * 8);
         if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
-        if (h->K <= 32) {
-            CUDA_TRY(cudaFuncSetAttribute(decode_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            decode_chain_kernel<1><<<grid, 32 * DC_WARPS, smem, st>>>(p);
-        } else {
-            CUDA_TRY(cudaFuncSetAttribute(decode_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            decode_chain_kernel<2><<<grid, 32 * DC_WARPS, smem, st>>>(p);
+        auto go = [&](auto kern) -> int {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 32 * DC_WARPS, smem, st>>>(p);
+            return CV_OK;
+        };
+        const bool regs = h->Kp == 8 * ((h->K + 7) / 8);     // register-resident logA column needs Kp = 4 * KQ
+        switch (regs ? (h->K + 7) / 8 : 9) {
+            case 1: rc = go(decode_chain_kernel<1, 2>); break;
+            case 2: rc = go(decode_chain_kernel<1, 4>); break;
+            case 3: rc = go(decode_chain_kernel<1, 6>); break;
+            case 4: rc = go(decode_chain_kernel<1, 8>); break;
+            default: rc = h->K <= 32 ? go(decode_chain_kernel<1, 0>) : go(decode_chain_kernel<2, 0>);
         }
+        if (rc) return rc;
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         if (timing) { CUDA_TRY(cudaEventRecord(h->ev1, st)); CUDA_TRY(cudaEventRecord(h->ev2, st)); }

@@ -32,7 +32,8 @@ constexpr size_t CHAIN_BT_SMEM_MAX = 96 * 1024;
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <int NSL>
+// KQ > 0 (K <= 32, NSL = 1): logA column in registers, KQ = 2*ceil(K/8); KQ = 0: logA read from shared memory
+template <int NSL, int KQ>
 __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const DecodeChainParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -54,6 +55,11 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
     const bool pf = !p.bt_in_smem;
 
     const double zero_pi[NSL] = {};
+    double acol[KQ > 0 ? 4 * KQ : 1];
+    if (KQ > 0) {
+#pragma unroll
+        for (int j = 0; j < 4 * KQ; j++) acol[j] = (j < K && lane < Kp) ? sA[(size_t)j * Kp + lane] : neg_inf();
+    }
     for (;;) {
         unsigned int r = 0;
         if (lane == 0) r = atomicAdd(p.counter, 1u);
@@ -99,7 +105,8 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
             for (int k = 0; k < CHAIN_PF; k++) oq[k] = oq[k + 1];
             oq[CHAIN_PF] = load_obs(t + 2 + CHAIN_PF);
             double best[NSL]; int idx[NSL];
-            chain_scan<NSL>(sdw + ((t - 1) & 1) * Kp, sA, Kp, K, lane, false, zero_pi, best, idx);   // viterbi.rs:15-16
+            if (KQ > 0) chain_scan_reg<(KQ > 0 ? KQ : 2)>(sdw + ((t - 1) & 1) * Kp, reinterpret_cast<const double (&)[4 * (KQ > 0 ? KQ : 2)]>(acol), best[0], idx[0]);
+            else chain_scan<NSL>(sdw + ((t - 1) & 1) * Kp, sA, Kp, K, lane, false, zero_pi, best, idx);   // viterbi.rs:15-16
 #pragma unroll
             for (int s = 0; s < NSL; s++) {
                 double v = best[s] + e[s];                                                         // viterbi.rs:17
