@@ -8,14 +8,61 @@ inputs CPSolver::new sees:
 
 recompute_constraints(prop) draws `rng.gen::<f64>() <= prop` from rand 0.8 StdRng seeded with 3019
 (utils.rs:101,170).  For prop in {0, 1} the outcome does not depend on the stream (gen::<f64>() is in
-[0,1)); for 0 < prop < 1 pass `uniform=` (a callable returning the next f64) -- the ChaCha12 stream is
-not reproduced here (SURVEY.md section 8 "next" row N2).
+[0,1)); for 0 < prop < 1 the stream comes from `StdRng` below, a restatement of ChaCha12 + the PCG32 seed
+expansion that cannot be checked against the crate here (SURVEY.md section 8 "next" row N2).
 """
 from __future__ import annotations
 
 import numpy as np
 
 from .hmm import HMM
+
+
+class StdRng:
+    """rand 0.8 `StdRng::seed_from_u64` + `gen::<f64>()` (ChaCha12, key expanded from the u64 with PCG32), the
+    same restatement as host/rng_chacha12.h -- UNVERIFIED against the crate (no Rust toolchain here); it only
+    matters for 0 < prop < 1."""
+
+    def __init__(self, seed: int):
+        M64 = (1 << 64) - 1
+        state, key = seed & M64, []
+        for _ in range(8):
+            state = (state * 6364136223846793005 + 11634580027462260723) & M64
+            xs = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+            rot = state >> 59
+            key.append(((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF)
+        self.key, self.counter, self.buf, self.idx = key, 0, [], 16
+
+    def _block(self):
+        M = 0xFFFFFFFF
+        inp = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + self.key + [self.counter & M, (self.counter >> 32) & M, 0, 0]
+        x = list(inp)
+
+        def rotl(v, n):
+            return ((v << n) | (v >> (32 - n))) & M
+
+        def qr(a, b, c, d):
+            x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 16)
+            x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 12)
+            x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 8)
+            x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 7)
+
+        for _ in range(6):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+        self.buf = [(x[i] + inp[i]) & M for i in range(16)]
+        self.counter += 1
+        self.idx = 0
+
+    def next_u64(self):
+        if self.idx >= 16:
+            self._block()
+        lo, hi = self.buf[self.idx], self.buf[self.idx + 1]
+        self.idx += 2
+        return (hi << 32) | lo
+
+    def gen_f64(self):
+        return float(self.next_u64() >> 11) * (1.0 / 9007199254740992.0)
 
 
 def load_sequences(path, D=2):
@@ -101,6 +148,7 @@ class SuperSequence:
                 self.comp[i] = lookup.get((sid, tt), -1)
                 i += 1
         self.active = self.comp >= 0                                # utils.rs:76
+        self.rng = StdRng(3019)                                     # utils.rs:101
         self._count_active()
 
     def _count_active(self):                                        # utils.rs:88-99 / 152-163
@@ -144,13 +192,12 @@ class SuperSequence:
         self._count_active()
 
     def recompute_constraints(self, proportion, uniform=None):      # utils.rs:168-177
-        if 0.0 < proportion < 1.0 and uniform is None:
-            raise NotImplementedError("0 < prop < 1 needs the rand 0.8 StdRng(3019) stream; pass uniform=")
+        if uniform is None:
+            uniform = self.rng.gen_f64                              # StdRng(3019) stream, state carries over calls
         act = np.zeros(len(self), dtype=bool)
         for i in range(len(self)):
             if self.comp[i] != -1:                                  # RNG consumed only for constrained elements
-                u = uniform() if uniform is not None else 0.5
-                act[i] = u <= proportion
+                act[i] = uniform() <= proportion
         self.active = act
         self.reorder()
 
