@@ -212,7 +212,7 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
         // measured on B200 (POS shape): TQ = 8 with two 6-warp CTAs per SM beats the balanced TQ = 12 shape
         // (12 vs 8 resident warps), so 8 stays the default; CV_TQ=12 / CV_TQ=auto select the alternatives
         const char *e = getenv("CV_TQ");
-        h->TQT = (e && !strcmp(e, "auto")) ? best_tq : (e && atoi(e) == 12) ? 12 : 8;
+        h->TQT = (e && !strcmp(e, "auto")) ? best_tq : (e && atoi(e) == 12) ? 12 : (e && atoi(e) == 6) ? 6 : 8;
     }
     h->G = (K + h->TQT - 1) / h->TQT;
     h->Kp = ((std::max(h->G * h->TQT, K) + 7) / 8) * 8;
@@ -375,6 +375,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.ntiles = ntiles;
     void (*kern)(DecodeSmallParams);
     if (h->TQT == 12) kern = variant == 1 ? decode_small_fwd_kernel<12, 512, 1> : decode_small_fwd_kernel<12, 256, 2>;
+    else if (h->TQT == 6) kern = variant == 1 ? decode_small_fwd_kernel<6, 512, 1> : decode_small_fwd_kernel<6, 256, 2>;
     else kern = variant == 1 ? decode_small_fwd_kernel<8, 512, 1>
               : variant == 2 ? decode_small_fwd_kernel<8, 384, 2> : decode_small_fwd_kernel<8, 256, 3>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
