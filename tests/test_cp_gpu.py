@@ -117,3 +117,11 @@ def test_cp_solver_interface_and_superseq(tmp_path):
     if ref["obj"] > -np.inf:
         for c in range(ncomp):
             assert len(set(int(x) for x in sol[comp == c])) == 1
+
+
+def test_cp_dense_deep_search():
+    """Dense model (no zero probabilities): bounds stay finite, so the search goes several components deep and
+    prunes by value; 400 nodes of it against the oracle, with every bound and the final state."""
+    import bench
+    w = bench.workload_cp("trucks")
+    _check(w["A"], w["B"], w["pi"], w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=400)

@@ -135,3 +135,38 @@ def test_pos_shape_sample_and_properties():
     for k in (0, 1, Bn // 2, Bn - 1):
         b = perm[k]
         assert (p2[off2[k]:off2[k + 1]] == paths[off[b]:off[b + 1]]).all()
+
+
+def test_chunked_pipeline_and_device_api():
+    """cv_decode_batch cuts large batches into chunks on two internal streams and cv_decode_batch_dev takes
+    device-resident buffers (torch tensors here, plain pointers at the ABI): force 3 chunks on a mid-size batch
+    and compare both entry points with the oracle."""
+    import torch
+    rng = np.random.default_rng(4242)
+    K, M, Bn = 45, 60, 5000
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    obs, off = random_batch(rng, Bn, M, 1, 40)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        L.cv_set_chain_max_batch(0)
+        for chunks in (1, 3, 8):
+            L.cv_set_chunks(chunks)
+            p, s = cv.decode_batch(h, obs, off)
+            assert (p == rp).all() and s.tobytes() == rs.tobytes(), f"host API, chunks={chunks}"
+            d_obs = torch.from_numpy(obs.view(np.int32)).cuda()
+            d_off = torch.from_numpy(off).cuda()
+            d_path = torch.zeros(len(obs), dtype=torch.int32, device="cuda")
+            d_score = torch.zeros(Bn, dtype=torch.float64, device="cuda")
+            st = torch.cuda.current_stream()
+            rc = L.cv_decode_batch_dev(h.device_handle(), d_obs.data_ptr(), d_off.data_ptr(), Bn, len(obs),
+                                       int(np.diff(off).max()), d_path.data_ptr(), d_score.data_ptr(), st.cuda_stream, 1)
+            cv._lib.check(rc)
+            torch.cuda.synchronize()
+            assert (d_path.cpu().numpy().view(np.uint32) == rp).all(), f"device API, chunks={chunks}"
+            assert d_score.cpu().numpy().tobytes() == rs.tobytes()
+    finally:
+        L.cv_set_chunks(-1)
+        L.cv_set_chain_max_batch(-1)
+    h.close()
