@@ -37,7 +37,7 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
     a.seg_from = r.d_seg_from + seg_begin; a.seg_len = r.d_seg_len + seg_begin;
     a.nseg = (int)nseg; a.ntiles = (int)((nseg + 63) / 64); a.node = node; a.init_mode = init_mode;
     a.tile_counter = r.d_counter;
-    CUDA_TRY(cudaMemsetAsync(r.d_counter, 0, sizeof(unsigned int), r.st));
+    // (the segment counter is zeroed by the previous node's sum kernel / the set-up memset)
     // one warp per segment (latency-oriented); the lock-step tile kernel only pays off with very many segments
     const size_t smem_c = (size_t)r.p.K * r.p.Kp * 8 + (r.p.bt_in_smem ? (size_t)r.p.M * r.p.Kp * 8 : 0) +
                           (size_t)CPW_WARPS * 16 * r.p.Kp;
@@ -54,6 +54,7 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
     }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    if (init_mode) CUDA_TRY(cudaMemsetAsync(r.d_counter, 0, sizeof(unsigned int), r.st));   // nodes reset it in their sum kernel
     return CV_OK;
 }
 
@@ -83,23 +84,19 @@ int cp_solve_r(CpRun &r, int32_t comp)
     for (int state = 0; state < K; state++) {
         if (r.max_nodes && r.explored >= r.max_nodes) break;            // builder-added, deterministic budget
         r.explored++;                                                    // cp.rs:97
-        cp_set_choice_kernel<<<1, 1, 0, r.st>>>(r.p.choice, comp, state);   // cp.rs:98
-        g_launches++;
         int rc = cp_sweep(r, r.seg_off[comp], npos, state, 0);          // cp.rs:99-102, phases A + B
         if (rc) return rc;
         r.steps += r.seg_steps[comp];
-        if (npos > 0) {
-            cp_fixup_kernel<<<(unsigned)((npos + 127) / 128), 128, 0, r.st>>>(r.p, r.d_cons_pos + r.cons_off[comp],
-                                                                              (int)npos, comp, state);
-            g_launches++;
-        }
+        cp_fixup_kernel<<<(unsigned)((std::max<int64_t>(npos, 1) + 127) / 128), 128, 0, r.st>>>(
+            r.p, r.d_cons_pos + r.cons_off[comp], (int)npos, comp, state);     // also records cstr_choices[comp] (cp.rs:98)
+        g_launches++;
         if (nterms > 0) {
             cp_terms_kernel<<<(nterms + 255) / 256, 256, 0, r.st>>>(r.p, r.d_cons_pos, r.d_term_comp, nterms, r.d_terms);
             g_launches++;
         }
         // cp.rs:103-116: the exact-order sum (parallel binade scan for long lists, plain loop for short ones)
-        if (nterms >= g_sum_parallel_min) cp_sum_exact_kernel<<<1, QS_THREADS, 0, r.st>>>(r.d_terms, nterms, r.d_ub);
-        else cp_sum_kernel<<<1, 256, 0, r.st>>>(r.d_terms, nterms, r.d_ub);
+        if (nterms >= g_sum_parallel_min) cp_sum_exact_kernel<<<1, QS_THREADS, 0, r.st>>>(r.d_terms, nterms, r.d_ub, r.d_counter);
+        else cp_sum_kernel<<<1, 256, 0, r.st>>>(r.d_terms, nterms, r.d_ub, r.d_counter);
         g_launches++;
         CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, sizeof(double), cudaMemcpyDeviceToHost, r.st));
         CUDA_TRY(cudaStreamSynchronize(r.st));
@@ -114,8 +111,8 @@ int cp_solve_r(CpRun &r, int32_t comp)
             }
         }
     }
-    cp_set_choice_kernel<<<1, 1, 0, r.st>>>(r.p.choice, comp, -1);      // cp.rs:125
-    g_launches++;
+    // cp.rs:125 (cstr_choices[comp] = None): which positions count as fixed is a function of the depth alone
+    // (segments are precomputed per depth) and choice[comp] is rewritten before it is read again.
     return CV_OK;
 }
 
@@ -216,6 +213,7 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     if ((rc = b[10].ensure(sizeof(double) * (cons_pos.size() + 8) + 256))) return rc;
     r.d_terms = (double *)b[10].p + 4; r.d_ub = (double *)b[10].p;                 // [0] ub, [1] obj
     r.d_end = (int *)((double *)b[10].p + 2); r.d_counter = (unsigned int *)((double *)b[10].p + 3);
+    CUDA_TRY(cudaMemsetAsync(b[10].p, 0, 32, st));
     const int nchunks = (int)((N + CP_BT_CHUNK - 1) / CP_BT_CHUNK);
     if ((rc = b[11].ensure((size_t)nchunks * K + 64))) return rc;
     if ((rc = b[12].ensure(sizeof(int) * (size_t)nchunks + 64))) return rc;
@@ -315,8 +313,8 @@ extern "C" int cv_debug_ordered_sum(const double *values, int64_t n, int mode, d
     double *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)(n + 1)));
     if (n) CUDA_TRY(cudaMemcpy(d + 1, values, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
-    if (mode == 1) cp_sum_exact_kernel<<<1, QS_THREADS>>>(d + 1, (int)n, d);
-    else cp_sum_kernel<<<1, 256>>>(d + 1, (int)n, d);
+    if (mode == 1) cp_sum_exact_kernel<<<1, QS_THREADS>>>(d + 1, (int)n, d, nullptr);
+    else cp_sum_kernel<<<1, 256>>>(d + 1, (int)n, d, nullptr);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(out, d, sizeof(double), cudaMemcpyDeviceToHost));

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
 __global__ void cp_fixup_kernel(const CpParams p, const int64_t *pos_list, int npos, int comp, int state)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) p.choice[comp] = state;        // cstr_choices[comp] = Some(state) (cp.rs:98); read by the terms kernel only
     if (k >= npos) return;
     const int64_t pos = pos_list[k];
     const int K = p.K, Kp = p.Kp;
@@ -221,8 +222,10 @@ __global__ void cp_terms_kernel(const CpParams p, const int64_t *term_pos, const
 // ub = ((0.0 + term_0) + term_1) + ...  exactly in order (cp.rs:103,109,114).  The order is part of the result,
 // so one thread performs the adds; the rest of the block streams the terms through a double-buffered shared
 // memory stage and the adder keeps 16 terms in registers ahead of the dependent DADD chain (8 clk per term).
-__global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, double *ub_out)
+__global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, double *ub_out,
+                                                     unsigned int *reset_counter)
 {
+    if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
     constexpr int CH = 2048;
     __shared__ double buf[2][CH];
     double ub = 0.0;
@@ -299,8 +302,10 @@ __device__ __forceinline__ QFn qfn_elem(double x, int e)
 
 constexpr int QS_THREADS = 1024, QS_EPT = 8;
 
-__global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *terms, int nterms, double *ub_out)
+__global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *terms, int nterms, double *ub_out,
+                                                                  unsigned int *reset_counter)
 {
+    if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
     __shared__ double s_sh; __shared__ int pos_sh, cross_sh, mode_sh;
     __shared__ unsigned long long qbefore_sh, qend_sh;
     __shared__ QFn warp_agg[QS_THREADS / 32];
