@@ -7,6 +7,7 @@
 // Nothing here computes Viterbi values on the CPU.
 
 static int g_sum_parallel_min = 4096;
+static double g_cp_prof[6];   // CV_CP_PROF=1: host-timed phases of a node (sweep, fixup, terms, sum, readback)
 
 namespace {
 
@@ -84,22 +85,36 @@ int cp_solve_r(CpRun &r, int32_t comp)
     for (int state = 0; state < K; state++) {
         if (r.max_nodes && r.explored >= r.max_nodes) break;            // builder-added, deterministic budget
         r.explored++;                                                    // cp.rs:97
+        static const bool prof = getenv("CV_CP_PROF") != nullptr;
+        auto tick = [&](int slot, std::chrono::steady_clock::time_point &t0) {
+            if (!prof) return;
+            cudaStreamSynchronize(r.st);
+            auto t1 = std::chrono::steady_clock::now();
+            g_cp_prof[slot] += std::chrono::duration<double, std::micro>(t1 - t0).count();
+            t0 = t1;
+        };
+        auto t0 = std::chrono::steady_clock::now();
         int rc = cp_sweep(r, r.seg_off[comp], npos, state, 0);          // cp.rs:99-102, phases A + B
         if (rc) return rc;
+        tick(0, t0);
         r.steps += r.seg_steps[comp];
         cp_fixup_kernel<<<(unsigned)((std::max<int64_t>(npos, 1) + 127) / 128), 128, 0, r.st>>>(
             r.p, r.d_cons_pos + r.cons_off[comp], (int)npos, comp, state);     // also records cstr_choices[comp] (cp.rs:98)
         g_launches++;
+        tick(1, t0);
         if (nterms > 0) {
             cp_terms_kernel<<<(nterms + 255) / 256, 256, 0, r.st>>>(r.p, r.d_cons_pos, r.d_term_comp, nterms, r.d_terms);
             g_launches++;
         }
+        tick(2, t0);
         // cp.rs:103-116: the exact-order sum (parallel binade scan for long lists, plain loop for short ones)
         if (nterms >= g_sum_parallel_min) cp_sum_exact_kernel<<<1, QS_THREADS, 0, r.st>>>(r.d_terms, nterms, r.d_ub, r.d_counter);
         else cp_sum_kernel<<<1, 256, 0, r.st>>>(r.d_terms, nterms, r.d_ub, r.d_counter);
         g_launches++;
+        tick(3, t0);
         CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, sizeof(double), cudaMemcpyDeviceToHost, r.st));
         CUDA_TRY(cudaStreamSynchronize(r.st));
+        tick(4, t0);
         const double ub = *r.h_ub;
         if (r.h->cp_ub.size() < (1u << 20)) r.h->cp_ub.push_back(ub);
         if (std::isnan(ub)) return fail(CV_ERR_NAN, "NaN upper bound");
@@ -271,6 +286,12 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms; else cudaGetLastError();
         h->last_bt_ms = 0.0;
+    }
+    if (getenv("CV_CP_PROF")) {
+        fprintf(stderr, "[cv] cp phases (us/node over %llu nodes): sweep %.1f fixup %.1f terms %.1f sum %.1f readback %.1f\n",
+                (unsigned long long)r.explored, g_cp_prof[0] / r.explored, g_cp_prof[1] / r.explored,
+                g_cp_prof[2] / r.explored, g_cp_prof[3] / r.explored, g_cp_prof[4] / r.explored);
+        for (double &v : g_cp_prof) v = 0.0;
     }
     if (obj_out) *obj_out = r.best_obj;
     if (explored_out) *explored_out = r.explored;
