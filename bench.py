@@ -523,7 +523,8 @@ def main():
             "clocks": clk.summary(),
             "roofline": {
                 "bound": "fp64_alu", "kernel": "decode_small_fwd_kernel" if K <= 64 else "decode_large_kernel",
-                "achieved": achieved_alu / 1e12, "peak": peak_mix / 1e12, "unit": "TFLOP/s(fp64 add+compare)",
+                "achieved": achieved_alu / 1e12, "peak": peak_mix / 1e12, "unit": "TFLOP/s",
+                "unit_note": "FP64 add+compare operations (2 per cell), not tensor FLOPs; frac = max(ALU view, HBM view) as SURVEY 8d defines",
                 "frac": achieved_alu / peak_mix, "traffic": traffic,
                 "peak_source": "measured in this run: DADD+DSETP issue rate over all SMs (cv_probe_fp64 mode 1); "
                                f"DADD alone {peak_dadd / 1e12:.2f}",

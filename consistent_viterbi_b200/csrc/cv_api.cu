@@ -339,10 +339,14 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     // Launch shape: S sequence groups of 64 per CTA, and which register budget (kernel instantiation) to use.
     int S = 1, variant = 1;
     if (g_small_cfg >= 0) { S = std::max(1, std::min(4, g_small_cfg / 10)); variant = std::max(1, g_small_cfg % 10); }
-    while (S > 1 && (B + 64 * S - 1) / (64 * S) < 4 * (int64_t)h->num_sms) S--;
-    size_t smem = decode_small_smem_bytes(h->K, h->Kp, 64 * S);
-    while (smem > 220 * 1024 && S > 1) { S--; smem = decode_small_smem_bytes(h->K, h->Kp, 64 * S); }
-    const int NS = 64 * S;
+    int tpt = 2;
+    if (const char *e = getenv("CV_TP")) tpt = atoi(e) == 4 ? 4 : 2;
+    if (h->TQT != 8) tpt = 2;
+    while (S > 1 && (B + 32 * tpt * S - 1) / (32 * tpt * S) < 4 * (int64_t)h->num_sms) S--;
+    size_t smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S);
+    while (smem > 220 * 1024 && S > 1) { S--; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
+    if (smem > 220 * 1024 && tpt == 4) { tpt = 2; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
+    const int NS = 32 * tpt * S;
     const int threads = 32 * G * S;
     if (variant == 3 && threads > 256) variant = 2;
     if (variant == 2 && threads > 384) variant = 1;
@@ -373,10 +377,12 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
     p.tile_base = (const long long *)w.base.p;
     p.hist = (double *)w.hist.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
-    p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.ntiles = ntiles;
+    p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.NS = NS; p.ntiles = ntiles;
     void (*kern)(DecodeSmallParams);
     if (h->TQT == 12) kern = variant == 1 ? decode_small_fwd_kernel<12, 512, 1> : decode_small_fwd_kernel<12, 256, 2>;
     else if (h->TQT == 6) kern = variant == 1 ? decode_small_fwd_kernel<6, 512, 1> : decode_small_fwd_kernel<6, 256, 2>;
+    else if (tpt == 4 && threads <= 256) kern = decode_small_fwd_kernel<8, 256, 1, 4>;
+    else if (tpt == 4) kern = decode_small_fwd_kernel<8, 512, 1, 4>;
     else kern = variant == 1 ? decode_small_fwd_kernel<8, 512, 1>
               : variant == 2 ? decode_small_fwd_kernel<8, 384, 2> : decode_small_fwd_kernel<8, 256, 3>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -386,8 +392,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     occ = std::max(1, occ);
     const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * occ, ntiles);
     if (getenv("CV_DEBUG"))
-        fprintf(stderr, "[cv] decode_small: K=%d TQ=%d G=%d S=%d variant=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
-                h->K, h->TQT, G, S, variant, threads, smem, occ, grid, ntiles);
+        fprintf(stderr, "[cv] decode_small: K=%d TQ=%d TP=%d G=%d S=%d variant=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
+                h->K, h->TQT, tpt, G, S, variant, threads, smem, occ, grid, ntiles);
     if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     kern<<<std::max(1, grid), threads, smem, st>>>(p);
     g_launches++;

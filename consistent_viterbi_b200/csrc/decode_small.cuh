@@ -55,7 +55,7 @@ struct DecodeSmallParams {
     unsigned int *tile_counter;
     int *status;             // 0 ok, else CV_ERR_*
     int64_t M, B;
-    int K, Kp, G, S, ntiles;
+    int K, Kp, G, S, NS, ntiles;   // NS = sequences per tile = 32 * TPT * S
 };
 
 __host__ __device__ inline int em_pitch(int Kp) { return Kp + 2; }   // doubles; bank-conflict-free row pitch
@@ -68,23 +68,27 @@ __host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS)
 
 // value-only TP x TQ micro-tile: best[p][q] = max_j ( dcol[j*ldd + p] + arow[j*lda + q] )
 // (strict > keeps the first maximum's bits, e.g. the sign of a zero, as the reference does).
-template <int TQT, int UNR = 2>
+template <int TQT, int UNR = 2, int TPT = TP>
 __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol, int ldd,
                                                  const double *__restrict__ arow, int lda, int nj,
-                                                 double (&best)[TP][TQT])
+                                                 double (&best)[TPT][TQT])
 {
 #pragma unroll UNR
     for (int j = 0; j < nj; j++) {
-        const double2 d = *reinterpret_cast<const double2 *>(dcol + (size_t)j * ldd);
+        double dd[TPT];
+#pragma unroll
+        for (int p = 0; p < TPT / 2; p++) {
+            const double2 d = *reinterpret_cast<const double2 *>(dcol + (size_t)j * ldd + 2 * p);
+            dd[2 * p] = d.x; dd[2 * p + 1] = d.y;
+        }
         double a[TQT];
 #pragma unroll
         for (int q = 0; q < TQT / 2; q++) {
             const double2 aa = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2 * q);
             a[2 * q] = aa.x; a[2 * q + 1] = aa.y;
         }
-        const double dd[TP] = {d.x, d.y};
 #pragma unroll
-        for (int p = 0; p < TP; p++)
+        for (int p = 0; p < TPT; p++)
 #pragma unroll
             for (int q = 0; q < TQT; q++) {
                 const double v = dd[p] + a[q];
@@ -112,11 +116,11 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 // TQT = target states per thread (8 or 12; a warp owns TQT adjacent states); MAXT/MINB only set the register
 // budget (launch bounds).  The host picks TQT and S so that a CTA has a multiple of 4 warps: warps map to the
 // four SM sub-partitions by warp id, and with the per-step barrier an uneven split leaves sub-partitions idle.
-template <int TQT, int MAXT, int MINB>
+template <int TQT, int MAXT, int MINB, int TPT = TP>
 __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = p.K, Kp = p.Kp, NS = 64 * p.S, EP = em_pitch(Kp);
+    const int K = p.K, Kp = p.Kp, NS = p.NS, EP = em_pitch(Kp);
     double *sA = reinterpret_cast<double *>(smem_raw);
     double *sD = sA + (size_t)K * Kp;
     double *sEm = sD + (size_t)2 * K * NS;
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = w % p.G, sg = w / p.G;
     const int i0 = g * TQT;
-    const int s0 = sg * SEQ_PER_WARP + lane * TP;
+    const int s0 = sg * (32 * TPT) + lane * TPT;
     const uint32_t slab_bytes = (uint32_t)((size_t)K * NS * 8);
     const uint32_t row_bytes = (uint32_t)(Kp * 8);
 
@@ -207,30 +211,34 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         }
 
         for (int t = 1; t < Tmax; t++) {
-            double best[TP][TQT];
+            double best[TPT][TQT];
 #pragma unroll
-            for (int q = 0; q < TP; q++)
+            for (int q = 0; q < TPT; q++)
 #pragma unroll
                 for (int k = 0; k < TQT; k++) best[q][k] = neg_inf();
             const double *dcur = sD + (size_t)((t - 1) & 1) * K * NS + s0;
-            maxplus_tile_val<TQT, 2>(dcur, NS, sA + i0, Kp, K, best);
+            maxplus_tile_val<TQT, 2, TPT>(dcur, NS, sA + i0, Kp, K, best);
 
             mbar_wait(sBar + 1, em_phase);      // emission rows of step t have landed
             em_phase ^= 1;
             double *dnext = sD + (size_t)(t & 1) * K * NS + s0;
-            const double *e0 = sEm + (size_t)s0 * EP + i0, *e1 = e0 + EP;
+            const double *e0 = sEm + (size_t)s0 * EP + i0;
 #pragma unroll
             for (int k = 0; k < TQT / 2; k++) {
-                const double2 x0 = *reinterpret_cast<const double2 *>(e0 + 2 * k);
-                const double2 x1 = *reinterpret_cast<const double2 *>(e1 + 2 * k);
+                double2 x[TPT];
+#pragma unroll
+                for (int q = 0; q < TPT; q++) x[q] = *reinterpret_cast<const double2 *>(e0 + (size_t)q * EP + 2 * k);
                 // (delta + a) + b (viterbi.rs:17).  Sequences that already ended compute garbage in their
                 // own column only; their last row is already in the history.
-                if (i0 + 2 * k < K)
-                    *reinterpret_cast<double2 *>(dnext + (size_t)(i0 + 2 * k) * NS) =
-                        make_double2(best[0][2 * k] + x0.x, best[1][2 * k] + x1.x);
-                if (i0 + 2 * k + 1 < K)
-                    *reinterpret_cast<double2 *>(dnext + (size_t)(i0 + 2 * k + 1) * NS) =
-                        make_double2(best[0][2 * k + 1] + x0.y, best[1][2 * k + 1] + x1.y);
+#pragma unroll
+                for (int q = 0; q < TPT; q += 2) {
+                    if (i0 + 2 * k < K)
+                        *reinterpret_cast<double2 *>(dnext + (size_t)(i0 + 2 * k) * NS + q) =
+                            make_double2(best[q][2 * k] + x[q].x, best[q + 1][2 * k] + x[q + 1].x);
+                    if (i0 + 2 * k + 1 < K)
+                        *reinterpret_cast<double2 *>(dnext + (size_t)(i0 + 2 * k + 1) * NS + q) =
+                            make_double2(best[q][2 * k + 1] + x[q].y, best[q + 1][2 * k + 1] + x[q + 1].y);
+                }
             }
             fence_proxy_async_smem();           // make this thread's delta writes visible to the TMA store
             if (tid == 0) tma_store_wait_read_all();   // slab t-1 has left the buffer step t+1 will overwrite
@@ -267,7 +275,7 @@ constexpr int BT_CHUNK = 16;   // predecessors per prefetch chunk
 __global__ void __launch_bounds__(128) backtrace_small_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int K = p.K, Kp = p.Kp, NS = 64 * p.S;
+    const int K = p.K, Kp = p.Kp, NS = p.NS;
     const int ATP = K | 1;                                   // odd pitch: rows of different states spread over banks
     double *sAT = reinterpret_cast<double *>(smem_raw);     // sAT[s*ATP + j] = logA[j][s]
     for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) {
