@@ -170,3 +170,61 @@ def test_chunked_pipeline_and_device_api():
         L.cv_set_chunks(-1)
         L.cv_set_chain_max_batch(-1)
     h.close()
+
+
+def _path_score(A, B, obs, path):
+    """Score of a decoded path under viterbi.rs's association ((d + a) + b), d0 = 0.0 -- plain Python floats."""
+    d = 0.0
+    for t in range(1, len(obs)):
+        d = (d + float(A[path[t - 1], path[t]])) + float(B[path[t], obs[t]])
+    return d
+
+
+def test_full_size_pos_properties():
+    """BASELINE configs[2] at full size (1M sentences, ~5e10 cells): too big for the oracle in a test, so check
+    size-independent properties: (1) the run is deterministic, (2) every sampled path re-scores, add by add in the
+    reference's order, to exactly the returned score (so the path is a valid witness of the value), (3) a sampled
+    sub-batch decoded alone gives the same paths/scores, and that sub-batch equals the oracle."""
+    import bench
+    wl = bench.workload_pos(0, 1_000_000)
+    h = cv.HMM(wl["A"], wl["B"], wl["pi"])
+    p1, s1 = cv.decode_batch(h, wl["obs"], wl["off"])
+    p2, s2 = cv.decode_batch(h, wl["obs"], wl["off"])
+    assert (p1 == p2).all() and s1.tobytes() == s2.tobytes()
+    rng = np.random.default_rng(1)
+    off = wl["off"]
+    pick = np.sort(rng.choice(len(off) - 1, size=3000, replace=False))
+    for b in pick[:400]:
+        o = wl["obs"][off[b]:off[b + 1]]
+        sc = _path_score(wl["A"], wl["B"], o, p1[off[b]:off[b + 1]])
+        assert np.float64(sc).tobytes() == np.float64(s1[b]).tobytes() or (sc == -np.inf and s1[b] == -np.inf)
+    sub_obs = np.concatenate([wl["obs"][off[b]:off[b + 1]] for b in pick])
+    sub_off = np.concatenate([[0], np.cumsum([off[b + 1] - off[b] for b in pick])]).astype(np.int64)
+    ps, ss = cv.decode_batch(h, sub_obs, sub_off)
+    assert ss.tobytes() == s1[pick].tobytes()
+    assert (ps == np.concatenate([p1[off[b]:off[b + 1]] for b in pick])).all()
+    rp, rs = po.decode_batch(wl["A"], wl["B"], sub_obs, sub_off, nthreads=8)
+    assert (ps == rp).all() and ss.tobytes() == rs.tobytes()
+    h.close()
+
+
+def test_large_state_properties():
+    """BASELINE configs[3] shape (K=1024, M=4096) at reduced batch/length: determinism, exact re-scoring of
+    sampled paths, and oracle parity on a few sequences."""
+    import bench
+    wl = bench.workload_large(0, 256, 96)
+    h = cv.HMM(wl["A"], wl["B"], wl["pi"])
+    p1, s1 = cv.decode_batch(h, wl["obs"], wl["off"])
+    p2, s2 = cv.decode_batch(h, wl["obs"], wl["off"])
+    assert (p1 == p2).all() and s1.tobytes() == s2.tobytes()
+    off = wl["off"]
+    for b in (0, 17, 128, 255):
+        o = wl["obs"][off[b]:off[b + 1]]
+        sc = _path_score(wl["A"], wl["B"], o, p1[off[b]:off[b + 1]])
+        assert np.float64(sc).tobytes() == np.float64(s1[b]).tobytes()
+    sel = [3, 200]
+    sub_obs = np.concatenate([wl["obs"][off[b]:off[b + 1]] for b in sel])
+    sub_off = np.array([0, 96, 192], dtype=np.int64)
+    rp, rs = po.decode_batch(wl["A"], wl["B"], sub_obs, sub_off, nthreads=2)
+    assert (np.concatenate([p1[off[b]:off[b + 1]] for b in sel]) == rp).all() and s1[sel].tobytes() == rs.tobytes()
+    h.close()
