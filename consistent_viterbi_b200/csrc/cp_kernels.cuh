@@ -301,6 +301,7 @@ __device__ __forceinline__ QFn qfn_elem(double x, int e)
 }
 
 constexpr int QS_THREADS = 1024, QS_EPT = 8;
+constexpr int QS_SERIAL_HEAD = 2048;                // leading terms summed by the plain loop
 
 __global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *terms, int nterms, double *ub_out,
                                                                   unsigned int *reset_counter)
@@ -329,10 +330,27 @@ __global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *
     }
     if (mode & 2) { if (tid == 0) *ub_out = neg_inf(); return; }
 
-    if (tid == 0) {
-        double s = 0.0; int pos = 0;
-        while (pos < nterms && s == 0.0) { s = s + terms[pos]; pos++; }      // 0.0 + x is exact
-        s_sh = s; pos_sh = pos;
+    // The first terms go through the plain loop: while the sum is small its binade changes every few adds, and a
+    // binade change costs a whole scan window.  After QS_SERIAL_HEAD terms a change needs ~pos more terms.
+    {
+        double *head = reinterpret_cast<double *>(warp_agg);    // reuse: 32 x 16 B = 64 doubles per round
+        double s = 0.0;
+        const int nhead = min(nterms, QS_SERIAL_HEAD);
+        for (int base = 0; base < nhead; base += 64) {
+            if (tid < 64 && base + tid < nhead) head[tid] = terms[base + tid];
+            __syncthreads();
+            if (tid == 0) {
+                const int n = min(64, nhead - base);
+#pragma unroll 8
+                for (int k = 0; k < n; k++) s = s + head[k];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            int pos = nhead;
+            while (pos < nterms && s == 0.0) { s = s + terms[pos]; pos++; }  // 0.0 + x is exact
+            s_sh = s; pos_sh = pos;
+        }
     }
     for (;;) {
         __syncthreads();
