@@ -228,3 +228,24 @@ def test_large_state_properties():
     rp, rs = po.decode_batch(wl["A"], wl["B"], sub_obs, sub_off, nthreads=2)
     assert (np.concatenate([p1[off[b]:off[b + 1]] for b in sel]) == rp).all() and s1[sel].tobytes() == rs.tobytes()
     h.close()
+
+
+def test_large_k_dataflow_stress():
+    """The large-K kernel synchronises work items of consecutive steps across CTAs with release/acquire counters and
+    reads the published rows through TMA.  Many row blocks x column blocks x steps, several runs: every run must be
+    identical, equal the oracle on the whole batch, and every path must re-score exactly."""
+    rng = np.random.default_rng(5150)
+    K, M, Bn, T = 260, 11, 1500, 48          # 24 row blocks x 3 column blocks x 47 steps = 3384 work items
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.25)
+    off = np.arange(Bn + 1, dtype=np.int64) * T
+    obs = rng.integers(0, M, size=Bn * T).astype(np.uint32)
+    h = cv.HMM(A, B, pi)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=16)
+    for run in range(4):
+        p, s = cv.decode_batch(h, obs, off)
+        assert (p == rp).all(), f"run {run}: paths differ from the oracle"
+        assert s.tobytes() == rs.tobytes(), f"run {run}: scores differ"
+    for b in range(0, Bn, 97):
+        sc = _path_score(A, B, obs[off[b]:off[b + 1]], p[off[b]:off[b + 1]])
+        assert np.float64(sc).tobytes() == np.float64(s[b]).tobytes() or (sc == -np.inf and s[b] == -np.inf)
+    h.close()
