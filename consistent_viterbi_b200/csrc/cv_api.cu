@@ -666,6 +666,7 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
                 case 21: e = launch_val(probe_tile_val_kernel<4>); break;
                 case 22: e = launch_val(probe_tile_val_kernel<5>); break;
                 case 23: e = launch_val(probe_tile_val_kernel<9>); break;
+                case 24: e = launch_val(probe_tile_val_kernel<0>); break;
                 case 7: probe_mix_kernel<1, 1><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 case 8: probe_mix_kernel<1, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
                 case 9: probe_mix_kernel<0, 3><<<blocks, threads>>>(d_out, iters, 1.0); break;

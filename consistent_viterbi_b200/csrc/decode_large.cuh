@@ -12,8 +12,8 @@
 // running CTAs and depend only on lower-numbered items, so the scheme cannot
 // deadlock and keeps all 148 SMs busy without clusters or grid-wide barriers.
 //
-// Inside an item, one producer thread streams 16-row chunks of logA[:, cb] (16 KB) and
-// of delta_{t-1}[rb] (8 KB) from L2 into a 4-stage shared-memory ring with TMA
+// Inside an item, a producer warp streams 16-row chunks of logA[:, cb] (16 KB) and
+// of delta_{t-1}[rb] (8 KB) from L2 into a 6-stage shared-memory ring with TMA
 // bulk copies (cp.async.bulk + mbarrier full/empty pairs); 16 warps each
 // own 8 target states x 64 sequences and run the same value-only 2x8 register
 // micro-tile as the small-K kernel.  Every delta row is kept: the history is
@@ -30,9 +30,9 @@ namespace cvb {
 
 constexpr int LG_BM = 64;        // sequences per row block
 constexpr int LG_BK = 16;        // predecessor rows per pipeline stage
-constexpr int LG_STAGES = 4;
+constexpr int LG_STAGES = 6;
 constexpr int LG_CONSUMER_WARPS = LARGE_BN / TQ;               // 16
-constexpr int LG_THREADS = 32 * LG_CONSUMER_WARPS;             // producer = lane 0 of warp 0
+constexpr int LG_THREADS = 32 * (LG_CONSUMER_WARPS + 1);       // + one producer warp (warp 16)
 constexpr int LG_STAGE_A = LG_BK * LARGE_BN;                   // doubles
 constexpr int LG_STAGE_D = LG_BK * LG_BM;                      // doubles
 constexpr size_t LG_SMEM_BYTES = (size_t)LG_STAGES * (LG_STAGE_A + LG_STAGE_D) * 8 + 256;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const DecodeLargeParams p)
+__global__ void __maxnreg__(96) decode_large_kernel(const DecodeLargeParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sA = reinterpret_cast<double *>(smem_raw);                       // [STAGES][BK][128]
@@ -140,31 +140,30 @@ __global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const Decod
         const double *dsrc = p.hist + (size_t)(t - 1) * slab + (size_t)rb * LG_BM;
         const double *asrc = p.A + (size_t)cb * LARGE_BN;
 
-        // The producer is lane 0 of warp 0: it waits for the dependency, then keeps the TMA ring
-        // LG_STAGES-1 chunks ahead of the consumers (itself included).
-        auto issue_chunk = [&](int c) {
-            const uint32_t g = chunk_ctr + c;
-            const int s = g % LG_STAGES;
-            if (g >= LG_STAGES) mbar_wait(empty + s, ((g / LG_STAGES) - 1) & 1);
-            mbar_expect_tx(full + s, (uint32_t)((LG_STAGE_A + LG_STAGE_D) * 8));
-            double *dstA = sA + (size_t)s * LG_STAGE_A;
-            double *dstD = sD + (size_t)s * LG_STAGE_D;
-            const int j0 = c * LG_BK;
+        if (w == LG_CONSUMER_WARPS) {
+            // =================== producer warp: one lane feeds the TMA ring ===================
+            if (lane == 0) {
+                // wait until step t-1 of this row block is fully published (step 1 reads the zeroed slab)
+                const unsigned int need = (unsigned int)(t - 1) * (unsigned int)p.NCB;
+                while (ld_acquire_u32(p.done + rb) < need) { __nanosleep(64); }
+                asm volatile("fence.proxy.async;" ::: "memory");
+                for (int c = 0; c < nchunks; c++) {
+                    const uint32_t g = chunk_ctr + c;
+                    const int s = g % LG_STAGES;
+                    if (g >= LG_STAGES) mbar_wait(empty + s, ((g / LG_STAGES) - 1) & 1);
+                    mbar_expect_tx(full + s, (uint32_t)((LG_STAGE_A + LG_STAGE_D) * 8));
+                    double *dstA = sA + (size_t)s * LG_STAGE_A;
+                    double *dstD = sD + (size_t)s * LG_STAGE_D;
+                    const int j0 = c * LG_BK;
 #pragma unroll 4
-            for (int jj = 0; jj < LG_BK; jj++) {
-                tma_bulk_g2s(dstA + jj * LARGE_BN, asrc + (size_t)(j0 + jj) * Kl, LARGE_BN * 8, full + s);
-                tma_bulk_g2s(dstD + jj * LG_BM, dsrc + (size_t)(j0 + jj) * p.Bpad, LG_BM * 8, full + s);
+                    for (int jj = 0; jj < LG_BK; jj++) {
+                        tma_bulk_g2s(dstA + jj * LARGE_BN, asrc + (size_t)(j0 + jj) * Kl, LARGE_BN * 8, full + s);
+                        tma_bulk_g2s(dstD + jj * LG_BM, dsrc + (size_t)(j0 + jj) * p.Bpad, LG_BM * 8, full + s);
+                    }
+                }
             }
-        };
-        if (tid == 0) {
-            // wait until step t-1 of this row block is fully published (step 1 reads the zeroed buffer)
-            const unsigned int need = (unsigned int)(t - 1) * (unsigned int)p.NCB;
-            while (ld_acquire_u32(p.done + rb) < need) { __nanosleep(64); }
-            asm volatile("fence.proxy.async;" ::: "memory");
-            for (int c = 0; c < LG_STAGES - 1 && c < nchunks; c++) issue_chunk(c);
-        }
-        __syncwarp();
-        {
+            chunk_ctr += nchunks;
+        } else {
             // =================== consumer warps ===================
             const int i0 = cb * LARGE_BN + w * TQ;        // global target state of q = 0
             const int r0 = rb * LG_BM + lane * TP;        // column (rank inside the group) of p = 0
@@ -175,8 +174,6 @@ __global__ void __launch_bounds__(LG_THREADS, 1) decode_large_kernel(const Decod
                 for (int k = 0; k < TQ; k++) best[q][k] = neg_inf();
 
             for (int c = 0; c < nchunks; c++) {
-                if (tid == 0 && c + LG_STAGES - 1 < nchunks) issue_chunk(c + LG_STAGES - 1);
-                __syncwarp();
                 const uint32_t g = chunk_ctr + c;
                 const int s = g % LG_STAGES;
                 mbar_wait(full + s, (g / LG_STAGES) & 1);

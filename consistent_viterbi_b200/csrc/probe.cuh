@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(512, 1) probe_tile_val_kernel(double *out, int
         for (int p = 0; p < TP; p++)
 #pragma unroll
             for (int q = 0; q < TQ; q++) best[p][q] = neg_inf();
-        maxplus_tile_val<TQ, UNR, TP>(sD + s0, NS, sA + i0, Kp, K, best);
+        if (UNR == 0) maxplus_tile_val_pipe<TQ, TP>(sD + s0, NS, sA + i0, Kp, K, best);
+        else maxplus_tile_val<TQ, (UNR > 0 ? UNR : 2), TP>(sD + s0, NS, sA + i0, Kp, K, best);
 #pragma unroll
         for (int p = 0; p < TP; p++)
 #pragma unroll
