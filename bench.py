@@ -264,7 +264,7 @@ def run_other(cv, L, device):
     other["ar_full_dataset"] = {"cells": cells, "e2e_ms": 1e3 * t_gpu, "e2e_cells_per_s": cells / t_gpu,
                                 "cpu_port_cells_per_s": cells / t_cpu,
                                 "note": "60 sequences, 1.5e7 cells: latency bound (serial in t), paths equal the golden fixture"}
-    # configs[3] shape at reduced batch/length (the full B=4096, T=4096 run is `--workload large`: 4.7 s/step)
+    # configs[3] shape at reduced batch/length (the full B=4096, T=4096 run is `--workload large`: 3.95 s/step)
     w = workload_large(0, 2048, 64)
     hm = cv.HMM(w["A"], w["B"], w["pi"])
     cv.decode_batch(hm, w["obs"], w["off"], device=device)
@@ -272,7 +272,7 @@ def run_other(cv, L, device):
     cv.decode_batch(hm, w["obs"], w["off"], device=device)
     dt = time.perf_counter() - t0
     other["large_K1024_B2048_T64"] = {"cells": w["cells"], "e2e_ms": 1e3 * dt, "e2e_cells_per_s": w["cells"] / dt,
-                                      "note": "full configs[3] (B=4096, T=4096): 3.71e12 cells/s, 43 % of the FP64 roofline (DESIGN.md)"}
+                                      "note": "full configs[3] (B=4096, T=4096, `--workload large`): 3.95 s/step = 4.45e12 cells/s, 52 % of the FP64 roofline (DESIGN.md)"}
     hm.close()
     # configs[0] stand-in and configs[4]: constrained decode with a node budget
     for kind, budget, cpu_budget in (("trucks", 0, 150), ("heavy", 60, 6)):      # trucks-like: complete search
