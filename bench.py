@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- Viterbi cells/s of the B200 hot path, one JSON line (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pos|large|ar|cp] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pos|large] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json
 configs[2], the POS-tagging shape (K=45 tags, 20k vocab, 1M sentences, avg T=25): the batched, sharding
 configuration the metric "cells/s at 1/2/4/8 B200" is quoted on (configs[1], datasets/ar, is 60 sequences /
-1.5e7 cells, latency bound and unshardable -- it is run as `--workload ar` and reported under "other").
+1.5e7 cells, latency bound and unshardable -- it is reported under "other" together with the constrained-decode
+configs and a reduced large-state run).
 N > 1: launched by torchrun, one rank per GPU, every rank decodes its own shard of 1M sentences (weak
 scaling, no data-path collective), max-over-ranks timing.
 
