@@ -39,6 +39,15 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
     a.nseg = (int)nseg; a.ntiles = (int)((nseg + 63) / 64); a.node = node; a.init_mode = init_mode;
     a.tile_counter = r.d_counter;
     // (the segment counter is zeroed by the previous node's sum kernel / the set-up memset)
+    if (r.p.K > SMALL_K_MAX) {                                  // generic path: states looped per lane, logA from L2
+        const size_t smem_g = (size_t)CPG_WARPS * 2 * r.p.Kp * sizeof(double);
+        const int grid_g = (int)std::min<int64_t>((nseg + CPG_WARPS - 1) / CPG_WARPS, (int64_t)r.h->num_sms * 8);
+        cp_sweep_generic_kernel<<<grid_g, 32 * CPG_WARPS, smem_g, r.st>>>(r.p, a);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (init_mode) CUDA_TRY(cudaMemsetAsync(r.d_counter, 0, sizeof(unsigned int), r.st));
+        return CV_OK;
+    }
     // one warp per segment (latency-oriented); the lock-step tile kernel only pays off with very many segments
     const size_t smem_c = (size_t)r.p.K * r.p.Kp * 8 + (r.p.bt_in_smem ? (size_t)r.p.M * r.p.Kp * 8 : 0) +
                           (size_t)CPW_WARPS * 16 * r.p.Kp;
@@ -151,7 +160,8 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     if (N <= 0) return fail(CV_ERR_EMPTY, "empty super-sequence (reference: array.row(len-1) panics)");
     if (!obs || !is_seq_start || !comp || !sol_out) return fail(CV_ERR_ARG, "NULL buffer");
     if (ncomp < 0) return fail(CV_ERR_ARG, "ncomp < 0");
-    if (h->K > SMALL_K_MAX) return fail(CV_ERR_UNSUPPORTED, "cv_cp_solve covers K <= %d (K = %d)", SMALL_K_MAX, h->K);
+    if ((size_t)4 * 2 * (h->K > SMALL_K_MAX ? h->Kl : h->Kp) * sizeof(double) > 200 * 1024)
+        return fail(CV_ERR_UNSUPPORTED, "cv_cp_solve: K = %d needs more shared memory than an SM has", h->K);
     for (int64_t t = 0; t < N; t++) {
         if ((int64_t)obs[t] >= h->M) return fail(CV_ERR_ARG, "observation index >= M at %lld (reference: ndarray index panic)", (long long)t);
         if (comp[t] >= ncomp) return fail(CV_ERR_ARG, "component id %d >= ncomp %d at %lld (reference: constraints[ucomp] index panic, cp.rs:25)", comp[t], ncomp, (long long)t);
@@ -230,7 +240,7 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     r.d_end = (int *)((double *)b[10].p + 2); r.d_counter = (unsigned int *)((double *)b[10].p + 3);
     CUDA_TRY(cudaMemsetAsync(b[10].p, 0, 32, st));
     const int nchunks = (int)((N + CP_BT_CHUNK - 1) / CP_BT_CHUNK);
-    if ((rc = b[11].ensure((size_t)nchunks * K + 64))) return rc;
+    if ((rc = b[11].ensure(sizeof(psi_t) * (size_t)nchunks * K + 64))) return rc;
     if ((rc = b[12].ensure(sizeof(int) * (size_t)nchunks + 64))) return rc;
     if ((rc = b[13].ensure(sizeof(uint64_t) * (size_t)N))) return rc;
     r.d_F = (psi_t *)b[11].p; r.d_entry = (int *)b[12].p; r.d_sol = (uint64_t *)b[13].p;
@@ -238,12 +248,17 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     r.h_ub = (double *)h->pinned_status + 1;
 
     CpParams &p = r.p;
-    p.A = h->dA; p.BT = h->dBT; p.Pi = h->dPi;
+    const bool small = K <= SMALL_K_MAX;
+    p.A = small ? h->dA : h->dAl; p.BT = small ? h->dBT : h->dBTl; p.Pi = h->dPi;
     p.obs = (const uint32_t *)b[2].p; p.start = (const uint8_t *)b[3].p; p.comp = (const int32_t *)b[4].p;
     p.delta = (double *)b[0].p; p.psi = (psi_t *)b[1].p; p.choice = d_choice;
-    p.N = N; p.M = h->M; p.K = K; p.Kp = h->Kp; p.G = h->G;
-    p.bt_in_smem = ((size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
-    {
+    p.N = N; p.M = h->M; p.K = K; p.Kp = small ? h->Kp : h->Kl; p.G = h->G;
+    p.bt_in_smem = (small && (size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
+    if (!small) {
+        const size_t smem_g = (size_t)CPG_WARPS * 2 * p.Kp * sizeof(double);
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    }
+    if (small) {
         const size_t smem_c = (size_t)K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) + (size_t)CPW_WARPS * 16 * h->Kp;
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
@@ -257,7 +272,7 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     // ---- init_viterbi (cp.rs:63-83) ----
     if (prefix >= 1) {
-        cp_row0_kernel<<<1, 64, 0, st>>>(p);
+        cp_row0_kernel<<<(K + 255) / 256, 256, 0, st>>>(p);
         g_launches++;
         if (prefix > 1) {
             if ((rc = cp_sweep(r, 0, 1, 0, 1))) return rc;

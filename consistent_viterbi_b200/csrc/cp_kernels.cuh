@@ -28,7 +28,7 @@
 
 namespace cvb {
 
-typedef uint8_t psi_t;   // K <= 64 on this path
+typedef uint16_t psi_t;   // backpointer type of the constrained path (K <= 65535)
 
 struct CpParams {
     const double *A;          // [K][Kp] padded -inf
@@ -62,7 +62,7 @@ __host__ __device__ inline size_t cp_sweep_smem_bytes(int K, int Kp)
 // delta[0][i] = fl(pi[i] + b[i][o_0])   (init_probs, hmm.rs:215-218; cp.rs:66-68)
 __global__ void cp_row0_kernel(const CpParams p)
 {
-    const int i = threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < p.K) p.delta[i] = p.Pi[i] + p.BT[(size_t)p.obs[0] * p.Kp + i];
 }
 
@@ -164,6 +164,62 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
                 }
                 d[s] = (i < K) ? v[s] : neg_inf();
                 if (i < K) sdw[(k & 1) * Kp + i] = v[s];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+
+// ---- sweeps for K > 64: one warp per segment, every lane loops over its states i = lane, lane+32, ... ----
+// Same phases and arithmetic as cp_sweep_chain_kernel; logA / logB^T are read from global memory (L2), the
+// delta rows of the warp live in shared memory.  A correctness-first path: constrained decodes with more than 64
+// states are outside BASELINE's configs.
+constexpr int CPG_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * CPG_WARPS) cp_sweep_generic_kernel(const CpParams p, const CpSweepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K, Kp = p.Kp;
+    const int lane = threadIdx.x & 31;
+    double *sdw = reinterpret_cast<double *>(smem_raw) + (size_t)(threadIdx.x >> 5) * 2 * Kp;
+    const int nsl = (K + 31) / 32;
+    for (;;) {
+        unsigned int r = 0;
+        if (lane == 0) r = atomicAdd(a.tile_counter, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if ((int)r >= a.nseg) break;
+        const int64_t from = a.seg_from[r];
+        const int len = a.seg_len[r];
+        for (int i = lane; i < Kp; i += 32) {
+            double v = neg_inf();
+            if (i < K) {
+                if (a.init_mode) v = p.delta[(size_t)from * K + i];
+                else { v = (i == a.node) ? 0.0 : neg_inf(); p.delta[(size_t)from * K + i] = v; }   // cp.rs:33-34
+            }
+            sdw[i] = v; sdw[Kp + i] = neg_inf();
+        }
+        __syncwarp();
+        for (int k = 1; k <= len; k++) {                                          // cp.rs:47-60 / 70-78
+            const int64_t t = from + k;
+            const bool st = p.start[t] != 0;
+            const uint32_t o = p.obs[t];
+            const double *sdo = sdw + ((k - 1) & 1) * Kp;
+            double *sdn = sdw + (k & 1) * Kp;
+            for (int s = 0; s < nsl; s++) {
+                const int i = lane + 32 * s;                                      // warp-uniform trip count
+                const int ic = min(i, Kp - 1);
+                const double pi_i[1] = {p.Pi[ic]};
+                double best[1]; int idx[1];
+                chain_scan<1>(sdo, p.A, Kp, K, i, st, pi_i, best, idx);           // argmax on delta + tr
+                const double tr = st ? pi_i[0] : p.A[(size_t)idx[0] * Kp + ic];
+                const double arc = tr + p.BT[(size_t)o * Kp + ic];                // arc_p (utils.rs:24-30)
+                const double v = sdo[idx[0]] + arc;                               // delta + (a + b)  cp.rs:55
+                if (i < K) {
+                    p.delta[(size_t)t * K + i] = v;
+                    p.psi[(size_t)t * K + i] = (psi_t)idx[0];
+                    sdn[i] = v;
+                }
             }
             __syncwarp();
         }

@@ -88,7 +88,7 @@ int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs_flat, const int64_t *d_
  *                   explored == max_nodes
  *   sol_out[N]      get_solution()      obj_out  get_objective()
  *   explored_out    get_explored_nodes() steps_out forward sweep steps executed
- * HOST pointers. */
+ * HOST pointers.  Any K that fits the kernels' shared memory (K <= ~3000); K <= 64 takes the tuned kernels. */
 int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq_start,
                 const int32_t *comp, int64_t N, int32_t ncomp, uint64_t max_nodes,
                 uint64_t *sol_out, double *obj_out, uint64_t *explored_out,

@@ -56,6 +56,16 @@ def test_cp_mid_k(K):
     _check(A, B, pi, obs, start, comp, ncomp, max_nodes=60)
 
 
+@pytest.mark.parametrize("K", [65, 100, 130, 300])
+def test_cp_large_k_generic_path(K):
+    """K > 64: generic sweep kernel (states looped per lane, logA from L2), u16 backpointers."""
+    rng = np.random.default_rng(650 + K)
+    M = 9
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    obs, start, comp, ncomp = random_superseq(rng, 8, M, 2, 0.1, 3, 25)
+    _check(A, B, pi, obs, start, comp, ncomp, max_nodes=12)
+
+
 def test_cp_no_constraints_and_prefix():
     rng = np.random.default_rng(77)
     A, B, pi = random_hmm(rng, 5, 4, zero_frac=0.0)
