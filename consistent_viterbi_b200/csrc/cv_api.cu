@@ -153,6 +153,8 @@ __global__ void build_layouts_kernel(const double *A, const double *Bm, const do
     }
 }
 
+extern "C" void cv_hmm_destroy(cv_hmm *h);
+
 __global__ void transpose_kernel(const double *in, double *out, int n)
 {
     __shared__ double tile[32][33];
@@ -193,6 +195,7 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     CUDA_TRY(cudaSetDevice(device));
 
     cv_hmm *h = new cv_hmm();
+    struct Guard { cv_hmm *h; ~Guard() { if (h) cv_hmm_destroy(h); } } guard{h};   // released on every early return
     h->device = device; h->K = K; h->D = D; h->M = M;
     // tile shape of the forward kernel: TQT target states per warp, G = ceil(K/TQT) state groups.  Pick the
     // shape with the least padded work among those whose warps per CTA (G*S, S in {1,2,4}) divide by 4.
@@ -262,6 +265,7 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
     }
+    guard.h = nullptr;
     *out = h;
     return CV_OK;
 }
