@@ -22,14 +22,12 @@ __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0
 // because predecessors are visited in ascending j.
 //
 // sm_100a has no 64-bit select and no DMNMX, so a cell is
-//   DADD + DSETP (FP64 pipe) + 2 x 32-bit select (value) + 1 x select (index).
-// SEL/FSEL issue on the ALU pipe only; VARIANT moves some selects onto the FMA
-// pipe as predicated IMADs (x*0+y with a zero the compiler cannot see) so that
-// ALU, FMA and FP64 pipes are all below the 1 instr/clk issue limit.
-//   VARIANT 0: compiler's choice (FSEL, FSEL, SEL)
-//   VARIANT 1: index select on the FMA pipe
-//   VARIANT 2: index + high word on the FMA pipe
-//   VARIANT 3: all three selects on the FMA pipe
+//   DADD + DSETP (FP64 pipe) + 2 x 32-bit select (value) + 1 x select (index),
+// and SEL/FSEL issue on the ALU pipe only.  VARIANT 1-3 were attempts to move selects onto the FMA pipe as
+// predicated IMADs; ptxas turns every predicated move back into op + SEL (checked in SASS, even at -O0), so they
+// compile to the same select count and are kept only for the probe (cv_probe_fp64 modes 3-5).  The production
+// kernels use VARIANT 0 where the index is part of the state (constrained decode) and the value-only tile of
+// decode_small.cuh / decode_large.cuh otherwise.
 // ---------------------------------------------------------------------------
 template <int VARIANT>
 __device__ __forceinline__ void cell(double d, double a, double &best, int &idx, int j, int zero)
