@@ -7,6 +7,7 @@
 // Nothing here computes Viterbi values on the CPU.
 
 static int g_sum_parallel_min = 4096;
+static int g_sum_force = -1;   // CV_CP_SUM=0|1|2 forces the plain loop / block-structured / single-CTA exact sum
 static double g_cp_prof[6];   // CV_CP_PROF=1: host-timed phases of a node (sweep, fixup, terms, sum, readback)
 
 namespace {
@@ -25,11 +26,35 @@ struct CpRun {
     std::vector<uint64_t> seg_steps;             // rows swept per node of depth c
     int64_t *d_seg_from = nullptr; int32_t *d_seg_len = nullptr;
     double *d_terms = nullptr, *d_ub = nullptr; int *d_end = nullptr; unsigned int *d_counter = nullptr;
+    SumWs sum_ws;                                // block statistics / functions of the exact-order sum
     psi_t *d_F = nullptr; int *d_entry = nullptr; uint64_t *d_sol = nullptr;
     double *h_ub = nullptr;                      // pinned
     int err = CV_OK;
     size_t smem;
 };
+
+// ub = ((0.0 + x_0) + x_1) + ... in order (cp.rs:103-116): plain loop for short lists, the block-structured
+// exact-order kernels for long ones, the single-CTA binade scan beyond SUM_MAX_BLOCKS blocks.
+int cp_launch_sum(const double *terms, int nterms, double *ub, unsigned int *counter, const SumWs &ws, bool have_stats,
+                  int force, cudaStream_t st)
+{
+    const int nblk = (nterms + SUM_BLK - 1) / SUM_BLK;
+    int kind = nterms < g_sum_parallel_min ? 0 : (nblk > SUM_MAX_BLOCKS ? 2 : 1);
+    if (force >= 0) kind = (force == 1 && nblk > SUM_MAX_BLOCKS) ? 2 : force;
+    if (kind == 0) { cp_sum_kernel<<<1, 256, 0, st>>>(terms, nterms, ub, counter); g_launches++; }
+    else if (kind == 2) { cp_sum_exact_kernel<<<1, QS_THREADS, 0, st>>>(terms, nterms, ub, counter); g_launches++; }
+    else {
+        if (nblk > 0) {
+            if (!have_stats) { cp_sum_stats_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bflag); g_launches++; }
+            cp_sum_blockfn_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bexp, ws.bfn);
+            g_launches++;
+        }
+        cp_sum_chain_kernel<<<1, SUMC_THREADS, 0, st>>>(terms, nterms, nblk, ws.bflag, ws.bexp, ws.bfn, ub, counter);
+        g_launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CV_OK;
+}
 
 int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
 {
@@ -50,12 +75,17 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
     }
     // one warp per segment (latency-oriented); the lock-step tile kernel only pays off with very many segments
     const size_t smem_c = (size_t)r.p.K * r.p.Kp * 8 + (r.p.bt_in_smem ? (size_t)r.p.M * r.p.Kp * 8 : 0) +
-                          (size_t)CPW_WARPS * 16 * r.p.Kp;
-    const int grid = (int)std::min<int64_t>((nseg + CPW_WARPS - 1) / CPW_WARPS, (int64_t)r.h->num_sms * 8);
+                          (size_t)CPW_WARPS * 2 * 16 * r.p.Kp;              // up to two segments per warp
+    static const bool fullwarp = getenv("CV_CP_FULLWARP") != nullptr;    // A/B hook: one segment per warp for every K
+    const int64_t segs_per_block = (int64_t)CPW_WARPS * (r.p.Kp <= 16 && !fullwarp ? 2 : 1);
+    const int grid = (int)std::min<int64_t>((nseg + segs_per_block - 1) / segs_per_block, (int64_t)r.h->num_sms * 8);
     const bool regs = r.p.Kp == 8 * ((r.p.K + 7) / 8);       // register-resident logA column needs Kp = 4 * KQ
-    switch (regs ? (r.p.K + 7) / 8 : 9) {
-        case 1: cp_sweep_chain_kernel<1, 2><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;
-        case 2: cp_sweep_chain_kernel<1, 4><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;
+    const int kq = regs ? (r.p.K + 7) / 8 : 9;
+    if (fullwarp && kq == 1) cp_sweep_chain_kernel<1, 2><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
+    else if (fullwarp && kq == 2) cp_sweep_chain_kernel<1, 4><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
+    else switch (kq) {
+        case 1: cp_sweep_chain_kernel<1, 2, 16><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;   // K <= 8
+        case 2: cp_sweep_chain_kernel<1, 4, 16><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;   // K <= 16
         case 3: cp_sweep_chain_kernel<1, 6><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;
         case 4: cp_sweep_chain_kernel<1, 8><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a); break;
         default:
@@ -112,14 +142,13 @@ int cp_solve_r(CpRun &r, int32_t comp)
         g_launches++;
         tick(1, t0);
         if (nterms > 0) {
-            cp_terms_kernel<<<(nterms + 255) / 256, 256, 0, r.st>>>(r.p, r.d_cons_pos, r.d_term_comp, nterms, r.d_terms);
+            cp_terms_kernel<<<(nterms + SUM_BLK - 1) / SUM_BLK, SUM_BLK, 0, r.st>>>(r.p, r.d_cons_pos, r.d_term_comp, nterms,
+                                                                                     r.d_terms, r.sum_ws.bsum, r.sum_ws.bflag);
             g_launches++;
         }
         tick(2, t0);
         // cp.rs:103-116: the exact-order sum (parallel binade scan for long lists, plain loop for short ones)
-        if (nterms >= g_sum_parallel_min) cp_sum_exact_kernel<<<1, QS_THREADS, 0, r.st>>>(r.d_terms, nterms, r.d_ub, r.d_counter);
-        else cp_sum_kernel<<<1, 256, 0, r.st>>>(r.d_terms, nterms, r.d_ub, r.d_counter);
-        g_launches++;
+        if ((rc = cp_launch_sum(r.d_terms, nterms, r.d_ub, r.d_counter, r.sum_ws, nterms > 0, g_sum_force, r.st))) return rc;
         tick(3, t0);
         CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, sizeof(double), cudaMemcpyDeviceToHost, r.st));
         CUDA_TRY(cudaStreamSynchronize(r.st));
@@ -243,6 +272,8 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     if ((rc = b[11].ensure(sizeof(psi_t) * (size_t)nchunks * K + 64))) return rc;
     if ((rc = b[12].ensure(sizeof(int) * (size_t)nchunks + 64))) return rc;
     if ((rc = b[13].ensure(sizeof(uint64_t) * (size_t)N))) return rc;
+    if ((rc = r.sum_ws.bind(b[14], cons_pos.size()))) return rc;
+    if (const char *e = getenv("CV_CP_SUM")) g_sum_force = atoi(e);
     r.d_F = (psi_t *)b[11].p; r.d_entry = (int *)b[12].p; r.d_sol = (uint64_t *)b[13].p;
     CUDA_TRY(cudaMemsetAsync(r.d_sol, 0, sizeof(uint64_t) * (size_t)N, st));       // best_sol = 0 (cp.rs:29)
     r.h_ub = (double *)h->pinned_status + 1;
@@ -259,7 +290,9 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
     }
     if (small) {
-        const size_t smem_c = (size_t)K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) + (size_t)CPW_WARPS * 16 * h->Kp;
+        const size_t smem_c = (size_t)K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) + (size_t)CPW_WARPS * 2 * 16 * h->Kp;
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
@@ -349,11 +382,13 @@ extern "C" int cv_debug_ordered_sum(const double *values, int64_t n, int mode, d
     double *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, sizeof(double) * (size_t)(n + 1)));
     if (n) CUDA_TRY(cudaMemcpy(d + 1, values, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
-    if (mode == 1) cp_sum_exact_kernel<<<1, QS_THREADS>>>(d + 1, (int)n, d, nullptr);
-    else cp_sum_kernel<<<1, 256>>>(d + 1, (int)n, d, nullptr);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
+    DevBuf wsb; SumWs ws;
+    if ((rc = ws.bind(wsb, (size_t)n))) { cudaFree(d); return rc; }
+    if (mode < 0 || mode > 2) mode = 0;
+    rc = cp_launch_sum(d + 1, (int)n, d, nullptr, ws, false, mode, nullptr);
+    if (rc) { cudaFree(d); wsb.release(); return rc; }
     CUDA_TRY(cudaMemcpy(out, d, sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(d);
+    wsb.release();
     return CV_OK;
 }

@@ -70,48 +70,57 @@ __global__ void cp_row0_kernel(const CpParams p)
 // Phases A (reset row) + B (sweep); segments are claimed longest first from a global counter.
 constexpr int CPW_WARPS = 4;
 
-template <int NSL, int KQ>
+// LPS = lanes per segment: 32, or 16 when K <= 16 (two segments per warp, adjacent in the length-sorted list).
+template <int NSL, int KQ, int LPS = 32>
 __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const CpParams p, const CpSweepArgs a)
 {
+    static_assert(LPS == 32 || (LPS == 16 && NSL == 1), "half-warp segments need one state per lane");
+    constexpr int GP = 32 / LPS;                                          // segments per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, Kp = p.Kp;
     double *sA = reinterpret_cast<double *>(smem_raw);
     double *sBT = sA + (size_t)K * Kp;
     const size_t nbt = p.bt_in_smem ? (size_t)p.M * Kp : 0;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane & (LPS - 1), grp = lane / LPS;
     for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) sA[e] = p.A[e];
     for (size_t e = threadIdx.x; e < nbt; e += blockDim.x) sBT[e] = p.BT[e];
     __syncthreads();
     const double *bt = p.bt_in_smem ? sBT : p.BT;
     const bool pf = !p.bt_in_smem;
-    double *sdw = sBT + nbt + (size_t)(threadIdx.x >> 5) * 2 * Kp;       // this warp's delta rows [2][Kp]
+    double *sdw = sBT + nbt + (size_t)((threadIdx.x >> 5) * GP + grp) * 2 * Kp;   // this segment's delta rows [2][Kp]
 
     double pi_i[NSL]; int col[NSL];
 #pragma unroll
-    for (int s = 0; s < NSL; s++) { col[s] = min(lane + 32 * s, Kp - 1); pi_i[s] = p.Pi[col[s]]; }
+    for (int s = 0; s < NSL; s++) { col[s] = min(sub + 32 * s, Kp - 1); pi_i[s] = p.Pi[col[s]]; }
     double acol[KQ > 0 ? 4 * KQ : 1];
     if (KQ > 0) {
 #pragma unroll
-        for (int j = 0; j < 4 * KQ; j++) acol[j] = (j < K && lane < Kp) ? sA[(size_t)j * Kp + lane] : neg_inf();
+        for (int j = 0; j < 4 * KQ; j++) acol[j] = (j < K && sub < Kp) ? sA[(size_t)j * Kp + sub] : neg_inf();
     }
 
     for (;;) {
-        unsigned int r = 0;
-        if (lane == 0) r = atomicAdd(a.tile_counter, 1u);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if ((int)r >= a.nseg) break;
-        const int64_t from = a.seg_from[r];
-        const int len = a.seg_len[r];
+        unsigned int r0 = 0;
+        if (lane == 0) r0 = atomicAdd(a.tile_counter, (unsigned int)GP);
+        r0 = __shfl_sync(0xffffffffu, r0, 0);
+        if ((int)r0 >= a.nseg) break;
+        const int r = (int)r0 + grp;
+        const bool valid = r < a.nseg;
+        const int64_t from = valid ? a.seg_from[r] : 0;
+        const int len = valid ? a.seg_len[r] : -1;
+        const int lenmax = __reduce_max_sync(0xffffffffu, len);
 
         double d[NSL];
 #pragma unroll
         for (int s = 0; s < NSL; s++) {
-            const int i = lane + 32 * s;
-            if (a.init_mode) {
-                d[s] = (i < K) ? p.delta[(size_t)from * K + i] : neg_inf();
-            } else {
-                d[s] = (i == a.node) ? 0.0 : neg_inf();                          // cp.rs:33-34
-                if (i < K) p.delta[(size_t)from * K + i] = d[s];
+            const int i = sub + 32 * s;
+            d[s] = neg_inf();
+            if (valid) {
+                if (a.init_mode) {
+                    d[s] = (i < K) ? p.delta[(size_t)from * K + i] : neg_inf();
+                } else {
+                    d[s] = (i == a.node) ? 0.0 : neg_inf();                      // cp.rs:33-34
+                    if (i < K) p.delta[(size_t)from * K + i] = d[s];
+                }
             }
             if (i < Kp) { sdw[i] = (i < K) ? d[s] : neg_inf(); sdw[Kp + i] = neg_inf(); }
         }
@@ -133,7 +142,8 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
             for (int q = 0; q < CHAIN_PF; q++) prefetch_l1(p.BT + (size_t)oq[q] * Kp + col[0]);
         }
 
-        for (int k = 1; k <= len; k++) {                                          // cp.rs:47-60 / 70-78
+        for (int k = 1; k <= lenmax; k++) {                                       // cp.rs:47-60 / 70-78
+            const bool act = k <= len;
             const int64_t t = from + k;
             const bool st = st1;
             double e[NSL];
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
             double best[NSL]; int idx[NSL];
             const double *sdo = sdw + ((k - 1) & 1) * Kp;
             if (KQ > 0 && !st) chain_scan_reg<(KQ > 0 ? KQ : 2)>(sdo, reinterpret_cast<const double (&)[4 * (KQ > 0 ? KQ : 2)]>(acol), best[0], idx[0]);
-            else chain_scan<NSL>(sdo, sA, Kp, K, lane, st, pi_i, best, idx);      // argmax on delta + tr
+            else chain_scan<NSL>(sdo, sA, Kp, K, sub, st, pi_i, best, idx);       // argmax on delta + tr
             double v[NSL];
 #pragma unroll
             for (int s = 0; s < NSL; s++) {
@@ -157,19 +167,17 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
             }
 #pragma unroll
             for (int s = 0; s < NSL; s++) {
-                const int i = lane + 32 * s;
-                if (i < K) {
+                const int i = sub + 32 * s;
+                if (act && i < K) {
                     p.delta[(size_t)t * K + i] = v[s];
                     p.psi[(size_t)t * K + i] = (psi_t)idx[s];
+                    sdw[(k & 1) * Kp + i] = v[s];
                 }
-                d[s] = (i < K) ? v[s] : neg_inf();
-                if (i < K) sdw[(k & 1) * Kp + i] = v[s];
             }
             __syncwarp();
         }
     }
 }
-
 
 // ---- sweeps for K > 64: one warp per segment, every lane loops over its states i = lane, lane+32, ... ----
 // Same phases and arithmetic as cp_sweep_chain_kernel; logA / logB^T are read from global memory (L2), the
@@ -253,26 +261,60 @@ __global__ void cp_fixup_kernel(const CpParams p, const int64_t *pos_list, int n
     }
 }
 
+// ---- block statistics for the block-structured exact sum (further down) -------------------------------------
+// Every SUM_BLK consecutive terms form a block; a block's plain f64 sum (any order -- it only PREDICTS the
+// binade of the running sum) and its special-value flags (1 = positive or NaN term, 2 = -inf term).
+constexpr int SUM_BLK = 128;
+
+__device__ __forceinline__ void sum_block_stats(double x, int block, double *bsum, int *bflag)
+{
+    __shared__ double ws[SUM_BLK / 32]; __shared__ int wf[SUM_BLK / 32];
+    int flag = 0;
+    if (!(x <= 0.0)) flag = 1; else if (x == neg_inf()) flag = 2;
+    double v = x;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    flag = __reduce_or_sync(0xffffffffu, flag);
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = v; wf[threadIdx.x >> 5] = flag; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0; int f = 0;
+#pragma unroll
+        for (int w = 0; w < SUM_BLK / 32; w++) { t += ws[w]; f |= wf[w]; }
+        bsum[block] = t; bflag[block] = f;
+    }
+}
+
 // Phase D: one bound term per clamped position of components 0..comp, in the reference's order
 // (cid ascending, position ascending; cp.rs:104-116).  term_pos[k] / term_comp[k] give position and component.
-__global__ void cp_terms_kernel(const CpParams p, const int64_t *term_pos, const int32_t *term_comp, int nterms,
-                                double *terms)
+// Launched with SUM_BLK threads per block; also leaves the block statistics of the exact sum.
+__global__ void __launch_bounds__(SUM_BLK) cp_terms_kernel(const CpParams p, const int64_t *term_pos, const int32_t *term_comp,
+                                                         int nterms, double *terms, double *bsum, int *bflag)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nterms) return;
-    const int64_t t = term_pos[k];
-    const int st = p.choice[term_comp[k]];
-    const int K = p.K, Kp = p.Kp;
-    const double b = p.BT[(size_t)p.obs[t] * Kp + st];
-    double term;
-    if (t == 0) {
-        term = p.Pi[st] + b;                                   // sequence[0].arc_p(hmm, 0, state), el.t == 0
-    } else {
-        const int sf = p.psi[(size_t)t * K + st];
-        const double arc = (p.start[t] ? p.Pi[st] : p.A[(size_t)sf * Kp + st]) + b;
-        term = p.delta[(size_t)(t - 1) * K + sf] + arc;
+    const int k = blockIdx.x * SUM_BLK + threadIdx.x;
+    double term = 0.0;
+    if (k < nterms) {
+        const int64_t t = term_pos[k];
+        const int st = p.choice[term_comp[k]];
+        const int K = p.K, Kp = p.Kp;
+        const double b = p.BT[(size_t)p.obs[t] * Kp + st];
+        if (t == 0) {
+            term = p.Pi[st] + b;                               // sequence[0].arc_p(hmm, 0, state), el.t == 0
+        } else {
+            const int sf = p.psi[(size_t)t * K + st];
+            const double arc = (p.start[t] ? p.Pi[st] : p.A[(size_t)sf * Kp + st]) + b;
+            term = p.delta[(size_t)(t - 1) * K + sf] + arc;
+        }
+        terms[k] = term;
     }
-    terms[k] = term;
+    sum_block_stats(term, blockIdx.x, bsum, bflag);
+}
+
+// block statistics of an existing term list (debug hook / lists not produced by cp_terms_kernel)
+__global__ void __launch_bounds__(SUM_BLK) cp_sum_stats_kernel(const double *terms, int nterms, double *bsum, int *bflag)
+{
+    const int k = blockIdx.x * SUM_BLK + threadIdx.x;
+    sum_block_stats(k < nterms ? terms[k] : 0.0, blockIdx.x, bsum, bflag);
 }
 
 // ub = ((0.0 + term_0) + term_1) + ...  exactly in order (cp.rs:103,109,114).  The order is part of the result,
@@ -488,6 +530,162 @@ __global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *
         }
     }
     if (tid == 0) *ub_out = s_sh;
+}
+
+// ---- exact-order sum, block-structured (many CTAs) ------------------------------------------------------
+// The same binade argument as above, arranged so that almost all work is parallel over CTAs:
+//  (1) cp_terms_kernel / cp_sum_stats_kernel leave a plain sum per block of SUM_BLK terms;
+//  (2) cp_sum_blockfn_kernel, one CTA per block: an approximate prefix (sum of the earlier block sums) predicts
+//      the binade e of the running sum while it passes through the block; if the prediction is safe (prefix and
+//      prefix + block sum in the same binade with a 2^-30 relative margin) the block's terms are composed into
+//      one function F_b : Q -> Q + (Q even ? a0 : a1) valid for that binade, else the block is marked open;
+//  (3) cp_sum_chain_kernel, one CTA: warps compose runs of 32 same-binade blocks into group functions, then
+//      one warp walks the groups in order.  A function is APPLIED only if the actual running sum is in the
+//      binade it was built for and the result stays inside it (Q' < 2^53; the sum is monotone because every
+//      term is <= 0), so a wrong prediction costs time, never exactness; open blocks and failed applications
+//      are summed term by term in floating point (SUM_BLK dependent adds).
+// Special values as in cp_sum_exact_kernel: a positive/NaN term => the plain loop over everything, -inf => -inf.
+constexpr int SUM_OPEN = -100000;                     // "no function for this block / group"
+constexpr int SUM_MAX_BLOCKS = 8192;                  // above this (1M terms) the single-CTA kernel is used
+
+__global__ void __launch_bounds__(SUM_BLK) cp_sum_blockfn_kernel(const double *terms, int nterms, const double *bsum,
+                                                               int *bexp, QFn *bfn)
+{
+    __shared__ double ws[SUM_BLK / 32]; __shared__ int e_sh; __shared__ QFn wagg[SUM_BLK / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double acc = 0.0;
+    for (int i = tid; i < b; i += SUM_BLK) acc += bsum[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) ws[w] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double P = 0.0;
+#pragma unroll
+        for (int k = 0; k < SUM_BLK / 32; k++) P += ws[k];
+        const double lo = fabs(P) * (1.0 - 9.313225746154785e-10), hi = fabs(P + bsum[b]) * (1.0 + 9.313225746154785e-10);
+        const int elo = (int)(((unsigned long long)__double_as_longlong(lo) >> 52) & 0x7ff);
+        const int ehi = (int)(((unsigned long long)__double_as_longlong(hi) >> 52) & 0x7ff);
+        e_sh = (lo > 0.0 && elo == ehi && elo != 0 && elo != 0x7ff) ? elo - 1023 : SUM_OPEN;
+    }
+    __syncthreads();
+    const int e = e_sh;
+    if (e == SUM_OPEN) { if (tid == 0) bexp[b] = SUM_OPEN; return; }
+    const int k = b * SUM_BLK + tid;
+    const double x = k < nterms ? terms[k] : 0.0;
+    QFn f; f.a0 = f.a1 = 0;
+    if (x <= 0.0 && x != neg_inf()) f = qfn_elem(x, e);        // special values: the chain kernel never applies F then
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        QFn o;
+        o.a0 = __shfl_up_sync(0xffffffffu, f.a0, d);
+        o.a1 = __shfl_up_sync(0xffffffffu, f.a1, d);
+        if (lane >= d) f = qfn_compose(o, f);
+    }
+    if (lane == 31) wagg[w] = f;
+    __syncthreads();
+    if (tid == 0) {
+        QFn t = wagg[0];
+#pragma unroll
+        for (int q = 1; q < SUM_BLK / 32; q++) t = qfn_compose(t, wagg[q]);
+        bfn[b] = t; bexp[b] = e;
+    }
+}
+
+// s (running sum, < 0, normal) in binade e and F built for e: apply if the result stays in the binade
+__device__ __forceinline__ bool qfn_try(double &s, int e, const QFn f)
+{
+    const unsigned long long sb = (unsigned long long)__double_as_longlong(s);
+    if ((sb >> 52) != (unsigned long long)(0x800 | (e + 1023))) return false;       // sign bit set + exponent field
+    const unsigned long long Q0 = (sb & ((1ULL << 52) - 1)) | (1ULL << 52);
+    const unsigned long long Q1 = Q0 + ((Q0 & 1ULL) == 0 ? f.a0 : f.a1);
+    if (Q1 >= (1ULL << 53)) return false;
+    s = __longlong_as_double((long long)((1ULL << 63) | ((unsigned long long)(e + 1023) << 52) | (Q1 & ((1ULL << 52) - 1))));
+    return true;
+}
+
+// workspace of the block-structured sum, carved out of one device buffer
+struct SumWs {
+    double *bsum = nullptr; QFn *bfn = nullptr; int *bflag = nullptr, *bexp = nullptr;
+    template <class Buf> int bind(Buf &b, size_t nterms)
+    {
+        const size_t nblk = (nterms + SUM_BLK - 1) / SUM_BLK + 1;
+        const int rc = b.ensure(nblk * (sizeof(double) + sizeof(QFn) + 2 * sizeof(int)) + 64);
+        if (rc) return rc;
+        bfn = (QFn *)b.p; bsum = (double *)(bfn + nblk); bflag = (int *)(bsum + nblk); bexp = bflag + nblk;
+        return 0;
+    }
+};
+
+constexpr int SUMC_THREADS = 1024;
+__global__ void __launch_bounds__(SUMC_THREADS) cp_sum_chain_kernel(const double *terms, int nterms, int nblk,
+                                                                   const int *bflag, const int *bexp, const QFn *bfn,
+                                                                   double *ub_out, unsigned int *reset_counter)
+{
+    if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
+    constexpr int MAXG = SUM_MAX_BLOCKS / 32;
+    __shared__ QFn gfn[MAXG]; __shared__ int gexp[MAXG]; __shared__ int mode_sh;
+    __shared__ double buf[SUM_BLK];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) mode_sh = 0;
+    __syncthreads();
+    int flag = 0;
+    for (int b = tid; b < nblk; b += SUMC_THREADS) flag |= bflag[b];
+    if (flag) atomicOr(&mode_sh, flag);
+    const int ngrp = (nblk + 31) / 32;
+    for (int g = w; g < ngrp; g += SUMC_THREADS / 32) {       // group functions
+        const int b = g * 32 + lane;
+        int e = b < nblk ? bexp[b] : SUM_OPEN;
+        QFn f; f.a0 = f.a1 = 0;
+        if (e != SUM_OPEN) f = bfn[b];
+        const int e0 = __shfl_sync(0xffffffffu, e, 0);
+        if (b >= nblk) e = e0;                                 // past the end: identity in the group's binade
+        const bool clean = __all_sync(0xffffffffu, e == e0) && e0 != SUM_OPEN;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            QFn o;
+            o.a0 = __shfl_up_sync(0xffffffffu, f.a0, d);
+            o.a1 = __shfl_up_sync(0xffffffffu, f.a1, d);
+            if (lane >= d) f = qfn_compose(o, f);
+        }
+        if (lane == 31) { gfn[g] = f; gexp[g] = clean ? e0 : SUM_OPEN; }
+    }
+    __syncthreads();
+    const int mode = mode_sh;
+    if (w != 0) return;
+    if (mode & 1) {                                            // reference loop, one thread
+        if (lane == 0) { double ub = 0.0; for (int k = 0; k < nterms; k++) ub += terms[k]; *ub_out = ub; }
+        return;
+    }
+    if (mode & 2) { if (lane == 0) *ub_out = neg_inf(); return; }
+    double s = 0.0;                                            // identical in every lane of the warp
+    for (int g = 0; g < ngrp; g++) {
+        if (gexp[g] != SUM_OPEN && qfn_try(s, gexp[g], gfn[g])) continue;
+        // mixed group: its 32 block functions arrive with one coalesced load, then go round by shuffle
+        const int bl = g * 32 + lane;
+        const int el = bl < nblk ? bexp[bl] : SUM_OPEN;
+        QFn fl; fl.a0 = fl.a1 = 0;
+        if (el != SUM_OPEN) fl = bfn[bl];
+        const int cnt = min(32, nblk - g * 32);
+        for (int i = 0; i < cnt; i++) {
+            const int e = __shfl_sync(0xffffffffu, el, i);
+            QFn f;
+            f.a0 = __shfl_sync(0xffffffffu, fl.a0, i);
+            f.a1 = __shfl_sync(0xffffffffu, fl.a1, i);
+            if (e != SUM_OPEN && qfn_try(s, e, f)) continue;
+            const int base = (g * 32 + i) * SUM_BLK, n = min(SUM_BLK, nterms - base);
+#pragma unroll
+            for (int q = 0; q < SUM_BLK / 32; q++) {
+                const int k = q * 32 + lane;
+                buf[k] = k < n ? terms[base + k] : 0.0;        // s + (+0.0) == s for every s this loop can hold
+            }
+            __syncwarp();
+#pragma unroll 16
+            for (int k = 0; k < SUM_BLK; k++) s = s + buf[k];
+            __syncwarp();
+        }
+    }
+    if (lane == 0) *ub_out = s;
 }
 
 // obj = max(delta[N-1][.]) for the no-constraint case (cp.rs:139-141) and cur = argmax (cp.rs:86)
