@@ -58,6 +58,12 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "cv_cp_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
                               C.c_void_p, _dp, _u64p, _u64p]),
+    "cv_cp_dist_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cv_cp_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cv_cp_dist_destroy": (None, [C.c_void_p]),
+    "cv_cp_solve_dist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
+                                   C.c_void_p, _dp, _u64p, _u64p]),
+    "cv_cp_plan_cuts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "cv_cp_last_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cv_cp_last_ub": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
     "cv_debug_ordered_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _dp]),

@@ -41,6 +41,56 @@ def cp_solve_arrays(hmm: HMM, obs, is_seq_start, comp, ncomp, max_nodes: int = 0
     return out
 
 
+IPC_HANDLE_BYTES = 64
+
+
+def plan_cuts(comp, nranks: int):
+    """Row cuts of the sharded solve (cv_cp_plan_cuts): int64[nranks + 1]; {0, N, N, ..} = cannot be cut."""
+    comp = np.ascontiguousarray(comp, dtype=np.int32)
+    cuts = np.zeros(nranks + 1, dtype=np.int64)
+    _lib.check(_lib.lib().cv_cp_plan_cuts(comp.ctypes.data, comp.shape[0], int(nranks), cuts.ctypes.data))
+    return cuts
+
+
+class CpDistGroup:
+    """This rank's exchange buffer for sharded constrained solves (cv_cp_dist_*).  The IPC handles travel over
+    torch.distributed (any backend); the per-node exchange itself is NVLink peer stores inside the kernels."""
+
+    def __init__(self, hmm: HMM, cap_N: int, cap_terms: int, device: int = -1, group=None):
+        import torch.distributed as dist
+
+        self.hmm, self.cap_N, self.cap_terms = hmm, int(cap_N), int(cap_terms)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L = _lib.lib()
+        self._h = C.c_void_p()
+        mine = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _lib.check(L.cv_cp_dist_create(hmm.device_handle(device), self.rank, self.world, self.cap_N, self.cap_terms,
+                                       mine, C.byref(self._h)))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine.raw, group=group)
+        _lib.check(L.cv_cp_dist_connect(self._h, b"".join(handles)))
+        dist.barrier(group=group)
+
+    def solve(self, obs, is_seq_start, comp, ncomp, max_nodes: int = 0):
+        """Collective cv_cp_solve_dist; every rank gets the full result."""
+        obs = np.ascontiguousarray(obs, dtype=np.uint32)
+        start = np.ascontiguousarray(is_seq_start, dtype=np.uint8)
+        comp = np.ascontiguousarray(comp, dtype=np.int32)
+        N = obs.shape[0]
+        sol = np.zeros(max(N, 1), dtype=np.uint64)
+        obj = C.c_double(0.0)
+        explored, steps = C.c_uint64(0), C.c_uint64(0)
+        rc = _lib.lib().cv_cp_solve_dist(self._h, obs.ctypes.data, start.ctypes.data, comp.ctypes.data, N, int(ncomp),
+                                         int(max_nodes), sol.ctypes.data, C.byref(obj), C.byref(explored), C.byref(steps))
+        _lib.check(rc)
+        return dict(sol=sol[:N], obj=obj.value, explored=explored.value, steps=steps.value)
+
+    def close(self):
+        if self._h:
+            _lib.lib().cv_cp_dist_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 class Solver:
     """trait Solver (viterbi_solver.rs:11-16)."""
 

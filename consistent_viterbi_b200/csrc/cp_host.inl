@@ -10,6 +10,19 @@ static int g_sum_parallel_min = 4096;
 static int g_sum_force = -1;   // CV_CP_SUM=0|1|2 forces the plain loop / block-structured / single-CTA exact sum
 static double g_cp_prof[6];   // CV_CP_PROF=1: host-timed phases of a node (sweep, fixup, terms, sum, readback)
 
+// The exchange buffer of one rank (cp_dist.cuh): [flags][maps x2][terms x2][solution], mapped into every rank of
+// the group through CUDA IPC.  Created once per (model, group, capacity) and reused across solves.
+struct cv_cp_dist {
+    cv_hmm *h = nullptr;
+    int rank = 0, R = 1, mapw = 0;
+    int64_t cap_N = 0, cap_terms = 0;
+    size_t maps_off = 0, terms_off = 0, sol_off = 0, bytes = 0;
+    void *mine = nullptr;
+    PeerTab tab{};
+    bool connected = false;
+    unsigned int epoch = 0;                      // exchanges so far; identical on every rank
+};
+
 namespace {
 
 struct CpRun {
@@ -27,6 +40,16 @@ struct CpRun {
     int64_t *d_seg_from = nullptr; int32_t *d_seg_len = nullptr;
     double *d_terms = nullptr, *d_ub = nullptr; int *d_end = nullptr; unsigned int *d_counter = nullptr;
     SumWs sum_ws;                                // block statistics / functions of the exact-order sum
+    // sharding (cp_dist.cuh): this rank's cut pair; R == 1 => lo = 0, hi = N and nothing is exchanged
+    cv_cp_dist *dx = nullptr;
+    int rank = 0, R = 1;
+    int64_t lo = 0, hi = 0;
+    std::vector<int64_t> fix_off;                // fix-up positions of depth c: d_fix_pos[fix_off[c] .. fix_off[c+1])
+    int64_t *d_fix_pos = nullptr;
+    std::vector<int64_t> lterm_off;              // local bound terms of components 0..c: first lterm_off[c+1] entries
+    int64_t *d_lterm_pos = nullptr; int32_t *d_lterm_comp = nullptr, *d_lterm_gidx = nullptr;
+    unsigned int *d_done = nullptr; int *d_err = nullptr;
+    uint64_t n_term_x = 0, n_map_x = 0;          // exchanges of each kind so far in this solve (buffer parity)
     psi_t *d_F = nullptr; int *d_entry = nullptr; uint64_t *d_sol = nullptr;
     double *h_ub = nullptr;                      // pinned
     int err = CV_OK;
@@ -103,14 +126,29 @@ int cp_backtrack(CpRun &r, double obj)
 {
     if (!(obj > r.best_obj)) return fail(CV_ERR_ASSERT, "assert!(obj > self.best_obj) would fire (cp.rs:87)");
     r.best_obj = obj;
-    const int nchunks = (int)((r.p.N + CP_BT_CHUNK - 1) / CP_BT_CHUNK);
-    double *d_obj = r.d_ub + 1;
-    cp_last_row_kernel<<<1, 32, 0, r.st>>>(r.p, d_obj, r.d_end);
+    const bool last = r.rank == r.R - 1;
+    const int64_t rtop = last ? r.p.N - 1 : r.hi;                       // rows rtop .. lo+1 are walked by this rank
+    const int nchunks = (int)std::max<int64_t>((rtop - r.lo + CP_BT_CHUNK - 1) / CP_BT_CHUNK, 1);
+    double *d_obj = r.d_ub + 2;
+    if (last) { cp_last_row_kernel<<<1, 32, 0, r.st>>>(r.p, d_obj, r.d_end); g_launches++; }
     const int64_t nmap = (int64_t)nchunks * r.p.K;
-    cp_bt_maps_kernel<<<(unsigned)((nmap + 127) / 128), 128, 0, r.st>>>(r.p, nchunks, r.d_F);
-    cp_bt_chain_kernel<<<1, 32, 0, r.st>>>(r.p, nchunks, r.d_F, r.d_end, r.d_entry);
-    cp_bt_fill_kernel<<<(nchunks + 127) / 128, 128, 0, r.st>>>(r.p, nchunks, r.d_entry, r.d_sol);
-    g_launches += 4;
+    cp_btr_maps_kernel<<<(unsigned)((nmap + 127) / 128), 128, 0, r.st>>>(r.p, r.lo, rtop, nchunks, r.d_F);
+    const psi_t *maps = nullptr;
+    int mapw = 0;
+    if (r.R > 1) {
+        cv_cp_dist *dx = r.dx;
+        mapw = dx->mapw;
+        const size_t maps_off = dx->maps_off + (size_t)(r.n_map_x & 1) * CP_MAX_RANKS * mapw * sizeof(psi_t);
+        r.n_map_x++;
+        const unsigned int epoch = ++dx->epoch;
+        cp_btr_total_kernel<<<1, 32 * ((r.p.K + 1 + 31) / 32), 0, r.st>>>(r.p, nchunks, r.d_F, r.d_end, dx->tab, maps_off, mapw, epoch);
+        cp_peer_wait_kernel<<<1, 32, 0, r.st>>>((const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err);
+        g_launches += 2;
+        maps = (const psi_t *)(dx->tab.base[r.rank] + maps_off);
+    }
+    cp_btr_chain_kernel<<<1, 32, 0, r.st>>>(r.p, nchunks, r.d_F, r.d_end, maps, mapw, r.rank, r.R, r.d_entry);
+    cp_btr_fill_kernel<<<(nchunks + 127) / 128, 128, 0, r.st>>>(r.p, r.lo, rtop, r.hi, nchunks, r.d_entry, r.d_sol);
+    g_launches += 3;
     CUDA_TRY(cudaGetLastError());
     return CV_OK;
 }
@@ -119,8 +157,10 @@ int cp_backtrack(CpRun &r, double obj)
 int cp_solve_r(CpRun &r, int32_t comp)
 {
     const int K = r.p.K;
-    const int64_t npos = r.cons_off[comp + 1] - r.cons_off[comp];
+    const int64_t nseg = r.seg_off[comp + 1] - r.seg_off[comp];        // this rank's sweeps of the component
+    const int64_t nfix = r.fix_off[comp + 1] - r.fix_off[comp];
     const int nterms = (int)r.cons_off[comp + 1];
+    const int nlocal = (int)r.lterm_off[comp + 1];
     for (int state = 0; state < K; state++) {
         if (r.max_nodes && r.explored >= r.max_nodes) break;            // builder-added, deterministic budget
         r.explored++;                                                    // cp.rs:97
@@ -133,27 +173,42 @@ int cp_solve_r(CpRun &r, int32_t comp)
             t0 = t1;
         };
         auto t0 = std::chrono::steady_clock::now();
-        int rc = cp_sweep(r, r.seg_off[comp], npos, state, 0);          // cp.rs:99-102, phases A + B
+        int rc = cp_sweep(r, r.seg_off[comp], nseg, state, 0);          // cp.rs:99-102, phases A + B
         if (rc) return rc;
         tick(0, t0);
         r.steps += r.seg_steps[comp];
-        cp_fixup_kernel<<<(unsigned)((std::max<int64_t>(npos, 1) + 127) / 128), 128, 0, r.st>>>(
-            r.p, r.d_cons_pos + r.cons_off[comp], (int)npos, comp, state);     // also records cstr_choices[comp] (cp.rs:98)
+        cp_fixup_kernel<<<(unsigned)((std::max<int64_t>(nfix, 1) + 127) / 128), 128, 0, r.st>>>(
+            r.p, r.d_fix_pos + r.fix_off[comp], (int)nfix, comp, state, r.lo, r.hi);   // also records cstr_choices[comp] (cp.rs:98)
         g_launches++;
         tick(1, t0);
-        if (nterms > 0) {
+        bool have_stats = nterms > 0;
+        if (r.R > 1) {
+            // the rank's terms go straight into every rank's term list (peer stores + flag), then wait for all ranks
+            cv_cp_dist *dx = r.dx;
+            const size_t toff = dx->terms_off + (size_t)(r.n_term_x & 1) * dx->cap_terms * sizeof(double);
+            r.n_term_x++;
+            const unsigned int epoch = ++dx->epoch;
+            cp_terms_peer_kernel<<<std::max((nlocal + SUM_BLK - 1) / SUM_BLK, 1), SUM_BLK, 0, r.st>>>(
+                r.p, r.d_lterm_pos, r.d_lterm_comp, r.d_lterm_gidx, nlocal, dx->tab, toff, epoch, r.d_done);
+            cp_peer_wait_kernel<<<1, 32, 0, r.st>>>((const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err);
+            g_launches += 2;
+            r.d_terms = (double *)(dx->tab.base[r.rank] + toff);
+            have_stats = false;
+        } else if (nterms > 0) {
             cp_terms_kernel<<<(nterms + SUM_BLK - 1) / SUM_BLK, SUM_BLK, 0, r.st>>>(r.p, r.d_cons_pos, r.d_term_comp, nterms,
                                                                                      r.d_terms, r.sum_ws.bsum, r.sum_ws.bflag);
             g_launches++;
         }
         tick(2, t0);
         // cp.rs:103-116: the exact-order sum (parallel binade scan for long lists, plain loop for short ones)
-        if ((rc = cp_launch_sum(r.d_terms, nterms, r.d_ub, r.d_counter, r.sum_ws, nterms > 0, g_sum_force, r.st))) return rc;
+        if ((rc = cp_launch_sum(r.d_terms, nterms, r.d_ub, r.d_counter, r.sum_ws, have_stats, g_sum_force, r.st))) return rc;
         tick(3, t0);
-        CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, sizeof(double), cudaMemcpyDeviceToHost, r.st));
+        // (the word after ub is the peer-timeout flag of the wait kernels, always 0.0 on a single rank)
+        CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, (r.R > 1 ? 2 : 1) * sizeof(double), cudaMemcpyDeviceToHost, r.st));
         CUDA_TRY(cudaStreamSynchronize(r.st));
         tick(4, t0);
         const double ub = *r.h_ub;
+        if (r.R > 1 && r.h_ub[1] != 0.0) return fail(CV_ERR_CUDA, "a peer rank did not publish its bound terms within the time limit");
         if (r.h->cp_ub.size() < (1u << 20)) r.h->cp_ub.push_back(ub);
         if (std::isnan(ub)) return fail(CV_ERR_NAN, "NaN upper bound");
         if (ub > r.best_obj) {                                           // cp.rs:117
@@ -181,9 +236,101 @@ int upload(DevBuf &b, const std::vector<T> &v, T **out, cudaStream_t st)
 
 }  // namespace
 
-extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq_start, const int32_t *comp, int64_t N,
-                           int32_t ncomp, uint64_t max_nodes, uint64_t *sol_out, double *obj_out,
-                           uint64_t *explored_out, uint64_t *steps_out)
+extern "C" int cv_cp_dist_create(cv_hmm *h, int rank, int nranks, int64_t cap_N, int64_t cap_terms, void *handle_out,
+                                 cv_cp_dist **out)
+{
+    if (!h || !out || !handle_out) return fail(CV_ERR_ARG, "NULL argument");
+    if (nranks < 1 || nranks > CP_MAX_RANKS || rank < 0 || rank >= nranks)
+        return fail(CV_ERR_ARG, "rank %d / nranks %d outside 1..%d", rank, nranks, CP_MAX_RANKS);
+    if (cap_N <= 0 || cap_terms < 0) return fail(CV_ERR_ARG, "bad capacity");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CV_IPC_HANDLE_BYTES, "cv_b200.h: CV_IPC_HANDLE_BYTES");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cv_cp_dist *d = new cv_cp_dist;
+    d->h = h; d->rank = rank; d->R = nranks; d->cap_N = cap_N; d->cap_terms = cap_terms;
+    d->mapw = (h->K + 1 + 7) / 8 * 8;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    d->maps_off = CP_FLAGS_BYTES;
+    d->terms_off = up(d->maps_off + (size_t)2 * CP_MAX_RANKS * d->mapw * sizeof(psi_t));
+    d->sol_off = up(d->terms_off + (size_t)2 * (cap_terms + 8) * sizeof(double));
+    d->bytes = up(d->sol_off + (size_t)cap_N * sizeof(uint64_t));
+    cudaError_t e = cudaMalloc(&d->mine, d->bytes);
+    if (e != cudaSuccess) { delete d; cudaGetLastError(); return fail(CV_ERR_OOM, "cudaMalloc(%zu) failed: %s", d->bytes, cudaGetErrorString(e)); }
+    e = cudaMemset(d->mine, 0, d->bytes);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle_out, d->mine);
+    if (e != cudaSuccess) { cudaFree(d->mine); delete d; cudaGetLastError(); return fail(CV_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    d->tab.R = nranks; d->tab.rank = rank;
+    d->tab.base[rank] = (unsigned char *)d->mine;
+    *out = d;
+    return CV_OK;
+}
+
+extern "C" int cv_cp_dist_connect(cv_cp_dist *d, const void *all_handles)
+{
+    if (!d || !all_handles) return fail(CV_ERR_ARG, "NULL argument");
+    if (d->connected) return CV_OK;
+    CUDA_TRY(cudaSetDevice(d->h->device));
+    const cudaIpcMemHandle_t *hs = (const cudaIpcMemHandle_t *)all_handles;
+    for (int q = 0; q < d->R; q++) {
+        if (q == d->rank) continue;
+        void *ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, hs[q], cudaIpcMemLazyEnablePeerAccess));
+        d->tab.base[q] = (unsigned char *)ptr;
+    }
+    d->connected = true;
+    return CV_OK;
+}
+
+extern "C" void cv_cp_dist_destroy(cv_cp_dist *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->h->device);
+    cudaDeviceSynchronize();
+    for (int q = 0; q < d->R; q++)
+        if (q != d->rank && d->tab.base[q]) cudaIpcCloseMemHandle(d->tab.base[q]);
+    if (d->mine) cudaFree(d->mine);
+    delete d;
+}
+
+// The row cuts of the sharded solve: cuts[0] = 0 < cuts[1] < .. < cuts[R] = N, inner cuts are positions of
+// component 0 closest to an even split.  Returns false when component 0 has too few positions (then every
+// rank solves the whole problem itself: "replicas").  Pure host logic, also exported for the CPU tests.
+static bool cp_plan_cuts(const int32_t *comp, int64_t N, int R, std::vector<int64_t> &cuts)
+{
+    cuts.assign((size_t)R + 1, 0);
+    cuts[R] = N;
+    if (R == 1) return true;
+    std::vector<int64_t> c0;
+    for (int64_t t = 1; t < N; t++) if (comp[t] == 0) c0.push_back(t);
+    for (int r = 1; r < R; r++) {
+        const int64_t want = N / R * r + (N % R) * r / R;
+        auto it = std::lower_bound(c0.begin(), c0.end(), want);
+        int64_t best = -1;
+        if (it != c0.end()) best = *it;
+        if (it != c0.begin() && (best < 0 || want - *(it - 1) <= best - want)) best = *(it - 1);
+        if (best <= cuts[r - 1]) {                                     // keep the cuts strictly increasing
+            auto nx = std::upper_bound(c0.begin(), c0.end(), cuts[r - 1]);
+            if (nx == c0.end()) return false;
+            best = *nx;
+        }
+        cuts[r] = best;
+    }
+    for (int r = 1; r <= R; r++) if (cuts[r] <= cuts[r - 1]) return false;
+    return true;
+}
+
+extern "C" int cv_cp_plan_cuts(const int32_t *comp, int64_t N, int nranks, int64_t *cuts_out)
+{
+    if (!comp || !cuts_out || N <= 0 || nranks < 1) return fail(CV_ERR_ARG, "bad argument");
+    std::vector<int64_t> cuts;
+    const bool ok = cp_plan_cuts(comp, N, nranks, cuts);
+    if (!ok) { for (int r = 0; r <= nranks; r++) cuts_out[r] = r == 0 ? 0 : N; return CV_OK; }   // replicas: rank 0 owns [0, N)
+    for (int r = 0; r <= nranks; r++) cuts_out[r] = cuts[r];
+    return CV_OK;
+}
+
+static int cp_solve_impl(cv_hmm *h, cv_cp_dist *dx, const uint32_t *obs, const uint8_t *is_seq_start, const int32_t *comp,
+                         int64_t N, int32_t ncomp, uint64_t max_nodes, uint64_t *sol_out, double *obj_out,
+                         uint64_t *explored_out, uint64_t *steps_out)
 {
     if (!h) return fail(CV_ERR_ARG, "NULL model");
     if (N <= 0) return fail(CV_ERR_EMPTY, "empty super-sequence (reference: array.row(len-1) panics)");
@@ -204,6 +351,21 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     CpRun r;
     r.h = h; r.st = st; r.ncomp = ncomp; r.max_nodes = max_nodes;
 
+    // ---- sharding: row cuts at positions of component 0 (cp_dist.cuh); too few of them => replicas ----
+    std::vector<int64_t> cuts;
+    r.lo = 0; r.hi = N;
+    if (dx && dx->R > 1) {
+        if (dx->h != h) return fail(CV_ERR_ARG, "exchange buffer belongs to another model handle");
+        if (!dx->connected) return fail(CV_ERR_ARG, "cv_cp_dist_connect has not run");
+        if (N > dx->cap_N) return fail(CV_ERR_ARG, "N = %lld exceeds the exchange buffer's capacity %lld", (long long)N, (long long)dx->cap_N);
+        if (ncomp > 0 && cp_plan_cuts(comp, N, dx->R, cuts)) {
+            r.dx = dx; r.R = dx->R; r.rank = dx->rank;
+            r.lo = cuts[r.rank]; r.hi = cuts[r.rank + 1];
+        }
+    }
+    const bool sharded = r.R > 1;
+    const int64_t lo = r.lo, hi = r.hi;
+
     // ---- CPSolver::new (cp.rs:20-30): positions of every component, ascending ----
     std::vector<std::vector<int64_t>> cons((size_t)ncomp);
     for (int64_t t = 0; t < N; t++) if (comp[t] >= 0) cons[comp[t]].push_back(t);
@@ -215,10 +377,29 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     }
     r.cons_off[ncomp] = (int64_t)cons_pos.size();
     if (cons_pos.size() > 0x7fffffffULL) return fail(CV_ERR_UNSUPPORTED, "too many clamped positions");
+    if (sharded && (int64_t)cons_pos.size() > dx->cap_terms)
+        return fail(CV_ERR_ARG, "%zu clamped positions exceed the exchange buffer's capacity %lld", cons_pos.size(), (long long)dx->cap_terms);
+
+    // fix-up positions of this rank per depth ([lo, hi]: C1 for pos < hi, C2 for pos > lo) and its bound terms
+    // (t in (lo, hi], t = 0 on the first rank) with their index in the reference's summation order
+    std::vector<int64_t> fix_pos, lterm_pos; std::vector<int32_t> lterm_comp, lterm_gidx;
+    r.fix_off.assign((size_t)ncomp + 1, 0); r.lterm_off.assign((size_t)ncomp + 1, 0);
+    for (int32_t c = 0; c < ncomp; c++) {
+        r.fix_off[c] = (int64_t)fix_pos.size(); r.lterm_off[c] = (int64_t)lterm_pos.size();
+        for (size_t i = 0; i < cons[c].size(); i++) {
+            const int64_t t = cons[c][i];
+            if (t >= lo && t <= hi) fix_pos.push_back(t);
+            if ((t > lo && t <= hi) || (t == 0 && lo == 0)) {
+                lterm_pos.push_back(t); lterm_comp.push_back(c); lterm_gidx.push_back((int32_t)(r.cons_off[c] + (int64_t)i));
+            }
+        }
+    }
+    r.fix_off[ncomp] = (int64_t)fix_pos.size(); r.lterm_off[ncomp] = (int64_t)lterm_pos.size();
 
     // ---- sweep segments ----
     // depth c (components 0..c assigned): one sweep per position of c, running to the next position whose
-    // component is <= c (cp.rs:48); segment 0 of the list is the init_viterbi prefix (cp.rs:63-83).
+    // component is <= c (cp.rs:48); segment 0 of the list is the init_viterbi prefix (cp.rs:63-83).  A rank
+    // keeps the sweeps that start in its rows; seg_steps counts every rank's rows (the reported work).
     std::vector<int64_t> seg_from; std::vector<int32_t> seg_len;
     int64_t prefix = 0;
     while (prefix < N && comp[prefix] < 0) prefix++;                 // rows 0 .. prefix-1 are swept by init_viterbi
@@ -235,8 +416,8 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
             for (int64_t pos : cons[c]) {
                 const int64_t len = next_fixed[pos] - pos - 1;
                 if (len > 0x7fffffffLL) return fail(CV_ERR_UNSUPPORTED, "segment too long");
-                segs.emplace_back(len, pos);
                 r.seg_steps[c] += (uint64_t)len;
+                if (pos >= lo && pos < hi) segs.emplace_back(len, pos);
             }
             std::stable_sort(segs.begin(), segs.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
             for (auto &s : segs) { seg_from.push_back(s.second); seg_len.push_back((int32_t)s.first); }
@@ -244,13 +425,14 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
         r.seg_off[ncomp] = (int64_t)seg_from.size();
     }
 
-    // ---- device state ----
+    // ---- device state: delta / psi rows [lo, hi] of this rank (indexed by global row through a shifted base) ----
     DevBuf *b = h->cpb;
     int rc;
-    if ((rc = b[0].ensure(sizeof(double) * (size_t)N * K))) return rc;
-    if ((rc = b[1].ensure(sizeof(psi_t) * (size_t)N * K))) return rc;
-    CUDA_TRY(cudaMemsetAsync(b[0].p, 0, sizeof(double) * (size_t)N * K, st));     // Array2::from_elem(.., 0.0) cp.rs:134
-    CUDA_TRY(cudaMemsetAsync(b[1].p, 0, sizeof(psi_t) * (size_t)N * K, st));      // bt = 0                    cp.rs:135
+    const int64_t nrows = std::min<int64_t>(hi + 1, N) - lo;
+    if ((rc = b[0].ensure(sizeof(double) * (size_t)nrows * K))) return rc;
+    if ((rc = b[1].ensure(sizeof(psi_t) * (size_t)nrows * K))) return rc;
+    CUDA_TRY(cudaMemsetAsync(b[0].p, 0, sizeof(double) * (size_t)nrows * K, st));     // Array2::from_elem(.., 0.0) cp.rs:134
+    CUDA_TRY(cudaMemsetAsync(b[1].p, 0, sizeof(psi_t) * (size_t)nrows * K, st));      // bt = 0                    cp.rs:135
     if ((rc = b[2].ensure(sizeof(uint32_t) * (size_t)N))) return rc;
     if ((rc = b[3].ensure((size_t)N))) return rc;
     if ((rc = b[4].ensure(sizeof(int32_t) * (size_t)N))) return rc;
@@ -262,27 +444,49 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     if ((rc = upload(b[5], choice0, &d_choice, st))) return rc;
     if ((rc = upload(b[6], seg_from, &r.d_seg_from, st))) return rc;
     if ((rc = upload(b[7], seg_len, &r.d_seg_len, st))) return rc;
-    if ((rc = upload(b[8], cons_pos, &r.d_cons_pos, st))) return rc;
-    if ((rc = upload(b[9], term_comp, &r.d_term_comp, st))) return rc;
-    if ((rc = b[10].ensure(sizeof(double) * (cons_pos.size() + 8) + 256))) return rc;
-    r.d_terms = (double *)b[10].p + 4; r.d_ub = (double *)b[10].p;                 // [0] ub, [1] obj
-    r.d_end = (int *)((double *)b[10].p + 2); r.d_counter = (unsigned int *)((double *)b[10].p + 3);
-    CUDA_TRY(cudaMemsetAsync(b[10].p, 0, 32, st));
-    const int nchunks = (int)((N + CP_BT_CHUNK - 1) / CP_BT_CHUNK);
+    if (sharded) {
+        // one upload: [fix_pos | lterm_pos] as i64, [lterm_comp | lterm_gidx] as i32
+        std::vector<int64_t> v64(fix_pos); v64.insert(v64.end(), lterm_pos.begin(), lterm_pos.end());
+        std::vector<int32_t> v32(lterm_comp); v32.insert(v32.end(), lterm_gidx.begin(), lterm_gidx.end());
+        int64_t *d64 = nullptr; int32_t *d32 = nullptr;
+        if ((rc = upload(b[8], v64, &d64, st))) return rc;
+        if ((rc = upload(b[9], v32, &d32, st))) return rc;
+        r.d_fix_pos = d64; r.d_lterm_pos = d64 + fix_pos.size();
+        r.d_lterm_comp = d32; r.d_lterm_gidx = d32 + lterm_comp.size();
+    } else {
+        if ((rc = upload(b[8], cons_pos, &r.d_cons_pos, st))) return rc;
+        if ((rc = upload(b[9], term_comp, &r.d_term_comp, st))) return rc;
+        r.d_fix_pos = r.d_cons_pos;                                                // [lo, hi] = everything
+    }
+    if ((rc = b[10].ensure(sizeof(double) * (cons_pos.size() + 16) + 256))) return rc;
+    // scalars: [0] ub  [1] peer-timeout flag  [2] obj  [3] end state  [4] segment counter | publish counter
+    double *sc = (double *)b[10].p;
+    r.d_ub = sc; r.d_err = (int *)(sc + 1); r.d_end = (int *)(sc + 3);
+    r.d_counter = (unsigned int *)(sc + 4); r.d_done = r.d_counter + 1;
+    r.d_terms = sc + 8;
+    CUDA_TRY(cudaMemsetAsync(b[10].p, 0, 64, st));
+    const int64_t walk_rows = (r.rank == r.R - 1 ? N - 1 : hi) - lo;
+    const int nchunks = (int)std::max<int64_t>((walk_rows + CP_BT_CHUNK - 1) / CP_BT_CHUNK, 1);
     if ((rc = b[11].ensure(sizeof(psi_t) * (size_t)nchunks * K + 64))) return rc;
     if ((rc = b[12].ensure(sizeof(int) * (size_t)nchunks + 64))) return rc;
-    if ((rc = b[13].ensure(sizeof(uint64_t) * (size_t)N))) return rc;
+    r.d_F = (psi_t *)b[11].p; r.d_entry = (int *)b[12].p;
+    if (sharded) {
+        r.d_sol = (uint64_t *)(dx->tab.base[r.rank] + dx->sol_off);                // own rows here, peers' rows arrive at the end
+    } else {
+        if ((rc = b[13].ensure(sizeof(uint64_t) * (size_t)N))) return rc;
+        r.d_sol = (uint64_t *)b[13].p;
+    }
+    CUDA_TRY(cudaMemsetAsync(r.d_sol, 0, sizeof(uint64_t) * (size_t)N, st));       // best_sol = 0 (cp.rs:29)
     if ((rc = r.sum_ws.bind(b[14], cons_pos.size()))) return rc;
     if (const char *e = getenv("CV_CP_SUM")) g_sum_force = atoi(e);
-    r.d_F = (psi_t *)b[11].p; r.d_entry = (int *)b[12].p; r.d_sol = (uint64_t *)b[13].p;
-    CUDA_TRY(cudaMemsetAsync(r.d_sol, 0, sizeof(uint64_t) * (size_t)N, st));       // best_sol = 0 (cp.rs:29)
     r.h_ub = (double *)h->pinned_status + 1;
+    r.h_ub[0] = r.h_ub[1] = 0.0;
 
     CpParams &p = r.p;
     const bool small = K <= SMALL_K_MAX;
     p.A = small ? h->dA : h->dAl; p.BT = small ? h->dBT : h->dBTl; p.Pi = h->dPi;
     p.obs = (const uint32_t *)b[2].p; p.start = (const uint8_t *)b[3].p; p.comp = (const int32_t *)b[4].p;
-    p.delta = (double *)b[0].p; p.psi = (psi_t *)b[1].p; p.choice = d_choice;
+    p.delta = (double *)b[0].p - (size_t)lo * K; p.psi = (psi_t *)b[1].p - (size_t)lo * K; p.choice = d_choice;
     p.N = N; p.M = h->M; p.K = K; p.Kp = small ? h->Kp : h->Kl; p.G = h->G;
     p.bt_in_smem = (small && (size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
     if (!small) {
@@ -303,33 +507,44 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
 
     const bool timing = g_timing.load() != 0;
     if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
-    // ---- init_viterbi (cp.rs:63-83) ----
-    if (prefix >= 1) {
+    // ---- init_viterbi (cp.rs:63-83): the prefix lies before the first cut, so it is the first rank's ----
+    if (prefix >= 1 && lo == 0) {
         cp_row0_kernel<<<(K + 255) / 256, 256, 0, st>>>(p);
         g_launches++;
         if (prefix > 1) {
             if ((rc = cp_sweep(r, 0, 1, 0, 1))) return rc;
-            r.steps += (uint64_t)(prefix - 1);
         }
     }
+    if (prefix > 1) r.steps += (uint64_t)(prefix - 1);
     // ---- solve (cp.rs:137-142) ----
     if (ncomp > 0) {
         rc = cp_solve_r(r, 0);
     } else {
-        double *d_obj = r.d_ub + 1;
+        double *d_obj = r.d_ub + 2;
         cp_last_row_kernel<<<1, 32, 0, st>>>(p, d_obj, r.d_end);
         g_launches++;
         CUDA_TRY(cudaMemcpyAsync(r.h_ub, d_obj, sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         rc = cp_backtrack(r, *r.h_ub);
     }
+    if (rc) return rc;
+    if (sharded) {
+        // every rank's rows of best_sol into every rank's buffer (peer stores + flag), then wait for all of them
+        const unsigned int epoch = ++dx->epoch;
+        const int grid = (int)std::min<int64_t>((hi - lo + 255) / 256, (int64_t)h->num_sms * 4);
+        cp_sol_publish_kernel<<<std::max(grid, 1), 256, 0, st>>>(r.d_sol, lo, hi, dx->tab, dx->sol_off, epoch, r.d_done);
+        cp_peer_wait_kernel<<<1, 32, 0, st>>>((const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err);
+        g_launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(r.h_ub + 1, r.d_err, sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     if (timing) {
         CUDA_TRY(cudaEventRecord(h->ev1, st));
         CUDA_TRY(cudaEventRecord(h->ev2, st));
     }
-    h->cp_N = N;
+    h->cp_N = sharded ? 0 : N;                                       // the state hooks read a whole-problem delta / psi
     CUDA_TRY(cudaMemcpyAsync(sol_out, r.d_sol, sizeof(uint64_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (sharded && r.h_ub[1] != 0.0) return fail(CV_ERR_CUDA, "a peer rank did not publish its part of the solution within the time limit");
     if (timing) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms; else cudaGetLastError();
@@ -345,6 +560,21 @@ extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq
     if (explored_out) *explored_out = r.explored;
     if (steps_out) *steps_out = r.steps;
     return rc;
+}
+
+extern "C" int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq_start, const int32_t *comp, int64_t N,
+                           int32_t ncomp, uint64_t max_nodes, uint64_t *sol_out, double *obj_out,
+                           uint64_t *explored_out, uint64_t *steps_out)
+{
+    return cp_solve_impl(h, nullptr, obs, is_seq_start, comp, N, ncomp, max_nodes, sol_out, obj_out, explored_out, steps_out);
+}
+
+extern "C" int cv_cp_solve_dist(cv_cp_dist *d, const uint32_t *obs, const uint8_t *is_seq_start, const int32_t *comp, int64_t N,
+                                int32_t ncomp, uint64_t max_nodes, uint64_t *sol_out, double *obj_out,
+                                uint64_t *explored_out, uint64_t *steps_out)
+{
+    if (!d) return fail(CV_ERR_ARG, "NULL exchange buffer");
+    return cp_solve_impl(d->h, d, obs, is_seq_start, comp, N, ncomp, max_nodes, sol_out, obj_out, explored_out, steps_out);
 }
 
 extern "C" int cv_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out)

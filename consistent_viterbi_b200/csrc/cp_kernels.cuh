@@ -238,14 +238,16 @@ __global__ void __launch_bounds__(32 * CPG_WARPS) cp_sweep_generic_kernel(const 
 //  C2: psi[pos][state] = first-argmax_j fl(delta[pos-1][j] + tr_j(state))          (pos != 0)
 //  C1: psi[pos+1][choice[comp[pos+1]]] = state when pos+1 is fixed.  If pos+1 belongs to the same component
 //      the reference overwrites that very entry in the next viterbi_from call (C2 of pos+1), so it is skipped.
-__global__ void cp_fixup_kernel(const CpParams p, const int64_t *pos_list, int npos, int comp, int state)
+// A shard (cp_dist.cuh) does C1 for the positions it owns, lo <= pos < hi, and C2 where it owns row pos-1,
+// lo < pos <= hi; a single rank passes lo = 0, hi = N.
+__global__ void cp_fixup_kernel(const CpParams p, const int64_t *pos_list, int npos, int comp, int state, int64_t lo, int64_t hi)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) p.choice[comp] = state;        // cstr_choices[comp] = Some(state) (cp.rs:98); read by the terms kernel only
     if (k >= npos) return;
     const int64_t pos = pos_list[k];
     const int K = p.K, Kp = p.Kp;
-    if (pos != 0) {
+    if (pos != 0 && pos > lo) {
         const double *prev = p.delta + (size_t)(pos - 1) * K;
         const bool st = p.start[pos] != 0;
         double bv = 0.0; int bi = 0;
@@ -255,7 +257,7 @@ __global__ void cp_fixup_kernel(const CpParams p, const int64_t *pos_list, int n
         }
         p.psi[(size_t)pos * K + state] = (psi_t)bi;
     }
-    if (pos + 1 < p.N) {
+    if (pos + 1 < p.N && pos < hi) {
         const int c1 = p.comp[pos + 1];
         if (c1 >= 0 && c1 < comp) p.psi[(size_t)(pos + 1) * K + p.choice[c1]] = (psi_t)state;
     }
@@ -698,38 +700,7 @@ __global__ void cp_last_row_kernel(const CpParams p, double *obj_out, int *end_o
     *obj_out = bv; *end_out = bi;
 }
 
-// ---- backtrack (cp.rs:85-93) as a composition of backpointer maps -------------------------------
-// The chain sol[t] = cur; cur = psi[t][cur] is cut into chunks of CP_BT_CHUNK rows.  (1) for every chunk
-// and every possible state at the chunk's last row, walk the chunk: F[chunk][e] = state entering the
-// previous chunk; (2) one thread chains the chunks; (3) every chunk replays its walk from its known
-// entry state and writes sol.  Integer-exact, N*K lookups instead of N dependent ones.
-constexpr int CP_BT_CHUNK = 256;
-
-__global__ void cp_bt_maps_kernel(const CpParams p, int nchunks, psi_t *F)
-{
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (int64_t)nchunks * p.K) return;
-    const int c = (int)(gid / p.K); int cur = (int)(gid % p.K);
-    const int64_t hi = min((int64_t)(c + 1) * CP_BT_CHUNK, p.N) - 1, lo = (int64_t)c * CP_BT_CHUNK;
-    for (int64_t t = hi; t >= lo; t--) cur = p.psi[(size_t)t * p.K + cur];
-    F[gid] = (psi_t)cur;
-}
-
-__global__ void cp_bt_chain_kernel(const CpParams p, int nchunks, const psi_t *F, const int *end_state, int *entry)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int cur = *end_state;
-    for (int c = nchunks - 1; c >= 0; c--) { entry[c] = cur; cur = F[(size_t)c * p.K + cur]; }
-}
-
-__global__ void cp_bt_fill_kernel(const CpParams p, int nchunks, const int *entry, uint64_t *sol)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nchunks) return;
-    int cur = entry[c];
-    const int64_t hi = min((int64_t)(c + 1) * CP_BT_CHUNK, p.N) - 1, lo = (int64_t)c * CP_BT_CHUNK;
-    for (int64_t t = hi; t >= lo; t--) { sol[t] = (uint64_t)cur; cur = p.psi[(size_t)t * p.K + cur]; }
-}
+constexpr int CP_BT_CHUNK = 256;   // rows per chunk of the backtrack's map composition (cp_dist.cuh)
 
 __global__ void cp_set_choice_kernel(int32_t *choice, int comp, int value) { choice[comp] = value; }
 

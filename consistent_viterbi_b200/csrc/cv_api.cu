@@ -26,6 +26,7 @@
 #include "decode_chain.cuh"
 #include "decode_large.cuh"
 #include "cp_kernels.cuh"
+#include "cp_dist.cuh"
 #include "probe.cuh"
 
 using namespace cvb;

@@ -94,6 +94,33 @@ int cv_cp_solve(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq_start,
                 uint64_t *sol_out, double *obj_out, uint64_t *explored_out,
                 uint64_t *steps_out);
 
+/* ---- constrained decode sharded over the GPUs of one NVSwitch box ------------
+ * One process per GPU.  The super-sequence is cut at positions of component 0 (no sweep of cp.rs:47-60 crosses
+ * such a position, cp.rs:48), every rank sweeps its own rows; per B&B node the ranks exchange the bound terms
+ * of cp.rs:103-116 by storing them into each other's term lists over NVLink (CUDA-IPC peer mappings, one flag
+ * per rank), then every rank runs the same exact-order sum and takes the same decision.  Results are
+ * bit-identical to cv_cp_solve on every rank.  When component 0 has fewer than nranks-1 usable positions every
+ * rank solves the whole problem itself (replicas).
+ *   cv_cp_dist_create   allocates this rank's exchange buffer (capacity: super-sequences of up to cap_N elements
+ *                       with up to cap_terms clamped positions) and returns its CV_IPC_HANDLE_BYTES-byte IPC handle
+ *   cv_cp_dist_connect  all_handles = the nranks handles in rank order (the host exchanges them: MPI,
+ *                       torch.distributed, a file -- any transport)
+ *   cv_cp_solve_dist    collective: every rank calls it with the same arguments; all ranks return the full result
+ * A rank that fails leaves its peers waiting for at most a few seconds before they fail with CV_ERR_CUDA. */
+#define CV_IPC_HANDLE_BYTES 64
+typedef struct cv_cp_dist cv_cp_dist;
+int  cv_cp_dist_create(cv_hmm *h, int rank, int nranks, int64_t cap_N, int64_t cap_terms,
+                       void *handle_out, cv_cp_dist **out);
+int  cv_cp_dist_connect(cv_cp_dist *d, const void *all_handles);
+void cv_cp_dist_destroy(cv_cp_dist *d);
+int  cv_cp_solve_dist(cv_cp_dist *d, const uint32_t *obs, const uint8_t *is_seq_start,
+                      const int32_t *comp, int64_t N, int32_t ncomp, uint64_t max_nodes,
+                      uint64_t *sol_out, double *obj_out, uint64_t *explored_out,
+                      uint64_t *steps_out);
+/* the row cuts cv_cp_solve_dist uses: cuts_out[nranks + 1], rank r owns rows [cuts[r], cuts[r+1]); when the
+ * problem cannot be cut, cuts = {0, N, N, ...} (replicas).  Pure host code, no device needed. */
+int  cv_cp_plan_cuts(const int32_t *comp, int64_t N, int nranks, int64_t *cuts_out);
+
 /* Debug/parity hooks for the CP path: after cv_cp_solve, copy out the final
  * delta[N*K] / psi[N*K] state and the per-node upper bounds (first `cap` nodes). */
 int cv_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out);
