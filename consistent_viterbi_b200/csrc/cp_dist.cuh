@@ -54,21 +54,9 @@ __device__ __forceinline__ void peer_publish_done(const PeerTab &pt, unsigned in
     }
 }
 
-// Wait until every rank has published exchange `epoch` into THIS rank's buffer.  Bounded: after ~4 s the error
-// word is set and the kernel returns (the host then fails the solve instead of hanging the GPU).
-__global__ void cp_peer_wait_kernel(const unsigned int *flags, int R, unsigned int epoch, int *err)
-{
-    const int q = threadIdx.x;
-    if (q >= R) return;
-    const long long t0 = clock64();
-    for (;;) {
-        unsigned int v;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + q) : "memory");
-        if ((int)(v - epoch) >= 0) break;
-        if (clock64() - t0 > (1LL << 33)) { *err = 1; break; }
-        __nanosleep(64);
-    }
-}
+// Wait until every rank has published exchange `epoch` into THIS rank's buffer (peer_wait_block, cp_kernels.cuh;
+// the bound sum waits inside its first kernel, the backtrack and the final gather use this stand-alone form).
+__global__ void cp_peer_wait_kernel(const PeerWait pw) { peer_wait_block(pw); }
 
 // Phase D on a shard: this rank's bound terms (clamped positions t in (lo, hi], t = 0 on the first rank), each
 // stored at its index in the reference's summation order in EVERY rank's term buffer, then the flag.
@@ -99,67 +87,150 @@ __global__ void __launch_bounds__(SUM_BLK) cp_terms_peer_kernel(const CpParams p
 // ---- backtrack (cp.rs:85-93) over a row range ------------------------------------------------------------
 // A rank walks the backpointer rows t = rtop .. rlo+1 (cur = psi[t][cur] is the state at t-1).  rtop is the
 // rank's upper cut (a row of the next rank whose STATE is the walk's entry) or N-1 on the last rank; sol[t] is
-// written for the rows the rank owns (t < own_hi) and for rlo.  Chunks of CP_BT_CHUNK rows, map composition as
-// in the single-GPU path: (1) per chunk and entry state the exit state, (2) K threads chain the chunks into the
-// rank's total map and publish it, (3) with every rank's map known, the rank's entry state, (4) replay.
-__global__ void cp_btr_maps_kernel(const CpParams p, int64_t rlo, int64_t rtop, int nchunks, psi_t *F)
+// written for the rows the rank owns (t < own_hi) and for rlo.  The walk is a chain of N dependent loads, so it
+// is cut into chunks of CP_BT_CHUNK rows and done as a composition of maps:
+//   (1) maps   per chunk and entry state the exit state        F[c][e]      one CTA per chunk, rows staged in smem
+//   (2) total  the rank's map M = F[0] o .. o F[n-1], published to every rank (sharded solve only)
+//   (3) chain  entry[c] = state at the last row of chunk c, from the end state pushed through the maps of the
+//              ranks above and the chunks above; F staged in smem, groups of BTR_GROUP chunks chained in parallel
+//   (4) fill   every chunk replays its walk from entry[c] and writes sol
+// Integer-exact; the dependent steps run against shared memory (~30 clk) instead of L2 (~500 clk).
+constexpr int BTR_GROUP = 64;
+constexpr size_t BTR_SMEM_MAX = 200 * 1024;
+
+__host__ __device__ inline size_t btr_rows_smem_bytes(int K) { return ((size_t)CP_BT_CHUNK * K * sizeof(psi_t) + 15) / 16 * 16 + 16; }
+__host__ __device__ inline size_t btr_chain_smem_bytes(int nchunks, int K)
 {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (int64_t)nchunks * p.K) return;
-    const int c = (int)(gid / p.K); int cur = (int)(gid % p.K);
+    const int ngroups = (nchunks + BTR_GROUP - 1) / BTR_GROUP;
+    return ((size_t)nchunks * K * sizeof(psi_t) + 15) / 16 * 16 + ((size_t)ngroups * K * sizeof(psi_t) + 15) / 16 * 16 +
+           (size_t)ngroups * sizeof(int) + 16;
+}
+
+// rows (lo, hi] of psi into shared memory: srow[(t - lo - 1) * K + s]
+__device__ __forceinline__ void btr_stage_rows(const CpParams &p, int64_t lo, int64_t hi, psi_t *srow)
+{
+    const size_t n = (size_t)(hi - lo) * p.K;
+    const psi_t *src = p.psi + (size_t)(lo + 1) * p.K;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const size_t n8 = n / 8;
+        for (size_t i = threadIdx.x; i < n8; i += blockDim.x) reinterpret_cast<uint4 *>(srow)[i] = reinterpret_cast<const uint4 *>(src)[i];
+        for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) srow[i] = src[i];
+    } else {
+        for (size_t i = threadIdx.x; i < n; i += blockDim.x) srow[i] = src[i];
+    }
+    __syncthreads();
+}
+
+// one CTA per chunk (64 threads); rows_in_smem = 0: K too large to stage, walk global memory
+__global__ void __launch_bounds__(64) cp_btr_maps_kernel(const CpParams p, int64_t rlo, int64_t rtop, int nchunks, psi_t *F,
+                                                        int rows_in_smem)
+{
+    extern __shared__ __align__(16) unsigned char btr_raw[];
+    psi_t *srow = reinterpret_cast<psi_t *>(btr_raw);
+    const int c = blockIdx.x;
     const int64_t hi = min(rlo + (int64_t)(c + 1) * CP_BT_CHUNK, rtop), lo = rlo + (int64_t)c * CP_BT_CHUNK;
-    for (int64_t t = hi; t > lo; t--) cur = p.psi[(size_t)t * p.K + cur];
-    F[gid] = (psi_t)cur;
+    if (rows_in_smem) btr_stage_rows(p, lo, hi, srow);
+    for (int e = threadIdx.x; e < p.K; e += blockDim.x) {
+        int cur = e;
+        if (rows_in_smem) for (int64_t t = hi; t > lo; t--) cur = srow[(size_t)(t - lo - 1) * p.K + cur];
+        else for (int64_t t = hi; t > lo; t--) cur = p.psi[(size_t)t * p.K + cur];
+        F[(size_t)c * p.K + e] = (psi_t)cur;
+    }
+}
+
+// F into shared memory and the group maps GF[g][e] (exit state of group g for entry state e); all threads
+__device__ __forceinline__ void btr_stage_groups(const psi_t *F, int nchunks, int K, psi_t *sF, psi_t *sGF)
+{
+    const size_t n = (size_t)nchunks * K;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) sF[i] = F[i];
+    __syncthreads();
+    const int ngroups = (nchunks + BTR_GROUP - 1) / BTR_GROUP;
+    for (int i = threadIdx.x; i < ngroups * K; i += blockDim.x) {
+        const int g = i / K; int cur = i % K;
+        for (int c = min((g + 1) * BTR_GROUP, nchunks) - 1; c >= g * BTR_GROUP; c--) cur = sF[(size_t)c * K + cur];
+        sGF[i] = (psi_t)cur;
+    }
+    __syncthreads();
 }
 
 // maps region of the exchange buffer: [2][CP_MAX_RANKS][mapw] psi_t, entry K of a rank's map = its end state
-// (argmax of delta[N-1], meaningful on the last rank only)
-__global__ void cp_btr_total_kernel(const CpParams p, int nchunks, const psi_t *F, const int *end_state, const PeerTab pt,
-                                    size_t maps_off, int mapw, unsigned int epoch)
+// (argmax of delta[N-1], meaningful on the last rank only).  in_smem = 0: F too large, chained from global.
+__global__ void __launch_bounds__(1024) cp_btr_total_kernel(const CpParams p, int nchunks, const psi_t *F, const int *end_state,
+                                                           const PeerTab pt, size_t maps_off, int mapw, unsigned int epoch, int in_smem)
 {
-    const int e = threadIdx.x;
-    if (e < p.K) {
+    extern __shared__ __align__(16) unsigned char btr_raw[];
+    const int K = p.K, ngroups = (nchunks + BTR_GROUP - 1) / BTR_GROUP;
+    psi_t *sF = reinterpret_cast<psi_t *>(btr_raw);
+    psi_t *sGF = reinterpret_cast<psi_t *>(btr_raw + ((size_t)nchunks * K * sizeof(psi_t) + 15) / 16 * 16);
+    if (in_smem) btr_stage_groups(F, nchunks, K, sF, sGF);
+    for (int e = threadIdx.x; e <= K; e += blockDim.x) {
         int cur = e;
-        for (int c = nchunks - 1; c >= 0; c--) cur = F[(size_t)c * p.K + cur];
+        if (e == K) cur = *end_state;
+        else if (in_smem) for (int g = ngroups - 1; g >= 0; g--) cur = sGF[(size_t)g * K + cur];
+        else for (int c = nchunks - 1; c >= 0; c--) cur = F[(size_t)c * K + cur];
         for (int q = 0; q < pt.R; q++)
             reinterpret_cast<psi_t *>(pt.base[q] + maps_off)[(size_t)pt.rank * mapw + e] = (psi_t)cur;
-    } else if (e == p.K) {
-        for (int q = 0; q < pt.R; q++)
-            reinterpret_cast<psi_t *>(pt.base[q] + maps_off)[(size_t)pt.rank * mapw + p.K] = (psi_t)*end_state;
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) peer_signal_all(pt, epoch);
 }
 
-// entry[c] = state at the last row of chunk c; the rank's own entry comes from the end state pushed through the
-// maps of the ranks above it (maps == nullptr: single rank, entry = *end_state)
-__global__ void cp_btr_chain_kernel(const CpParams p, int nchunks, const psi_t *F, const int *end_state, const psi_t *maps,
-                                    int mapw, int rank, int R, int *entry)
+// maps == nullptr: single rank, the entry is *end_state; pw: the ranks' maps must have arrived
+__global__ void __launch_bounds__(1024) cp_btr_chain_kernel(const CpParams p, int nchunks, const psi_t *F, const int *end_state,
+                                                           const psi_t *maps, int mapw, int rank, int R, int *entry, int in_smem,
+                                                           const PeerWait pw)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int cur;
-    if (maps) {
-        cur = maps[(size_t)(R - 1) * mapw + p.K];
-        for (int q = R - 1; q > rank; q--) cur = maps[(size_t)q * mapw + cur];
-    } else {
-        cur = *end_state;
+    extern __shared__ __align__(16) unsigned char btr_raw[];
+    peer_wait_block(pw);
+    const int K = p.K, ngroups = (nchunks + BTR_GROUP - 1) / BTR_GROUP;
+    int cur = 0;
+    if (threadIdx.x == 0) {
+        if (maps) {
+            cur = maps[(size_t)(R - 1) * mapw + K];
+            for (int q = R - 1; q > rank; q--) cur = maps[(size_t)q * mapw + cur];
+        } else {
+            cur = *end_state;
+        }
     }
-    for (int c = nchunks - 1; c >= 0; c--) { entry[c] = cur; cur = F[(size_t)c * p.K + cur]; }
+    if (!in_smem) {
+        if (threadIdx.x == 0) for (int c = nchunks - 1; c >= 0; c--) { entry[c] = cur; cur = F[(size_t)c * K + cur]; }
+        return;
+    }
+    psi_t *sF = reinterpret_cast<psi_t *>(btr_raw);
+    psi_t *sGF = reinterpret_cast<psi_t *>(btr_raw + ((size_t)nchunks * K * sizeof(psi_t) + 15) / 16 * 16);
+    int *gentry = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(sGF) + ((size_t)ngroups * K * sizeof(psi_t) + 15) / 16 * 16);
+    btr_stage_groups(F, nchunks, K, sF, sGF);
+    if (threadIdx.x == 0) for (int g = ngroups - 1; g >= 0; g--) { gentry[g] = cur; cur = sGF[(size_t)g * K + cur]; }
+    __syncthreads();
+    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) {
+        int c2 = gentry[g];
+        for (int c = min((g + 1) * BTR_GROUP, nchunks) - 1; c >= g * BTR_GROUP; c--) { entry[c] = c2; c2 = sF[(size_t)c * K + c2]; }
+    }
 }
 
-__global__ void cp_btr_fill_kernel(const CpParams p, int64_t rlo, int64_t rtop, int64_t own_hi, int nchunks, const int *entry,
-                                   uint64_t *sol)
+// one CTA per chunk (64 threads): thread 0 replays the walk against the staged rows, all threads write sol
+__global__ void __launch_bounds__(64) cp_btr_fill_kernel(const CpParams p, int64_t rlo, int64_t rtop, int64_t own_hi, int nchunks,
+                                                        const int *entry, uint64_t *sol, int rows_in_smem)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nchunks) return;
-    int cur = entry[c];
+    extern __shared__ __align__(16) unsigned char btr_raw[];
+    __shared__ psi_t st[CP_BT_CHUNK + 1];
+    psi_t *srow = reinterpret_cast<psi_t *>(btr_raw);
+    const int c = blockIdx.x;
     const int64_t hi = min(rlo + (int64_t)(c + 1) * CP_BT_CHUNK, rtop), lo = rlo + (int64_t)c * CP_BT_CHUNK;
-    for (int64_t t = hi; t > lo; t--) {
-        if (t < own_hi) sol[t] = (uint64_t)cur;
-        cur = p.psi[(size_t)t * p.K + cur];
+    if (rows_in_smem) btr_stage_rows(p, lo, hi, srow);
+    if (threadIdx.x == 0) {
+        int cur = entry[c];
+        for (int64_t t = hi; t > lo; t--) {                    // st[t - lo] = state at row t
+            st[t - lo] = (psi_t)cur;
+            cur = rows_in_smem ? srow[(size_t)(t - lo - 1) * p.K + cur] : p.psi[(size_t)t * p.K + cur];
+        }
+        st[0] = (psi_t)cur;
     }
-    if (c == 0) sol[rlo] = (uint64_t)cur;
+    __syncthreads();
+    for (int64_t t = lo + 1 + threadIdx.x; t <= hi; t += blockDim.x)
+        if (t < own_hi) sol[t] = (uint64_t)st[t - lo];
+    if (c == 0 && threadIdx.x == 0) sol[rlo] = (uint64_t)st[0];
 }
 
 // the rank's rows of the solution, stored into every rank's solution buffer, then the flag

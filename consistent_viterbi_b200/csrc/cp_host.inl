@@ -50,6 +50,9 @@ struct CpRun {
     int64_t *d_lterm_pos = nullptr; int32_t *d_lterm_comp = nullptr, *d_lterm_gidx = nullptr;
     unsigned int *d_done = nullptr; int *d_err = nullptr;
     uint64_t n_term_x = 0, n_map_x = 0;          // exchanges of each kind so far in this solve (buffer parity)
+    unsigned long long node_seq = 0;             // sequence number of the node whose bound the host polls for
+    int sweep_blocks_per_sm = 8;                 // co-resident CTAs of the sweep kernel (occupancy query)
+    bool poll = true;                            // CV_CP_HOSTPOLL=0: copy + stream synchronise instead
     psi_t *d_F = nullptr; int *d_entry = nullptr; uint64_t *d_sol = nullptr;
     double *h_ub = nullptr;                      // pinned
     int err = CV_OK;
@@ -58,23 +61,26 @@ struct CpRun {
 
 // ub = ((0.0 + x_0) + x_1) + ... in order (cp.rs:103-116): plain loop for short lists, the block-structured
 // exact-order kernels for long ones, the single-CTA binade scan beyond SUM_MAX_BLOCKS blocks.
-int cp_launch_sum(const double *terms, int nterms, double *ub, unsigned int *counter, const SumWs &ws, bool have_stats,
-                  int force, cudaStream_t st)
+int cp_launch_sum(const double *terms, int nterms, const UbSink &ub, unsigned int *counter, const SumWs &ws, bool have_stats,
+                  int force, cudaStream_t st, const PeerWait &pw)
 {
     const int nblk = (nterms + SUM_BLK - 1) / SUM_BLK;
     int kind = nterms < g_sum_parallel_min ? 0 : (nblk > SUM_MAX_BLOCKS ? 2 : 1);
     if (force >= 0) kind = (force == 1 && nblk > SUM_MAX_BLOCKS) ? 2 : force;
-    if (kind == 0) { cp_sum_kernel<<<1, 256, 0, st>>>(terms, nterms, ub, counter); g_launches++; }
-    else if (kind == 2) { cp_sum_exact_kernel<<<1, QS_THREADS, 0, st>>>(terms, nterms, ub, counter); g_launches++; }
-    else {
-        if (nblk > 0) {
-            if (!have_stats) { cp_sum_stats_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bflag); g_launches++; }
-            cp_sum_blockfn_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bexp, ws.bfn);
-            g_launches++;
-        }
-        cp_sum_chain_kernel<<<1, SUMC_THREADS, 0, st>>>(terms, nterms, nblk, ws.bflag, ws.bexp, ws.bfn, ub, counter);
+    if (kind == 1 && nblk == 0) kind = 0;
+    const PeerWait none{nullptr, 1, 0u, nullptr};
+    if (kind == 0) { cp_sum_kernel<<<1, 256, 0, st>>>(terms, nterms, ub, counter, pw); g_launches++; }
+    else if (kind == 2) {
+        if (pw.R > 1) { cp_peer_wait_kernel<<<1, 32, 0, st>>>(pw); g_launches++; }
+        cp_sum_exact_kernel<<<1, QS_THREADS, 0, st>>>(terms, nterms, ub, counter);
         g_launches++;
+    } else {
+        if (!have_stats || pw.R > 1) { cp_sum_stats_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bflag, pw); g_launches++; }
+        cp_sum_blockfn_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bexp, ws.bfn);
+        cp_sum_chain_kernel<<<1, SUMC_THREADS, sum_chain_smem_bytes(nblk), st>>>(terms, nterms, nblk, ws.bflag, ws.bexp, ws.bfn, ub, counter);
+        g_launches += 2;
     }
+    (void)none;
     CUDA_TRY(cudaGetLastError());
     return CV_OK;
 }
@@ -101,7 +107,7 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
                           (size_t)CPW_WARPS * 2 * 16 * r.p.Kp;              // up to two segments per warp
     static const bool fullwarp = getenv("CV_CP_FULLWARP") != nullptr;    // A/B hook: one segment per warp for every K
     const int64_t segs_per_block = (int64_t)CPW_WARPS * (r.p.Kp <= 16 && !fullwarp ? 2 : 1);
-    const int grid = (int)std::min<int64_t>((nseg + segs_per_block - 1) / segs_per_block, (int64_t)r.h->num_sms * 8);
+    const int grid = (int)std::min<int64_t>((nseg + segs_per_block - 1) / segs_per_block, (int64_t)r.h->num_sms * r.sweep_blocks_per_sm);
     const bool regs = r.p.Kp == 8 * ((r.p.K + 7) / 8);       // register-resident logA column needs Kp = 4 * KQ
     const int kq = regs ? (r.p.K + 7) / 8 : 9;
     if (fullwarp && kq == 1) cp_sweep_chain_kernel<1, 2><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
@@ -131,23 +137,27 @@ int cp_backtrack(CpRun &r, double obj)
     const int nchunks = (int)std::max<int64_t>((rtop - r.lo + CP_BT_CHUNK - 1) / CP_BT_CHUNK, 1);
     double *d_obj = r.d_ub + 2;
     if (last) { cp_last_row_kernel<<<1, 32, 0, r.st>>>(r.p, d_obj, r.d_end); g_launches++; }
-    const int64_t nmap = (int64_t)nchunks * r.p.K;
-    cp_btr_maps_kernel<<<(unsigned)((nmap + 127) / 128), 128, 0, r.st>>>(r.p, r.lo, rtop, nchunks, r.d_F);
+    const int K = r.p.K;
+    const size_t rows_b = btr_rows_smem_bytes(K), chain_b = btr_chain_smem_bytes(nchunks, K);
+    const int rows_in = rows_b <= BTR_SMEM_MAX ? 1 : 0, chain_in = chain_b <= BTR_SMEM_MAX ? 1 : 0;
+    cp_btr_maps_kernel<<<nchunks, 64, rows_in ? rows_b : 0, r.st>>>(r.p, r.lo, rtop, nchunks, r.d_F, rows_in);
     const psi_t *maps = nullptr;
     int mapw = 0;
+    PeerWait pw{nullptr, 1, 0u, nullptr};
     if (r.R > 1) {
         cv_cp_dist *dx = r.dx;
         mapw = dx->mapw;
         const size_t maps_off = dx->maps_off + (size_t)(r.n_map_x & 1) * CP_MAX_RANKS * mapw * sizeof(psi_t);
         r.n_map_x++;
         const unsigned int epoch = ++dx->epoch;
-        cp_btr_total_kernel<<<1, 32 * ((r.p.K + 1 + 31) / 32), 0, r.st>>>(r.p, nchunks, r.d_F, r.d_end, dx->tab, maps_off, mapw, epoch);
-        cp_peer_wait_kernel<<<1, 32, 0, r.st>>>((const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err);
-        g_launches += 2;
+        cp_btr_total_kernel<<<1, 1024, chain_in ? chain_b : 0, r.st>>>(r.p, nchunks, r.d_F, r.d_end, dx->tab, maps_off, mapw, epoch, chain_in);
+        g_launches++;
+        pw = PeerWait{(const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err};
         maps = (const psi_t *)(dx->tab.base[r.rank] + maps_off);
     }
-    cp_btr_chain_kernel<<<1, 32, 0, r.st>>>(r.p, nchunks, r.d_F, r.d_end, maps, mapw, r.rank, r.R, r.d_entry);
-    cp_btr_fill_kernel<<<(nchunks + 127) / 128, 128, 0, r.st>>>(r.p, r.lo, rtop, r.hi, nchunks, r.d_entry, r.d_sol);
+    cp_btr_chain_kernel<<<1, 1024, chain_in ? chain_b : 0, r.st>>>(r.p, nchunks, r.d_F, r.d_end, maps, mapw, r.rank, r.R, r.d_entry,
+                                                                 chain_in, pw);
+    cp_btr_fill_kernel<<<nchunks, 64, rows_in ? rows_b : 0, r.st>>>(r.p, r.lo, rtop, r.hi, nchunks, r.d_entry, r.d_sol, rows_in);
     g_launches += 3;
     CUDA_TRY(cudaGetLastError());
     return CV_OK;
@@ -182,6 +192,7 @@ int cp_solve_r(CpRun &r, int32_t comp)
         g_launches++;
         tick(1, t0);
         bool have_stats = nterms > 0;
+        PeerWait pw{nullptr, 1, 0u, nullptr};
         if (r.R > 1) {
             // the rank's terms go straight into every rank's term list (peer stores + flag), then wait for all ranks
             cv_cp_dist *dx = r.dx;
@@ -190,10 +201,10 @@ int cp_solve_r(CpRun &r, int32_t comp)
             const unsigned int epoch = ++dx->epoch;
             cp_terms_peer_kernel<<<std::max((nlocal + SUM_BLK - 1) / SUM_BLK, 1), SUM_BLK, 0, r.st>>>(
                 r.p, r.d_lterm_pos, r.d_lterm_comp, r.d_lterm_gidx, nlocal, dx->tab, toff, epoch, r.d_done);
-            cp_peer_wait_kernel<<<1, 32, 0, r.st>>>((const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err);
-            g_launches += 2;
+            g_launches++;
             r.d_terms = (double *)(dx->tab.base[r.rank] + toff);
             have_stats = false;
+            pw = PeerWait{(const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err};
         } else if (nterms > 0) {
             cp_terms_kernel<<<(nterms + SUM_BLK - 1) / SUM_BLK, SUM_BLK, 0, r.st>>>(r.p, r.d_cons_pos, r.d_term_comp, nterms,
                                                                                      r.d_terms, r.sum_ws.bsum, r.sum_ws.bflag);
@@ -201,11 +212,25 @@ int cp_solve_r(CpRun &r, int32_t comp)
         }
         tick(2, t0);
         // cp.rs:103-116: the exact-order sum (parallel binade scan for long lists, plain loop for short ones)
-        if ((rc = cp_launch_sum(r.d_terms, nterms, r.d_ub, r.d_counter, r.sum_ws, have_stats, g_sum_force, r.st))) return rc;
+        const unsigned long long seq = ++r.node_seq;
+        const UbSink sink{r.d_ub, r.poll ? r.h_ub : nullptr, r.R > 1 ? r.d_err : nullptr, seq};
+        if ((rc = cp_launch_sum(r.d_terms, nterms, sink, r.d_counter, r.sum_ws, have_stats, g_sum_force, r.st, pw))) return rc;
         tick(3, t0);
-        // (the word after ub is the peer-timeout flag of the wait kernels, always 0.0 on a single rank)
-        CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, (r.R > 1 ? 2 : 1) * sizeof(double), cudaMemcpyDeviceToHost, r.st));
-        CUDA_TRY(cudaStreamSynchronize(r.st));
+        if (r.poll) {
+            // the sum kernel writes ub + the node's sequence number into pinned host memory; poll for it
+            volatile unsigned long long *seqp = reinterpret_cast<volatile unsigned long long *>(r.h_ub + 2);
+            for (unsigned int spin = 1; *seqp != seq; spin++) {
+                if ((spin & 0x3fff) == 0) {
+                    const cudaError_t e = cudaStreamQuery(r.st);
+                    if (e == cudaSuccess) { if (*seqp == seq) break; return fail(CV_ERR_CUDA, "bound of node %llu never arrived", seq); }
+                    if (e != cudaErrorNotReady) return fail(CV_ERR_CUDA, "stream error while waiting for a node's bound: %s", cudaGetErrorString(e));
+                }
+            }
+        } else {
+            // (the word after ub is the peer-timeout flag of the wait kernels, always 0.0 on a single rank)
+            CUDA_TRY(cudaMemcpyAsync(r.h_ub, r.d_ub, (r.R > 1 ? 2 : 1) * sizeof(double), cudaMemcpyDeviceToHost, r.st));
+            CUDA_TRY(cudaStreamSynchronize(r.st));
+        }
         tick(4, t0);
         const double ub = *r.h_ub;
         if (r.R > 1 && r.h_ub[1] != 0.0) return fail(CV_ERR_CUDA, "a peer rank did not publish its bound terms within the time limit");
@@ -357,6 +382,7 @@ static int cp_solve_impl(cv_hmm *h, cv_cp_dist *dx, const uint32_t *obs, const u
     if (dx && dx->R > 1) {
         if (dx->h != h) return fail(CV_ERR_ARG, "exchange buffer belongs to another model handle");
         if (!dx->connected) return fail(CV_ERR_ARG, "cv_cp_dist_connect has not run");
+        if (h->K + 1 > 1024) return fail(CV_ERR_UNSUPPORTED, "sharded constrained decode supports K <= 1023");
         if (N > dx->cap_N) return fail(CV_ERR_ARG, "N = %lld exceeds the exchange buffer's capacity %lld", (long long)N, (long long)dx->cap_N);
         if (ncomp > 0 && cp_plan_cuts(comp, N, dx->R, cuts)) {
             r.dx = dx; r.R = dx->R; r.rank = dx->rank;
@@ -480,7 +506,8 @@ static int cp_solve_impl(cv_hmm *h, cv_cp_dist *dx, const uint32_t *obs, const u
     if ((rc = r.sum_ws.bind(b[14], cons_pos.size()))) return rc;
     if (const char *e = getenv("CV_CP_SUM")) g_sum_force = atoi(e);
     r.h_ub = (double *)h->pinned_status + 1;
-    r.h_ub[0] = r.h_ub[1] = 0.0;
+    r.h_ub[0] = r.h_ub[1] = r.h_ub[2] = 0.0;
+    if (const char *e = getenv("CV_CP_HOSTPOLL")) r.poll = atoi(e) != 0;
 
     CpParams &p = r.p;
     const bool small = K <= SMALL_K_MAX;
@@ -503,7 +530,27 @@ static int cp_solve_impl(cv_hmm *h, cv_cp_dist *dx, const uint32_t *obs, const u
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         CUDA_TRY(cudaFuncSetAttribute(cp_sweep_chain_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        // segments are dealt statically to the resident warps: one wave of CTAs
+        int nb = 0;
+        const bool regs = h->Kp == 8 * ((K + 7) / 8);
+        const int kq = regs ? (K + 7) / 8 : 9;
+        cudaError_t oe;
+        if (kq == 1) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cp_sweep_chain_kernel<1, 2, 16>, 32 * CPW_WARPS, smem_c);
+        else if (kq == 2) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cp_sweep_chain_kernel<1, 4, 16>, 32 * CPW_WARPS, smem_c);
+        else if (kq == 3) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cp_sweep_chain_kernel<1, 6>, 32 * CPW_WARPS, smem_c);
+        else if (kq == 4) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cp_sweep_chain_kernel<1, 8>, 32 * CPW_WARPS, smem_c);
+        else if (K <= 32) oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cp_sweep_chain_kernel<1, 0>, 32 * CPW_WARPS, smem_c);
+        else oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cp_sweep_chain_kernel<2, 0>, 32 * CPW_WARPS, smem_c);
+        if (oe != cudaSuccess) { cudaGetLastError(); nb = 0; }
+        r.sweep_blocks_per_sm = std::max(1, std::min(nb, 16));
     }
+
+    CUDA_TRY(cudaFuncSetAttribute(cp_sum_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sum_chain_smem_bytes(SUM_MAX_BLOCKS)));
+    CUDA_TRY(cudaFuncSetAttribute(cp_btr_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BTR_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cp_btr_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BTR_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cp_btr_total_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BTR_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cp_btr_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BTR_SMEM_MAX));
 
     const bool timing = g_timing.load() != 0;
     if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
@@ -533,7 +580,7 @@ static int cp_solve_impl(cv_hmm *h, cv_cp_dist *dx, const uint32_t *obs, const u
         const unsigned int epoch = ++dx->epoch;
         const int grid = (int)std::min<int64_t>((hi - lo + 255) / 256, (int64_t)h->num_sms * 4);
         cp_sol_publish_kernel<<<std::max(grid, 1), 256, 0, st>>>(r.d_sol, lo, hi, dx->tab, dx->sol_off, epoch, r.d_done);
-        cp_peer_wait_kernel<<<1, 32, 0, st>>>((const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err);
+        cp_peer_wait_kernel<<<1, 32, 0, st>>>(PeerWait{(const unsigned int *)dx->tab.base[r.rank], r.R, epoch, r.d_err});
         g_launches += 2;
         CUDA_TRY(cudaMemcpyAsync(r.h_ub + 1, r.d_err, sizeof(double), cudaMemcpyDeviceToHost, st));
     }
@@ -615,7 +662,9 @@ extern "C" int cv_debug_ordered_sum(const double *values, int64_t n, int mode, d
     DevBuf wsb; SumWs ws;
     if ((rc = ws.bind(wsb, (size_t)n))) { cudaFree(d); return rc; }
     if (mode < 0 || mode > 2) mode = 0;
-    rc = cp_launch_sum(d + 1, (int)n, d, nullptr, ws, false, mode, nullptr);
+    if (cudaFuncSetAttribute(cp_sum_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sum_chain_smem_bytes(SUM_MAX_BLOCKS)) != cudaSuccess) { cudaFree(d); wsb.release(); return fail(CV_ERR_CUDA, "cudaFuncSetAttribute"); }
+    rc = cp_launch_sum(d + 1, (int)n, UbSink{d, nullptr, nullptr, 0ULL}, nullptr, ws, false, mode, nullptr, PeerWait{nullptr, 1, 0u, nullptr});
     if (rc) { cudaFree(d); wsb.release(); return rc; }
     CUDA_TRY(cudaMemcpy(out, d, sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(d);

@@ -67,7 +67,7 @@ __global__ void cp_row0_kernel(const CpParams p)
 }
 
 // ---- sweeps, one warp per segment (latency-oriented; see chain_warp.cuh) -----------------------------
-// Phases A (reset row) + B (sweep); segments are claimed longest first from a global counter.
+// Phases A (reset row) + B (sweep); segments are listed longest first.
 constexpr int CPW_WARPS = 4;
 
 // LPS = lanes per segment: 32, or 16 when K <= 16 (two segments per warp, adjacent in the length-sorted list).
@@ -98,15 +98,19 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
         for (int j = 0; j < 4 * KQ; j++) acol[j] = (j < K && sub < Kp) ? sA[(size_t)j * Kp + sub] : neg_inf();
     }
 
-    for (;;) {
-        unsigned int r0 = 0;
-        if (lane == 0) r0 = atomicAdd(a.tile_counter, (unsigned int)GP);
-        r0 = __shfl_sync(0xffffffffu, r0, 0);
-        if ((int)r0 >= a.nseg) break;
-        const int r = (int)r0 + grp;
+    // Segments are sorted longest first and dealt to the warps round-robin (static: no claim round trip); the next
+    // segment's start / length are fetched while the current one is swept.
+    const int stride = (int)gridDim.x * CPW_WARPS * GP;
+    int r = ((int)blockIdx.x * CPW_WARPS + (int)(threadIdx.x >> 5)) * GP + grp;
+    int64_t from_n = 0; int len_n = -1;
+    if (r < a.nseg) { from_n = __ldg(a.seg_from + r); len_n = __ldg(a.seg_len + r); }
+    for (;; r += stride) {
+        if (r - grp >= a.nseg) break;                                         // warp-uniform
         const bool valid = r < a.nseg;
-        const int64_t from = valid ? a.seg_from[r] : 0;
-        const int len = valid ? a.seg_len[r] : -1;
+        const int64_t from = from_n;
+        const int len = len_n;
+        from_n = 0; len_n = -1;
+        if (r + stride < a.nseg) { from_n = __ldg(a.seg_from + r + stride); len_n = __ldg(a.seg_len + r + stride); }
         const int lenmax = __reduce_max_sync(0xffffffffu, len);
 
         double d[NSL];
@@ -263,6 +267,44 @@ __global__ void cp_fixup_kernel(const CpParams p, const int64_t *pos_list, int n
     }
 }
 
+// ---- where a node's bound goes, and whom the sum has to wait for --------------------------------------------
+// UbSink: the sum kernels store ub in device memory and, when `host` is set, in pinned host memory followed by
+// the node's sequence number -- the host polls that word instead of paying a copy + stream synchronisation
+// per node (host[0] = ub, host[1] = peer-timeout flag, host[2] = sequence number as u64).
+struct UbSink {
+    double *dev; double *host; const int *err; unsigned long long seq;
+};
+__device__ __forceinline__ void ub_store(const UbSink &o, double ub)
+{
+    *o.dev = ub;
+    if (o.host) {
+        o.host[0] = ub;
+        o.host[1] = (o.err && *o.err) ? 1.0 : 0.0;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(o.host + 2) = o.seq;
+    }
+}
+// PeerWait: sharded solve (cp_dist.cuh) -- every rank's terms of exchange `epoch` must have arrived (flags[q] >=
+// epoch) before the list is read.  R <= 1: nothing to wait for.  Bounded (~4 s), then *err = 1.
+struct PeerWait {
+    const unsigned int *flags; int R; unsigned int epoch; int *err;
+};
+__device__ __forceinline__ void peer_wait_block(const PeerWait &w)
+{
+    if (w.R <= 1) return;
+    if ((int)threadIdx.x < w.R) {
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned int v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w.flags + threadIdx.x) : "memory");
+            if ((int)(v - w.epoch) >= 0) break;
+            if (clock64() - t0 > (1LL << 33)) { *w.err = 1; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
 // ---- block statistics for the block-structured exact sum (further down) -------------------------------------
 // Every SUM_BLK consecutive terms form a block; a block's plain f64 sum (any order -- it only PREDICTS the
 // binade of the running sum) and its special-value flags (1 = positive or NaN term, 2 = -inf term).
@@ -313,8 +355,10 @@ __global__ void __launch_bounds__(SUM_BLK) cp_terms_kernel(const CpParams p, con
 }
 
 // block statistics of an existing term list (debug hook / lists not produced by cp_terms_kernel)
-__global__ void __launch_bounds__(SUM_BLK) cp_sum_stats_kernel(const double *terms, int nterms, double *bsum, int *bflag)
+__global__ void __launch_bounds__(SUM_BLK) cp_sum_stats_kernel(const double *terms, int nterms, double *bsum, int *bflag,
+                                                             const PeerWait pw)
 {
+    peer_wait_block(pw);
     const int k = blockIdx.x * SUM_BLK + threadIdx.x;
     sum_block_stats(k < nterms ? terms[k] : 0.0, blockIdx.x, bsum, bflag);
 }
@@ -322,9 +366,10 @@ __global__ void __launch_bounds__(SUM_BLK) cp_sum_stats_kernel(const double *ter
 // ub = ((0.0 + term_0) + term_1) + ...  exactly in order (cp.rs:103,109,114).  The order is part of the result,
 // so one thread performs the adds; the rest of the block streams the terms through a double-buffered shared
 // memory stage and the adder keeps 16 terms in registers ahead of the dependent DADD chain (8 clk per term).
-__global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, double *ub_out,
-                                                     unsigned int *reset_counter)
+__global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, const UbSink ub_out,
+                                                     unsigned int *reset_counter, const PeerWait pw)
 {
+    peer_wait_block(pw);
     if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
     constexpr int CH = 2048;
     __shared__ double buf[2][CH];
@@ -351,7 +396,7 @@ __global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nt
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *ub_out = ub;
+    if (threadIdx.x == 0) ub_store(ub_out, ub);
 }
 
 
@@ -403,7 +448,7 @@ __device__ __forceinline__ QFn qfn_elem(double x, int e)
 constexpr int QS_THREADS = 1024, QS_EPT = 8;
 constexpr int QS_SERIAL_HEAD = 2048;                // leading terms summed by the plain loop
 
-__global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *terms, int nterms, double *ub_out,
+__global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *terms, int nterms, const UbSink ub_out,
                                                                   unsigned int *reset_counter)
 {
     if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
@@ -425,10 +470,10 @@ __global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *
     __syncthreads();
     const int mode = mode_sh;
     if (mode & 1) {                                 // reference loop, one thread
-        if (tid == 0) { double ub = 0.0; for (int k = 0; k < nterms; k++) ub += terms[k]; *ub_out = ub; }
+        if (tid == 0) { double ub = 0.0; for (int k = 0; k < nterms; k++) ub += terms[k]; ub_store(ub_out, ub); }
         return;
     }
-    if (mode & 2) { if (tid == 0) *ub_out = neg_inf(); return; }
+    if (mode & 2) { if (tid == 0) ub_store(ub_out, neg_inf()); return; }
 
     // The first terms go through the plain loop: while the sum is small its binade changes every few adds, and a
     // binade change costs a whole scan window.  After QS_SERIAL_HEAD terms a change needs ~pos more terms.
@@ -531,7 +576,7 @@ __global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *
             else { s_sh = sk + terms[cross]; pos_sh = cross + 1; }          // the one add that changes binade
         }
     }
-    if (tid == 0) *ub_out = s_sh;
+    if (tid == 0) ub_store(ub_out, s_sh);
 }
 
 // ---- exact-order sum, block-structured (many CTAs) ------------------------------------------------------
@@ -548,7 +593,7 @@ __global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *
 //      are summed term by term in floating point (SUM_BLK dependent adds).
 // Special values as in cp_sum_exact_kernel: a positive/NaN term => the plain loop over everything, -inf => -inf.
 constexpr int SUM_OPEN = -100000;                     // "no function for this block / group"
-constexpr int SUM_MAX_BLOCKS = 8192;                  // above this (1M terms) the single-CTA kernel is used
+constexpr int SUM_MAX_BLOCKS = 4096;                  // above this (512k terms) the single-CTA kernel is used
 
 __global__ void __launch_bounds__(SUM_BLK) cp_sum_blockfn_kernel(const double *terms, int nterms, const double *bsum,
                                                                int *bexp, QFn *bfn)
@@ -620,74 +665,139 @@ struct SumWs {
 };
 
 constexpr int SUMC_THREADS = 1024;
+constexpr int SUMC_CACHE = 32;                         // open blocks whose terms are staged in shared memory
+__host__ __device__ inline size_t sum_chain_smem_bytes(int nblk) { return (size_t)(nblk + 32) * (sizeof(QFn) + 2 * sizeof(int)); }
+
+// Everything the serial walk touches is staged in shared memory first (block functions, the terms of the blocks
+// known to be open): the walk is a chain of dependent steps, a global-memory latency per step would dominate it.
 __global__ void __launch_bounds__(SUMC_THREADS) cp_sum_chain_kernel(const double *terms, int nterms, int nblk,
                                                                    const int *bflag, const int *bexp, const QFn *bfn,
-                                                                   double *ub_out, unsigned int *reset_counter)
+                                                                   const UbSink ub_out, unsigned int *reset_counter)
 {
     if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
     constexpr int MAXG = SUM_MAX_BLOCKS / 32;
-    __shared__ QFn gfn[MAXG]; __shared__ int gexp[MAXG]; __shared__ int mode_sh;
+    extern __shared__ __align__(16) unsigned char sumc_raw[];
+    __shared__ QFn gfn[MAXG]; __shared__ int gexp[MAXG]; __shared__ int mode_sh, ncache_sh;
+    __shared__ int cache_blk[SUMC_CACHE];
+    __shared__ double cache[SUMC_CACHE][SUM_BLK];
     __shared__ double buf[SUM_BLK];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) mode_sh = 0;
+    const int nblk_pad = (nblk + 31) & ~31;
+    QFn *sfn = reinterpret_cast<QFn *>(sumc_raw);
+    int *sexp = reinterpret_cast<int *>(sfn + nblk_pad);   // binade or SUM_OPEN; SUM_OPEN - 1 - slot = open + cached
+    int *stail = sexp + nblk_pad;                          // at the first block of a run: lane of the run's last block
+    if (tid == 0) { mode_sh = 0; ncache_sh = 0; }
     __syncthreads();
     int flag = 0;
-    for (int b = tid; b < nblk; b += SUMC_THREADS) flag |= bflag[b];
+    for (int b = tid; b < nblk_pad; b += SUMC_THREADS) {
+        int e = SUM_OPEN; QFn f; f.a0 = f.a1 = 0;
+        if (b < nblk) {
+            flag |= bflag[b];
+            e = bexp[b];
+            if (e != SUM_OPEN) f = bfn[b];
+            else { const int slot = atomicAdd(&ncache_sh, 1); if (slot < SUMC_CACHE) { cache_blk[slot] = b; e = SUM_OPEN - 1 - slot; } }
+        }
+        sexp[b] = e; sfn[b] = f;
+    }
     if (flag) atomicOr(&mode_sh, flag);
-    const int ngrp = (nblk + 31) / 32;
-    for (int g = w; g < ngrp; g += SUMC_THREADS / 32) {       // group functions
+    __syncthreads();
+    const int ngrp = nblk_pad / 32;
+    // Runs: maximal stretches of consecutive blocks of a group with a function for the same binade.  A segmented
+    // scan leaves in sfn[b] the composition from the run's first block up to b, so the walk takes a run in one
+    // step; a group that is a single run is "clean" and is taken through gfn.
+    for (int g = w; g < ngrp; g += SUMC_THREADS / 32) {
         const int b = g * 32 + lane;
-        int e = b < nblk ? bexp[b] : SUM_OPEN;
-        QFn f; f.a0 = f.a1 = 0;
-        if (e != SUM_OPEN) f = bfn[b];
-        const int e0 = __shfl_sync(0xffffffffu, e, 0);
-        if (b >= nblk) e = e0;                                 // past the end: identity in the group's binade
-        const bool clean = __all_sync(0xffffffffu, e == e0) && e0 != SUM_OPEN;
+        const int e = sexp[b];
+        QFn f = sfn[b];
+        const int e_prev = __shfl_up_sync(0xffffffffu, e, 1);
+        const bool open = e <= SUM_OPEN;
+        const bool head = lane == 0 || open || e_prev <= SUM_OPEN || e != e_prev;
+        const unsigned int heads = __ballot_sync(0xffffffffu, head);
+        const int my_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             QFn o;
             o.a0 = __shfl_up_sync(0xffffffffu, f.a0, d);
             o.a1 = __shfl_up_sync(0xffffffffu, f.a1, d);
-            if (lane >= d) f = qfn_compose(o, f);
+            if (lane - d >= my_head) f = qfn_compose(o, f);
         }
-        if (lane == 31) { gfn[g] = f; gexp[g] = clean ? e0 : SUM_OPEN; }
+        const unsigned int later = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
+        sfn[b] = f;
+        stail[b] = later ? __ffs(later) - 2 : 31;
+        // clean = one run over the whole group (blocks past the end count as identity in the same binade)
+        const int nreal = min(32, nblk - g * 32);
+        const bool one_run = (heads & (nreal >= 32 ? 0xffffffffu : ((1u << nreal) - 1u))) == 1u && !open;
+        const int src = nreal - 1;
+        const QFn fl = QFn{__shfl_sync(0xffffffffu, f.a0, src), __shfl_sync(0xffffffffu, f.a1, src)};
+        const int e0 = __shfl_sync(0xffffffffu, e, 0);
+        const bool clean = __shfl_sync(0xffffffffu, (int)one_run, 0) != 0;
+        if (lane == 0) { gfn[g] = fl; gexp[g] = clean ? e0 : SUM_OPEN; }
+    }
+    {                                                          // terms of the open blocks, one warp per block
+        const int nc = min(ncache_sh, SUMC_CACHE);
+        if (w < nc) {
+            const int base = cache_blk[w] * SUM_BLK, n = min(SUM_BLK, nterms - base);
+#pragma unroll
+            for (int q = 0; q < SUM_BLK / 32; q++) {
+                const int k = q * 32 + lane;
+                cache[w][k] = k < n ? terms[base + k] : 0.0;   // s + (+0.0) == s for every s the walk can hold
+            }
+        }
     }
     __syncthreads();
     const int mode = mode_sh;
     if (w != 0) return;
     if (mode & 1) {                                            // reference loop, one thread
-        if (lane == 0) { double ub = 0.0; for (int k = 0; k < nterms; k++) ub += terms[k]; *ub_out = ub; }
+        if (lane == 0) { double ub = 0.0; for (int k = 0; k < nterms; k++) ub += terms[k]; ub_store(ub_out, ub); }
         return;
     }
-    if (mode & 2) { if (lane == 0) *ub_out = neg_inf(); return; }
+    if (mode & 2) { if (lane == 0) ub_store(ub_out, neg_inf()); return; }
     double s = 0.0;                                            // identical in every lane of the warp
     for (int g = 0; g < ngrp; g++) {
         if (gexp[g] != SUM_OPEN && qfn_try(s, gexp[g], gfn[g])) continue;
-        // mixed group: its 32 block functions arrive with one coalesced load, then go round by shuffle
-        const int bl = g * 32 + lane;
-        const int el = bl < nblk ? bexp[bl] : SUM_OPEN;
-        QFn fl; fl.a0 = fl.a1 = 0;
-        if (el != SUM_OPEN) fl = bfn[bl];
         const int cnt = min(32, nblk - g * 32);
-        for (int i = 0; i < cnt; i++) {
-            const int e = __shfl_sync(0xffffffffu, el, i);
-            QFn f;
-            f.a0 = __shfl_sync(0xffffffffu, fl.a0, i);
-            f.a1 = __shfl_sync(0xffffffffu, fl.a1, i);
-            if (e != SUM_OPEN && qfn_try(s, e, f)) continue;
-            const int base = (g * 32 + i) * SUM_BLK, n = min(SUM_BLK, nterms - base);
+        for (int i = 0; i < cnt;) {                            // mixed group: run by run
+            const int b = g * 32 + i;
+            const int e = sexp[b];
+            if (e > SUM_OPEN) {
+                const int j = min(stail[b], cnt - 1);
+                if (qfn_try(s, e, sfn[g * 32 + j])) { i = j + 1; continue; }
+                // (rare) the run as a whole does not apply -- a prediction was off: block by block
+                for (int ii = i; ii <= j; ii++) {
+                    if (qfn_try(s, e, bfn[g * 32 + ii])) continue;
+                    const int base = (g * 32 + ii) * SUM_BLK, n = min(SUM_BLK, nterms - base);
 #pragma unroll
-            for (int q = 0; q < SUM_BLK / 32; q++) {
-                const int k = q * 32 + lane;
-                buf[k] = k < n ? terms[base + k] : 0.0;        // s + (+0.0) == s for every s this loop can hold
-            }
-            __syncwarp();
+                    for (int q = 0; q < SUM_BLK / 32; q++) {
+                        const int k = q * 32 + lane;
+                        buf[k] = k < n ? terms[base + k] : 0.0;
+                    }
+                    __syncwarp();
 #pragma unroll 16
-            for (int k = 0; k < SUM_BLK; k++) s = s + buf[k];
+                    for (int k = 0; k < SUM_BLK; k++) s = s + buf[k];
+                    __syncwarp();
+                }
+                i = j + 1;
+                continue;
+            }
+            const double *src = buf;                           // open block: term by term
+            if (e < SUM_OPEN) {
+                src = cache[SUM_OPEN - 1 - e];
+            } else {                                           // more than SUMC_CACHE open blocks: not staged
+                const int base = b * SUM_BLK, n = min(SUM_BLK, nterms - base);
+#pragma unroll
+                for (int q = 0; q < SUM_BLK / 32; q++) {
+                    const int k = q * 32 + lane;
+                    buf[k] = k < n ? terms[base + k] : 0.0;
+                }
+                __syncwarp();
+            }
+#pragma unroll 16
+            for (int k = 0; k < SUM_BLK; k++) s = s + src[k];
             __syncwarp();
+            i++;
         }
     }
-    if (lane == 0) *ub_out = s;
+    if (lane == 0) ub_store(ub_out, s);
 }
 
 // obj = max(delta[N-1][.]) for the no-constraint case (cp.rs:139-141) and cur = argmax (cp.rs:86)

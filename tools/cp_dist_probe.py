@@ -17,20 +17,24 @@ w = bench.workload_cp(kind)
 hm = cv.HMM(w["A"], w["B"], w["pi"])
 args = (w["obs"], w["start"], w["comp"], w["ncomp"])
 single = cv.cp_solve_arrays(hm, *args, max_nodes=2, device=local)
+cv._lib.lib().cv_set_timing(1)
 t0 = time.perf_counter()
 single = cv.cp_solve_arrays(hm, *args, max_nodes=budget, device=local)
 t_single = time.perf_counter() - t0
+loop_single = cv._lib.lib().cv_last_kernel_ms(hm.device_handle(local))
 grp = cv.CpDistGroup(hm, cap_N=w["N"], cap_terms=int((w["comp"] >= 0).sum()), device=local)
 grp.solve(*args, max_nodes=2)
 dist.barrier()
 t0 = time.perf_counter()
 r = grp.solve(*args, max_nodes=budget)
 t_dist = time.perf_counter() - t0
+loop_dist = cv._lib.lib().cv_last_kernel_ms(hm.device_handle(local))
 same = bool((r["sol"] == single["sol"]).all() and r["obj"] == single["obj"] and r["explored"] == single["explored"])
-tt = torch.tensor([t_dist], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+tt = torch.tensor([t_dist, loop_dist], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(f"{kind} world {world} cuts {cv.plan_cuts(w['comp'], world).tolist()} nodes {r['explored']} identical {same} "
-          f"sharded ms/node {1e3 * tt.item() / r['explored']:.4f} single-GPU ms/node {1e3 * t_single / single['explored']:.4f}")
+          f"sharded ms/node {1e3 * tt[0].item() / r['explored']:.4f} (device loop {tt[1].item() / r['explored']:.4f}) "
+          f"single-GPU ms/node {1e3 * t_single / single['explored']:.4f} (device loop {loop_single / single['explored']:.4f})")
 assert same
 grp.close()
 dist.barrier()
