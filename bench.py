@@ -275,14 +275,31 @@ def run_other(cv, L, device):
     other["large_K1024_B2048_T64"] = {"cells": w["cells"], "e2e_ms": 1e3 * dt, "e2e_cells_per_s": w["cells"] / dt,
                                       "note": "full configs[3] (B=4096, T=4096, `--workload large`): 3.95 s/step = 4.45e12 cells/s, 52 % of the FP64 roofline (DESIGN.md)"}
     hm.close()
+    # supervised MLE event counts (hmm.rs:35-48) at the POS shape, 1M sentences, random tags
+    w = workload_pos(0, 1000000)
+    tg = np.random.default_rng(3019).integers(0, w["K"], len(w["obs"])).astype(np.int32)
+    hm = cv.HMM.new(w["K"], (w["B"].shape[1],))
+    hm.mle_arrays(w["obs"], tg, w["off"], device=device)
+    hm2 = cv.HMM.new(w["K"], (w["B"].shape[1],))
+    t0 = time.perf_counter()
+    cms = hm2.mle_arrays(w["obs"], tg, w["off"], device=device)
+    dt = time.perf_counter() - t0
+    nel = len(w["obs"])
+    other["mle_counts_pos_1M"] = {"elements": nel, "count_kernels_ms": cms, "count_GBps": 10.0 * nel / (cms * 1e-3) / 1e9,
+                                    "e2e_ms": 1e3 * dt, "bytes_per_element": 10,
+                                    "note": "cv_mle: device event counts (u64 atomics; 10 B/element: obs u32, tag i32, start flag written + read) + host replay of the "
+                                            "reference's += 1.0 / divide / ln(x)/ln(10); e2e includes H2D of obs+tags and the K*M finalisation"}
     # configs[0] stand-in and configs[4]: constrained decode with a node budget
-    for kind, budget, cpu_budget in (("trucks", 0, 150), ("heavy", 60, 6)):      # trucks-like: complete search
+    for kind, budget, cpu_budget in (("trucks", 0, 150), ("heavy", 2000, 6)):    # trucks-like: complete search
         w = workload_cp(kind)
         hm = cv.HMM(w["A"], w["B"], w["pi"])
         cv.cp_solve_arrays(hm, w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=3, device=device)
+        L.cv_set_timing(1)
         t0 = time.perf_counter()
         r = cv.cp_solve_arrays(hm, w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=budget, device=device)
         dt = time.perf_counter() - t0
+        loop_ms = L.cv_last_kernel_ms(hm.device_handle(device))
+        L.cv_set_timing(0)
         t0 = time.perf_counter()
         rc = po.cp_solve(w["A"], w["B"], w["pi"], w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=cpu_budget)
         dtc = time.perf_counter() - t0
@@ -290,6 +307,7 @@ def run_other(cv, L, device):
         other[w["name"]] = {"N": w["N"], "K": K, "nodes": int(r["explored"]), "sweep_steps": int(r["steps"]),
                             "cells": float(r["steps"]) * K * K, "e2e_ms": 1e3 * dt,
                             "e2e_cells_per_s": float(r["steps"]) * K * K / dt, "ms_per_node": 1e3 * dt / max(1, r["explored"]),
+                            "device_loop_ms_per_node": loop_ms / max(1, r["explored"]),
                             "cpu_port_cells_per_s": float(rc["steps"]) * K * K / dtc, "cpu_nodes": int(rc["explored"]),
                             "cpu_ms_per_node": 1e3 * dtc / max(1, rc["explored"]), "objective": r["obj"],
                             "max_nodes": budget, "clamped_fraction": w["clamped"],
@@ -297,6 +315,42 @@ def run_other(cv, L, device):
                                     "reference) runs a node-budgeted prefix of the same search"}
         hm.close()
     return other
+
+
+def run_cp_sharded(cv, L, spec, local, rank, world, dist, torch):
+    """Constrained decode sharded over the ranks (NVLink peer stores, no NCCL on the data path) next to the same
+    solve on one GPU; every rank must return the single-GPU result bit for bit.  Device-loop times (CUDA events,
+    set-up and copies excluded), max over ranks."""
+    kind, _, budget = spec.partition(":")
+    budget = int(budget or 0)
+    w = workload_cp(kind)
+    hm = cv.HMM(w["A"], w["B"], w["pi"])
+    args = (w["obs"], w["start"], w["comp"], w["ncomp"])
+    h = hm.device_handle(local)
+    L.cv_set_timing(1)
+    cv.cp_solve_arrays(hm, *args, max_nodes=3, device=local)
+    single = cv.cp_solve_arrays(hm, *args, max_nodes=budget, device=local)
+    ms_single = L.cv_last_kernel_ms(h)
+    grp = cv.CpDistGroup(hm, cap_N=w["N"], cap_terms=int((w["comp"] >= 0).sum()), device=local)
+    grp.solve(*args, max_nodes=3)
+    dist.barrier()
+    t0 = time.perf_counter()
+    r = grp.solve(*args, max_nodes=budget)
+    wall = time.perf_counter() - t0
+    ms_sharded = L.cv_last_kernel_ms(h)
+    L.cv_set_timing(0)
+    same = bool((r["sol"] == single["sol"]).all() and r["obj"] == single["obj"] and r["explored"] == single["explored"])
+    t = torch.tensor([ms_sharded, ms_single, 1e3 * wall, 0.0 if same else 1.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cuts = cv.plan_cuts(w["comp"], world).tolist()
+    grp.close()
+    hm.close()
+    nodes = max(1, int(r["explored"]))
+    return {"workload": w["name"], "N": w["N"], "K": w["K"], "nodes": nodes, "row_cuts": cuts,
+            "identical_to_single_gpu_on_every_rank": bool(t[3].item() == 0.0),
+            "sharded_ms_per_node": t[0].item() / nodes, "single_gpu_ms_per_node": t[1].item() / nodes,
+            "sharded_wall_ms": t[2].item(),
+            "exchange": "bound terms, backtrack maps and solution rows by NVLink peer stores + flags (CUDA IPC); no NCCL"}
 
 
 def parse():
@@ -310,6 +364,9 @@ def parse():
     ap.add_argument("--seqlen", type=int, default=0, help="T for --workload large (0 = 4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other configs")
+    ap.add_argument("--cp-sharded", default="", metavar="KIND:NODES",
+                    help="with --gpus > 1: also time the constrained decode sharded over the ranks (csrc/cp_dist.cuh), "
+                         "e.g. heavy:2000 (configs[4]) or trucks:0; reported under \"cp_sharded\"")
     return ap.parse_args()
 
 
@@ -482,6 +539,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    cp_sharded = None
+    if args.cp_sharded and world > 1:
+        try:
+            cp_sharded = run_cp_sharded(cv, L, args.cp_sharded, local, rank, world, dist, torch)
+        except Exception as e:  # noqa: BLE001
+            cp_sharded = {"error": repr(e)}
+
     total_cells = allsum(wl["cells"])
     dev_ms = allmax(dev_ms)
     e2e_s = allmax(e2e_s)
@@ -543,6 +607,8 @@ def main():
                 line["other"] = run_other(cv, L, local)
             except Exception as e:  # the headline numbers stand on their own
                 line["other"] = {"error": repr(e)}
+        if cp_sharded is not None:
+            line["cp_sharded"] = cp_sharded
         print(json.dumps(line), flush=True)
     for p in (p_obs, p_off, p_path, p_score):
         L.cv_host_free(p)

@@ -27,6 +27,7 @@
 #include "decode_large.cuh"
 #include "cp_kernels.cuh"
 #include "cp_dist.cuh"
+#include "mle.cuh"
 #include "probe.cuh"
 
 using namespace cvb;
@@ -717,3 +718,4 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
 }
 
 #include "cp_host.inl"
+#include "mle_host.inl"

@@ -27,6 +27,51 @@ class HMM:
         self.bdims = tuple(int(x) for x in self.b.shape[1:])
         self._handles = {}
 
+    # ---- construction / supervised training (hmm.rs:22-62) ----
+    @classmethod
+    def new(cls, nstates: int, bdims, rng=None):
+        """HMM::new (hmm.rs:22-28): a random row-normalised model.  The reference draws from `thread_rng()` (not
+        reproducible by construction); pass a numpy Generator, or rng=None for the all-zero model that turns
+        maximum_likelihood_estimation into the plain count-based estimate."""
+        bdims = tuple(int(x) for x in bdims)
+        if rng is None:
+            return cls(np.zeros((nstates, nstates)), np.zeros((nstates,) + bdims), np.zeros(nstates))
+        a = rng.random((nstates, nstates))
+        b = rng.random((nstates,) + bdims)
+        pi = rng.random(nstates)
+        a /= a.sum(axis=1, keepdims=True)
+        b /= b.reshape(nstates, -1).sum(axis=1).reshape((nstates,) + (1,) * len(bdims))
+        return cls(a, b, pi / pi.sum())
+
+    def maximum_likelihood_estimation(self, sequences, tags, device: int = -1):
+        """HMM::maximum_likelihood_estimation + log (hmm.rs:30-62,192-205) through cv_mle: events are counted on
+        the GPU and added on top of this model's current (probability) values exactly as the reference's
+        `+= 1.0` loop would; afterwards a, b, pi hold ln(x)/ln(10) (-inf for 0).
+        sequences: list of [T, D] observation arrays, tags: list of tag lists (None / -1 = missing -> error)."""
+        self.close()                                                     # device copies become stale
+        obs = [self.flatten_obs(sq) for sq in sequences]
+        off = np.zeros(len(obs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(o) for o in obs])
+        obs_flat = np.concatenate(obs) if obs else np.zeros(0, dtype=np.uint32)
+        tg = np.array([(-1 if t is None else int(t)) for tl in tags for t in tl], dtype=np.int32)
+        if len(tg) != len(obs_flat):
+            raise ValueError("sequences and tags differ in length")
+        return self.mle_arrays(obs_flat, tg, off, device)
+
+    def mle_arrays(self, obs_flat, tags_flat, seq_off, device: int = -1):
+        """cv_mle on flat arrays; returns the device time (ms) of the counting kernels."""
+        obs_flat = np.ascontiguousarray(obs_flat, dtype=np.uint32)
+        tags_flat = np.ascontiguousarray(tags_flat, dtype=np.int32)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+        K = self.nstates()
+        bd = (C.c_uint64 * len(self.bdims))(*self.bdims)
+        ms = C.c_double(0.0)
+        rc = _lib.lib().cv_mle(K, len(self.bdims), bd, self.a.ctypes.data, self.b.ctypes.data, self.pi.ctypes.data,
+                               obs_flat.ctypes.data, tags_flat.ctypes.data, seq_off.ctypes.data, len(seq_off) - 1,
+                               int(device), C.byref(ms))
+        _lib.check(rc)
+        return ms.value
+
     # ---- reference accessors (host-side, used by SuperSequence.reorder and tests) ----
     def nstates(self) -> int:                       # hmm.rs:207-209
         return self.a.shape[0]

@@ -130,6 +130,19 @@ int cv_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *n_out);
  * mode 0 = one-thread loop, mode 1 = the parallel exact-order kernel; both must agree bit for bit. */
 int cv_debug_ordered_sum(const double *values, int64_t n, int mode, double *out);
 
+/* ---- supervised maximum-likelihood estimation --------------------------------
+ * Replaces: HMM::maximum_likelihood_estimation(&mut self, sequences, tags) followed by HMM::log
+ * (src/hmm/hmm.rs:30-62,192-205).  a [K*K], b [K*M], pi [K] hold the model the reference would call it on --
+ * HMM::new's random model (hmm.rs:22-28), or zeros for a plain count-based estimate -- as PROBABILITIES on entry;
+ * on exit they hold what the reference holds after log(): ln(x)/ln(10), -inf for 0.  The events are counted on
+ * the device; given the same initial model the result is the reference's bit for bit (each entry is its initial
+ * value with `+= 1.0` applied count times, then the reference's divisions).  tags < 0 = None.
+ *   CV_ERR_EMPTY  an empty sequence (tag[0] / len()-1 panics)   CV_ERR_ARG  a None tag, tag >= K, observation >= M
+ * count_ms_out (may be NULL): device time of the counting kernels.  HOST pointers. */
+int cv_mle(int K, int D, const uint64_t *bdims, double *a, double *b, double *pi,
+           const uint32_t *obs_flat, const int32_t *tags_flat, const int64_t *seq_off,
+           int64_t B, int device, double *count_ms_out);
+
 /* ---- plumbing --------------------------------------------------------------*/
 const char *cv_last_error(void);
 /* kernels launched by this library in this process (bench.py "gpu_launches") */

@@ -381,3 +381,49 @@ int cvo_cp_solve(int K, int64_t M, const double *logA, const double *logB,
     free(s.cons); free(s.cons_len); free(s.choice); free(s.delta); free(s.psi); free(s.probs); free(at);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Supervised maximum-likelihood estimation, HMM::maximum_likelihood_estimation (hmm.rs:30-62) followed by
+ * HMM::log (hmm.rs:192-205).  Literal: the counts are added one `+= 1.0` at a time ON TOP of whatever the
+ * model holds (the reference calls this on HMM::new's random model, hmm.rs:22-28), in the reference's order.
+ * tags[t] < 0 stands for None (reference: unwrap() panic).  a [K*K], b [K*M], pi [K] are probabilities on
+ * entry and log10-as-the-reference-computes-it on exit: f64::log(10.0) = ln(x) / ln(10).
+ * ------------------------------------------------------------------------------------------------ */
+int cvo_mle(int K, int64_t M, double *a, double *b, double *pi, const uint32_t *obs, const int32_t *tags,
+            const int64_t *seq_off, int64_t B)
+{
+    if (K <= 0 || M <= 0 || !a || !b || !pi || B < 0) return CVO_ERR_ARG;
+    double *seen = (double *)calloc((size_t)K, sizeof(double)), *end = (double *)calloc((size_t)K, sizeof(double));
+    if (!seen || !end) { free(seen); free(end); return CVO_ERR_ARG; }
+    int rc = CVO_OK;
+    for (int64_t i = 0; i < B && !rc; i++) {                               /* hmm.rs:35-48 */
+        const int64_t o = seq_off[i], T = seq_off[i + 1] - seq_off[i];
+        if (T <= 0) { rc = CVO_ERR_EMPTY; break; }                         /* tag[0] / len()-1 panics */
+        for (int64_t t = 0; t < T; t++)
+            if (tags[o + t] < 0 || tags[o + t] >= K || (int64_t)obs[o + t] >= M) rc = CVO_ERR_ARG;
+        if (rc) break;
+        pi[tags[o]] += 1.0;                                                /* :39 */
+        for (int64_t t = 0; t < T - 1; t++) {                              /* :40-44 */
+            b[(int64_t)tags[o + t] * M + obs[o + t]] += 1.0;
+            a[(int64_t)tags[o + t] * K + tags[o + t + 1]] += 1.0;
+            seen[tags[o + t]] += 1.0;
+        }
+        b[(int64_t)tags[o + T - 1] * M + obs[o + T - 1]] += 1.0;           /* :45-47 */
+        seen[tags[o + T - 1]] += 1.0;
+        end[tags[o + T - 1]] += 1.0;
+    }
+    if (!rc) {
+        for (int s = 0; s < K; s++) {                                      /* hmm.rs:50-59 */
+            if (seen[s] != end[s]) { const double d = seen[s] - end[s]; for (int j = 0; j < K; j++) a[(int64_t)s * K + j] /= d; }
+            else for (int j = 0; j < K; j++) a[(int64_t)s * K + j] = 0.0;
+            pi[s] /= (double)B;
+            for (int64_t m = 0; m < M; m++) b[(int64_t)s * M + m] /= seen[s];
+        }
+        const double ln10 = log(10.0);                                     /* hmm.rs:192-205: x.log(10.0) */
+        for (int64_t e = 0; e < (int64_t)K * K; e++) a[e] = a[e] == 0.0 ? -INFINITY : log(a[e]) / ln10;
+        for (int64_t e = 0; e < (int64_t)K * M; e++) b[e] = b[e] == 0.0 ? -INFINITY : log(b[e]) / ln10;
+        for (int e = 0; e < K; e++) pi[e] = pi[e] == 0.0 ? -INFINITY : log(pi[e]) / ln10;
+    }
+    free(seen); free(end);
+    return rc;
+}

@@ -80,6 +80,12 @@ int cvo_cp_solve(int K, int64_t M, const double *logA, const double *logB,
                  double *delta_out /* optional [N*K] final state */,
                  uint64_t *psi_out /* optional [N*K] final state */);
 
+/* HMM::maximum_likelihood_estimation + HMM::log (hmm.rs:30-62,192-205), literal: counts are added with one
+ * `+= 1.0` per event on top of the model passed in (the reference starts from HMM::new's random model);
+ * a/b/pi are probabilities on entry, ln(x)/ln(10) (-inf for 0) on exit.  tags < 0 = None (unwrap panic). */
+int cvo_mle(int K, int64_t M, double *a, double *b, double *pi, const uint32_t *obs, const int32_t *tags,
+            const int64_t *seq_off, int64_t B);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
             u64p, dp, u64p, u64p, u64p, C.c_uint64, dp, dp, u64p,
         ]
         L.cvo_cp_solve.restype = C.c_int
+        L.cvo_mle.argtypes = [C.c_int, C.c_int64, dp, dp, dp, u32p, i32p, i64p, C.c_int64]
+        L.cvo_mle.restype = C.c_int
         _lib = L
     return _lib
 
@@ -143,3 +145,18 @@ def cp_solve(logA, logB, logPi, obs, is_seq_start, comp, ncomp, max_nodes: int =
         raise OracleError(rc)
     return dict(sol=sol[:N], obj=obj.value, explored=explored.value, steps=steps.value,
                 node_hash=nh, ub=ub, delta=delta, psi=psi)
+
+
+def mle(a, b, pi, obs_flat, tags_flat, seq_off):
+    """HMM::maximum_likelihood_estimation + log (hmm.rs:30-62,192-205) on top of the model (a, b, pi);
+    returns new (logA, logB, logPi)."""
+    a, b, pi = _f64(a).copy(), _f64(b).copy(), _f64(pi).copy()
+    K, M = b.shape
+    obs = np.ascontiguousarray(obs_flat, dtype=np.uint32)
+    tags = np.ascontiguousarray(tags_flat, dtype=np.int32)
+    off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    rc = lib().cvo_mle(K, M, _p(a, C.c_double), _p(b, C.c_double), _p(pi, C.c_double), _p(obs, C.c_uint32),
+                       _p(tags, C.c_int32), _p(off, C.c_int64), len(off) - 1)
+    if rc:
+        raise OracleError(rc)
+    return a, b, pi

@@ -145,3 +145,38 @@ def test_r2_max_nodes_budget():
     full = po.cp_solve(A, B, pi, obs, start, comp, ncomp)
     cut = po.cp_solve(A, B, pi, obs, start, comp, ncomp, max_nodes=3)
     assert cut["explored"] == min(3, full["explored"])
+
+
+def test_oracle_mle_against_numpy_counts():
+    """cvo_mle (literal hmm.rs:30-62 + log) on a zero initial model = count ratios; numpy's log is not glibc's, so
+    values are compared to 1e-15 relative and zeros / -inf exactly.  A random initial model changes every entry."""
+    rng = np.random.default_rng(11)
+    K, M, B = 5, 7, 300
+    lens = rng.integers(1, 9, size=B)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    obs = rng.integers(0, M, off[-1]).astype(np.uint32)
+    tags = rng.integers(0, K, off[-1]).astype(np.int32)
+    la, lb, lpi = po.mle(np.zeros((K, K)), np.zeros((K, M)), np.zeros(K), obs, tags, off)
+    ca, cb, cpi, seen, end = np.zeros((K, K)), np.zeros((K, M)), np.zeros(K), np.zeros(K), np.zeros(K)
+    for i in range(B):
+        s, e = off[i], off[i + 1]
+        cpi[tags[s]] += 1
+        for t in range(s, e):
+            cb[tags[t], obs[t]] += 1
+            seen[tags[t]] += 1
+            if t + 1 < e:
+                ca[tags[t], tags[t + 1]] += 1
+        end[tags[e - 1]] += 1
+    with np.errstate(divide="ignore"):
+        ra = np.log(ca / (seen - end)[:, None]) / np.log(10.0)
+        rb = np.log(cb / seen[:, None]) / np.log(10.0)
+        rpi = np.log(cpi / B) / np.log(10.0)
+    for got, ref in ((la, ra), (lb, rb), (lpi, rpi)):
+        assert (np.isneginf(got) == np.isneginf(ref)).all()
+        fin = np.isfinite(ref)
+        assert np.allclose(got[fin], ref[fin], rtol=1e-15, atol=0)
+    a0 = rng.random((K, K))
+    la2, _, _ = po.mle(a0, np.zeros((K, M)), np.zeros(K), obs, tags, off)
+    assert not np.isneginf(la2).any() and (la2 != la).any()
+    with pytest.raises(po.OracleError):
+        po.mle(np.zeros((K, K)), np.zeros((K, M)), np.zeros(K), obs, np.where(np.arange(len(tags)) == 3, -1, tags), off)
