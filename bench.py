@@ -109,6 +109,8 @@ def workload_cp(kind):
     rng = np.random.default_rng(3019)
     if kind == "trucks":
         K, M, nseq, pact, tlo, thi, zf = 12, 128, 200, 0.30, 50, 400, 0.0
+    elif kind == "heavy10":                                   # configs[4] with ten times the sequences (N = 6.4M)
+        K, M, nseq, pact, tlo, thi, zf = 16, 64, 640, 0.80, 10000, 10000, 0.0
     else:
         K, M, nseq, pact, tlo, thi, zf = 16, 64, 64, 0.80, 10000, 10000, 0.0
     A, B, pi = make_hmm(3019, K, M, 0.5, zf)

@@ -76,7 +76,9 @@ int cp_launch_sum(const double *terms, int nterms, const UbSink &ub, unsigned in
         g_launches++;
     } else {
         if (!have_stats || pw.R > 1) { cp_sum_stats_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bflag, pw); g_launches++; }
-        cp_sum_blockfn_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bexp, ws.bfn);
+        const double *bpre = nullptr;
+        if (nblk >= SUM_PREFIX_MIN) { cp_sum_prefix_kernel<<<1, 1024, 0, st>>>(ws.bsum, nblk, ws.bpre); g_launches++; bpre = ws.bpre; }
+        cp_sum_blockfn_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, bpre, ws.bexp, ws.bfn);
         cp_sum_chain_kernel<<<1, SUMC_THREADS, sum_chain_smem_bytes(nblk), st>>>(terms, nterms, nblk, ws.bflag, ws.bexp, ws.bfn, ub, counter);
         g_launches += 2;
     }

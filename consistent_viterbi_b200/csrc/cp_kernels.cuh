@@ -593,15 +593,38 @@ __global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *
 //      are summed term by term in floating point (SUM_BLK dependent adds).
 // Special values as in cp_sum_exact_kernel: a positive/NaN term => the plain loop over everything, -inf => -inf.
 constexpr int SUM_OPEN = -100000;                     // "no function for this block / group"
-constexpr int SUM_MAX_BLOCKS = 4096;                  // above this (512k terms) the single-CTA kernel is used
+constexpr int SUM_MAX_BLOCKS = 1 << 16;               // above this (8M terms) the single-CTA kernel is used
+constexpr int SUM_TILE_BLOCKS = 4096;                 // blocks the chain kernel stages in shared memory at a time
+constexpr int SUM_PREFIX_MIN = 2048;                  // from here on the approximate prefixes come from their own kernel
+
+// approximate exclusive prefix of the block sums for long lists (short ones sum the earlier blocks inside
+// cp_sum_blockfn_kernel): every thread a contiguous stretch, then a scan of the 1024 partial sums
+__global__ void __launch_bounds__(1024) cp_sum_prefix_kernel(const double *bsum, int nblk, double *bpre)
+{
+    __shared__ double part[1024];
+    const int tid = threadIdx.x, per = (nblk + 1023) / 1024, lo = min(tid * per, nblk), hi = min(lo + per, nblk);
+    double acc = 0.0;
+    for (int i = lo; i < hi; i++) acc += bsum[i];
+    part[tid] = acc;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const double v = tid >= d ? part[tid - d] : 0.0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    double run = tid ? part[tid - 1] : 0.0;
+    for (int i = lo; i < hi; i++) { bpre[i] = run; run += bsum[i]; }
+}
 
 __global__ void __launch_bounds__(SUM_BLK) cp_sum_blockfn_kernel(const double *terms, int nterms, const double *bsum,
-                                                               int *bexp, QFn *bfn)
+                                                               const double *bpre, int *bexp, QFn *bfn)
 {
     __shared__ double ws[SUM_BLK / 32]; __shared__ int e_sh; __shared__ QFn wagg[SUM_BLK / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     double acc = 0.0;
-    for (int i = tid; i < b; i += SUM_BLK) acc += bsum[i];
+    if (bpre) { if (tid == 0) acc = bpre[b]; }
+    else for (int i = tid; i < b; i += SUM_BLK) acc += bsum[i];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     if (lane == 0) ws[w] = acc;
@@ -653,151 +676,166 @@ __device__ __forceinline__ bool qfn_try(double &s, int e, const QFn f)
 
 // workspace of the block-structured sum, carved out of one device buffer
 struct SumWs {
-    double *bsum = nullptr; QFn *bfn = nullptr; int *bflag = nullptr, *bexp = nullptr;
+    double *bsum = nullptr, *bpre = nullptr; QFn *bfn = nullptr; int *bflag = nullptr, *bexp = nullptr;
     template <class Buf> int bind(Buf &b, size_t nterms)
     {
         const size_t nblk = (nterms + SUM_BLK - 1) / SUM_BLK + 1;
-        const int rc = b.ensure(nblk * (sizeof(double) + sizeof(QFn) + 2 * sizeof(int)) + 64);
+        const int rc = b.ensure(nblk * (2 * sizeof(double) + sizeof(QFn) + 2 * sizeof(int)) + 64);
         if (rc) return rc;
-        bfn = (QFn *)b.p; bsum = (double *)(bfn + nblk); bflag = (int *)(bsum + nblk); bexp = bflag + nblk;
+        bfn = (QFn *)b.p; bsum = (double *)(bfn + nblk); bpre = bsum + nblk; bflag = (int *)(bpre + nblk); bexp = bflag + nblk;
         return 0;
     }
 };
 
 constexpr int SUMC_THREADS = 1024;
 constexpr int SUMC_CACHE = 32;                         // open blocks whose terms are staged in shared memory
-__host__ __device__ inline size_t sum_chain_smem_bytes(int nblk) { return (size_t)(nblk + 32) * (sizeof(QFn) + 2 * sizeof(int)); }
+__host__ __device__ inline size_t sum_chain_smem_bytes(int nblk)
+{
+    return (size_t)((nblk < SUM_TILE_BLOCKS ? nblk : SUM_TILE_BLOCKS) + 32) * (sizeof(QFn) + 2 * sizeof(int));
+}
 
 // Everything the serial walk touches is staged in shared memory first (block functions, the terms of the blocks
 // known to be open): the walk is a chain of dependent steps, a global-memory latency per step would dominate it.
+// Lists longer than SUM_TILE_BLOCKS blocks go through in tiles, the running sum carried from tile to tile.
 __global__ void __launch_bounds__(SUMC_THREADS) cp_sum_chain_kernel(const double *terms, int nterms, int nblk,
                                                                    const int *bflag, const int *bexp, const QFn *bfn,
                                                                    const UbSink ub_out, unsigned int *reset_counter)
 {
     if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
-    constexpr int MAXG = SUM_MAX_BLOCKS / 32;
+    constexpr int MAXG = SUM_TILE_BLOCKS / 32;
     extern __shared__ __align__(16) unsigned char sumc_raw[];
     __shared__ QFn gfn[MAXG]; __shared__ int gexp[MAXG]; __shared__ int mode_sh, ncache_sh;
     __shared__ int cache_blk[SUMC_CACHE];
     __shared__ double cache[SUMC_CACHE][SUM_BLK];
     __shared__ double buf[SUM_BLK];
+    __shared__ double s_sh;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int nblk_pad = (nblk + 31) & ~31;
+    const int cap = (min(nblk, SUM_TILE_BLOCKS) + 31) & ~31;
     QFn *sfn = reinterpret_cast<QFn *>(sumc_raw);
-    int *sexp = reinterpret_cast<int *>(sfn + nblk_pad);   // binade or SUM_OPEN; SUM_OPEN - 1 - slot = open + cached
-    int *stail = sexp + nblk_pad;                          // at the first block of a run: lane of the run's last block
-    if (tid == 0) { mode_sh = 0; ncache_sh = 0; }
+    int *sexp = reinterpret_cast<int *>(sfn + cap);        // binade or SUM_OPEN; SUM_OPEN - 1 - slot = open + cached
+    int *stail = sexp + cap;                               // at the first block of a run: lane of the run's last block
+    if (tid == 0) { mode_sh = 0; s_sh = 0.0; }
     __syncthreads();
     int flag = 0;
-    for (int b = tid; b < nblk_pad; b += SUMC_THREADS) {
-        int e = SUM_OPEN; QFn f; f.a0 = f.a1 = 0;
-        if (b < nblk) {
-            flag |= bflag[b];
-            e = bexp[b];
-            if (e != SUM_OPEN) f = bfn[b];
-            else { const int slot = atomicAdd(&ncache_sh, 1); if (slot < SUMC_CACHE) { cache_blk[slot] = b; e = SUM_OPEN - 1 - slot; } }
-        }
-        sexp[b] = e; sfn[b] = f;
-    }
+    for (int b = tid; b < nblk; b += SUMC_THREADS) flag |= bflag[b];
     if (flag) atomicOr(&mode_sh, flag);
     __syncthreads();
-    const int ngrp = nblk_pad / 32;
-    // Runs: maximal stretches of consecutive blocks of a group with a function for the same binade.  A segmented
-    // scan leaves in sfn[b] the composition from the run's first block up to b, so the walk takes a run in one
-    // step; a group that is a single run is "clean" and is taken through gfn.
-    for (int g = w; g < ngrp; g += SUMC_THREADS / 32) {
-        const int b = g * 32 + lane;
-        const int e = sexp[b];
-        QFn f = sfn[b];
-        const int e_prev = __shfl_up_sync(0xffffffffu, e, 1);
-        const bool open = e <= SUM_OPEN;
-        const bool head = lane == 0 || open || e_prev <= SUM_OPEN || e != e_prev;
-        const unsigned int heads = __ballot_sync(0xffffffffu, head);
-        const int my_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            QFn o;
-            o.a0 = __shfl_up_sync(0xffffffffu, f.a0, d);
-            o.a1 = __shfl_up_sync(0xffffffffu, f.a1, d);
-            if (lane - d >= my_head) f = qfn_compose(o, f);
-        }
-        const unsigned int later = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
-        sfn[b] = f;
-        stail[b] = later ? __ffs(later) - 2 : 31;
-        // clean = one run over the whole group (blocks past the end count as identity in the same binade)
-        const int nreal = min(32, nblk - g * 32);
-        const bool one_run = (heads & (nreal >= 32 ? 0xffffffffu : ((1u << nreal) - 1u))) == 1u && !open;
-        const int src = nreal - 1;
-        const QFn fl = QFn{__shfl_sync(0xffffffffu, f.a0, src), __shfl_sync(0xffffffffu, f.a1, src)};
-        const int e0 = __shfl_sync(0xffffffffu, e, 0);
-        const bool clean = __shfl_sync(0xffffffffu, (int)one_run, 0) != 0;
-        if (lane == 0) { gfn[g] = fl; gexp[g] = clean ? e0 : SUM_OPEN; }
-    }
-    {                                                          // terms of the open blocks, one warp per block
-        const int nc = min(ncache_sh, SUMC_CACHE);
-        if (w < nc) {
-            const int base = cache_blk[w] * SUM_BLK, n = min(SUM_BLK, nterms - base);
-#pragma unroll
-            for (int q = 0; q < SUM_BLK / 32; q++) {
-                const int k = q * 32 + lane;
-                cache[w][k] = k < n ? terms[base + k] : 0.0;   // s + (+0.0) == s for every s the walk can hold
-            }
-        }
-    }
-    __syncthreads();
     const int mode = mode_sh;
-    if (w != 0) return;
     if (mode & 1) {                                            // reference loop, one thread
-        if (lane == 0) { double ub = 0.0; for (int k = 0; k < nterms; k++) ub += terms[k]; ub_store(ub_out, ub); }
+        if (tid == 0) { double ub = 0.0; for (int k = 0; k < nterms; k++) ub += terms[k]; ub_store(ub_out, ub); }
         return;
     }
-    if (mode & 2) { if (lane == 0) ub_store(ub_out, neg_inf()); return; }
-    double s = 0.0;                                            // identical in every lane of the warp
-    for (int g = 0; g < ngrp; g++) {
-        if (gexp[g] != SUM_OPEN && qfn_try(s, gexp[g], gfn[g])) continue;
-        const int cnt = min(32, nblk - g * 32);
-        for (int i = 0; i < cnt;) {                            // mixed group: run by run
-            const int b = g * 32 + i;
-            const int e = sexp[b];
-            if (e > SUM_OPEN) {
-                const int j = min(stail[b], cnt - 1);
-                if (qfn_try(s, e, sfn[g * 32 + j])) { i = j + 1; continue; }
-                // (rare) the run as a whole does not apply -- a prediction was off: block by block
-                for (int ii = i; ii <= j; ii++) {
-                    if (qfn_try(s, e, bfn[g * 32 + ii])) continue;
-                    const int base = (g * 32 + ii) * SUM_BLK, n = min(SUM_BLK, nterms - base);
-#pragma unroll
-                    for (int q = 0; q < SUM_BLK / 32; q++) {
-                        const int k = q * 32 + lane;
-                        buf[k] = k < n ? terms[base + k] : 0.0;
-                    }
-                    __syncwarp();
-#pragma unroll 16
-                    for (int k = 0; k < SUM_BLK; k++) s = s + buf[k];
-                    __syncwarp();
-                }
-                i = j + 1;
-                continue;
+    if (mode & 2) { if (tid == 0) ub_store(ub_out, neg_inf()); return; }
+
+    for (int t0 = 0; t0 < nblk; t0 += SUM_TILE_BLOCKS) {
+        const int nb = min(SUM_TILE_BLOCKS, nblk - t0), nb_pad = (nb + 31) & ~31;
+        if (tid == 0) ncache_sh = 0;
+        __syncthreads();
+        for (int b = tid; b < nb_pad; b += SUMC_THREADS) {
+            int e = SUM_OPEN; QFn f; f.a0 = f.a1 = 0;
+            if (b < nb) {
+                e = bexp[t0 + b];
+                if (e != SUM_OPEN) f = bfn[t0 + b];
+                else { const int slot = atomicAdd(&ncache_sh, 1); if (slot < SUMC_CACHE) { cache_blk[slot] = t0 + b; e = SUM_OPEN - 1 - slot; } }
             }
-            const double *src = buf;                           // open block: term by term
-            if (e < SUM_OPEN) {
-                src = cache[SUM_OPEN - 1 - e];
-            } else {                                           // more than SUMC_CACHE open blocks: not staged
-                const int base = b * SUM_BLK, n = min(SUM_BLK, nterms - base);
+            sexp[b] = e; sfn[b] = f;
+        }
+        __syncthreads();
+        const int ngrp = nb_pad / 32;
+        // Runs: maximal stretches of consecutive blocks of a group with a function for the same binade.  A segmented
+        // scan leaves in sfn[b] the composition from the run's first block up to b, so the walk takes a run in one
+        // step; a group that is a single run is "clean" and is taken through gfn.
+        for (int g = w; g < ngrp; g += SUMC_THREADS / 32) {
+            const int b = g * 32 + lane;
+            const int e = sexp[b];
+            QFn f = sfn[b];
+            const int e_prev = __shfl_up_sync(0xffffffffu, e, 1);
+            const bool open = e <= SUM_OPEN;
+            const bool head = lane == 0 || open || e_prev <= SUM_OPEN || e != e_prev;
+            const unsigned int heads = __ballot_sync(0xffffffffu, head);
+            const int my_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                QFn o;
+                o.a0 = __shfl_up_sync(0xffffffffu, f.a0, d);
+                o.a1 = __shfl_up_sync(0xffffffffu, f.a1, d);
+                if (lane - d >= my_head) f = qfn_compose(o, f);
+            }
+            const unsigned int later = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
+            sfn[b] = f;
+            stail[b] = later ? __ffs(later) - 2 : 31;
+            // clean = one run over the whole group (blocks past the end count as identity in the same binade)
+            const int nreal = min(32, nb - g * 32);
+            const bool one_run = (heads & (nreal >= 32 ? 0xffffffffu : ((1u << nreal) - 1u))) == 1u && !open;
+            const int src = nreal - 1;
+            const QFn fl = QFn{__shfl_sync(0xffffffffu, f.a0, src), __shfl_sync(0xffffffffu, f.a1, src)};
+            const int e0 = __shfl_sync(0xffffffffu, e, 0);
+            const bool clean = __shfl_sync(0xffffffffu, (int)one_run, 0) != 0;
+            if (lane == 0) { gfn[g] = fl; gexp[g] = clean ? e0 : SUM_OPEN; }
+        }
+        {                                                      // terms of the open blocks, one warp per block
+            const int nc = min(ncache_sh, SUMC_CACHE);
+            if (w < nc) {
+                const int base = cache_blk[w] * SUM_BLK, n = min(SUM_BLK, nterms - base);
 #pragma unroll
                 for (int q = 0; q < SUM_BLK / 32; q++) {
                     const int k = q * 32 + lane;
-                    buf[k] = k < n ? terms[base + k] : 0.0;
+                    cache[w][k] = k < n ? terms[base + k] : 0.0;   // s + (+0.0) == s for every s the walk can hold
                 }
-                __syncwarp();
             }
-#pragma unroll 16
-            for (int k = 0; k < SUM_BLK; k++) s = s + src[k];
-            __syncwarp();
-            i++;
         }
+        __syncthreads();
+        if (w == 0) {
+            double s = s_sh;                                   // identical in every lane of the warp
+            for (int g = 0; g < ngrp; g++) {
+                if (gexp[g] != SUM_OPEN && qfn_try(s, gexp[g], gfn[g])) continue;
+                const int cnt = min(32, nb - g * 32);
+                for (int i = 0; i < cnt;) {                    // mixed group: run by run
+                    const int b = g * 32 + i;
+                    const int e = sexp[b];
+                    if (e > SUM_OPEN) {
+                        const int j = min(stail[b], cnt - 1);
+                        if (qfn_try(s, e, sfn[g * 32 + j])) { i = j + 1; continue; }
+                        // (rare) the run as a whole does not apply -- a prediction was off: block by block
+                        for (int ii = i; ii <= j; ii++) {
+                            if (qfn_try(s, e, bfn[t0 + g * 32 + ii])) continue;
+                            const int base = (t0 + g * 32 + ii) * SUM_BLK, n = min(SUM_BLK, nterms - base);
+#pragma unroll
+                            for (int q = 0; q < SUM_BLK / 32; q++) {
+                                const int k = q * 32 + lane;
+                                buf[k] = k < n ? terms[base + k] : 0.0;
+                            }
+                            __syncwarp();
+#pragma unroll 16
+                            for (int k = 0; k < SUM_BLK; k++) s = s + buf[k];
+                            __syncwarp();
+                        }
+                        i = j + 1;
+                        continue;
+                    }
+                    const double *src = buf;                   // open block: term by term
+                    if (e < SUM_OPEN) {
+                        src = cache[SUM_OPEN - 1 - e];
+                    } else {                                   // more than SUMC_CACHE open blocks in the tile: not staged
+                        const int base = (t0 + b) * SUM_BLK, n = min(SUM_BLK, nterms - base);
+#pragma unroll
+                        for (int q = 0; q < SUM_BLK / 32; q++) {
+                            const int k = q * 32 + lane;
+                            buf[k] = k < n ? terms[base + k] : 0.0;
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll 16
+                    for (int k = 0; k < SUM_BLK; k++) s = s + src[k];
+                    __syncwarp();
+                    i++;
+                }
+            }
+            if (lane == 0) s_sh = s;
+        }
+        __syncthreads();
     }
-    if (lane == 0) ub_store(ub_out, s);
+    if (tid == 0) ub_store(ub_out, s_sh);
 }
 
 // obj = max(delta[N-1][.]) for the no-constraint case (cp.rs:139-141) and cur = argmax (cp.rs:86)

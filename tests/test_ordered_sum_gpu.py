@@ -82,7 +82,10 @@ def test_ordered_sum_block_edges():
     for total in (2.0 ** 10, 2.0 ** 14):                          # creep over a binade boundary in tiny steps
         x = np.concatenate([[-(total - 1e-9)], -np.full(6000, 1e-12), -rng.random(3000)])
         assert _same(_gpu(x, 1), _serial(x))
-    x = -rng.random(128 * 4096 + 300) * 2                         # > SUM_MAX_BLOCKS blocks -> single-CTA path
-    assert _same(_gpu(x, 1), float(np.cumsum(x)[-1]))
-    x = -rng.random(128 * 4096 - 77) * 2                          # just below: 4096 blocks on the block path
+    for n in (128 * 2048 - 5, 128 * 2048 + 5,                     # around SUM_PREFIX_MIN (prefix kernel on / off)
+              128 * 4096 - 77, 128 * 4096 + 300,                  # one tile / two tiles of the chain kernel
+              128 * 4096 * 3 + 5):                                # four tiles
+        x = -rng.random(n) * 2
+        assert _same(_gpu(x, 1), float(np.cumsum(x)[-1])), n
+    x = np.log10(rng.random(128 * 65536 + 5))                     # > SUM_MAX_BLOCKS blocks -> single-CTA path
     assert _same(_gpu(x, 1), float(np.cumsum(x)[-1]))
