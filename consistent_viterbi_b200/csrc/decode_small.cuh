@@ -180,11 +180,12 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     const int s0 = sg * (32 * TPT) + lane * TPT;
     const uint32_t slab_bytes = (uint32_t)((size_t)K * NS * 8);
     const uint32_t row_bytes = (uint32_t)(Kp * 8);
+    constexpr int EMK = 2 * TPT;   // emission slots a lane may serve: NS / (32 * warps) <= 32 * TPT * S / (32 * S) = TPT, x2 slack
 
     // ---- stage logA once per CTA (TMA bulk copy, UBLKCP) ----
     if (tid == 0) {
         mbar_init(sBar, 1);
-        mbar_init(sBar + 1, 1);
+        mbar_init(sBar + 1, blockDim.x >> 5);      // one arrival per warp and step
         fence_proxy_async_smem();
         const uint32_t bytes = (uint32_t)((size_t)K * Kp * 8);
         mbar_expect_tx(sBar, bytes);
@@ -194,21 +195,24 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     mbar_wait(sBar, 0);
     uint32_t em_phase = 0;
 
-    // producer (warp 0): fetch the emission rows of step t for every sequence still running.
-    // Lane l serves slots l, l+32, ...; `o_cur` holds obs[off + t] of those slots.
-    auto issue_emissions = [&](int t, const uint32_t (&o_cur)[8]) {
+    // Emission rows of step t for every sequence still running.  EVERY warp fetches a share of the slots (slot s
+    // belongs to warp s % nw, lane (s / nw) % 32): the per-step barrier makes the slowest warp's step time the
+    // CTA's, so the producer work is spread instead of sitting on one warp.  Each warp arrives once on the
+    // emission mbarrier with the byte count of its share.
+    const int nw = (int)blockDim.x >> 5;
+    auto issue_emissions = [&](int t, const uint32_t (&o_cur)[EMK]) {
         int nact = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int s = lane + 32 * k;
+        for (int k = 0; k < EMK; k++) {
+            const int s = w + nw * (lane + 32 * k);
             if (s < NS && t < sLen[s]) nact++;
         }
         const int total = __reduce_add_sync(0xffffffffu, nact);
         if (lane == 0) mbar_expect_tx(sBar + 1, (uint32_t)total * row_bytes);   // arrive + expected bytes (0 is fine)
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int s = lane + 32 * k;
+        for (int k = 0; k < EMK; k++) {
+            const int s = w + nw * (lane + 32 * k);
             if (s < NS && t < sLen[s]) {
                 uint32_t o = o_cur[k];
                 if ((int64_t)o >= p.M) { *p.status = 3; o = 0; }   // index panic in the reference
@@ -242,12 +246,12 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         double *slab = p.hist + (size_t)p.tile_base[tile] * K * NS;
         if (tid == 0) tma_bulk_s2g(slab, sD, slab_bytes);   // history slab 0 = delta(0)
 
-        uint32_t o_nxt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                // producer: obs of the NEXT step to fetch
-        if (w == 0) {
-            uint32_t o1[8];
+        uint32_t o_nxt[EMK];                                                  // obs of the NEXT step to fetch
+        {
+            uint32_t o1[EMK];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int s = lane + 32 * k;
+            for (int k = 0; k < EMK; k++) {
+                const int s = w + nw * (lane + 32 * k);
                 const bool in = s < NS;
                 o1[k] = (in && 1 < sLen[s]) ? __ldg(p.obs + sOff[s] + 1) : 0u;
                 o_nxt[k] = (in && 2 < sLen[s]) ? __ldg(p.obs + sOff[s] + 2) : 0u;
@@ -289,11 +293,11 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
             if (tid == 0) tma_store_wait_read_all();   // slab t-1 has left the buffer step t+1 will overwrite
             __syncthreads();
             if (tid == 0) tma_bulk_s2g(slab + (size_t)t * K * NS, sD + (size_t)(t & 1) * K * NS, slab_bytes);
-            if (w == 0 && t + 1 < Tmax) {
+            if (t + 1 < Tmax) {
                 issue_emissions(t + 1, o_nxt);
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int s = lane + 32 * k;
+                for (int k = 0; k < EMK; k++) {
+                    const int s = w + nw * (lane + 32 * k);
                     o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? __ldg(p.obs + sOff[s] + t + 2) : 0u;
                 }
             }
