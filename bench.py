@@ -291,6 +291,30 @@ def run_other(cv, L, device):
                                     "e2e_ms": 1e3 * dt, "bytes_per_element": 10,
                                     "note": "cv_mle: device event counts (u64 atomics; 10 B/element: obs u32, tag i32, start flag written + read) + host replay of the "
                                             "reference's += 1.0 / divide / ln(x)/ln(10); e2e includes H2D of obs+tags and the K*M finalisation"}
+    # CFN cost tables (cfn.rs:82-167) on the configs[4] super-sequence; CPU port on a prefix
+    w = workload_cp("heavy")
+    hm = cv.HMM(w["A"], w["B"], w["pi"])
+    cv.cfn_tables(hm, w["obs"][:5000], w["start"][:5000], w["comp"][:5000], w["ncomp"], device=device)
+    t0 = time.perf_counter()
+    r = cv.cfn_tables(hm, w["obs"], w["start"], w["comp"], w["ncomp"], device=device)
+    dt = time.perf_counter() - t0
+    act = np.flatnonzero(w["comp"] >= 0)
+    chg = np.concatenate([[True], w["comp"][act][1:] != w["comp"][act][:-1]])
+    bnd = act[chg]
+    K = w["K"]
+    cells = float(np.diff(bnd).sum()) * K ** 3
+    npre = 40000
+    t0 = time.perf_counter()
+    rc = po.cfn_tables(w["A"], w["B"], w["pi"], w["obs"][:npre], w["start"][:npre], w["comp"][:npre], w["ncomp"])
+    dtc = time.perf_counter() - t0
+    bpre = bnd[bnd < npre]
+    other["cfn_tables_heavy"] = {"N": w["N"], "K": K, "boundaries": int(r["nboundaries"]), "cells": cells,
+                                 "device_ms": r["device_ms"], "device_cells_per_s": cells / (r["device_ms"] * 1e-3),
+                                 "e2e_ms": 1e3 * dt, "cpu_port_cells_per_s": float(np.diff(bpre).sum()) * K ** 3 / dtc * 1.0,
+                                 "cpu_sample": f"first {npre} elements, single thread; the literal port runs K*K sweeps per pair "
+                                               "(K-fold the device's work for the same tables), cells counted as K sweeps per pair",
+                                 "lower_bound": r["lower_bound"]}
+    hm.close()
     # configs[0] stand-in and configs[4]: constrained decode with a node budget
     for kind, budget, cpu_budget in (("trucks", 0, 150), ("heavy", 2000, 6)):    # trucks-like: complete search
         w = workload_cp(kind)

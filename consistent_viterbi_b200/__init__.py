@@ -8,8 +8,8 @@ from . import _lib
 from ._lib import CvError
 from .hmm import HMM
 from .viterbi import decode, decode_batch
-from .cp import CPSolver, CpDistGroup, Solver, cp_solve_arrays, plan_cuts
+from .cp import CPSolver, CpDistGroup, Solver, cfn_tables, cp_solve_arrays, plan_cuts
 from .superseq import Constraints, SuperSequence, load_sequences, load_tags
 
-__all__ = ["HMM", "decode", "decode_batch", "CPSolver", "Solver", "cp_solve_arrays", "CpDistGroup", "plan_cuts", "Constraints",
+__all__ = ["HMM", "decode", "decode_batch", "CPSolver", "Solver", "cp_solve_arrays", "CpDistGroup", "plan_cuts", "cfn_tables", "Constraints",
            "SuperSequence", "load_sequences", "load_tags", "CvError", "_lib"]

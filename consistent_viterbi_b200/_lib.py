@@ -67,6 +67,8 @@ SIGNATURES = {
     "cv_cp_last_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cv_cp_last_ub": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
     "cv_debug_ordered_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _dp]),
+    "cv_cfn_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                C.c_void_p, _dp, _i64p, _dp]),
     "cv_mle": (C.c_int, [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                          C.c_void_p, C.c_int64, C.c_int, _dp]),
     "cv_last_error": (C.c_char_p, []),

@@ -41,6 +41,22 @@ def cp_solve_arrays(hmm: HMM, obs, is_seq_start, comp, ncomp, max_nodes: int = 0
     return out
 
 
+def cfn_tables(hmm: HMM, obs, is_seq_start, comp, k: int, device: int = -1):
+    """cv_cfn_tables: write_cfn's cost tables [k,k,K,K], unary costs [k,K], lower bound (cfn.rs:82-167)."""
+    obs = np.ascontiguousarray(obs, dtype=np.uint32)
+    start = np.ascontiguousarray(is_seq_start, dtype=np.uint8)
+    comp = np.ascontiguousarray(comp, dtype=np.int32)
+    K = hmm.nstates()
+    tables = np.zeros((max(k, 0), max(k, 0), K, K), dtype=np.float64)
+    unary = np.zeros((max(k, 0), K), dtype=np.float64)
+    lb, ms, nb = C.c_double(0.0), C.c_double(0.0), C.c_int64(0)
+    rc = _lib.lib().cv_cfn_tables(hmm.device_handle(device), obs.ctypes.data, start.ctypes.data, comp.ctypes.data,
+                                  obs.shape[0], int(k), tables.ctypes.data, unary.ctypes.data, C.byref(lb), C.byref(nb),
+                                  C.byref(ms))
+    _lib.check(rc)
+    return dict(tables=tables, unary=unary, lower_bound=lb.value, nboundaries=nb.value, device_ms=ms.value)
+
+
 IPC_HANDLE_BYTES = 64
 
 

@@ -28,6 +28,7 @@
 #include "cp_kernels.cuh"
 #include "cp_dist.cuh"
 #include "mle.cuh"
+#include "cfn.cuh"
 #include "probe.cuh"
 
 using namespace cvb;
@@ -719,3 +720,4 @@ extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_
 
 #include "cp_host.inl"
 #include "mle_host.inl"
+#include "cfn_host.inl"

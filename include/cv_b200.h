@@ -130,6 +130,19 @@ int cv_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *n_out);
  * mode 0 = one-thread loop, mode 1 = the parallel exact-order kernel; both must agree bit for bit. */
 int cv_debug_ordered_sum(const double *values, int64_t n, int mode, double *out);
 
+/* ---- CFN cost tables -------------------------------------------------------------
+ * Replaces the numeric part of write_cfn(hmm, super_seq, ..) (src/viterbi_solver/cfn.rs:82-167): the boundaries
+ * between constraint components, the K*K clamped longest_path runs (cfn.rs:11-35) of every consecutive boundary
+ * pair accumulated into the k*k cost tables with the reference's `== 0.0 => assign, else +=` rule, the unary
+ * start / end costs (cfn.rs:37-80), the lower bound and the -inf -> lower_bound patch.  Arithmetic order
+ * (max_j (row[j] + tr_j)) + emit.  obs / is_seq_start / comp as for cv_cp_solve; k = number_constraints().
+ *   cost_tables[k*k*K*K]  [c1][c2][n1][n2]     unary[k*K]     lower_bound_out, nboundaries_out, device_ms_out may be NULL
+ * No constrained element => CV_ERR_EMPTY (the reference unwraps None).  K <= 64.  The .cfn text file itself
+ * (cfn.rs:169-205) is host formatting of these arrays and is left to the caller.  HOST pointers. */
+int cv_cfn_tables(cv_hmm *h, const uint32_t *obs, const uint8_t *is_seq_start, const int32_t *comp,
+                  int64_t N, int32_t k, double *cost_tables, double *unary, double *lower_bound_out,
+                  int64_t *nboundaries_out, double *device_ms_out);
+
 /* ---- supervised maximum-likelihood estimation --------------------------------
  * Replaces: HMM::maximum_likelihood_estimation(&mut self, sequences, tags) followed by HMM::log
  * (src/hmm/hmm.rs:30-62,192-205).  a [K*K], b [K*M], pi [K] hold the model the reference would call it on --

@@ -427,3 +427,132 @@ int cvo_mle(int K, int64_t M, double *a, double *b, double *pi, const uint32_t *
     free(seen); free(end);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * CFN cost-table compilation, write_cfn's numeric part (reference src/viterbi_solver/cfn.rs:11-167): the
+ * boundaries between constraint components, K*K clamped longest_path runs per consecutive boundary pair,
+ * their accumulation into the k*k cost tables (with the reference's `== 0.0 => assign, else +=` rule), the
+ * unary start/end costs, the lower bound and the -inf -> lower_bound patch of the unary costs.  The file
+ * writer (cfn.rs:169-205) is not restated.  Step arithmetic: max_j fl(row[j] + tr_j) (first maximum), + emit.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int K; int64_t M, N;
+    const double *A, *B, *Pi; const uint32_t *obs; const uint8_t *start; const int32_t *comp;
+} cfn_t;
+
+static double cfn_cell(const cfn_t *s, const double *prev, int64_t t, int n)
+{
+    /* transitions(hmm, n) (utils.rs:32-38) added to the previous row, max (ndarray-stats), + emit_prob */
+    double best = 0.0;
+    for (int j = 0; j < s->K; j++) {
+        const double tr = s->start[t] ? s->Pi[n] : s->A[(int64_t)j * s->K + n];
+        const double v = prev[j] + tr;
+        if (j == 0 || v > best) best = v;
+    }
+    return best + s->B[(int64_t)n * s->M + s->obs[t]];
+}
+
+/* cfn.rs:11-35 */
+static double cfn_longest_path(const cfn_t *s, double *array, int64_t t_from, int n_from, int64_t t_to, int n_to)
+{
+    const int K = s->K;
+    for (int j = 0; j < K; j++) array[j] = -INFINITY;
+    array[n_from] = 0.0;
+    int64_t t = 1;
+    while (t_from + t <= t_to) {
+        double *row = array + t * K; const double *prev = row - K;
+        if (s->comp[t_from + t] >= 0) {
+            for (int j = 0; j < K; j++) row[j] = -INFINITY;
+            const int n = (t_from + t < t_to) ? n_from : n_to;
+            row[n] = cfn_cell(s, prev, t_from + t, n);
+        } else {
+            for (int n = 0; n < K; n++) row[n] = cfn_cell(s, prev, t_from + t, n);
+        }
+        t++;
+    }
+    const double *last = array + (t - 1) * K;
+    double m = last[0];
+    for (int j = 1; j < K; j++) if (last[j] > m) m = last[j];
+    return m;
+}
+
+int cvo_cfn_tables(int K, int64_t M, const double *logA, const double *logB, const double *logPi, int64_t N,
+                   const uint32_t *obs, const uint8_t *is_seq_start, const int32_t *comp, int32_t k,
+                   double *cost_tables /* [k][k][K][K] */, double *unary /* [k][K] */, double *lower_bound_out,
+                   int64_t *nboundaries_out)
+{
+    if (K <= 0 || N <= 0 || k <= 0) return CVO_ERR_ARG;
+    cfn_t s = {K, M, N, logA, logB, logPi, obs, is_seq_start, comp};
+    for (int64_t t = 0; t < N; t++) if ((int64_t)obs[t] >= M || comp[t] >= k) return CVO_ERR_ARG;
+    /* cfn.rs:82-112: boundaries (t, cid) where the component changes; longest segment */
+    int64_t *bt = (int64_t *)malloc(sizeof(int64_t) * (size_t)N); int32_t *bc = (int32_t *)malloc(sizeof(int32_t) * (size_t)N);
+    int64_t nb = 0, longest = 0; int32_t last_cid = -1;
+    for (int64_t t = 0; t < N; t++) {
+        if (comp[t] >= 0) {
+            const int32_t cid = comp[t];
+            if (last_cid < 0) { longest = t + 1; bt[nb] = t; bc[nb] = cid; nb++; }
+            else if (last_cid != cid) {
+                const int64_t seg = t - bt[nb - 1] + 1;
+                if (seg > longest) longest = seg;
+                bt[nb] = t; bc[nb] = cid; nb++;
+            }
+            last_cid = cid;
+        }
+    }
+    if (nb == 0) { free(bt); free(bc); return CVO_ERR_EMPTY; }            /* constraint_boundaries.last().unwrap() panics */
+    { const int64_t seg = N - bt[nb - 1] + 1; if (seg > longest) longest = seg; }
+    double *array = (double *)calloc((size_t)(longest + 1) * K, sizeof(double));
+    for (int64_t e = 0; e < (int64_t)k * k * K * K; e++) cost_tables[e] = 0.0;
+    #define TAB(c1, c2, n1, n2) cost_tables[(((int64_t)(c1) * k + (c2)) * K + (n1)) * K + (n2)]
+    for (int64_t i = 0; i + 1 < nb; i++) {                                  /* cfn.rs:118-137 */
+        for (int n1 = 0; n1 < K; n1++)
+            for (int n2 = 0; n2 < K; n2++) {
+                const double cost = cfn_longest_path(&s, array, bt[i], n1, bt[i + 1], n2);
+                if (cost != -INFINITY) {
+                    if (TAB(bc[i], bc[i + 1], n1, n2) == 0.0) TAB(bc[i], bc[i + 1], n1, n2) = cost; else TAB(bc[i], bc[i + 1], n1, n2) += cost;
+                    if (TAB(bc[i + 1], bc[i], n2, n1) == 0.0) TAB(bc[i + 1], bc[i], n2, n1) = cost; else TAB(bc[i + 1], bc[i], n2, n1) += cost;
+                }
+            }
+    }
+    for (int64_t e = 0; e < (int64_t)k * K; e++) unary[e] = 0.0;          /* cfn.rs:139-145 */
+    {   /* get_unary_start_cost, cfn.rs:37-55 */
+        const int64_t tl = bt[0];
+        for (int n = 0; n < K; n++) array[n] = logPi[n] + logB[(int64_t)n * M + obs[0]];
+        for (int64_t t = 1; t <= tl; t++)
+            for (int n = 0; n < K; n++) array[t * K + n] = cfn_cell(&s, array + (t - 1) * K, t, n);
+        for (int n = 0; n < K; n++) unary[(int64_t)bc[0] * K + n] += array[tl * K + n];
+    }
+    {   /* get_unary_end_cost, cfn.rs:57-80 */
+        const int64_t ts = bt[nb - 1];
+        for (int n = 0; n < K; n++) {
+            double c = 0.0;
+            if (ts != N - 1) {
+                for (int j = 0; j < K; j++) array[j] = -INFINITY;
+                array[n] = 0.0;
+                for (int64_t t = ts + 1; t < N; t++) {
+                    double *row = array + (t - ts) * K; const double *prev = row - K;
+                    if (comp[t] >= 0) { for (int j = 0; j < K; j++) row[j] = -INFINITY; row[n] = cfn_cell(&s, prev, t, n); }
+                    else for (int nn = 0; nn < K; nn++) row[nn] = cfn_cell(&s, prev, t, nn);
+                }
+                const double *last = array + (N - 1 - ts) * K;
+                c = last[0];
+                for (int j = 1; j < K; j++) if (last[j] > c) c = last[j];
+            }
+            unary[(int64_t)bc[nb - 1] * K + n] += c;
+        }
+    }
+    double lb = -1.0;                                                        /* cfn.rs:149-157 */
+    for (int k1 = 0; k1 < k; k1++)
+        for (int k2 = k1 + 1; k2 < k; k2++) {
+            const double *tb = &TAB(k1, k2, 0, 0);
+            double m = tb[0];
+            for (int e = 1; e < K * K; e++) if (tb[e] < m) m = tb[e];
+            lb += m;
+        }
+    for (int64_t e = 0; e < (int64_t)k * K; e++) if (unary[e] == -INFINITY) unary[e] = lb;   /* cfn.rs:160-166 */
+    #undef TAB
+    if (lower_bound_out) *lower_bound_out = lb;
+    if (nboundaries_out) *nboundaries_out = nb;
+    free(array); free(bt); free(bc);
+    return CVO_OK;
+}

@@ -86,6 +86,13 @@ int cvo_cp_solve(int K, int64_t M, const double *logA, const double *logB,
 int cvo_mle(int K, int64_t M, double *a, double *b, double *pi, const uint32_t *obs, const int32_t *tags,
             const int64_t *seq_off, int64_t B);
 
+/* write_cfn's numeric part (cfn.rs:11-167): cost tables [k][k][K][K], unary costs [k][K] (with -inf replaced by
+ * the lower bound), the lower bound, the number of component boundaries.  comp[t] = component of ACTIVE elements,
+ * -1 otherwise; k = number_constraints().  No boundary at all => CVO_ERR_EMPTY (the reference unwraps None). */
+int cvo_cfn_tables(int K, int64_t M, const double *logA, const double *logB, const double *logPi, int64_t N,
+                   const uint32_t *obs, const uint8_t *is_seq_start, const int32_t *comp, int32_t k,
+                   double *cost_tables, double *unary, double *lower_bound_out, int64_t *nboundaries_out);
+
 #ifdef __cplusplus
 }
 #endif

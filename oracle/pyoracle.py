@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
         L.cvo_cp_solve.restype = C.c_int
         L.cvo_mle.argtypes = [C.c_int, C.c_int64, dp, dp, dp, u32p, i32p, i64p, C.c_int64]
         L.cvo_mle.restype = C.c_int
+        L.cvo_cfn_tables.argtypes = [C.c_int, C.c_int64, dp, dp, dp, C.c_int64, u32p, u8p, i32p, C.c_int32, dp, dp, dp, i64p]
+        L.cvo_cfn_tables.restype = C.c_int
         _lib = L
     return _lib
 
@@ -160,3 +162,22 @@ def mle(a, b, pi, obs_flat, tags_flat, seq_off):
     if rc:
         raise OracleError(rc)
     return a, b, pi
+
+
+def cfn_tables(logA, logB, logPi, obs, is_seq_start, comp, k):
+    """write_cfn's cost tables / unary costs / lower bound (cfn.rs:11-167)."""
+    logA, logB, logPi = _f64(logA), _f64(logB), _f64(logPi)
+    K, M = logB.shape
+    obs = np.ascontiguousarray(obs, dtype=np.uint32)
+    start = np.ascontiguousarray(is_seq_start, dtype=np.uint8)
+    comp = np.ascontiguousarray(comp, dtype=np.int32)
+    tables = np.zeros((k, k, K, K), dtype=np.float64)
+    unary = np.zeros((k, K), dtype=np.float64)
+    lb = C.c_double(0.0)
+    nb = C.c_int64(0)
+    rc = lib().cvo_cfn_tables(K, M, _p(logA, C.c_double), _p(logB, C.c_double), _p(logPi, C.c_double), len(obs),
+                              _p(obs, C.c_uint32), _p(start, C.c_uint8), _p(comp, C.c_int32), int(k),
+                              _p(tables, C.c_double), _p(unary, C.c_double), C.byref(lb), C.byref(nb))
+    if rc:
+        raise OracleError(rc)
+    return dict(tables=tables, unary=unary, lower_bound=lb.value, nboundaries=nb.value)

@@ -180,3 +180,43 @@ def test_oracle_mle_against_numpy_counts():
     assert not np.isneginf(la2).any() and (la2 != la).any()
     with pytest.raises(po.OracleError):
         po.mle(np.zeros((K, K)), np.zeros((K, M)), np.zeros(K), obs, np.where(np.arange(len(tags)) == 3, -1, tags), off)
+
+
+def test_oracle_cfn_longest_path_bruteforce():
+    """cvo_cfn_tables on a super-sequence with exactly two boundaries: the (c0, c1) table is longest_path
+    (cfn.rs:11-35) for every (n1, n2); checked against enumeration of all state paths between the boundaries with
+    the left-to-right rounded score (the DP's value, fl being monotone) and the clamps of cfn.rs:16-22."""
+    import itertools
+
+    rng = np.random.default_rng(21)
+    for it in range(30):
+        K, M = int(rng.integers(2, 4)), 4
+        A, B, pi = random_hmm(rng, K, M, zero_frac=0.15, ties=(it % 4 == 0))
+        L = int(rng.integers(1, 6))                                # rows between the two boundaries + 1
+        N = L + 3
+        obs = rng.integers(0, M, N).astype(np.uint32)
+        start = np.zeros(N, dtype=np.uint8); start[0] = 1
+        if it % 3 == 0 and L > 1:
+            start[2] = 1                                          # a sequence start inside the segment: pi instead of a
+        comp = np.full(N, -1, dtype=np.int32)
+        t0, t1 = 1, 1 + L
+        comp[t0], comp[t1] = 0, 1
+        if L > 2 and it % 2 == 0:
+            comp[t0 + 1] = 0                                      # same component again: clamped to n_from, no new boundary
+        r = po.cfn_tables(A, B, pi, obs, start, comp, 2)
+        assert r["nboundaries"] == 2
+        for n1 in range(K):
+            for n2 in range(K):
+                best = -math.inf
+                for mid in itertools.product(range(K), repeat=L - 1):
+                    path = (n1,) + mid + (n2,)
+                    if any(comp[t0 + i] >= 0 and path[i] != n1 for i in range(1, L)):
+                        continue                                  # clamped rows only keep n_from
+                    s = 0.0
+                    for i in range(1, L + 1):
+                        t = t0 + i
+                        tr = pi[path[i]] if start[t] else A[path[i - 1], path[i]]
+                        s = (s + tr) + B[path[i], obs[t]]
+                    best = max(best, s)
+                exp = 0.0 if best == -math.inf else best          # -inf costs are not accumulated (cfn.rs:123)
+                assert r["tables"][0, 1, n1, n2] == exp and r["tables"][1, 0, n2, n1] == exp
