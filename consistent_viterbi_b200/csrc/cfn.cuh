@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(32 * CFN_WARPS) cfn_chain_kernel(const CpParam
             const uint32_t o = __ldg(p.obs + t);
             const bool st = __ldg(p.start + t) != 0;
             const bool clamped = ch.clamp >= 0 && __ldg(p.comp + t) >= 0 && !(ch.kind == 0 && t == ch.t1);
-            double best[NSL]; int idx[NSL];
-            chain_scan<NSL>(sd + cur * Kp, sA, Kp, K, lane, st, pi_i, best, idx);   // max_j fl(row[j] + tr_j), first max
+            double best[NSL];
+            chain_scan_val<NSL>(sd + cur * Kp, sA, Kp, K, lane, st, pi_i, best);    // max_j fl(row[j] + tr_j), first max
 #pragma unroll
             for (int s = 0; s < NSL; s++) {
                 const int i = lane + 32 * s;
@@ -95,22 +95,36 @@ __global__ void __launch_bounds__(32 * CFN_WARPS) cfn_chain_kernel(const CpParam
 // cfn.rs:118-137: tables[cf][ct][n1][n2] and tables[ct][cf][n2][n1] take the pair's cost when it is not -inf:
 // assigned if the entry is still 0.0, added otherwise.  costs[i][n1][n2]; pair i = boundaries (i, i+1).
 // The two entries always receive the same updates, and an entry is fed by pairs (cf, ct) through cost[n1][n2] and
-// by pairs (ct, cf) through cost[n2][n1]; thread (a, b) owns {tables[c1][c2][a][b], tables[c2][c1][b][a]} for all
-// c1 < c2 and applies every pair's contribution to them in pair order -- the reference's order per entry.
-__global__ void cfn_accumulate_kernel(const double *costs, const int32_t *bcomp, int64_t npairs, int K, int k, double *tables)
+// by pairs (ct, cf) through cost[n2][n1].  One CTA per unordered component pair c1 < c2 (the host lists its
+// boundary pairs in ascending order, bit 0 = the pair runs c2 -> c1); thread (a, b) owns
+// {tables[c1][c2][a][b], tables[c2][c1][b][a]} and adds the contributions in list order -- the reference's order
+// per entry.  The costs of 16 pairs are fetched before the dependent add chain touches them.
+constexpr int CFN_ACC_U = 16;
+__global__ void __launch_bounds__(1024) cfn_accumulate_kernel(const double *costs, const int64_t *plist, const int64_t *toff,
+                                                             const int32_t *tc1, const int32_t *tc2, int K, int k, double *tables)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= K * K) return;
-    const int a = e / K, b = e % K;
-    for (int64_t i = 0; i < npairs; i++) {
-        const int cf = bcomp[i], ct = bcomp[i + 1];
-        const int c1 = min(cf, ct), c2 = max(cf, ct);
-        const double cost = costs[(size_t)i * K * K + (cf < ct ? a * K + b : b * K + a)];
-        if (cost == neg_inf()) continue;
-        double *x = tables + (((size_t)c1 * k + c2) * K + a) * K + b;
-        double *y = tables + (((size_t)c2 * k + c1) * K + b) * K + a;
-        const double v = (*x == 0.0) ? cost : *x + cost;
-        *x = v; *y = v;
+    const int tab = blockIdx.x, c1 = tc1[tab], c2 = tc2[tab];
+    const int64_t p0 = toff[tab], p1 = toff[tab + 1];
+    for (int e = threadIdx.x; e < K * K; e += blockDim.x) {
+        const int a = e / K, b = e % K;
+        const size_t fwd = (size_t)a * K + b, rev = (size_t)b * K + a;
+        double acc = 0.0;                                       // Array2::from_elem(.., 0.0), cfn.rs:116
+        for (int64_t q = p0; q < p1; q += CFN_ACC_U) {
+            double c[CFN_ACC_U];
+#pragma unroll
+            for (int u = 0; u < CFN_ACC_U; u++) {
+                c[u] = neg_inf();
+                if (q + u < p1) {
+                    const int64_t pl = plist[q + u];
+                    c[u] = costs[(size_t)(pl >> 1) * K * K + ((pl & 1) ? rev : fwd)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CFN_ACC_U; u++)
+                if (c[u] != neg_inf()) acc = (acc == 0.0) ? c[u] : acc + c[u];
+        }
+        tables[(((size_t)c1 * k + c2) * K + a) * K + b] = acc;
+        tables[(((size_t)c2 * k + c1) * K + b) * K + a] = acc;
     }
 }
 

@@ -37,13 +37,32 @@ extern "C" int cv_cfn_tables(cv_hmm *h, const uint32_t *obs, const uint8_t *is_s
     const bool has_tail = bt[nb - 1] != N - 1;
     if (has_tail) for (int n = 0; n < K; n++) chains.push_back(CfnChain{bt[nb - 1], N - 1, n, 2, out_end + n});
     const int64_t nout = out_end + K, nchains = (int64_t)chains.size();
+    // boundary pairs of every unordered component pair c1 < c2, ascending; bit 0 = the pair runs c2 -> c1
+    std::vector<std::vector<int64_t>> per_tab((size_t)k * k);
+    for (int64_t i = 0; i < npairs; i++) {
+        const int cf = bc[i], ct = bc[i + 1];
+        per_tab[(size_t)std::min(cf, ct) * k + std::max(cf, ct)].push_back(i * 2 + (cf < ct ? 0 : 1));
+    }
+    std::vector<int64_t> plist, toff{0}; std::vector<int32_t> tcs;             // tcs = [c1 of every table | c2 of every table]
+    std::vector<int32_t> t1s, t2s;
+    for (int c1 = 0; c1 < k; c1++)
+        for (int c2 = c1 + 1; c2 < k; c2++) {
+            const auto &v = per_tab[(size_t)c1 * k + c2];
+            if (v.empty()) continue;
+            plist.insert(plist.end(), v.begin(), v.end());
+            toff.push_back((int64_t)plist.size()); t1s.push_back(c1); t2s.push_back(c2);
+        }
+    const int ntab = (int)t1s.size();
+    std::vector<int64_t> acc_i64(plist); acc_i64.insert(acc_i64.end(), toff.begin(), toff.end());
+    tcs = t1s; tcs.insert(tcs.end(), t2s.begin(), t2s.end());
 
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     DevBuf *b = h->cpb;
     int rc;
     if ((rc = b[2].ensure(sizeof(uint32_t) * (size_t)N)) || (rc = b[3].ensure((size_t)N)) || (rc = b[4].ensure(sizeof(int32_t) * (size_t)N)) ||
-        (rc = b[6].ensure(sizeof(CfnChain) * (size_t)nchains)) || (rc = b[7].ensure(sizeof(int32_t) * (size_t)nb)) ||
+        (rc = b[6].ensure(sizeof(CfnChain) * (size_t)nchains)) || (rc = b[7].ensure(sizeof(int32_t) * (tcs.size() + 4))) ||
+        (rc = b[8].ensure(sizeof(int64_t) * (acc_i64.size() + 4))) ||
         (rc = b[10].ensure(sizeof(double) * (size_t)nout)) || (rc = b[14].ensure(sizeof(double) * (size_t)k * k * K * K)))
         return rc;
     h->cp_N = 0;                                                                   // the CP state hooks no longer describe these buffers
@@ -51,7 +70,10 @@ extern "C" int cv_cfn_tables(cv_hmm *h, const uint32_t *obs, const uint8_t *is_s
     CUDA_TRY(cudaMemcpyAsync(b[3].p, is_seq_start, (size_t)N, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b[4].p, comp, sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b[6].p, chains.data(), sizeof(CfnChain) * (size_t)nchains, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(b[7].p, bc.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, st));
+    if (ntab > 0) {
+        CUDA_TRY(cudaMemcpyAsync(b[7].p, tcs.data(), sizeof(int32_t) * tcs.size(), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b[8].p, acc_i64.data(), sizeof(int64_t) * acc_i64.size(), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemsetAsync(b[10].p, 0, sizeof(double) * (size_t)nout, st));
     CUDA_TRY(cudaMemsetAsync(b[14].p, 0, sizeof(double) * (size_t)k * k * K * K, st));   // Array2::from_elem(.., 0.0) cfn.rs:116
     CpParams p{};
@@ -66,8 +88,10 @@ extern "C" int cv_cfn_tables(cv_hmm *h, const uint32_t *obs, const uint8_t *is_s
     if (K <= 32) cfn_chain_kernel<1><<<grid, 32 * CFN_WARPS, smem, st>>>(p, (const CfnChain *)b[6].p, nchains, (double *)b[10].p);
     else cfn_chain_kernel<2><<<grid, 32 * CFN_WARPS, smem, st>>>(p, (const CfnChain *)b[6].p, nchains, (double *)b[10].p);
     g_launches++;
-    if (npairs > 0) {
-        cfn_accumulate_kernel<<<(K * K + 127) / 128, 128, 0, st>>>((const double *)b[10].p, (const int32_t *)b[7].p, npairs, K, k, (double *)b[14].p);
+    if (ntab > 0) {
+        const int64_t *d_plist = (const int64_t *)b[8].p, *d_toff = d_plist + plist.size();
+        const int32_t *d_t1 = (const int32_t *)b[7].p, *d_t2 = d_t1 + ntab;
+        cfn_accumulate_kernel<<<ntab, std::min(K * K, 1024), 0, st>>>((const double *)b[10].p, d_plist, d_toff, d_t1, d_t2, K, k, (double *)b[14].p);
         g_launches++;
     }
     CUDA_TRY(cudaEventRecord(h->ev1, st));

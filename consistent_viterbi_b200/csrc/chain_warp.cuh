@@ -83,6 +83,57 @@ __device__ __forceinline__ void chain_scan(const double *__restrict__ sd, const 
 }
 
 
+// Value-only variant of chain_scan (the CFN sweeps need max_j fl(d_old[j] + tr_j(i)) but no backpointer):
+// DADD + DSETP + 2 selects per predecessor instead of 3.  Ranges ascending, strict >: the first maximum's bits.
+template <int CW_NSL>
+__device__ __forceinline__ void chain_scan_val(const double *__restrict__ sd, const double *__restrict__ sA, int Kp, int K,
+                                               int lane, bool use_pi, const double (&pi_i)[CW_NSL], double (&best)[CW_NSL])
+{
+    const int Kq = (((K + 3) >> 2) + 1) & ~1;
+    double b[4][CW_NSL];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int s = 0; s < CW_NSL; s++) b[r][s] = neg_inf();
+    int col[CW_NSL];
+#pragma unroll
+    for (int s = 0; s < CW_NSL; s++) col[s] = min(lane + 32 * s, Kp - 1);
+#pragma unroll 2
+    for (int jj = 0; jj < Kq; jj += 2) {
+        double2 dj[4]; double tr[4][2][CW_NSL];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int j = r * Kq + jj;
+            const int jc = min(j, Kp - 2);
+            dj[r] = *reinterpret_cast<const double2 *>(sd + jc);
+            if (j >= K) dj[r] = make_double2(neg_inf(), neg_inf());
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int s = 0; s < CW_NSL; s++) {
+                    const int ju = min(j + u, K - 1);
+                    const double a = use_pi ? pi_i[s] : sA[(size_t)ju * Kp + col[s]];
+                    tr[r][u][s] = (j + u < K) ? a : neg_inf();
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int s = 0; s < CW_NSL; s++) {
+                const double v0 = dj[r].x + tr[r][0][s];
+                b[r][s] = v0 > b[r][s] ? v0 : b[r][s];
+                const double v1 = dj[r].y + tr[r][1][s];
+                b[r][s] = v1 > b[r][s] ? v1 : b[r][s];
+            }
+    }
+#pragma unroll
+    for (int s = 0; s < CW_NSL; s++) {
+        best[s] = b[0][s];
+#pragma unroll
+        for (int r = 1; r < 4; r++) best[s] = b[r][s] > best[s] ? b[r][s] : best[s];
+    }
+}
+
 // Register-resident variant for K <= 32 (one state per lane): the lane's logA column acol[j] = logA[j][lane]
 // (-inf for j >= K) stays in registers for the whole kernel, so a predecessor costs half a broadcast LDS.128
 // plus DADD / DSETP / 3 selects.  KQ = 2*ceil(K/8) predecessors per range, fully unrolled; sd[j] = -inf, j >= K.
