@@ -492,11 +492,11 @@ static int chunk_count(const cv_hmm *h, int64_t B, bool timing, bool host_buffer
 {
     if (timing || h->K > SMALL_K_MAX) return 1;          // kernel timing wants one launch for the whole batch
     if (g_chunks > 0) return (int)std::min<int64_t>(g_chunks, std::max<int64_t>(B, 1));
-    // >= ~6 tiles per resident CTA per chunk keeps the dynamic tile scheduler balanced.  Host buffers: many
-    // chunks so that H2D / D2H copies hide behind the kernels; device buffers: two (backtrace of one chunk
-    // overlaps the forward pass of the other; measured best on B200)
+    // >= ~6 tiles per resident CTA per chunk keeps the dynamic tile scheduler balanced.  Host buffers: six
+    // chunks so that H2D / D2H copies hide behind the kernels (measured at the POS shape: 2 chunks 16.5 ms,
+    // 4: 15.4, 6: 15.3, 8: 15.7, 12: 19.2); device buffers: two (measured best on B200)
     const int64_t per_chunk = (int64_t)h->num_sms * 2 * 6 * 64;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 8 : 2, B / per_chunk));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 6 : 2, B / per_chunk));
 }
 
 static int report_status(const int *status_words, int n)
