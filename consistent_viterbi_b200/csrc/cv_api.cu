@@ -111,6 +111,8 @@ struct cv_hmm {
         DevBuf order, keys_in, keys_out, vals_in, cub_tmp, hist, tmax, base, misc, lg_arr, lg_start, lg_done, delta_g;
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
+        cudaStream_t st_bt = nullptr;                      // concurrent backtrace (launch_decode_small)
+        cudaEvent_t ev_pre = nullptr, ev_bt = nullptr;
     } ws[2];
     cudaEvent_t ev_fork = nullptr;
     DevBuf cpb[16];     // constrained-solver state (kept after cv_cp_solve for the parity hooks)
@@ -238,6 +240,9 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     for (auto &w : h->ws) {
         CUDA_TRY(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&w.st_bt, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&w.ev_pre, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&w.ev_bt, cudaEventDisableTiming));
     }
 
     const int Kp = (K <= SMALL_K_MAX) ? h->Kp : ((K + LARGE_BN - 1) / LARGE_BN) * LARGE_BN;
@@ -286,6 +291,9 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
             b->release();
         if (w.st) cudaStreamDestroy(w.st);
         if (w.done) cudaEventDestroy(w.done);
+        if (w.st_bt) cudaStreamDestroy(w.st_bt);
+        if (w.ev_pre) cudaEventDestroy(w.ev_pre);
+        if (w.ev_bt) cudaEventDestroy(w.ev_bt);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (auto &b : h->cpb) b.release();
@@ -336,6 +344,25 @@ static int g_chunks = -1;      // test/bench override of the chunk count (see cv
 static long long g_chain_max_b = -1;   // batches up to this size use the warp-per-sequence kernel (-1: 8192)
 
 #include "decode_large_host.inl"
+
+// cuStreamWaitValue32 through the runtime's driver entry-point lookup (no link-time dependency on libcuda):
+// lets a stream wait until a word in device memory reaches a value.  nullptr when unavailable.
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static StreamWaitValue32Fn stream_wait_value32()
+{
+    static StreamWaitValue32Fn fn = []() -> StreamWaitValue32Fn {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (StreamWaitValue32Fn)f;
+    }();
+    return fn;
+}
+// CV_BT_CONCURRENT=0: backtrace after the forward kernel (A/B hook)
+static int g_bt_concurrent = []() { const char *e = getenv("CV_BT_CONCURRENT"); return e ? atoi(e) : 1; }();
 
 static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int64_t *d_off, int64_t B,
                                int64_t N, uint32_t *d_path, double *d_score, unsigned int *d_counter, int *d_status,
@@ -401,17 +428,53 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     if (getenv("CV_DEBUG"))
         fprintf(stderr, "[cv] decode_small: K=%d TQ=%d TP=%d G=%d S=%d variant=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
                 h->K, h->TQT, tpt, G, S, variant, threads, smem, occ, grid, ntiles);
-    if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
+    // Concurrent backtrace: the backtrace kernel runs next to the forward kernel on a second stream and follows
+    // it tile by tile (tile_done flags).  It is released only when every forward CTA is resident (stream wait on
+    // the `started` counter), so its spinning CTAs can never keep a forward CTA off an SM; it then lives on the
+    // registers / shared memory the forward CTAs leave free.
+    StreamWaitValue32Fn wait32 = stream_wait_value32();
+    const bool concurrent = !timing && g_bt_concurrent && wait32 != nullptr && w.st_bt != nullptr;
+    p.tile_done = nullptr; p.started = nullptr;
+    if (concurrent) {
+        if ((rc = w.lg_done.ensure(sizeof(int) * ((size_t)ntiles + 8)))) return rc;
+        CUDA_TRY(cudaMemsetAsync(w.lg_done.p, 0, sizeof(int) * ((size_t)ntiles + 8), st));
+        p.tile_done = (int *)w.lg_done.p;
+        p.started = (unsigned int *)w.lg_done.p + ntiles;
+        CUDA_TRY(cudaEventRecord(w.ev_pre, st));
+    }
+    static const bool bt_prof = getenv("CV_BT_PROF") != nullptr;   // prints forward / forward+backtrace times of the concurrent mode
+    if (timing || bt_prof) CUDA_TRY(cudaEventRecord(h->ev0, st));
     kern<<<std::max(1, grid), threads, smem, st>>>(p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    if (timing) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    if (timing || bt_prof) CUDA_TRY(cudaEventRecord(h->ev1, st));
     // end state + backtrace with lazy backpointers: one thread per sequence
     const size_t smem_bt = (size_t)h->K * (h->K | 1) * 8;
-    CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
+    CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
+    CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
+    // same shared-memory carve-out as the forward kernel, or the two kernels cannot share an SM
+    CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel<8, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const int64_t nblk = ((int64_t)ntiles * NS + 127) / 128;
+    if (concurrent) {
+        CUDA_TRY(cudaStreamWaitEvent(w.st_bt, w.ev_pre, 0));
+        if (wait32(w.st_bt, (unsigned long long)(uintptr_t)p.started, (unsigned int)std::max(1, grid), 0x0 /* GEQ */) != 0)
+            return fail(CV_ERR_CUDA, "cuStreamWaitValue32 failed");
+        backtrace_small_kernel<8, 8><<<(unsigned)std::max<int64_t>(1, nblk), 128, smem_bt, w.st_bt>>>(p);   // blocks in tile order
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(w.ev_bt, w.st_bt));
+        CUDA_TRY(cudaStreamWaitEvent(st, w.ev_bt, 0));
+        if (bt_prof) {
+            CUDA_TRY(cudaEventRecord(h->ev2, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, h->ev0, h->ev1); cudaEventElapsedTime(&b, h->ev0, h->ev2);
+            fprintf(stderr, "[cv] concurrent: forward %.3f ms, forward + backtrace %.3f ms (B = %lld)\n", a, b, (long long)B);
+        }
+        return CV_OK;
+    }
     const int grid_bt = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, (int64_t)h->num_sms * 12));
-    backtrace_small_kernel<<<grid_bt, 128, smem_bt, st>>>(p);
+    backtrace_small_kernel<16, 4><<<grid_bt, 128, smem_bt, st>>>(p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (timing) CUDA_TRY(cudaEventRecord(h->ev2, st));
@@ -494,9 +557,12 @@ static int chunk_count(const cv_hmm *h, int64_t B, bool timing, bool host_buffer
     if (g_chunks > 0) return (int)std::min<int64_t>(g_chunks, std::max<int64_t>(B, 1));
     // >= ~6 tiles per resident CTA per chunk keeps the dynamic tile scheduler balanced.  Host buffers: six
     // chunks so that H2D / D2H copies hide behind the kernels (measured at the POS shape: 2 chunks 16.5 ms,
-    // 4: 15.4, 6: 15.3, 8: 15.7, 12: 19.2); device buffers: two (measured best on B200)
+    // 4: 15.4, 6: 15.3, 8: 15.7, 12: 19.2).
+    // Device buffers: one launch when the backtrace can run next to the forward kernel (launch_decode_small), else two
+    // chunks so that the backtrace of one overlaps the forward pass of the other.
     const int64_t per_chunk = (int64_t)h->num_sms * 2 * 6 * 64;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 6 : 2, B / per_chunk));
+    const int dev_chunks = (g_bt_concurrent && stream_wait_value32() != nullptr) ? 1 : 2;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 6 : dev_chunks, B / per_chunk));
 }
 
 static int report_status(const int *status_words, int n)

@@ -54,6 +54,10 @@ struct DecodeSmallParams {
     double *score;           // [B] or nullptr
     unsigned int *tile_counter;
     int *status;             // 0 ok, else CV_ERR_*
+    // concurrent backtrace (nullptr = the backtrace runs after the forward kernel): tile_done[tile] is raised when
+    // the tile's history is complete in global memory, *started counts the forward CTAs that have begun
+    int *tile_done;
+    unsigned int *started;
     int64_t M, B;
     int K, Kp, G, S, NS, ntiles;   // NS = sequences per tile = 32 * TPT * S
 };
@@ -153,6 +157,11 @@ __device__ __forceinline__ void tma_store_wait_read_all()
 {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// all bulk stores of this thread have been written (not only read out of shared memory)
+__device__ __forceinline__ void tma_store_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -184,6 +193,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 
     // ---- stage logA once per CTA (TMA bulk copy, UBLKCP) ----
     if (tid == 0) {
+        if (p.started) atomicAdd(p.started, 1u);   // the backtrace kernel is released once every forward CTA is resident
         mbar_init(sBar, 1);
         mbar_init(sBar + 1, blockDim.x >> 5);      // one arrival per warp and step
         fence_proxy_async_smem();
@@ -302,7 +312,17 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
                 }
             }
         }
-        if (tid == 0) tma_store_wait_read_all();   // last slab read out before the buffers are reused
+        if (tid == 0) {
+            if (p.tile_done) {
+                // the tile's history is complete in global memory: hand it to the concurrent backtrace
+                tma_store_wait_all();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_done + tile), "r"(1) : "memory");
+            } else {
+                tma_store_wait_read_all();         // last slab read out before the buffers are reused
+            }
+        }
         __syncthreads();
     }
 }
@@ -315,13 +335,15 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 // emission was finite and the argmax is recomputed here.  If delta[t][s] = -inf then either the emission was
 // -inf (psi = 0) or every candidate was -inf (argmax of an all -inf vector = 0): psi = 0 both ways.
 // ---------------------------------------------------------------------------
-constexpr int BT_CHUNK = 16;   // predecessors per prefetch chunk
+// BT_CHUNK = predecessors per prefetch chunk: 16 when the kernel has the GPU to itself (124 registers), 8 with at most
+// 64 registers for the concurrent mode, where it lives on the 16 K registers per SM two forward CTAs leave free
 
 // One thread per sequence; the 32 lanes of a warp hold 32 adjacent sequences of one tile, so the loads of
 // predecessor j are one coalesced 256-byte run of the slab row.  Rows do not depend on the decoded path, so
 // the next chunk of 16 predecessors is always in flight while the current one is reduced; the only dependent
 // chain per step is 16 x (DADD, DSETP, select) x ceil(K/16).
-__global__ void __launch_bounds__(128) backtrace_small_kernel(const DecodeSmallParams p)
+template <int BT_CHUNK, int MINB>
+__global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, Kp = p.Kp, NS = p.NS;
@@ -340,6 +362,17 @@ __global__ void __launch_bounds__(128) backtrace_small_kernel(const DecodeSmallP
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += nthreads) {
         if (r >= p.B) continue;
         const int tile = (int)(r / NS), s = (int)(r % NS);
+        if (p.tile_done) {
+            // concurrent mode: the forward kernel is still running; wait for this tile (bounded: ~2 s, then error)
+            const long long t0 = clock64();
+            for (;;) {
+                int v;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.tile_done + tile) : "memory");
+                if (v) break;
+                if (clock64() - t0 > (1LL << 32)) { *p.status = 5; break; }
+                __nanosleep(256);
+            }
+        }
         const uint32_t b = p.order[r];
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
