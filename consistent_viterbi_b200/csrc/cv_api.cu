@@ -647,8 +647,15 @@ extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_
     const int nch = chunk_count(h, B, timing, true);
     // Chunk k: H2D of its observations -> order/forward/backtrace -> D2H of its paths, on stream k % 2, so the
     // copies of one chunk overlap the kernels of its neighbours.  Offsets are validated while the first copy flies.
-    for (int k = 0; k < nch; k++) {
-        const int64_t b0 = B * k / nch, b1 = B * (k + 1) / nch;
+    std::vector<int64_t> cb;                                            // chunk boundaries (sequence indices)
+    for (int k = 0; k <= nch; k++) cb.push_back(B * k / nch);
+    const int nck = (int)cb.size() - 1;
+    static const bool e2e_prof = getenv("CV_E2E_PROF") != nullptr;      // prints a per-chunk timeline (copy in / kernels / copy out)
+    std::vector<cudaEvent_t> pev;
+    auto mark = [&](cudaStream_t s_) { if (e2e_prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); pev.push_back(e); } };
+    if (e2e_prof) { cudaDeviceSynchronize(); mark(h->ws[0].st); }
+    for (int k = 0; k < nck; k++) {
+        const int64_t b0 = cb[k], b1 = cb[k + 1];
         int64_t max_len = 0;
         for (int64_t b = b0; b < b1; b++) {
             const int64_t len = seq_off[b + 1] - seq_off[b];
@@ -660,11 +667,24 @@ extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_
         cudaStream_t st = nch == 1 ? h->stream : w.st;
         const int64_t e0 = seq_off[b0], e1 = seq_off[b1];
         CUDA_TRY(cudaMemcpyAsync(d_off + b0, seq_off + b0, sizeof(int64_t) * (size_t)(b1 - b0 + 1), cudaMemcpyHostToDevice, st));
+        mark(st);
         CUDA_TRY(cudaMemcpyAsync(d_obs + e0, obs_flat + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, st));
+        mark(st);
         if ((rc = decode_chunk(h, w, d_obs, d_off + b0, b1 - b0, e1 - e0, max_len, d_path, d_score + b0, st, timing))) return rc;
+        mark(st);
         CUDA_TRY(cudaMemcpyAsync(path_out + e0, d_path + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, st));
         if (score_out)
             CUDA_TRY(cudaMemcpyAsync(score_out + b0, d_score + b0, sizeof(double) * (size_t)(b1 - b0), cudaMemcpyDeviceToHost, st));
+        mark(st);
+    }
+    if (e2e_prof) {
+        cudaDeviceSynchronize();
+        for (int k = 0; k < nck; k++) {
+            float t[4];
+            for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], pev[0], pev[1 + 4 * k + i]);
+            fprintf(stderr, "[cv] chunk %d (%lld seqs): in %.2f-%.2f  kernels -%.2f  out -%.2f ms\n", k, (long long)(cb[k + 1] - cb[k]), t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t e : pev) cudaEventDestroy(e);
     }
     int *hs = (int *)h->pinned_status + 8;
     hs[0] = hs[1] = 0;
