@@ -79,6 +79,7 @@ SIGNATURES = {
     "cv_set_small_config": (None, [C.c_int]),
     "cv_set_chunks": (None, [C.c_int]),
     "cv_set_chain_max_batch": (None, [C.c_longlong]),
+    "cv_set_pipeline": (None, [C.c_int, C.c_int]),
     "cv_host_alloc": (C.c_void_p, [C.c_uint64]),
     "cv_host_free": (None, [C.c_void_p]),
     "cv_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),

@@ -338,10 +338,59 @@ __global__ void tile_tmax_kernel(const uint32_t *sorted_len, int ntiles, int NS,
     if (t < ntiles) tmax[t] = (long long)sorted_len[(size_t)t * NS];
 }
 
+// ---- streamed host path: keys = (chunk descending-coded, length) so that one descending sort orders the batch by
+// chunk (ascending) and, inside a chunk, by length (longest first); lengths must fit 24 bits
+constexpr int STREAM_MAX_CHUNKS = 16;
+struct ChunkBounds { int nch; int64_t cb[STREAM_MAX_CHUNKS + 2]; };
+
+__global__ void seq_chunk_keys_kernel(const int64_t *seq_off, int64_t B, const ChunkBounds cbs, uint32_t *keys, uint32_t *vals,
+                                      int *status, unsigned int *max_len)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t len = seq_off[b + 1] - seq_off[b];
+    if (len == 0) atomicMax(status, CV_ERR_EMPTY);            // reference: sequence.len()-1 underflow panic
+    if (len < 0) atomicMax(status, CV_ERR_ARG);               // offsets not monotone
+    const uint32_t l = (uint32_t)(len < 0 ? 0 : (len > 0xffffffLL ? 0xffffffLL : len));
+    if (len > 0xffffffLL) atomicMax(status, CV_ERR_UNSUPPORTED);
+    atomicMax(max_len, l);
+    int c = 0;
+    while (c + 1 < cbs.nch && b >= cbs.cb[c + 1]) c++;
+    keys[b] = ((uint32_t)(cbs.nch - 1 - c) << 24) | l;
+    vals[b] = (uint32_t)b;
+}
+
+// per tile of NS sorted sequences: the longest length and the last chunk it takes sequences from
+__global__ void tile_meta_kernel(const uint32_t *sorted_keys, int ntiles, int NS, int64_t B, int nch, long long *tmax, int *tchunk)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    uint32_t lmax = 0; int cmax = 0;
+    for (int s = 0; s < NS; s++) {
+        const int64_t r = (int64_t)t * NS + s;
+        if (r >= B) break;
+        const uint32_t k = sorted_keys[r];
+        lmax = max(lmax, k & 0xffffffu);
+        cmax = max(cmax, nch - 1 - (int)(k >> 24));
+    }
+    tmax[t] = (long long)lmax; tchunk[t] = cmax;
+}
+
+// what launch_decode_small needs to know about the streamed host path
+struct StreamedIO {
+    ChunkBounds cbs;
+    unsigned int *d_arrived;        // chunks whose observations have arrived
+    unsigned int *d_chunk_done;     // [nch] finished sequences per chunk
+};
+
 typedef cv_hmm::DecodeWs DecodeWs;
 static int g_small_cfg = -1;   // test/bench override of the small-K launch shape (see cv_set_small_config)
 static int g_chunks = -1;      // test/bench override of the chunk count (see cv_set_chunks)
 static long long g_chain_max_b = -1;   // batches up to this size use the warp-per-sequence kernel (-1: 8192)
+// pipeline switches (cv_set_pipeline / environment): CV_BT_CONCURRENT=0 runs the backtrace after the forward kernel,
+// CV_STREAMED=0 makes cv_decode_batch launch once per chunk instead of streaming the copies past one launch
+static int g_bt_concurrent = []() { const char *e = getenv("CV_BT_CONCURRENT"); return e ? atoi(e) : 1; }();
+static int g_streamed = []() { const char *e = getenv("CV_STREAMED"); return e ? atoi(e) : 1; }();
 
 #include "decode_large_host.inl"
 
@@ -361,12 +410,11 @@ static StreamWaitValue32Fn stream_wait_value32()
     }();
     return fn;
 }
-// CV_BT_CONCURRENT=0: backtrace after the forward kernel (A/B hook)
-static int g_bt_concurrent = []() { const char *e = getenv("CV_BT_CONCURRENT"); return e ? atoi(e) : 1; }();
+
 
 static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int64_t *d_off, int64_t B,
                                int64_t N, uint32_t *d_path, double *d_score, unsigned int *d_counter, int *d_status,
-                               int64_t max_len, cudaStream_t st, bool timing)
+                               int64_t max_len, cudaStream_t st, bool timing, const StreamedIO *sio = nullptr)
 {
     const int G = h->G;
     const uint32_t *d_order = (const uint32_t *)w.order.p, *d_sorted_len = (const uint32_t *)w.keys_out.p;
@@ -395,12 +443,19 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
         CUDA_TRY(cudaStreamSynchronize(st));
         max_len = L;
     }
-    // history slabs: sum over tiles of NS * Tmax(tile) <= N + NS * max_len because lengths are sorted
-    const size_t hist_elems = ((size_t)N + (size_t)NS * (size_t)max_len) * (size_t)h->K;
+    // history slabs: sum over tiles of NS * Tmax(tile) <= N + NS * max_len because lengths are sorted (per chunk, plus
+    // the tiles that straddle two chunks, on the streamed path)
+    const size_t stairs = sio ? (size_t)sio->cbs.nch + 1 : 1;
+    const size_t hist_elems = ((size_t)N + (size_t)NS * (size_t)max_len * stairs) * (size_t)h->K;
     if ((rc = w.hist.ensure(hist_elems * sizeof(double)))) return rc;
     if ((rc = w.tmax.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
     if ((rc = w.base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
-    tile_tmax_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_sorted_len, ntiles, NS, (long long *)w.tmax.p);
+    if (sio) {
+        if ((rc = w.delta_g.ensure(sizeof(int) * (size_t)ntiles + 64))) return rc;     // tile -> chunk (buffer unused for K <= 64)
+        tile_meta_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(d_sorted_len, ntiles, NS, B, sio->cbs.nch, (long long *)w.tmax.p, (int *)w.delta_g.p);
+    } else {
+        tile_tmax_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_sorted_len, ntiles, NS, (long long *)w.tmax.p);
+    }
     g_launches++;
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (long long *)w.tmax.p, (long long *)w.base.p, ntiles, st));
@@ -412,6 +467,12 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     p.tile_base = (const long long *)w.base.p;
     p.hist = (double *)w.hist.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
     p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.NS = NS; p.ntiles = ntiles;
+    p.tile_tmax = nullptr; p.tile_chunk = nullptr; p.arrived = nullptr; p.chunk_done = nullptr; p.nch = 0;
+    if (sio) {
+        p.tile_tmax = (const long long *)w.tmax.p; p.tile_chunk = (const int *)w.delta_g.p;
+        p.arrived = sio->d_arrived; p.chunk_done = sio->d_chunk_done; p.nch = sio->cbs.nch;
+        for (int c = 0; c <= sio->cbs.nch; c++) p.cb[c] = sio->cbs.cb[c];
+    }
     void (*kern)(DecodeSmallParams);
     if (h->TQT == 12) kern = variant == 1 ? decode_small_fwd_kernel<12, 512, 1> : decode_small_fwd_kernel<12, 256, 2>;
     else if (h->TQT == 6) kern = variant == 1 ? decode_small_fwd_kernel<6, 512, 1> : decode_small_fwd_kernel<6, 256, 2>;
@@ -434,6 +495,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     // registers / shared memory the forward CTAs leave free.
     StreamWaitValue32Fn wait32 = stream_wait_value32();
     const bool concurrent = !timing && g_bt_concurrent && wait32 != nullptr && w.st_bt != nullptr;
+    if (sio && !concurrent) return fail(CV_ERR_UNSUPPORTED, "the streamed path needs the concurrent backtrace");
     p.tile_done = nullptr; p.started = nullptr;
     if (concurrent) {
         if ((rc = w.lg_done.ensure(sizeof(int) * ((size_t)ntiles + 8)))) return rc;
@@ -484,6 +546,11 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
 extern "C" void cv_set_small_config(int cfg) { g_small_cfg = cfg; }
 extern "C" void cv_set_chunks(int n) { g_chunks = n; }
 extern "C" void cv_set_chain_max_batch(long long b) { g_chain_max_b = b; }
+extern "C" void cv_set_pipeline(int bt_concurrent, int streamed)
+{
+    if (bt_concurrent >= 0) g_bt_concurrent = bt_concurrent;
+    if (streamed >= 0) g_streamed = streamed;
+}
 
 // One chunk of sequences [0, B) of d_off (offsets are absolute into d_obs / d_path): order by length,
 // forward, backtrace; everything enqueued on `st` with workspace set `w`.
@@ -625,6 +692,103 @@ extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64
     return CV_OK;
 }
 
+// cuStreamWriteValue32: a stream writes a word once everything before it in the stream is done
+typedef int (*StreamWriteValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static StreamWriteValue32Fn stream_write_value32()
+{
+    static StreamWriteValue32Fn fn = []() -> StreamWriteValue32Fn {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (StreamWriteValue32Fn)f;
+    }();
+    return fn;
+}
+
+// Streamed host path (K <= 64, large batches): ONE forward + backtrace launch over the whole batch while the
+// observations still arrive chunk by chunk on a copy stream (each chunk followed by a stream write of the
+// `arrived` word the forward CTAs poll) and the paths / scores of a chunk leave on another copy stream as soon as
+// the backtrace has counted the chunk's sequences done (stream wait on chunk_done[c]).  The batch is ordered by
+// (chunk, length), so the kernels consume the chunks in arrival order.  Against one launch per chunk this
+// removes the per-chunk sort / launch / ramp costs: the copies hide behind 13 ms of kernels instead of 6 x 2.3 ms.
+static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B, uint32_t *path_out,
+                           double *score_out, int nch, bool *handled)
+{
+    *handled = false;
+    StreamWaitValue32Fn wait32 = stream_wait_value32();
+    StreamWriteValue32Fn write32 = stream_write_value32();
+    if (!g_streamed || !g_bt_concurrent || !wait32 || !write32 || nch < 2 || nch > STREAM_MAX_CHUNKS) return CV_OK;
+    if (h->K > SMALL_K_MAX || (g_chain_max_b < 0 ? B <= 8192 : B <= g_chain_max_b) || B > 0x7fffffffLL) return CV_OK;
+    const int64_t N = seq_off[B];
+    DecodeWs &w = h->ws[0];
+    cudaStream_t sk = w.st, s_in = h->ws[1].st, s_out = h->ws[1].st_bt;
+    uint32_t *d_obs = (uint32_t *)h->obs.p, *d_path = (uint32_t *)h->path.p;
+    int64_t *d_off = (int64_t *)h->seq_off.p;
+    double *d_score = (double *)h->score.p;
+    int rc;
+    if ((rc = w.order.ensure(sizeof(uint32_t) * (size_t)B)) || (rc = w.keys_in.ensure(sizeof(uint32_t) * (size_t)B)) ||
+        (rc = w.keys_out.ensure(sizeof(uint32_t) * (size_t)B)) || (rc = w.vals_in.ensure(sizeof(uint32_t) * (size_t)B)) ||
+        (rc = w.misc.ensure(256)))
+        return rc;
+    unsigned int *d_counter = (unsigned int *)w.misc.p;
+    int *d_status = (int *)w.misc.p + 16;
+    unsigned int *d_maxlen = (unsigned int *)w.misc.p + 17, *d_arrived = (unsigned int *)w.misc.p + 32, *d_chunk_done = d_arrived + 1;
+    StreamedIO sio;
+    sio.cbs.nch = nch;
+    for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
+    sio.d_arrived = d_arrived; sio.d_chunk_done = d_chunk_done;
+
+    // offsets first (the ordering needs nothing else), then the observations chunk by chunk on the copy stream
+    CUDA_TRY(cudaMemsetAsync(w.misc.p, 0, 256, sk));
+    CUDA_TRY(cudaEventRecord(w.ev_pre, sk));
+    CUDA_TRY(cudaMemcpyAsync(d_off, seq_off, sizeof(int64_t) * (size_t)(B + 1), cudaMemcpyHostToDevice, sk));
+    seq_chunk_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, sk>>>(d_off, B, sio.cbs, (uint32_t *)w.keys_in.p,
+                                                                      (uint32_t *)w.vals_in.p, d_status, d_maxlen);
+    g_launches++;
+    int *hs = (int *)h->pinned_status + 8;
+    CUDA_TRY(cudaMemcpyAsync(hs, d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, sk));      // status, longest length
+    CUDA_TRY(cudaStreamWaitEvent(s_in, w.ev_pre, 0));                                          // `arrived` is zeroed first
+    for (int k = 0; k < nch; k++) {
+        const int64_t e0 = seq_off[sio.cbs.cb[k]], e1 = seq_off[sio.cbs.cb[k + 1]];
+        if (e1 < e0 || e1 > N) return fail(CV_ERR_ARG, "seq_off not monotone");
+        if (e1 > e0) CUDA_TRY(cudaMemcpyAsync(d_obs + e0, obs_flat + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, s_in));
+        if (write32(s_in, (unsigned long long)(uintptr_t)d_arrived, (unsigned int)(k + 1), 0x0) != 0) return fail(CV_ERR_CUDA, "cuStreamWriteValue32 failed");
+    }
+    CUDA_TRY(cudaStreamSynchronize(sk));                                                       // ~0.2 ms: offsets in, lengths checked
+    if (hs[0] == CV_ERR_EMPTY) { cudaStreamSynchronize(s_in); return fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)"); }
+    if (hs[0] == CV_ERR_ARG) { cudaStreamSynchronize(s_in); return fail(CV_ERR_ARG, "seq_off not monotone"); }
+    if (hs[0]) { cudaStreamSynchronize(s_in); *handled = false; return CV_OK; }                // e.g. a sequence longer than 2^24: chunked path
+    const int64_t max_len = (int64_t)(unsigned int)hs[1];
+
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)w.keys_in.p, (uint32_t *)w.keys_out.p,
+                                                       (uint32_t *)w.vals_in.p, (uint32_t *)w.order.p, (int)B, 0, 32, sk));
+    if ((rc = w.cub_tmp.ensure(tmp_bytes))) return rc;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p, (uint32_t *)w.keys_out.p,
+                                                       (uint32_t *)w.vals_in.p, (uint32_t *)w.order.p, (int)B, 0, 32, sk));
+    if ((rc = launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, sk, false, &sio))) return rc;
+    // paths / scores of chunk c leave as soon as the backtrace has counted all its sequences
+    CUDA_TRY(cudaStreamWaitEvent(s_out, w.ev_pre, 0));
+    for (int k = 0; k < nch; k++) {
+        const int64_t b0 = sio.cbs.cb[k], b1 = sio.cbs.cb[k + 1], e0 = seq_off[b0], e1 = seq_off[b1];
+        if (b1 == b0) continue;
+        if (wait32(s_out, (unsigned long long)(uintptr_t)(d_chunk_done + k), (unsigned int)(b1 - b0), 0x0 /* GEQ */) != 0)
+            return fail(CV_ERR_CUDA, "cuStreamWaitValue32 failed");
+        CUDA_TRY(cudaMemcpyAsync(path_out + e0, d_path + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, s_out));
+        if (score_out) CUDA_TRY(cudaMemcpyAsync(score_out + b0, d_score + b0, sizeof(double) * (size_t)(b1 - b0), cudaMemcpyDeviceToHost, s_out));
+    }
+    CUDA_TRY(cudaMemcpyAsync(hs, d_status, sizeof(int), cudaMemcpyDeviceToHost, sk));
+    hs[1] = 0;
+    CUDA_TRY(cudaStreamSynchronize(sk));
+    CUDA_TRY(cudaStreamSynchronize(s_out));
+    CUDA_TRY(cudaStreamSynchronize(s_in));
+    *handled = true;
+    return report_status(hs, 1);
+}
+
 extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B,
                                uint32_t *path_out, double *score_out)
 {
@@ -645,6 +809,11 @@ extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_
     double *d_score = (double *)h->score.p;
     const bool timing = g_timing.load() != 0;
     const int nch = chunk_count(h, B, timing, true);
+    if (!timing) {
+        bool handled = false;
+        if ((rc = decode_streamed(h, obs_flat, seq_off, B, path_out, score_out, nch, &handled))) return rc;
+        if (handled) return CV_OK;
+    }
     // Chunk k: H2D of its observations -> order/forward/backtrace -> D2H of its paths, on stream k % 2, so the
     // copies of one chunk overlap the kernels of its neighbours.  Offsets are validated while the first copy flies.
     std::vector<int64_t> cb;                                            // chunk boundaries (sequence indices)

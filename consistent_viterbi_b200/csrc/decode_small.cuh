@@ -58,6 +58,15 @@ struct DecodeSmallParams {
     // the tile's history is complete in global memory, *started counts the forward CTAs that have begun
     int *tile_done;
     unsigned int *started;
+    // streamed host path (nullptr / 0 otherwise): one launch over the whole batch while the observations still
+    // arrive chunk by chunk and the paths already leave chunk by chunk.  Sequences are ordered by (chunk, length);
+    // a tile may start once *arrived > tile_chunk[tile]; chunk_done[c] counts the finished sequences of chunk c.
+    const long long *tile_tmax;      // longest sequence of every tile (a tile can straddle two chunks)
+    const int *tile_chunk;           // last chunk a tile takes sequences from
+    const unsigned int *arrived;     // chunks whose observations are on the device (written by the copy stream)
+    unsigned int *chunk_done;
+    int nch;
+    int64_t cb[18];                  // chunk boundaries: chunk c = sequences [cb[c], cb[c+1])
     int64_t M, B;
     int K, Kp, G, S, NS, ntiles;   // NS = sequences per tile = 32 * TPT * S
 };
@@ -249,10 +258,23 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
             sOff[s] = off; sLen[s] = len;
         }
         for (int e = tid; e < K * NS; e += blockDim.x) sD[e] = 0.0;
+        if (p.arrived && tid == 0) {
+            // streamed input: the tile's observations must have arrived (bounded wait, then error)
+            const unsigned int need = (unsigned int)p.tile_chunk[tile] + 1u;
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned int v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.arrived) : "memory");
+                if (v >= need) break;
+                if (clock64() - t0 > (1LL << 32)) { *p.status = 5; break; }
+                __nanosleep(128);
+            }
+        }
         fence_proxy_async_smem();
         __syncthreads();
 
-        const int Tmax = sLen[0];   // slot 0 holds the longest sequence of the tile
+        // the longest sequence of the tile: slot 0 when the tile is sorted by length, else precomputed
+        const int Tmax = p.tile_tmax ? (int)p.tile_tmax[tile] : sLen[0];
         double *slab = p.hist + (size_t)p.tile_base[tile] * K * NS;
         if (tid == 0) tma_bulk_s2g(slab, sD, slab_bytes);   // history slab 0 = delta(0)
 
@@ -342,6 +364,16 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 // predecessor j are one coalesced 256-byte run of the slab row.  Rows do not depend on the decoded path, so
 // the next chunk of 16 predecessors is always in flight while the current one is reduced; the only dependent
 // chain per step is 16 x (DADD, DSETP, select) x ceil(K/16).
+// streamed host path: sequence b is decoded -- its path and score may be copied out once its whole chunk is
+__device__ __forceinline__ void bt_mark_done(const DecodeSmallParams &p, uint32_t b)
+{
+    if (!p.chunk_done) return;
+    int c = 0;
+    while (c + 1 < p.nch && (int64_t)b >= p.cb[c + 1]) c++;
+    __threadfence_system();                                  // path / score stores before the count the copy stream waits for
+    atomicAdd(p.chunk_done + c, 1u);
+}
+
 template <int BT_CHUNK, int MINB>
 __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const DecodeSmallParams p)
 {
@@ -387,7 +419,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         }
         if (p.score) p.score[b] = bv;
         p.path[off + len - 1] = (uint32_t)cur;
-        if (len == 1) continue;
+        if (len == 1) { bt_mark_done(p, b); continue; }
 
         // walk back (viterbi.rs:27-30) over the flat stream of (step, chunk) pairs
         double dcur = bv;                                     // delta[tt][cur]
@@ -424,6 +456,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
                 p.path[off + tt - 1] = (uint32_t)cur;
             }
         }
+        bt_mark_done(p, b);
     }
 }
 

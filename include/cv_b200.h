@@ -174,6 +174,10 @@ void   cv_set_chunks(int n);
 /* tuning hook: batches of at most b sequences (K <= 64) use the warp-per-sequence kernel; -1 = default (8192),
  * 0 = always the tile kernel */
 void   cv_set_chain_max_batch(long long b);
+/* tuning hook: bt_concurrent = 1 runs the backtrace kernel next to the forward kernel (tile by tile), streamed = 1
+ * lets cv_decode_batch stream its copies past ONE launch instead of launching once per chunk; -1 = leave as is.
+ * Both default to 1 (environment: CV_BT_CONCURRENT, CV_STREAMED). */
+void   cv_set_pipeline(int bt_concurrent, int streamed);
 /* pinned host memory helpers */
 void *cv_host_alloc(uint64_t bytes);
 void  cv_host_free(void *p);

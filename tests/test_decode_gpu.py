@@ -172,6 +172,44 @@ def test_chunked_pipeline_and_device_api():
     h.close()
 
 
+def test_pipeline_modes_agree():
+    """The host path in all its forms -- streamed copies past one launch / one launch per chunk, backtrace next to
+    or after the forward kernel -- on a ragged batch with many length-1 sequences and up to 16 chunks."""
+    rng = np.random.default_rng(99)
+    K, M, Bn = 37, 50, 30000
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    obs, off = random_batch(rng, Bn, M, 1, 30)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        L.cv_set_chain_max_batch(0)
+        for conc, streamed in ((1, 1), (1, 0), (0, 0)):
+            L.cv_set_pipeline(conc, streamed)
+            for chunks in (2, 5, 16):
+                L.cv_set_chunks(chunks)
+                for _ in range(2):                                # second call reuses flags / counters / buffers
+                    p, s = cv.decode_batch(h, obs, off)
+                    assert (p == rp).all() and s.tobytes() == rs.tobytes(), (conc, streamed, chunks)
+        L.cv_set_pipeline(1, 1)
+        L.cv_set_chunks(4)
+        bad = off.copy(); bad[1000] = bad[1001]                   # an empty sequence in the third chunk's range... any chunk
+        with pytest.raises(cv.CvError) as e:
+            cv.decode_batch(h, obs, bad)
+        assert e.value.code == cv._lib.ERR_EMPTY
+        o2 = obs.copy(); o2[len(o2) // 2] = M                      # observation out of range (index panic)
+        with pytest.raises(cv.CvError) as e:
+            cv.decode_batch(h, o2, off)
+        assert e.value.code == cv._lib.ERR_ARG
+        p, s = cv.decode_batch(h, obs, off)                       # and the handle still works afterwards
+        assert (p == rp).all() and s.tobytes() == rs.tobytes()
+    finally:
+        L.cv_set_pipeline(1, 1)
+        L.cv_set_chunks(-1)
+        L.cv_set_chain_max_batch(-1)
+    h.close()
+
+
 def _path_score(A, B, obs, path):
     """Score of a decoded path under viterbi.rs's association ((d + a) + b), d0 = 0.0 -- plain Python floats."""
     d = 0.0
