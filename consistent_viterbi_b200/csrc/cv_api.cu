@@ -629,7 +629,10 @@ static int chunk_count(const cv_hmm *h, int64_t B, bool timing, bool host_buffer
     // chunks so that the backtrace of one overlaps the forward pass of the other.
     const int64_t per_chunk = (int64_t)h->num_sms * 2 * 6 * 64;
     const int dev_chunks = (g_bt_concurrent && stream_wait_value32() != nullptr) ? 1 : 2;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 6 : dev_chunks, B / per_chunk));
+    // Host buffers, streamed past one launch (decode_streamed): 4 chunks measured best (2: 14.8 ms, 3: 14.3, 4: 14.2-14.3,
+    // 6: 14.4, 10: 14.8, 16: 15.0 -- every chunk restarts the longest-first tile order); one launch per chunk: 6.
+    const bool can_stream = g_streamed && g_bt_concurrent && stream_wait_value32() != nullptr;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? (can_stream ? 4 : 6) : dev_chunks, B / per_chunk));
 }
 
 static int report_status(const int *status_words, int n)
