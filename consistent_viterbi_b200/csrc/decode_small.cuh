@@ -395,13 +395,14 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         if (r >= p.B) continue;
         const int tile = (int)(r / NS), s = (int)(r % NS);
         if (p.tile_done) {
-            // concurrent mode: the forward kernel is still running; wait for this tile (bounded: ~2 s, then error)
+            // concurrent mode: the forward kernel is still running; wait for this tile (bounded: ~17 s -- a tile of
+            // a million steps takes ~3 s --, then error)
             const long long t0 = clock64();
             for (;;) {
                 int v;
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.tile_done + tile) : "memory");
                 if (v) break;
-                if (clock64() - t0 > (1LL << 32)) { *p.status = 5; break; }
+                if (clock64() - t0 > (1LL << 35)) { *p.status = 5; break; }
                 __nanosleep(256);
             }
         }
