@@ -40,6 +40,10 @@
 
 #include "common.cuh"
 
+#ifndef CVB_FWD_UNROLL
+#define CVB_FWD_UNROLL 2      // predecessors per unrolled iteration of the forward tile loop
+#endif
+
 namespace cvb {
 
 struct DecodeSmallParams {
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 #pragma unroll
                 for (int k = 0; k < TQT; k++) best[q][k] = neg_inf();
             const double *dcur = sD + (size_t)((t - 1) & 1) * K * NS + s0;
-            maxplus_tile_val<TQT, 2, TPT>(dcur, NS, sA + i0, Kp, K, best);
+            maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT>(dcur, NS, sA + i0, Kp, K, best);
 
             mbar_wait(sBar + 1, em_phase);      // emission rows of step t have landed
             em_phase ^= 1;
