@@ -400,15 +400,21 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         const int tile = (int)(r / NS), s = (int)(r % NS);
         if (p.tile_done) {
             // concurrent mode: the forward kernel is still running; wait for this tile (bounded: ~17 s -- a tile of
-            // a million steps takes ~3 s --, then error)
-            const long long t0 = clock64();
-            for (;;) {
-                int v;
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.tile_done + tile) : "memory");
-                if (v) break;
-                if (clock64() - t0 > (1LL << 35)) { *p.status = 5; break; }
-                __nanosleep(256);
+            // a million steps takes ~3 s --, then error).  One lane per warp polls (a warp = 32 sequences of one
+            // tile), about once a microsecond: tens of thousands of threads polling L2 would slow the forward kernel.
+            const unsigned int am = __activemask();
+            if ((int)(threadIdx.x & 31) == __ffs(am) - 1) {
+                const long long t0 = clock64();
+                for (;;) {
+                    int v;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.tile_done + tile) : "memory");
+                    if (v) break;
+                    if (clock64() - t0 > (1LL << 35)) { *p.status = 5; break; }
+                    __nanosleep(1000);
+                }
             }
+            __syncwarp(am);
+            __threadfence();                                   // the leader's acquire, extended to the lanes that waited
         }
         const uint32_t b = p.order[r];
         const int64_t off = p.seq_off[b];
