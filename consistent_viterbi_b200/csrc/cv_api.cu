@@ -511,17 +511,19 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     CUDA_TRY(cudaGetLastError());
     if (timing || bt_prof) CUDA_TRY(cudaEventRecord(h->ev1, st));
     // end state + backtrace with lazy backpointers: one thread per sequence
-    const size_t smem_bt = (size_t)h->K * (h->K | 1) * 8;
-    CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
-    CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
+    const size_t smem_bt = (size_t)h->K * (h->K | 1) * 8 + 16 * 8;      // + one chunk of padding behind the last row
+    void (*bt_seq)(DecodeSmallParams) = NS == 64 ? backtrace_small_kernel<16, 4, 64> : backtrace_small_kernel<16, 4, 0>;
+    void (*bt_con)(DecodeSmallParams) = NS == 64 ? backtrace_small_kernel<8, 8, 64> : backtrace_small_kernel<8, 8, 0>;
+    CUDA_TRY(cudaFuncSetAttribute(bt_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
+    CUDA_TRY(cudaFuncSetAttribute(bt_con, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
     // same shared-memory carve-out as the forward kernel, or the two kernels cannot share an SM
-    CUDA_TRY(cudaFuncSetAttribute(backtrace_small_kernel<8, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(bt_con, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const int64_t nblk = ((int64_t)ntiles * NS + 127) / 128;
     if (concurrent) {
         CUDA_TRY(cudaStreamWaitEvent(w.st_bt, w.ev_pre, 0));
         if (wait32(w.st_bt, (unsigned long long)(uintptr_t)p.started, (unsigned int)std::max(1, grid), 0x0 /* GEQ */) != 0)
             return fail(CV_ERR_CUDA, "cuStreamWaitValue32 failed");
-        backtrace_small_kernel<8, 8><<<(unsigned)std::max<int64_t>(1, nblk), 128, smem_bt, w.st_bt>>>(p);   // blocks in tile order
+        bt_con<<<(unsigned)std::max<int64_t>(1, nblk), 128, smem_bt, w.st_bt>>>(p);   // blocks in tile order
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(w.ev_bt, w.st_bt));
@@ -536,7 +538,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
         return CV_OK;
     }
     const int grid_bt = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, (int64_t)h->num_sms * 12));
-    backtrace_small_kernel<16, 4><<<grid_bt, 128, smem_bt, st>>>(p);
+    bt_seq<<<grid_bt, 128, smem_bt, st>>>(p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (timing) CUDA_TRY(cudaEventRecord(h->ev2, st));

@@ -378,11 +378,12 @@ __device__ __forceinline__ void bt_mark_done(const DecodeSmallParams &p, uint32_
     atomicAdd(p.chunk_done + c, 1u);
 }
 
-template <int BT_CHUNK, int MINB>
+// NSC = sequences per tile when known at compile time (64: the load offsets become immediates), 0 = p.NS
+template <int BT_CHUNK, int MINB, int NSC>
 __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int K = p.K, Kp = p.Kp, NS = p.NS;
+    const int K = p.K, Kp = p.Kp, NS = NSC ? NSC : p.NS;
     const int ATP = K | 1;                                   // odd pitch: rows of different states spread over banks
     double *sAT = reinterpret_cast<double *>(smem_raw);     // sAT[s*ATP + j] = logA[j][s]
     for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) {
@@ -392,7 +393,8 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
     __syncthreads();
 
     const size_t sl = (size_t)K * NS;
-    const int nchunk = (K + BT_CHUNK - 1) / BT_CHUNK;
+    const int nfull = K / BT_CHUNK, ktail = K - nfull * BT_CHUNK;   // full chunks, predecessors of the partial last chunk
+    const int nchunk = nfull + (ktail ? 1 : 0);
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t total = (int64_t)p.ntiles * NS;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += nthreads) {
@@ -432,40 +434,55 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         p.path[off + len - 1] = (uint32_t)cur;
         if (len == 1) { bt_mark_done(p, b); continue; }
 
-        // walk back (viterbi.rs:27-30) over the flat stream of (step, chunk) pairs
+        // walk back (viterbi.rs:27-30): steps tt = len-1 .. 1, each a scan of row tt-1 in chunks of BT_CHUNK predecessors;
+        // the next chunk (of this step, or the first of the next step -- rows do not depend on the path) is always
+        // in flight while the current one is reduced.  Pointers advance by constants: no division in the loop.
         double dcur = bv;                                     // delta[tt][cur]
         double nx[BT_CHUNK];
-        const int64_t nq = (int64_t)(len - 1) * nchunk;
-        auto load_chunk = [&](int64_t q, double (&dst)[BT_CHUNK]) {
-            const int tt = len - 1 - (int)(q / nchunk), c = (int)(q % nchunk);
-            const double *prow = col + (size_t)(tt - 1) * sl + (size_t)c * BT_CHUNK * NS;
+        const double *rowp = col + (size_t)(len - 2) * sl;    // row tt-1
+        uint32_t *pout = p.path + off + (len - 2);
+        auto load_chunk = [&](const double *prow, int c, double (&dst)[BT_CHUNK]) {
+            const double *q = prow + (size_t)c * (BT_CHUNK * (size_t)NS);
+            if (c < nfull) {
 #pragma unroll
-            for (int k = 0; k < BT_CHUNK; k++) dst[k] = (c * BT_CHUNK + k < K) ? __ldcs(prow + (size_t)k * NS) : neg_inf();
+                for (int k = 0; k < BT_CHUNK; k++) dst[k] = __ldcs(q + (size_t)k * NS);
+            } else {
+#pragma unroll
+                for (int k = 0; k < BT_CHUNK; k++) dst[k] = (k < ktail) ? __ldcs(q + (size_t)k * NS) : neg_inf();
+            }
         };
-        load_chunk(0, nx);
-        double mv = neg_inf(); int mi = 0;
-        for (int64_t q = 0; q < nq; q++) {
-            double cu[BT_CHUNK];
+        load_chunk(rowp, 0, nx);
+        for (int tt = len - 1; tt >= 1; tt--) {
+            const double *at = sAT + (size_t)cur * ATP;
+            double mv = 0.0; int mi = 0;
+            for (int c = 0; c < nchunk; c++) {
+                double cu[BT_CHUNK];
 #pragma unroll
-            for (int k = 0; k < BT_CHUNK; k++) cu[k] = nx[k];
-            if (q + 1 < nq) load_chunk(q + 1, nx);
-            const int tt = len - 1 - (int)(q / nchunk), c = (int)(q % nchunk);
-            const double *at = sAT + (size_t)cur * ATP + c * BT_CHUNK;
-            if (c == 0) { mv = cu[0] + at[0]; mi = 0; }                    // viterbi.rs:15-16: first candidate
+                for (int k = 0; k < BT_CHUNK; k++) cu[k] = nx[k];
+                if (c + 1 < nchunk) load_chunk(rowp, c + 1, nx);
+                else if (tt > 1) load_chunk(rowp - sl, 0, nx);
+                const double *ac = at + c * BT_CHUNK;            // (reads up to BT_CHUNK-1 doubles past K: padded, never win)
+                if (c == 0) {
+                    mv = cu[0] + ac[0]; mi = 0;                  // viterbi.rs:15-16: first candidate
 #pragma unroll
-            for (int k = 0; k < BT_CHUNK; k++) {
-                const int j = c * BT_CHUNK + k;
-                if (j < K && j > 0) {
-                    const double v = cu[k] + at[k];
-                    if (v > mv) { mv = v; mi = j; }
+                    for (int k = 1; k < BT_CHUNK; k++) {
+                        const double v = cu[k] + ac[k];          // predecessors >= K hold -inf: never strictly greater
+                        if (v > mv) { mv = v; mi = k; }
+                    }
+                } else {
+                    const int j0 = c * BT_CHUNK;
+#pragma unroll
+                    for (int k = 0; k < BT_CHUNK; k++) {
+                        const double v = cu[k] + ac[k];
+                        if (v > mv) { mv = v; mi = j0 + k; }
+                    }
                 }
             }
-            if (c == nchunk - 1) {
-                // psi = 0 when delta[tt][cur] = -inf (emission -inf or all candidates -inf; see header comment)
-                cur = (dcur > neg_inf()) ? mi : 0;
-                dcur = __ldcg(col + (size_t)(tt - 1) * sl + (size_t)cur * NS);   // delta[tt-1][cur]
-                p.path[off + tt - 1] = (uint32_t)cur;
-            }
+            // psi = 0 when delta[tt][cur] = -inf (emission -inf or all candidates -inf; see header comment)
+            cur = (dcur > neg_inf()) ? mi : 0;
+            dcur = __ldcg(rowp + (size_t)cur * NS);              // delta[tt-1][cur]
+            *pout = (uint32_t)cur;
+            pout--; rowp -= sl;
         }
         bt_mark_done(p, b);
     }
