@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         // the next chunk (of this step, or the first of the next step -- rows do not depend on the path) is always
         // in flight while the current one is reduced.  Pointers advance by constants: no division in the loop.
         double dcur = bv;                                     // delta[tt][cur]
-        double nx[BT_CHUNK];
+        double bufA[BT_CHUNK], bufB[BT_CHUNK];                // two chunk buffers used alternately: no register copies
         const double *rowp = col + (size_t)(len - 2) * sl;    // row tt-1
         uint32_t *pout = p.path + off + (len - 2);
         auto load_chunk = [&](const double *prow, int c, double (&dst)[BT_CHUNK]) {
@@ -451,38 +451,58 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
                 for (int k = 0; k < BT_CHUNK; k++) dst[k] = (k < ktail) ? __ldcs(q + (size_t)k * NS) : neg_inf();
             }
         };
-        load_chunk(rowp, 0, nx);
-        for (int tt = len - 1; tt >= 1; tt--) {
-            const double *at = sAT + (size_t)cur * ATP;
-            double mv = 0.0; int mi = 0;
-            for (int c = 0; c < nchunk; c++) {
-                double cu[BT_CHUNK];
+        double mv = 0.0; int mi = 0;
+        const double *at = sAT;
+        // chunk c of the current step: candidates fl(delta[tt-1][j] + logA[j][cur]), first maximum (viterbi.rs:15-16);
+        // predecessors >= K hold -inf and can never be strictly greater (logA is read up to BT_CHUNK-1 doubles past
+        // K: padded)
+        auto reduce_chunk = [&](const double (&cu)[BT_CHUNK], int c) {
+            const double *ac = at + c * BT_CHUNK;
+            if (c == 0) {
+                mv = cu[0] + ac[0]; mi = 0;
 #pragma unroll
-                for (int k = 0; k < BT_CHUNK; k++) cu[k] = nx[k];
-                if (c + 1 < nchunk) load_chunk(rowp, c + 1, nx);
-                else if (tt > 1) load_chunk(rowp - sl, 0, nx);
-                const double *ac = at + c * BT_CHUNK;            // (reads up to BT_CHUNK-1 doubles past K: padded, never win)
-                if (c == 0) {
-                    mv = cu[0] + ac[0]; mi = 0;                  // viterbi.rs:15-16: first candidate
-#pragma unroll
-                    for (int k = 1; k < BT_CHUNK; k++) {
-                        const double v = cu[k] + ac[k];          // predecessors >= K hold -inf: never strictly greater
-                        if (v > mv) { mv = v; mi = k; }
-                    }
-                } else {
-                    const int j0 = c * BT_CHUNK;
-#pragma unroll
-                    for (int k = 0; k < BT_CHUNK; k++) {
-                        const double v = cu[k] + ac[k];
-                        if (v > mv) { mv = v; mi = j0 + k; }
-                    }
+                for (int k = 1; k < BT_CHUNK; k++) {
+                    const double v = cu[k] + ac[k];
+                    if (v > mv) { mv = v; mi = k; }
                 }
+            } else {
+                const int j0 = c * BT_CHUNK;
+#pragma unroll
+                for (int k = 0; k < BT_CHUNK; k++) {
+                    const double v = cu[k] + ac[k];
+                    if (v > mv) { mv = v; mi = j0 + k; }
+                }
+            }
+        };
+        // one step: X holds chunk 0 on entry; the chunk after the one being reduced is always in flight (the next
+        // chunk of this step, or chunk 0 of the next step -- rows do not depend on the path)
+        auto step = [&](double (&X)[BT_CHUNK], double (&Y)[BT_CHUNK], int tt) {
+            at = sAT + (size_t)cur * ATP;
+            int c = 0;
+            for (; c + 1 < nchunk; c += 2) {
+                load_chunk(rowp, c + 1, Y);
+                reduce_chunk(X, c);
+                if (c + 2 < nchunk) load_chunk(rowp, c + 2, X);
+                else if (tt > 1) load_chunk(rowp - sl, 0, X);
+                reduce_chunk(Y, c + 1);
+            }
+            if (c < nchunk) {                                  // odd number of chunks: the next step starts in Y
+                if (tt > 1) load_chunk(rowp - sl, 0, Y);
+                reduce_chunk(X, c);
             }
             // psi = 0 when delta[tt][cur] = -inf (emission -inf or all candidates -inf; see header comment)
             cur = (dcur > neg_inf()) ? mi : 0;
             dcur = __ldcg(rowp + (size_t)cur * NS);              // delta[tt-1][cur]
             *pout = (uint32_t)cur;
             pout--; rowp -= sl;
+        };
+        load_chunk(rowp, 0, bufA);
+        if (nchunk & 1) {
+            int tt = len - 1;
+            for (; tt >= 2; tt -= 2) { step(bufA, bufB, tt); step(bufB, bufA, tt - 1); }
+            if (tt >= 1) step(bufA, bufB, tt);
+        } else {
+            for (int tt = len - 1; tt >= 1; tt--) step(bufA, bufB, tt);
         }
         bt_mark_done(p, b);
     }
