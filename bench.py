@@ -462,9 +462,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = cv._lib.lib()
     if os.environ.get("CV_CHUNKS"):
-        L.cv_set_chunks(int(os.environ["CV_CHUNKS"]))
+        L.cv_debug_set_chunks(int(os.environ["CV_CHUNKS"]))
     if os.environ.get("CV_SMALL_CFG"):
-        L.cv_set_small_config(int(os.environ["CV_SMALL_CFG"]))
+        L.cv_debug_set_small_config(int(os.environ["CV_SMALL_CFG"]))
     wl = build_workload(args, rank)
     hmm = cv.HMM(wl["A"], wl["B"], wl["pi"])
     h = hmm.device_handle(local)
@@ -474,9 +474,9 @@ def main():
 
     # ---- FP64 issue peak of this GPU, measured now (roofline denominator) ----
     ops, ms = C.c_double(), C.c_double()
-    cv._lib.check(L.cv_probe_fp64(local, 0, 20000, C.byref(ops), C.byref(ms)))
+    cv._lib.check(L.cv_debug_probe_fp64(local, 0, 20000, C.byref(ops), C.byref(ms)))
     peak_dadd = ops.value
-    cv._lib.check(L.cv_probe_fp64(local, 1, 20000, C.byref(ops), C.byref(ms)))
+    cv._lib.check(L.cv_debug_probe_fp64(local, 1, 20000, C.byref(ops), C.byref(ms)))
     peak_mix = ops.value
 
     # ---- device-resident inputs ----
@@ -617,7 +617,7 @@ def main():
                 "achieved": achieved_alu / 1e12, "peak": peak_mix / 1e12, "unit": "TFLOP/s",
                 "unit_note": "FP64 add+compare operations (2 per cell), not tensor FLOPs; frac = max(ALU view, HBM view) as SURVEY 8d defines",
                 "frac": achieved_alu / peak_mix, "traffic": traffic,
-                "peak_source": "measured in this run: DADD+DSETP issue rate over all SMs (cv_probe_fp64 mode 1); "
+                "peak_source": "measured in this run: DADD+DSETP issue rate over all SMs (cv_debug_probe_fp64 mode 1); "
                                f"DADD alone {peak_dadd / 1e12:.2f}",
                 "kernel_ms": fwd, "backtrace_ms": float(np.mean(bt_ms)),
                 "hbm": {"achieved": wl["steps"] * bytes_per_step / ((fwd + float(np.mean(bt_ms))) * 1e-3) / 1e9,

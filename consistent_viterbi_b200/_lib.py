@@ -30,10 +30,10 @@ class CvError(RuntimeError):
 def build(force: bool = False, variant: int | None = None) -> str:
     """Compile csrc/ for sm_100a with nvcc (in-tree, so the .so travels to the GPU box)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl"))]
-    srcs.append(os.path.join(_HERE, "..", "include", "cv_b200.h"))
+    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("cv_b200.h", "cv_b200_debug.h")]
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:
-        cmd = ["make", "-C", CSRC, "-s", "-B"]
+        cmd = ["make", "-C", CSRC, "-s", "-B", "-j4"]
         if variant is not None:
             cmd.append(f"VARIANT={variant}")
         subprocess.check_call(cmd)
@@ -47,7 +47,7 @@ _dp, _u32p, _i64p, _u64p, _u8p, _i32p = (
     C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
 )
 
-# name -> (restype, argtypes); mirrors include/cv_b200.h one to one
+# name -> (restype, argtypes); mirrors include/cv_b200.h (the drop-in boundary) one to one
 SIGNATURES = {
     "cv_hmm_create": (C.c_int, [C.c_int, C.c_int, _u64p, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_void_p)]),
     "cv_hmm_destroy": (None, [C.c_void_p]),
@@ -64,9 +64,6 @@ SIGNATURES = {
     "cv_cp_solve_dist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
                                    C.c_void_p, _dp, _u64p, _u64p]),
     "cv_cp_plan_cuts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
-    "cv_cp_last_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "cv_cp_last_ub": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
-    "cv_debug_ordered_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _dp]),
     "cv_cfn_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                 C.c_void_p, _dp, _i64p, _dp]),
     "cv_mle": (C.c_int, [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -76,13 +73,23 @@ SIGNATURES = {
     "cv_set_timing": (None, [C.c_int]),
     "cv_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "cv_last_backtrace_ms": (C.c_double, [C.c_void_p]),
-    "cv_set_small_config": (None, [C.c_int]),
-    "cv_set_chunks": (None, [C.c_int]),
-    "cv_set_chain_max_batch": (None, [C.c_longlong]),
-    "cv_set_pipeline": (None, [C.c_int, C.c_int]),
     "cv_host_alloc": (C.c_void_p, [C.c_uint64]),
     "cv_host_free": (None, [C.c_void_p]),
-    "cv_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
+}
+
+# test / bench hooks, include/cv_b200_debug.h
+DEBUG_SIGNATURES = {
+    "cv_debug_cp_last_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cv_debug_cp_last_ub": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _u64p]),
+    "cv_debug_ordered_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _dp]),
+    "cv_debug_set_small_config": (None, [C.c_int]),
+    "cv_debug_set_chunks": (None, [C.c_int]),
+    "cv_debug_set_chain_max_batch": (None, [C.c_longlong]),
+    "cv_debug_set_pipeline": (None, [C.c_int, C.c_int]),
+    "cv_debug_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
+    "cv_debug_set_fwd_variant": (None, [C.c_int]),
+    "cv_debug_set_large_group_rb": (None, [C.c_longlong]),
+    "cv_debug_set_cp_leaf_batch": (None, [C.c_int]),
 }
 
 
@@ -95,7 +102,7 @@ def lib() -> C.CDLL:
                 "(nvcc, sm_100a). There is no CPU fallback."
             )
         L = C.CDLL(SO_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in {**SIGNATURES, **DEBUG_SIGNATURES}.items():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype, fn.argtypes = res, args
         _lib = L

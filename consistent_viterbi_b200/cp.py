@@ -31,12 +31,12 @@ def cp_solve_arrays(hmm: HMM, obs, is_seq_start, comp, ncomp, max_nodes: int = 0
         K = hmm.nstates()
         delta = np.zeros((N, K), dtype=np.float64)
         psi = np.zeros((N, K), dtype=np.uint64)
-        _lib.check(L.cv_cp_last_state(h, delta.ctypes.data, psi.ctypes.data))
+        _lib.check(L.cv_debug_cp_last_state(h, delta.ctypes.data, psi.ctypes.data))
         out["delta"], out["psi"] = delta, psi
     if want_ub:
         ub = np.zeros(want_ub, dtype=np.float64)
         n = C.c_uint64(0)
-        _lib.check(L.cv_cp_last_ub(h, ub.ctypes.data, want_ub, C.byref(n)))
+        _lib.check(L.cv_debug_cp_last_ub(h, ub.ctypes.data, want_ub, C.byref(n)))
         out["ub"] = ub[: min(want_ub, n.value)]
     return out
 

@@ -25,7 +25,7 @@ __device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0
 //   DADD + DSETP (FP64 pipe) + 2 x 32-bit select (value) + 1 x select (index),
 // and SEL/FSEL issue on the ALU pipe only.  VARIANT 1-3 were attempts to move selects onto the FMA pipe as
 // predicated IMADs; ptxas turns every predicated move back into op + SEL (checked in SASS, even at -O0), so they
-// compile to the same select count and are kept only for the probe (cv_probe_fp64 modes 3-5).  The production
+// compile to the same select count and are kept only for the probe (cv_debug_probe_fp64 modes 3-5).  The production
 // kernels use VARIANT 0 where the index is part of the state (constrained decode) and the value-only tile of
 // decode_small.cuh / decode_large.cuh otherwise.
 // ---------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-// cp_host.inl -- host control loop of the constrained solver (included by cv_api.cu).
+// cp_host.inl -- host control loop of the constrained solver (included by cv_cp.cu).
 //
 // Mirrors CPSolver::{new, solve, solve_r, backtrack} (reference src/viterbi_solver/cp.rs:20-30,
 // 85-143): the recursion over components and states, the pruning test `ub > best_obj` and the
@@ -107,7 +107,7 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
     // one warp per segment (latency-oriented); the lock-step tile kernel only pays off with very many segments
     const size_t smem_c = (size_t)r.p.K * r.p.Kp * 8 + (r.p.bt_in_smem ? (size_t)r.p.M * r.p.Kp * 8 : 0) +
                           (size_t)CPW_WARPS * 2 * 16 * r.p.Kp;              // up to two segments per warp
-    static const bool fullwarp = getenv("CV_CP_FULLWARP") != nullptr;    // A/B hook: one segment per warp for every K
+    const bool fullwarp = g_tune.cp_fullwarp != 0;    // A/B hook: one segment per warp for every K
     const int64_t segs_per_block = (int64_t)CPW_WARPS * (r.p.Kp <= 16 && !fullwarp ? 2 : 1);
     const int grid = (int)std::min<int64_t>((nseg + segs_per_block - 1) / segs_per_block, (int64_t)r.h->num_sms * r.sweep_blocks_per_sm);
     const bool regs = r.p.Kp == 8 * ((r.p.K + 7) / 8);       // register-resident logA column needs Kp = 4 * KQ
@@ -176,7 +176,7 @@ int cp_solve_r(CpRun &r, int32_t comp)
     for (int state = 0; state < K; state++) {
         if (r.max_nodes && r.explored >= r.max_nodes) break;            // builder-added, deterministic budget
         r.explored++;                                                    // cp.rs:97
-        static const bool prof = getenv("CV_CP_PROF") != nullptr;
+        const bool prof = g_tune.cp_prof != 0;
         auto tick = [&](int slot, std::chrono::steady_clock::time_point &t0) {
             if (!prof) return;
             cudaStreamSynchronize(r.st);
@@ -506,10 +506,10 @@ static int cp_solve_impl(cv_hmm *h, cv_cp_dist *dx, const uint32_t *obs, const u
     }
     CUDA_TRY(cudaMemsetAsync(r.d_sol, 0, sizeof(uint64_t) * (size_t)N, st));       // best_sol = 0 (cp.rs:29)
     if ((rc = r.sum_ws.bind(b[14], cons_pos.size()))) return rc;
-    if (const char *e = getenv("CV_CP_SUM")) g_sum_force = atoi(e);
+    g_sum_force = g_tune.cp_sum;
     r.h_ub = (double *)h->pinned_status + 1;
     r.h_ub[0] = r.h_ub[1] = r.h_ub[2] = 0.0;
-    if (const char *e = getenv("CV_CP_HOSTPOLL")) r.poll = atoi(e) != 0;
+    r.poll = g_tune.cp_hostpoll != 0;
 
     CpParams &p = r.p;
     const bool small = K <= SMALL_K_MAX;
@@ -599,7 +599,7 @@ static int cp_solve_impl(cv_hmm *h, cv_cp_dist *dx, const uint32_t *obs, const u
         if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms; else cudaGetLastError();
         h->last_bt_ms = 0.0;
     }
-    if (getenv("CV_CP_PROF")) {
+    if (g_tune.cp_prof) {
         fprintf(stderr, "[cv] cp phases (us/node over %llu nodes): sweep %.1f fixup %.1f terms %.1f sum %.1f readback %.1f\n",
                 (unsigned long long)r.explored, g_cp_prof[0] / r.explored, g_cp_prof[1] / r.explored,
                 g_cp_prof[2] / r.explored, g_cp_prof[3] / r.explored, g_cp_prof[4] / r.explored);
@@ -626,7 +626,7 @@ extern "C" int cv_cp_solve_dist(cv_cp_dist *d, const uint32_t *obs, const uint8_
     return cp_solve_impl(d->h, d, obs, is_seq_start, comp, N, ncomp, max_nodes, sol_out, obj_out, explored_out, steps_out);
 }
 
-extern "C" int cv_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out)
+extern "C" int cv_debug_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out)
 {
     if (!h || h->cp_N <= 0) return fail(CV_ERR_ARG, "no constrained solve has run on this model");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -643,7 +643,7 @@ extern "C" int cv_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out)
     return CV_OK;
 }
 
-extern "C" int cv_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *n_out)
+extern "C" int cv_debug_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *n_out)
 {
     if (!h) return fail(CV_ERR_ARG, "NULL model");
     const uint64_t n = std::min<uint64_t>(cap, h->cp_ub.size());

@@ -852,7 +852,7 @@ constexpr int CP_BT_CHUNK = 256;   // rows per chunk of the backtrack's map comp
 
 __global__ void cp_set_choice_kernel(int32_t *choice, int comp, int value) { choice[comp] = value; }
 
-// psi widened to u64 for the parity hook (cv_cp_last_state)
+// psi widened to u64 for the parity hook (cv_debug_cp_last_state)
 __global__ void cp_widen_psi_kernel(const psi_t *psi, int64_t n, uint64_t *out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -4,43 +4,25 @@
 // logic and the branch-and-bound control loop of the constrained solver.  No
 // CPU compute fallback exists anywhere in this file: if CUDA is unavailable the
 // entry points return CV_ERR_CUDA.
-#include "../../include/cv_b200.h"
+#include "cv_internal.cuh"
 
-#include <cuda_runtime.h>
 #include <cub/cub.cuh>
-
-#include <algorithm>
-#include <atomic>
-#include <chrono>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <limits>
-#include <string>
-#include <vector>
 
 #include "common.cuh"
 #include "decode_small.cuh"
 #include "decode_chain.cuh"
 #include "decode_large.cuh"
-#include "cp_kernels.cuh"
-#include "cp_dist.cuh"
-#include "mle.cuh"
-#include "cfn.cuh"
-#include "probe.cuh"
 
 using namespace cvb;
 
 // ---------------------------------------------------------------------------
-// errors, counters
+// errors, counters, tuning block
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
-static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_timing{0};
+std::atomic<uint64_t> cvb::g_launches{0};
+std::atomic<int> cvb::g_timing{0};
 
-static int fail(int code, const char *fmt, ...)
+int cvb::fail(int code, const char *fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -51,81 +33,37 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t _e = (expr);                                                               \
-        if (_e != cudaSuccess) {                                                               \
-            int _c = (_e == cudaErrorMemoryAllocation) ? CV_ERR_OOM : CV_ERR_CUDA;             \
-            return fail(_c, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-        }                                                                                      \
-    } while (0)
+// The environment is read once, here, when the library is loaded.
+static Tuning tuning_from_env()
+{
+    Tuning t;
+    auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    t.chunks = geti("CV_CHUNKS", t.chunks);
+    t.small_cfg = geti("CV_SMALL_CFG", t.small_cfg);
+    t.bt_concurrent = geti("CV_BT_CONCURRENT", t.bt_concurrent);
+    t.streamed = geti("CV_STREAMED", t.streamed);
+    if (const char *e = getenv("CV_TQ")) t.tq = !strcmp(e, "auto") ? 0 : (atoi(e) == 12 ? 12 : atoi(e) == 6 ? 6 : 8);
+    t.tp = geti("CV_TP", 2) == 4 ? 4 : 2;
+    t.fwd_variant = geti("CV_FWD", t.fwd_variant);
+    t.debug = getenv("CV_DEBUG") != nullptr;
+    t.bt_prof = getenv("CV_BT_PROF") != nullptr;
+    t.e2e_prof = getenv("CV_E2E_PROF") != nullptr;
+    if (const char *e = getenv("CV_LARGE_GROUP_RB")) t.large_group_rb = atoll(e);
+    t.cp_fullwarp = getenv("CV_CP_FULLWARP") != nullptr;
+    t.cp_prof = getenv("CV_CP_PROF") != nullptr;
+    t.cp_sum = geti("CV_CP_SUM", t.cp_sum);
+    t.cp_hostpoll = geti("CV_CP_HOSTPOLL", t.cp_hostpoll);
+    t.cp_leaf_batch = geti("CV_CP_LEAF_BATCH", t.cp_leaf_batch);
+    t.probe_threads = geti("CV_PROBE_THREADS", t.probe_threads);
+    return t;
+}
+Tuning cvb::g_tune = tuning_from_env();
 
 extern "C" const char *cv_last_error(void) { return g_err.c_str(); }
 extern "C" uint64_t cv_launch_count(void) { return g_launches.load(); }
 extern "C" void cv_set_timing(int on) { g_timing.store(on); }
 
-// ---------------------------------------------------------------------------
-// model handle
-// ---------------------------------------------------------------------------
-struct DevBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    int ensure(size_t need)
-    {
-        if (need <= bytes) return CV_OK;
-        if (p) cudaFree(p);
-        p = nullptr; bytes = 0;
-        size_t want = need + need / 8;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            e = cudaMalloc(&p, need);
-            want = need;
-        }
-        if (e != cudaSuccess) { p = nullptr; return fail(CV_ERR_OOM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); }
-        bytes = want;
-        return CV_OK;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-};
-
-struct cv_hmm {
-    int device = 0, K = 0, Kp = 0, G = 0, D = 0, num_sms = 0, TQT = 8;
-    int64_t M = 1;
-    // device model
-    double *dA = nullptr;    // [K][Kp]   small-K layout (Kp = 8*ceil(K/8)), pad = -inf
-    double *dBT = nullptr;   // [M][Kp]
-    double *dPi = nullptr;   // [Kp]
-    // large-K layout
-    int Kl = 0;              // K padded to a multiple of LARGE_BN
-    double *dAl = nullptr;   // [Kl][Kl]
-    double *dATl = nullptr;  // [Kl][Kl] transposed (lazy-psi backtrace)
-    double *dBTl = nullptr;  // [M][Kl]
-    // host copy (control logic of the CP solver)
-    std::vector<double> hA, hB, hPi;
-    // workspaces
-    DevBuf obs, seq_off, path, score;   // device copies of the host-API buffers
-    // decode workspaces: two sets so that consecutive chunks of a batch overlap (forward of chunk k+1 with the
-    // backtrace / copies of chunk k) on two internal streams
-    struct DecodeWs {
-        DevBuf order, keys_in, keys_out, vals_in, cub_tmp, hist, tmax, base, misc, lg_arr, lg_start, lg_done, delta_g;
-        cudaStream_t st = nullptr;
-        cudaEvent_t done = nullptr;
-        cudaStream_t st_bt = nullptr;                      // concurrent backtrace (launch_decode_small)
-        cudaEvent_t ev_pre = nullptr, ev_bt = nullptr;
-    } ws[2];
-    cudaEvent_t ev_fork = nullptr;
-    DevBuf cpb[16];     // constrained-solver state (kept after cv_cp_solve for the parity hooks)
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-    double last_ms = 0.0, last_bt_ms = 0.0;   // forward kernel / backtrace kernel
-    // CP debug state
-    int64_t cp_N = 0;
-    std::vector<double> cp_ub;
-    void *pinned_status = nullptr;
-};
-
-static int check_device(int device)
+int cvb::check_device(int device)
 {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -219,9 +157,8 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
             if (eff > best_eff + 1e-9) { best_eff = eff; best_tq = tq; }
         }
         // measured on B200 (POS shape): TQ = 8 with two 6-warp CTAs per SM beats the balanced TQ = 12 shape
-        // (12 vs 8 resident warps), so 8 stays the default; CV_TQ=12 / CV_TQ=auto select the alternatives
-        const char *e = getenv("CV_TQ");
-        h->TQT = (e && !strcmp(e, "auto")) ? best_tq : (e && atoi(e) == 12) ? 12 : (e && atoi(e) == 6) ? 6 : 8;
+        // (12 vs 8 resident warps), so 8 stays the default; CV_TQ=12 / 6 / auto select the alternatives
+        h->TQT = g_tune.tq == 0 ? best_tq : g_tune.tq;
     }
     h->G = (K + h->TQT - 1) / h->TQT;
     h->Kp = ((std::max(h->G * h->TQT, K) + 7) / 8) * 8;
@@ -248,13 +185,15 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     const int Kp = (K <= SMALL_K_MAX) ? h->Kp : ((K + LARGE_BN - 1) / LARGE_BN) * LARGE_BN;
     if (K > SMALL_K_MAX) { h->Kl = Kp; }
     double *tA = nullptr, *tB = nullptr, *tPi = nullptr;
+    double *pA = nullptr, *pBT = nullptr, *pPi = nullptr;
+    // staging + layout buffers are freed on every early return (the layout buffers are handed to the handle at the end)
+    struct Staging { double **p[6]; ~Staging() { for (double **q : p) if (*q) { cudaFree(*q); *q = nullptr; } } } staging{{&tA, &tB, &tPi, &pA, &pBT, &pPi}};
     CUDA_TRY(cudaMalloc(&tA, sizeof(double) * (size_t)K * K));
     CUDA_TRY(cudaMalloc(&tB, sizeof(double) * (size_t)K * M));
     CUDA_TRY(cudaMalloc(&tPi, sizeof(double) * (size_t)K));
     CUDA_TRY(cudaMemcpy(tA, logA, sizeof(double) * (size_t)K * K, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(tB, logB, sizeof(double) * (size_t)K * M, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(tPi, logPi, sizeof(double) * (size_t)K, cudaMemcpyHostToDevice));
-    double *pA = nullptr, *pBT = nullptr, *pPi = nullptr;
     const int rowsA = (K <= SMALL_K_MAX) ? K : Kp;   // the large-K TMA ring reads whole 16-row chunks
     CUDA_TRY(cudaMalloc(&pA, sizeof(double) * (size_t)rowsA * Kp));
     CUDA_TRY(cudaMalloc(&pBT, sizeof(double) * (size_t)M * Kp));
@@ -263,12 +202,12 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
-    cudaFree(tA); cudaFree(tB); cudaFree(tPi);
     if (K <= SMALL_K_MAX) { h->dA = pA; h->dBT = pBT; h->dPi = pPi; }
-    else {
-        h->dAl = pA; h->dBTl = pBT; h->dPi = pPi;
+    else { h->dAl = pA; h->dBTl = pBT; h->dPi = pPi; }
+    pA = pBT = pPi = nullptr;                      // owned by the handle now (cv_hmm_destroy)
+    if (K > SMALL_K_MAX) {
         CUDA_TRY(cudaMalloc(&h->dATl, sizeof(double) * (size_t)Kp * Kp));
-        transpose_kernel<<<dim3((Kp + 31) / 32, (Kp + 31) / 32), dim3(32, 8)>>>(pA, h->dATl, Kp);
+        transpose_kernel<<<dim3((Kp + 31) / 32, (Kp + 31) / 32), dim3(32, 8)>>>(h->dAl, h->dATl, Kp);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
@@ -384,14 +323,6 @@ struct StreamedIO {
 };
 
 typedef cv_hmm::DecodeWs DecodeWs;
-static int g_small_cfg = -1;   // test/bench override of the small-K launch shape (see cv_set_small_config)
-static int g_chunks = -1;      // test/bench override of the chunk count (see cv_set_chunks)
-static long long g_chain_max_b = -1;   // batches up to this size use the warp-per-sequence kernel (-1: 8192)
-// pipeline switches (cv_set_pipeline / environment): CV_BT_CONCURRENT=0 runs the backtrace after the forward kernel,
-// CV_STREAMED=0 makes cv_decode_batch launch once per chunk instead of streaming the copies past one launch
-static int g_bt_concurrent = []() { const char *e = getenv("CV_BT_CONCURRENT"); return e ? atoi(e) : 1; }();
-static int g_streamed = []() { const char *e = getenv("CV_STREAMED"); return e ? atoi(e) : 1; }();
-
 #include "decode_large_host.inl"
 
 // cuStreamWaitValue32 through the runtime's driver entry-point lookup (no link-time dependency on libcuda):
@@ -420,9 +351,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     const uint32_t *d_order = (const uint32_t *)w.order.p, *d_sorted_len = (const uint32_t *)w.keys_out.p;
     // Launch shape: S sequence groups of 64 per CTA, and which register budget (kernel instantiation) to use.
     int S = 1, variant = 1;
-    if (g_small_cfg >= 0) { S = std::max(1, std::min(4, g_small_cfg / 10)); variant = std::max(1, g_small_cfg % 10); }
-    int tpt = 2;
-    if (const char *e = getenv("CV_TP")) tpt = atoi(e) == 4 ? 4 : 2;
+    if (g_tune.small_cfg >= 0) { S = std::max(1, std::min(4, g_tune.small_cfg / 10)); variant = std::max(1, g_tune.small_cfg % 10); }
+    int tpt = g_tune.tp;
     if (h->TQT != 8) tpt = 2;
     while (S > 1 && (B + 32 * tpt * S - 1) / (32 * tpt * S) < 4 * (int64_t)h->num_sms) S--;
     size_t smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S);
@@ -445,8 +375,13 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     }
     // history slabs: sum over tiles of NS * Tmax(tile) <= N + NS * max_len because lengths are sorted (per chunk, plus
     // the tiles that straddle two chunks, on the streamed path)
-    const size_t stairs = sio ? (size_t)sio->cbs.nch + 1 : 1;
-    const size_t hist_elems = ((size_t)N + (size_t)NS * (size_t)max_len * stairs) * (size_t)h->K;
+    // Streamed path: tiles are ordered by (chunk, length).  Inside a chunk the staircase bound above holds (one
+    // NS * max_len term per chunk); a tile that straddles two chunks takes its length from either and adds up to
+    // NS * max_len of its own, and there are at most nch - 1 of those: 2 * nch - 1 terms in all.  The forward kernel
+    // also checks every tile against hist_cap_rows and reports CV_ERR_UNSUPPORTED instead of storing past the end.
+    const size_t stairs = sio ? 2 * (size_t)sio->cbs.nch - 1 : 1;
+    const size_t hist_rows = (size_t)N + (size_t)NS * (size_t)max_len * stairs;     // in units of K doubles
+    const size_t hist_elems = hist_rows * (size_t)h->K;
     if ((rc = w.hist.ensure(hist_elems * sizeof(double)))) return rc;
     if ((rc = w.tmax.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
     if ((rc = w.base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
@@ -465,7 +400,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     DecodeSmallParams p;
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
     p.tile_base = (const long long *)w.base.p;
-    p.hist = (double *)w.hist.p; p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
+    p.hist = (double *)w.hist.p; p.hist_cap_slabs = (long long)(hist_rows / (size_t)NS); p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
     p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.NS = NS; p.ntiles = ntiles;
     p.tile_tmax = nullptr; p.tile_chunk = nullptr; p.arrived = nullptr; p.chunk_done = nullptr; p.nch = 0;
     if (sio) {
@@ -486,7 +421,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     occ = std::max(1, occ);
     const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * occ, ntiles);
-    if (getenv("CV_DEBUG"))
+    if (g_tune.debug)
         fprintf(stderr, "[cv] decode_small: K=%d TQ=%d TP=%d G=%d S=%d variant=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
                 h->K, h->TQT, tpt, G, S, variant, threads, smem, occ, grid, ntiles);
     // Concurrent backtrace: the backtrace kernel runs next to the forward kernel on a second stream and follows
@@ -494,7 +429,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     // the `started` counter), so its spinning CTAs can never keep a forward CTA off an SM; it then lives on the
     // registers / shared memory the forward CTAs leave free.
     StreamWaitValue32Fn wait32 = stream_wait_value32();
-    const bool concurrent = !timing && g_bt_concurrent && wait32 != nullptr && w.st_bt != nullptr;
+    const bool concurrent = !timing && g_tune.bt_concurrent && wait32 != nullptr && w.st_bt != nullptr;
     if (sio && !concurrent) return fail(CV_ERR_UNSUPPORTED, "the streamed path needs the concurrent backtrace");
     p.tile_done = nullptr; p.started = nullptr;
     if (concurrent) {
@@ -504,7 +439,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
         p.started = (unsigned int *)w.lg_done.p + ntiles;
         CUDA_TRY(cudaEventRecord(w.ev_pre, st));
     }
-    static const bool bt_prof = getenv("CV_BT_PROF") != nullptr;   // prints forward / forward+backtrace times of the concurrent mode
+    const bool bt_prof = g_tune.bt_prof != 0;   // prints forward / forward+backtrace times of the concurrent mode
     if (timing || bt_prof) CUDA_TRY(cudaEventRecord(h->ev0, st));
     kern<<<std::max(1, grid), threads, smem, st>>>(p);
     g_launches++;
@@ -545,15 +480,6 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     return CV_OK;
 }
 
-extern "C" void cv_set_small_config(int cfg) { g_small_cfg = cfg; }
-extern "C" void cv_set_chunks(int n) { g_chunks = n; }
-extern "C" void cv_set_chain_max_batch(long long b) { g_chain_max_b = b; }
-extern "C" void cv_set_pipeline(int bt_concurrent, int streamed)
-{
-    if (bt_concurrent >= 0) g_bt_concurrent = bt_concurrent;
-    if (streamed >= 0) g_streamed = streamed;
-}
-
 // One chunk of sequences [0, B) of d_off (offsets are absolute into d_obs / d_path): order by length,
 // forward, backtrace; everything enqueued on `st` with workspace set `w`.
 static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
@@ -581,7 +507,7 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p,
                                                        (uint32_t *)w.keys_out.p, (uint32_t *)w.vals_in.p,
                                                        (uint32_t *)w.order.p, (int)B, 0, 32, st));
-    if (h->K <= SMALL_K_MAX && (g_chain_max_b < 0 ? B <= 8192 : B <= g_chain_max_b)) {
+    if (h->K <= SMALL_K_MAX && (g_tune.chain_max_b < 0 ? B <= 8192 : B <= g_tune.chain_max_b)) {
         // few sequences: one warp per sequence (latency-oriented), backpointers as u8 rows
         if ((rc = w.hist.ensure((size_t)N * h->Kp + 64))) return rc;
         DecodeChainParams p;
@@ -623,17 +549,17 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
 static int chunk_count(const cv_hmm *h, int64_t B, bool timing, bool host_buffers)
 {
     if (timing || h->K > SMALL_K_MAX) return 1;          // kernel timing wants one launch for the whole batch
-    if (g_chunks > 0) return (int)std::min<int64_t>(g_chunks, std::max<int64_t>(B, 1));
+    if (g_tune.chunks > 0) return (int)std::min<int64_t>(g_tune.chunks, std::max<int64_t>(B, 1));
     // >= ~6 tiles per resident CTA per chunk keeps the dynamic tile scheduler balanced.  Host buffers: six
     // chunks so that H2D / D2H copies hide behind the kernels (measured at the POS shape: 2 chunks 16.5 ms,
     // 4: 15.4, 6: 15.3, 8: 15.7, 12: 19.2).
     // Device buffers: one launch when the backtrace can run next to the forward kernel (launch_decode_small), else two
     // chunks so that the backtrace of one overlaps the forward pass of the other.
     const int64_t per_chunk = (int64_t)h->num_sms * 2 * 6 * 64;
-    const int dev_chunks = (g_bt_concurrent && stream_wait_value32() != nullptr) ? 1 : 2;
+    const int dev_chunks = (g_tune.bt_concurrent && stream_wait_value32() != nullptr) ? 1 : 2;
     // Host buffers, streamed past one launch (decode_streamed): 4 chunks measured best (2: 14.8 ms, 3: 14.3, 4: 14.2-14.3,
     // 6: 14.4, 10: 14.8, 16: 15.0 -- every chunk restarts the longest-first tile order); one launch per chunk: 6.
-    const bool can_stream = g_streamed && g_bt_concurrent && stream_wait_value32() != nullptr;
+    const bool can_stream = g_tune.streamed && g_tune.bt_concurrent && stream_wait_value32() != nullptr;
     return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? (can_stream ? 4 : 6) : dev_chunks, B / per_chunk));
 }
 
@@ -725,8 +651,8 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     *handled = false;
     StreamWaitValue32Fn wait32 = stream_wait_value32();
     StreamWriteValue32Fn write32 = stream_write_value32();
-    if (!g_streamed || !g_bt_concurrent || !wait32 || !write32 || nch < 2 || nch > STREAM_MAX_CHUNKS) return CV_OK;
-    if (h->K > SMALL_K_MAX || (g_chain_max_b < 0 ? B <= 8192 : B <= g_chain_max_b) || B > 0x7fffffffLL) return CV_OK;
+    if (!g_tune.streamed || !g_tune.bt_concurrent || !wait32 || !write32 || nch < 2 || nch > STREAM_MAX_CHUNKS) return CV_OK;
+    if (h->K > SMALL_K_MAX || (g_tune.chain_max_b < 0 ? B <= 8192 : B <= g_tune.chain_max_b) || B > 0x7fffffffLL) return CV_OK;
     const int64_t N = seq_off[B];
     DecodeWs &w = h->ws[0];
     cudaStream_t sk = w.st, s_in = h->ws[1].st, s_out = h->ws[1].st_bt;
@@ -746,6 +672,9 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
     sio.d_arrived = d_arrived; sio.d_chunk_done = d_chunk_done;
 
+    // From here on copies from / to the caller's host buffers are in flight: every return (error or not) first drains
+    // the three streams, so the caller may free or reuse its buffers as soon as this function returns.
+    struct Drain { cudaStream_t s[3]; ~Drain() { for (cudaStream_t x : s) cudaStreamSynchronize(x); cudaGetLastError(); } } drain{{sk, s_in, s_out}};
     // offsets first (the ordering needs nothing else), then the observations chunk by chunk on the copy stream
     CUDA_TRY(cudaMemsetAsync(w.misc.p, 0, 256, sk));
     CUDA_TRY(cudaEventRecord(w.ev_pre, sk));
@@ -824,7 +753,7 @@ extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_
     std::vector<int64_t> cb;                                            // chunk boundaries (sequence indices)
     for (int k = 0; k <= nch; k++) cb.push_back(B * k / nch);
     const int nck = (int)cb.size() - 1;
-    static const bool e2e_prof = getenv("CV_E2E_PROF") != nullptr;      // prints a per-chunk timeline (copy in / kernels / copy out)
+    const bool e2e_prof = g_tune.e2e_prof != 0;      // prints a per-chunk timeline (copy in / kernels / copy out)
     std::vector<cudaEvent_t> pev;
     auto mark = [&](cudaStream_t s_) { if (e2e_prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); pev.push_back(e); } };
     if (e2e_prof) { cudaDeviceSynchronize(); mark(h->ws[0].st); }
@@ -879,105 +808,3 @@ extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_
     return report_status(hs, 2);
 }
 
-// ---------------------------------------------------------------------------
-// FP64 probe
-// ---------------------------------------------------------------------------
-extern "C" int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_out, double *ms_out)
-{
-    int rc = check_device(device < 0 ? 0 : device);
-    if (rc) return rc;
-    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-    int threads = 384; if (const char *e = getenv("CV_PROBE_THREADS")) threads = atoi(e);
-    const int blocks = prop.multiProcessorCount;
-    double *d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * (size_t)threads * blocks));
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
-    const int K = 45;
-    const size_t smem = (size_t)K * 48 * 8 + (size_t)K * ((threads / 32 + 5) / 6) * 64 * 8;
-    double fp64_ops = 0.0;
-    for (int rep = 0; rep < 2; rep++) {   // rep 0 = warm-up
-        CUDA_TRY(cudaEventRecord(e0));
-        if (mode == 0) {
-            probe_fp64_kernel<0><<<blocks, threads>>>(d_out, iters, 1.0);
-            fp64_ops = 16.0 * iters * threads * blocks;
-        } else if (mode == 1) {
-            probe_fp64_kernel<1><<<blocks, threads>>>(d_out, iters, 1.0);
-            fp64_ops = 32.0 * iters * threads * blocks;
-        } else {
-            auto launch = [&](auto kern) -> cudaError_t {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return e;
-                kern<<<blocks, threads, smem>>>(d_out, K, iters, 0, 1.0);
-                return cudaSuccess;
-            };
-            auto launch_val = [&](auto kern) -> cudaError_t {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return e;
-                kern<<<blocks, threads, smem>>>(d_out, K, iters, 1.0);
-                return cudaSuccess;
-            };
-            cudaError_t e = cudaSuccess;
-            switch (mode) {
-                case 2: e = launch(probe_tile_kernel<0>); break;
-                case 3: e = launch(probe_tile_kernel<1>); break;
-                case 4: e = launch(probe_tile_kernel<2>); break;
-                case 5: e = launch(probe_tile_kernel<3>); break;
-                case 6: e = launch_val(probe_tile_val_kernel<2>); break;
-                case 20: e = launch_val(probe_tile_val_kernel<3>); break;
-                case 21: e = launch_val(probe_tile_val_kernel<4>); break;
-                case 22: e = launch_val(probe_tile_val_kernel<5>); break;
-                case 23: e = launch_val(probe_tile_val_kernel<9>); break;
-                case 24: e = launch_val(probe_tile_val_kernel<0>); break;
-                case 7: probe_mix_kernel<1, 1><<<blocks, threads>>>(d_out, iters, 1.0); break;
-                case 8: probe_mix_kernel<1, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
-                case 9: probe_mix_kernel<0, 3><<<blocks, threads>>>(d_out, iters, 1.0); break;
-                case 10: probe_mix_kernel<1, 0><<<blocks, threads>>>(d_out, iters, 1.0); break;
-                case 17: probe_tile_val_reg_kernel<<<blocks, threads>>>(d_out, K, iters, 1.0); break;
-                case 18: probe_tile_val_var_kernel<1><<<blocks, threads>>>(d_out, K, iters, 1.0); break;
-                case 19: probe_tile_val_var_kernel<2><<<blocks, threads>>>(d_out, K, iters, 1.0); break;
-                case 14: probe_mix_alu_kernel<1, 1><<<blocks, threads>>>(d_out, iters, 1.0); break;
-                case 15: probe_mix_alu_kernel<1, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
-                case 16: probe_mix_alu_kernel<0, 2><<<blocks, threads>>>(d_out, iters, 1.0); break;
-                case 11: case 12: case 13: {
-                    long long *d_cyc = nullptr, h_cyc = 0;
-                    CUDA_TRY(cudaMalloc(&d_cyc, sizeof(long long)));
-                    if (mode == 11) probe_latency_kernel<0><<<1, 32>>>(d_out, iters, 1.0, d_cyc);
-                    else if (mode == 12) probe_latency_kernel<1><<<1, 32>>>(d_out, iters, 1.0, d_cyc);
-                    else probe_latency_kernel<2><<<1, 32>>>(d_out, iters, 1.0, d_cyc);
-                    CUDA_TRY(cudaMemcpy(&h_cyc, d_cyc, sizeof(long long), cudaMemcpyDeviceToHost));
-                    cudaFree(d_cyc);
-                    if (ms_out) *ms_out = (double)h_cyc / (16.0 * iters);      // cycles per dependent op
-                    if (ops_per_s_out) *ops_per_s_out = (double)h_cyc / (16.0 * iters);
-                    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
-                    g_launches++;
-                    return CV_OK;
-                }
-                default: return fail(CV_ERR_ARG, "unknown probe mode %d", mode);
-            }
-            CUDA_TRY(e);
-            fp64_ops = 2.0 * 16.0 * K * (double)iters * threads * blocks;   // DADD + DSETP per cell
-            if (mode >= 7) fp64_ops = 8.0 * (double)iters * threads * blocks;   // DADD count (8 chains) per iteration
-            if (mode >= 17) fp64_ops = 2.0 * 16.0 * K * (double)iters * threads * blocks;
-        }
-        g_launches++;
-        CUDA_TRY(cudaEventRecord(e1));
-        CUDA_TRY(cudaEventSynchronize(e1));
-        CUDA_TRY(cudaGetLastError());
-    }
-    float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    if (ops_per_s_out) *ops_per_s_out = fp64_ops / (ms * 1e-3);
-    if (ms_out) *ms_out = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
-    return CV_OK;
-}
-
-#include "cp_host.inl"
-#include "mle_host.inl"
-#include "cfn_host.inl"

@@ -16,7 +16,7 @@ struct DecodeChainParams {
     const uint32_t *obs;     // [N]
     const int64_t *seq_off;  // [B+1]
     const uint32_t *order;   // [B] longest first
-    uint8_t *psi;            // [N][Kp]
+    uint8_t *psi;            // [N][Kp], row (off - seq_off[0] + t): the batch (or chunk) is contiguous from seq_off[0]
     uint32_t *path;          // [N]
     double *score;           // [B] or nullptr
     unsigned int *counter;
@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
     __syncthreads();
     const double *bt = p.bt_in_smem ? sBT : p.BT;
     const bool pf = !p.bt_in_smem;
+    const int64_t psi_base = p.seq_off[0];      // offsets are absolute into obs / path; the psi buffer is chunk-local
 
     const double zero_pi[NSL] = {};
     double acol[KQ > 0 ? 4 * KQ : 1];
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
                 int ix = idx[s];
                 if (!(e[s] > neg_inf())) { v = neg_inf(); ix = 0; }                              // viterbi.rs:19-21
                 const int i = lane + 32 * s;
-                if (i < K) p.psi[(size_t)(off + t) * Kp + i] = (uint8_t)ix;                      // viterbi.rs:18
+                if (i < K) p.psi[(size_t)(off - psi_base + t) * Kp + i] = (uint8_t)ix;                      // viterbi.rs:18
                 d[s] = (i < K) ? v : neg_inf();
                 if (i < K) sdw[(t & 1) * Kp + i] = v;
             }
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
         for (int thi = len - 1; thi >= 1; thi -= 32) {
             const int nrows = min(32, thi);                       // rows thi, thi-1, ..., thi-nrows+1
             if (lane < nrows) {
-                const uint2 *src = reinterpret_cast<const uint2 *>(p.psi + (size_t)(off + thi - lane) * Kp);
+                const uint2 *src = reinterpret_cast<const uint2 *>(p.psi + (size_t)(off - psi_base + thi - lane) * Kp);
                 uint2 *dst = reinterpret_cast<uint2 *>(stage + (size_t)lane * Kp);
                 for (int k = 0; k < Kp / 8; k++) dst[k] = __ldcg(src + k);
             }

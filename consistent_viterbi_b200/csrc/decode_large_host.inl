@@ -41,7 +41,7 @@ static int launch_decode_large(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::max<size_t>(w.hist.bytes, (size_t)((free_b + w.hist.bytes) * 0.85));
     int64_t rb_per_group = (int64_t)std::min<size_t>((size_t)NRB_all, budget / std::max<size_t>(per_rb, 1));
-    if (const char *e = getenv("CV_LARGE_GROUP_RB")) rb_per_group = std::max<int64_t>(1, std::min<int64_t>(NRB_all, atoll(e)));
+    if (g_tune.large_group_rb > 0) rb_per_group = std::max<int64_t>(1, std::min<int64_t>(NRB_all, (int64_t)g_tune.large_group_rb));
     if (rb_per_group < 1) return fail(CV_ERR_OOM, "delta history of one row block (%zu bytes) does not fit in device memory", per_rb);
     if ((rc = w.hist.ensure(per_rb * (size_t)rb_per_group))) return rc;
     DevBuf &b_arr = w.lg_arr, &b_start = w.lg_start, &b_done = w.lg_done, &b_tmp = w.cub_tmp;

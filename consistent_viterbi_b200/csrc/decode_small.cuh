@@ -54,6 +54,7 @@ struct DecodeSmallParams {
     const uint32_t *order;   // [B] sequence ids, longest first
     const long long *tile_base;  // [ntiles] first slab of each tile
     double *hist;            // delta history slabs, [K][NS] each
+    long long hist_cap_slabs;    // slabs the history buffer holds (a tile past it is refused, status 7)
     uint32_t *path;          // [N]
     double *score;           // [B] or nullptr
     unsigned int *tile_counter;
@@ -244,6 +245,13 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         }
     };
 
+    // Observations.  On the streamed host path the copy engine is still writing later chunks of p.obs while this
+    // kernel runs, so the read-only (non-coherent) path and L1 must not be used: a sector that straddles a chunk
+    // boundary could be served stale.  ld.global.cg reads through to L2, where the copy engine's writes land before
+    // the `arrived` word that releases the chunk.
+    const bool obs_streamed = p.arrived != nullptr;
+    auto ld_obs = [&](const uint32_t *q) -> uint32_t { return obs_streamed ? __ldcg(q) : __ldg(q); };
+
     for (;;) {
         if (tid == 0) *sTile = (int)atomicAdd(p.tile_counter, 1u);
         __syncthreads();
@@ -278,9 +286,14 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         __syncthreads();
 
         // the longest sequence of the tile: slot 0 when the tile is sorted by length, else precomputed
-        const int Tmax = p.tile_tmax ? (int)p.tile_tmax[tile] : sLen[0];
+        int Tmax = p.tile_tmax ? (int)p.tile_tmax[tile] : sLen[0];
+        if (p.tile_base[tile] + (long long)Tmax > p.hist_cap_slabs) {
+            // cannot happen with the host's sizing (launch_decode_small); never store past the history buffer
+            if (tid == 0) atomicMax(p.status, 7);
+            Tmax = 0;
+        }
         double *slab = p.hist + (size_t)p.tile_base[tile] * K * NS;
-        if (tid == 0) tma_bulk_s2g(slab, sD, slab_bytes);   // history slab 0 = delta(0)
+        if (tid == 0 && Tmax > 0) tma_bulk_s2g(slab, sD, slab_bytes);   // history slab 0 = delta(0)
 
         uint32_t o_nxt[EMK];                                                  // obs of the NEXT step to fetch
         {
@@ -289,8 +302,8 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
             for (int k = 0; k < EMK; k++) {
                 const int s = w + nw * (lane + 32 * k);
                 const bool in = s < NS;
-                o1[k] = (in && 1 < sLen[s]) ? __ldg(p.obs + sOff[s] + 1) : 0u;
-                o_nxt[k] = (in && 2 < sLen[s]) ? __ldg(p.obs + sOff[s] + 2) : 0u;
+                o1[k] = (in && 1 < sLen[s]) ? ld_obs(p.obs + sOff[s] + 1) : 0u;
+                o_nxt[k] = (in && 2 < sLen[s]) ? ld_obs(p.obs + sOff[s] + 2) : 0u;
             }
             if (Tmax > 1) issue_emissions(1, o1);
         }
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 #pragma unroll
                 for (int k = 0; k < EMK; k++) {
                     const int s = w + nw * (lane + 32 * k);
-                    o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? __ldg(p.obs + sOff[s] + t + 2) : 0u;
+                    o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? ld_obs(p.obs + sOff[s] + t + 2) : 0u;
                 }
             }
         }
@@ -421,6 +434,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         const uint32_t b = p.order[r];
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
+        if (p.tile_base[tile] + (long long)len > p.hist_cap_slabs) { bt_mark_done(p, b); continue; }   // tile refused by the forward kernel (status 7)
         const double *col = p.hist + (size_t)p.tile_base[tile] * sl + s;   // column s of slab 0
 
         // end state: argmax of the last row (viterbi.rs:24)

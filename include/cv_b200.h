@@ -121,15 +121,6 @@ int  cv_cp_solve_dist(cv_cp_dist *d, const uint32_t *obs, const uint8_t *is_seq_
  * problem cannot be cut, cuts = {0, N, N, ...} (replicas).  Pure host code, no device needed. */
 int  cv_cp_plan_cuts(const int32_t *comp, int64_t N, int nranks, int64_t *cuts_out);
 
-/* Debug/parity hooks for the CP path: after cv_cp_solve, copy out the final
- * delta[N*K] / psi[N*K] state and the per-node upper bounds (first `cap` nodes). */
-int cv_cp_last_state(cv_hmm *h, double *delta_out, uint64_t *psi_out);
-int cv_cp_last_ub(cv_hmm *h, double *ub_out, uint64_t cap, uint64_t *n_out);
-
-/* Debug/parity hook for the bound sum of solve_r (cp.rs:103-116): ((0.0 + v[0]) + v[1]) + ... of n host values,
- * mode 0 = one-thread loop, mode 1 = the parallel exact-order kernel; both must agree bit for bit. */
-int cv_debug_ordered_sum(const double *values, int64_t n, int mode, double *out);
-
 /* ---- CFN cost tables -------------------------------------------------------------
  * Replaces the numeric part of write_cfn(hmm, super_seq, ..) (src/viterbi_solver/cfn.rs:82-167): the boundaries
  * between constraint components, the K*K clamped longest_path runs (cfn.rs:11-35) of every consecutive boundary
@@ -166,25 +157,11 @@ uint64_t cv_launch_count(void);
 void   cv_set_timing(int on);
 double cv_last_kernel_ms(const cv_hmm *h);     /* forward (dominant) kernel */
 double cv_last_backtrace_ms(const cv_hmm *h);  /* end-state + backtrace kernel */
-/* tuning hook: force the small-K launch shape, cfg = 10*S + MINB (S sequence groups of 64 per CTA,
- * MINB co-resident CTAs per SM); -1 = automatic. */
-void   cv_set_small_config(int cfg);
-/* tuning hook: number of chunks a batch is cut into (chunks overlap on two internal streams); -1 = automatic */
-void   cv_set_chunks(int n);
-/* tuning hook: batches of at most b sequences (K <= 64) use the warp-per-sequence kernel; -1 = default (8192),
- * 0 = always the tile kernel */
-void   cv_set_chain_max_batch(long long b);
-/* tuning hook: bt_concurrent = 1 runs the backtrace kernel next to the forward kernel (tile by tile), streamed = 1
- * lets cv_decode_batch stream its copies past ONE launch instead of launching once per chunk; -1 = leave as is.
- * Both default to 1 (environment: CV_BT_CONCURRENT, CV_STREAMED). */
-void   cv_set_pipeline(int bt_concurrent, int streamed);
 /* pinned host memory helpers */
 void *cv_host_alloc(uint64_t bytes);
 void  cv_host_free(void *p);
-/* FP64 issue-rate probe used as the ALU roofline denominator: runs `iters`
- * dependent-free DADD (mode 0), DADD+DSETP pairs (mode 1) or the decode inner
- * loop body (mode >= 2) on every SM and returns FP64 instructions per second. */
-int cv_probe_fp64(int device, int mode, int iters, double *ops_per_s_out, double *ms_out);
+/* Test / bench hooks (launch-shape overrides, parity dumps, the FP64 issue-rate probe) are declared in
+ * cv_b200_debug.h; nothing a caller of this header needs. */
 
 #ifdef __cplusplus
 }

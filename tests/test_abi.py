@@ -12,19 +12,43 @@ from util import random_hmm
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "cv_b200.h")).read()
+def _declared_symbols(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(cv_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_exported():
     L = cv._lib.lib()
-    names = _declared_symbols()
+    names = _declared_symbols("cv_b200.h")
     assert len(names) >= 14
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/cv_b200.h but not exported"
     assert set(names) == set(cv._lib.SIGNATURES), "ctypes table out of sync with the header"
+    # the drop-in boundary carries no experiment scaffolding: tuning / probe / dump hooks live in the debug header
+    assert not [n for n in names if "debug" in n or "probe" in n or n.startswith("cv_set_") and n != "cv_set_timing"]
+
+
+def test_debug_header_symbols_exported():
+    L = cv._lib.lib()
+    names = _declared_symbols("cv_b200_debug.h")
+    assert names and all(n.startswith("cv_debug_") for n in names)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/cv_b200_debug.h but not exported"
+    assert set(names) == set(cv._lib.DEBUG_SIGNATURES), "ctypes table out of sync with the debug header"
+
+
+def test_environment_is_read_once_at_load():
+    """No getenv on a launch path: the only getenv calls of the library are in the load-time tuning block."""
+    csrc = os.path.join(ROOT, "consistent_viterbi_b200", "csrc")
+    for f in os.listdir(csrc):
+        if not f.endswith((".cu", ".cuh", ".inl")):
+            continue
+        src = open(os.path.join(csrc, f)).read()
+        if f == "cv_api.cu":
+            a, b = src.index("static Tuning tuning_from_env()"), src.index("Tuning cvb::g_tune = tuning_from_env();")
+            src = src[:a] + src[b:]
+        assert "getenv" not in src, f"{f} reads the environment outside the load-time tuning block"
 
 
 def test_no_cpu_fallback_without_device():

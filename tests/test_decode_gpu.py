@@ -12,19 +12,19 @@ pytestmark = pytest.mark.gpu
 
 def _check(A, B, pi, obs, off):
     """Both K <= 64 kernels are exercised: the warp-per-sequence kernel (default for small batches) and the
-    lock-step tile kernel (forced with cv_set_chain_max_batch(0))."""
+    lock-step tile kernel (forced with cv_debug_set_chain_max_batch(0))."""
     h = cv.HMM(A, B, pi)
     rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
     L = cv._lib.lib()
     try:
         for chain_max in (-1, 0):
-            L.cv_set_chain_max_batch(chain_max)
+            L.cv_debug_set_chain_max_batch(chain_max)
             paths, scores = cv.decode_batch(h, obs, off)
             bad = np.nonzero(paths != rp)[0]
             assert bad.size == 0, f"chain_max={chain_max}: {bad.size} path mismatches, first at {bad[:5]}"
             assert scores.tobytes() == rs.tobytes(), f"chain_max={chain_max}: scores differ"
     finally:
-        L.cv_set_chain_max_batch(-1)
+        L.cv_debug_set_chain_max_batch(-1)
     h.close()
 
 
@@ -150,9 +150,9 @@ def test_chunked_pipeline_and_device_api():
     h = cv.HMM(A, B, pi)
     L = cv._lib.lib()
     try:
-        L.cv_set_chain_max_batch(0)
+        L.cv_debug_set_chain_max_batch(0)
         for chunks in (1, 3, 8):
-            L.cv_set_chunks(chunks)
+            L.cv_debug_set_chunks(chunks)
             p, s = cv.decode_batch(h, obs, off)
             assert (p == rp).all() and s.tobytes() == rs.tobytes(), f"host API, chunks={chunks}"
             d_obs = torch.from_numpy(obs.view(np.int32)).cuda()
@@ -167,8 +167,8 @@ def test_chunked_pipeline_and_device_api():
             assert (d_path.cpu().numpy().view(np.uint32) == rp).all(), f"device API, chunks={chunks}"
             assert d_score.cpu().numpy().tobytes() == rs.tobytes()
     finally:
-        L.cv_set_chunks(-1)
-        L.cv_set_chain_max_batch(-1)
+        L.cv_debug_set_chunks(-1)
+        L.cv_debug_set_chain_max_batch(-1)
     h.close()
 
 
@@ -183,16 +183,16 @@ def test_pipeline_modes_agree():
     h = cv.HMM(A, B, pi)
     L = cv._lib.lib()
     try:
-        L.cv_set_chain_max_batch(0)
+        L.cv_debug_set_chain_max_batch(0)
         for conc, streamed in ((1, 1), (1, 0), (0, 0)):
-            L.cv_set_pipeline(conc, streamed)
+            L.cv_debug_set_pipeline(conc, streamed)
             for chunks in (2, 5, 16):
-                L.cv_set_chunks(chunks)
+                L.cv_debug_set_chunks(chunks)
                 for _ in range(2):                                # second call reuses flags / counters / buffers
                     p, s = cv.decode_batch(h, obs, off)
                     assert (p == rp).all() and s.tobytes() == rs.tobytes(), (conc, streamed, chunks)
-        L.cv_set_pipeline(1, 1)
-        L.cv_set_chunks(4)
+        L.cv_debug_set_pipeline(1, 1)
+        L.cv_debug_set_chunks(4)
         bad = off.copy(); bad[1000] = bad[1001]                   # an empty sequence in the third chunk's range... any chunk
         with pytest.raises(cv.CvError) as e:
             cv.decode_batch(h, obs, bad)
@@ -204,9 +204,9 @@ def test_pipeline_modes_agree():
         p, s = cv.decode_batch(h, obs, off)                       # and the handle still works afterwards
         assert (p == rp).all() and s.tobytes() == rs.tobytes()
     finally:
-        L.cv_set_pipeline(1, 1)
-        L.cv_set_chunks(-1)
-        L.cv_set_chain_max_batch(-1)
+        L.cv_debug_set_pipeline(1, 1)
+        L.cv_debug_set_chunks(-1)
+        L.cv_debug_set_chain_max_batch(-1)
     h.close()
 
 

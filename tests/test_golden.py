@@ -73,11 +73,11 @@ def test_gpu_matches_golden_r1():
         h = cv.HMM(c["A"], c["B"], c["pi"])
         try:
             for chain_max in (-1, 0):           # warp-per-sequence kernel, then the tile kernel
-                L.cv_set_chain_max_batch(chain_max)
+                L.cv_debug_set_chain_max_batch(chain_max)
                 p, s = cv.decode_batch(h, c["obs"], c["off"])
                 assert (p == c["paths"]).all() and _bits(s) == _bits(c["scores"])
         finally:
-            L.cv_set_chain_max_batch(-1)
+            L.cv_debug_set_chain_max_batch(-1)
         h.close()
 
 

@@ -25,12 +25,12 @@ def test_r1_random_shapes(seed):
         h = cv.HMM(A, B, pi)
         try:
             for chain_max in ((-1, 0) if K <= 64 else (-1,)):
-                L.cv_set_chain_max_batch(chain_max)
+                L.cv_debug_set_chain_max_batch(chain_max)
                 p, s = cv.decode_batch(h, obs, off)
                 assert (p == rp).all(), f"K={K} M={M} B={Bn} tmax={tmax} chain_max={chain_max}"
                 assert s.tobytes() == rs.tobytes(), f"K={K} M={M} B={Bn} tmax={tmax} chain_max={chain_max}"
         finally:
-            L.cv_set_chain_max_batch(-1)
+            L.cv_debug_set_chain_max_batch(-1)
         h.close()
 
 

@@ -16,7 +16,7 @@ L = cv._lib.lib()
 out = {}
 for mode, iters in [(0, 20000), (1, 20000), (2, 300), (6, 300), (10, 20000), (7, 20000), (8, 20000), (9, 20000)]:
     ops, ms = C.c_double(), C.c_double()
-    cv._lib.check(L.cv_probe_fp64(0, mode, iters, C.byref(ops), C.byref(ms)))
+    cv._lib.check(L.cv_debug_probe_fp64(0, mode, iters, C.byref(ops), C.byref(ms)))
     out[f"probe_mode{mode}"] = {"fp64_ops_per_s": ops.value, "ms": ms.value}
     print(mode, f"{ops.value:.4e} fp64 ops/s  {ms.value:.3f} ms", flush=True)
 
@@ -32,7 +32,7 @@ h = cv.HMM(A, B, pi)
 L.cv_set_timing(1)
 res = {}
 for cfg in [int(c) for c in os.environ.get("CFGS", "-1,11,13,21,12").split(",")]:
-    L.cv_set_small_config(cfg)
+    L.cv_debug_set_small_config(cfg)
     for it in range(3):
         t0 = time.perf_counter()
         paths, scores = cv.decode_batch(h, obs, off)

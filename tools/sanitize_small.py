@@ -11,9 +11,9 @@ A, B, pi = random_hmm(rng, 13, 7)
 obs, off = random_batch(rng, 150, 7, 1, 12)
 h = cv.HMM(A, B, pi)
 p1, s1 = cv.decode_batch(h, obs, off)             # chain kernel
-L.cv_set_chain_max_batch(0)
+L.cv_debug_set_chain_max_batch(0)
 p2, s2 = cv.decode_batch(h, obs, off)             # tile kernel + backtrace
-L.cv_set_chain_max_batch(-1)
+L.cv_debug_set_chain_max_batch(-1)
 assert (p1 == p2).all() and s1.tobytes() == s2.tobytes()
 o2, st, comp, nc = random_superseq(rng, 6, 7, 2, 0.2, 3, 15)
 r = cv.cp_solve_arrays(h, o2, st, comp, nc, max_nodes=30)

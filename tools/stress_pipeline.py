@@ -21,11 +21,11 @@ h = cv.HMM(A, B, pi)
 L = cv._lib.lib()
 bad = 0
 for it in range(iters):
-    L.cv_set_chunks((2, 3, 4, 7)[it % 4])
+    L.cv_debug_set_chunks((2, 3, 4, 7)[it % 4])
     p, s = cv.decode_batch(h, obs, off)
     if not ((p == rp).all() and s.tobytes() == rs.tobytes()):
         bad += 1
         print("MISMATCH at iteration", it, "paths differing:", int((p != rp).sum()))
-L.cv_set_chunks(-1)
+L.cv_debug_set_chunks(-1)
 print("iterations", iters, "mismatches", bad)
 sys.exit(1 if bad else 0)
