@@ -8,8 +8,11 @@ inputs CPSolver::new sees:
 
 recompute_constraints(prop) draws `rng.gen::<f64>() <= prop` from rand 0.8 StdRng seeded with 3019
 (utils.rs:101,170).  For prop in {0, 1} the outcome does not depend on the stream (gen::<f64>() is in
-[0,1)); for 0 < prop < 1 the stream comes from `StdRng` below, a restatement of ChaCha12 + the PCG32 seed
-expansion that cannot be checked against the crate here (SURVEY.md section 8 "next" row N2).
+[0,1)); for 0 < prop < 1 the stream comes from `StdRng` below, a restatement of ChaCha12 + the PCG32 seed expansion.
+No Rust toolchain exists here, but the restatement is pinned by the value-stability vectors the crates
+themselves publish in their test suites (tests/test_cli.py::test_stdrng_matches_published_rand_vectors):
+rand 0.8 `rngs::std::test_stdrng_construction`, rand_chacha 0.3 `test_chacha_construction`, rand_pcg 0.3
+`test_lcg64xsh32_construction` (seed_from_u64) and rand 0.8 `distributions::float::value_stability` (f64).
 """
 from __future__ import annotations
 
@@ -20,18 +23,42 @@ from .hmm import HMM
 
 class StdRng:
     """rand 0.8 `StdRng::seed_from_u64` + `gen::<f64>()` (ChaCha12, key expanded from the u64 with PCG32), the
-    same restatement as host/rng_chacha12.h -- UNVERIFIED against the crate (no Rust toolchain here); it only
-    matters for 0 < prop < 1."""
+    same restatement as host/rng_chacha12.h; it only matters for 0 < prop < 1.  `ROUNDS` = 12 (StdRng of
+    rand 0.8 = ChaCha12Rng); the value-stability test also runs the 20-round variant the crate publishes."""
 
-    def __init__(self, seed: int):
+    ROUNDS = 12
+
+    @staticmethod
+    def seed_words_from_u64(state: int, nwords: int = 8):
+        """rand_core 0.6 `SeedableRng::seed_from_u64`: a PCG32 (XSH-RR) stream fills the seed, 4 bytes at a time."""
         M64 = (1 << 64) - 1
-        state, key = seed & M64, []
-        for _ in range(8):
+        state, words = state & M64, []
+        for _ in range(nwords):
             state = (state * 6364136223846793005 + 11634580027462260723) & M64
             xs = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
             rot = state >> 59
-            key.append(((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF)
-        self.key, self.counter, self.buf, self.idx = key, 0, [], 16
+            words.append(((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF)
+        return words
+
+    def __init__(self, seed: int):
+        self.key, self.counter, self.buf, self.idx = self.seed_words_from_u64(seed), 0, [], 16
+
+    @classmethod
+    def from_seed(cls, seed: bytes):
+        """`SeedableRng::from_seed` with the 32-byte ChaCha key (little-endian words)."""
+        assert len(seed) == 32
+        r = cls(0)
+        r.key = [int.from_bytes(seed[4 * i: 4 * i + 4], "little") for i in range(8)]
+        return r
+
+    @classmethod
+    def from_rng(cls, other: "StdRng"):
+        """`SeedableRng::from_rng`: the new key is the next 32 bytes of `other` (fill_bytes = consecutive words)."""
+        words = []
+        for _ in range(4):
+            v = other.next_u64()
+            words += [v & 0xFFFFFFFF, v >> 32]
+        return cls.from_seed(b"".join(w.to_bytes(4, "little") for w in words))
 
     def _block(self):
         M = 0xFFFFFFFF
@@ -47,7 +74,7 @@ class StdRng:
             x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 8)
             x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 7)
 
-        for _ in range(6):
+        for _ in range(self.ROUNDS // 2):
             qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
             qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
         self.buf = [(x[i] + inp[i]) & M for i in range(16)]
@@ -61,8 +88,13 @@ class StdRng:
         self.idx += 2
         return (hi << 32) | lo
 
+    @staticmethod
+    def f64_from_u64(v: int) -> float:
+        """rand 0.8 `Standard` for f64: 53 random bits scaled into [0, 1)."""
+        return float(v >> 11) * (1.0 / 9007199254740992.0)
+
     def gen_f64(self):
-        return float(self.next_u64() >> 11) * (1.0 / 9007199254740992.0)
+        return self.f64_from_u64(self.next_u64())
 
 
 def load_sequences(path, D=2):

@@ -5,8 +5,10 @@
 // PCG32 stream into the 32-byte key; ChaCha12 runs with a 64-bit block counter (words 12,13) and stream id 0
 // (words 14,15); BlockRng hands out the 16-word blocks in order (rand_chacha buffers four blocks, which does
 // not change the order); next_u64 = two consecutive words, low word first; Standard f64 =
-// (next_u64 >> 11) * 2^-53.  UNVERIFIED against the crate (no Rust toolchain, no network): it only matters
-// for 0 < prop < 1, and parity tests use prop in {0, 1}, where gen() <= prop does not depend on the stream.
+// (next_u64 >> 11) * 2^-53.  No Rust toolchain exists here; the Python twin of this file (superseq.py StdRng) is
+// pinned to the value-stability vectors the rand / rand_chacha / rand_pcg crates publish in their own tests
+// (tests/test_cli.py::test_stdrng_matches_published_rand_vectors), and the CLI tests check that this file
+// produces the same active masks as the Python twin for 0 < prop < 1.
 #pragma once
 #include <cstdint>
 

@@ -68,21 +68,73 @@ def test_cli_rejects_training_and_bad_args(tmp_path):
     assert r.returncode != 0
 
 
-def test_chacha_block_matches_published_vector():
-    """StdRng (superseq.py / host/rng_chacha12.h) restates rand 0.8's ChaCha12 stream and cannot be checked against
-    the crate here.  What can be pinned: with 20 rounds and an all-zero key the block function must give the
-    published ChaCha20 keystream (76 b8 e0 ad a0 f1 3d 90 ...), i.e. state layout and quarter rounds are right;
-    ChaCha12 only changes the round count.  Also: gen_f64 is in [0, 1) and the stream is deterministic."""
-    import inspect
-    import textwrap
+def test_stdrng_matches_published_rand_vectors():
+    """Pins the RNG stream of `SuperSequence::recompute_constraints` (viterbi_solver/utils.rs:101,168-177:
+    `StdRng::seed_from_u64(3019)`, `rng.gen::<f64>() <= prop`) to value-stability vectors that the rand crates
+    publish in their own test suites (restated here, the crates are not in /root/reference):
+
+      rand 0.8        rngs/std.rs            test_stdrng_construction   StdRng = ChaCha12, from_seed / from_rng, next_u64
+      rand_chacha 0.3 src/chacha.rs          test_chacha_construction   same block function with 20 rounds
+      rand_pcg 0.3    tests/lcg64xsh32.rs    test_lcg64xsh32_construction   seed_from_u64(0): the PCG32 seed expansion
+      rand 0.8        distributions/float.rs value_stability            Standard f64 = (u64 >> 11) * 2^-53
+    """
     from consistent_viterbi_b200.superseq import StdRng
-    r = StdRng(0)
-    r.key = [0] * 8
-    ns = {}
-    exec(textwrap.dedent(inspect.getsource(StdRng._block)).replace("for _ in range(6):", "for _ in range(10):"), ns)
-    ns["_block"](r)
-    ks = b"".join(w.to_bytes(4, "little") for w in r.buf)
-    assert ks[:16].hex() == "76b8e0ada0f13d90405d6ae55386bd28"
+    M64 = (1 << 64) - 1
+    # -- StdRng::from_seed(seed).next_u64(), StdRng::from_rng(rng0).next_u64()  (ChaCha12)
+    seed = bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16)
+    rng0 = StdRng.from_seed(seed)
+    x0 = rng0.next_u64()
+    x1 = StdRng.from_rng(rng0).next_u64()
+    assert [x0, x1] == [10719222850664546238, 14064965282130556830]
+
+    # -- ChaChaRng (20 rounds): from_seed(..).next_u32() == 137206642, from_rng(..).next_u32() == 1325750369
+    class ChaCha20Rng(StdRng):
+        ROUNDS = 20
+    r1 = ChaCha20Rng.from_seed(bytes([0] * 8 + [1] + [0] * 7 + [2] + [0] * 7 + [3] + [0] * 7))
+    r1._block()
+    assert r1.buf[0] == 137206642
+    r2 = ChaCha20Rng.from_seed(b"".join(w.to_bytes(4, "little") for w in r1.buf[1:9]))
+    r2._block()
+    assert r2.buf[0] == 1325750369
+    # and the RFC 7539 keystream of the all-zero key
+    z = ChaCha20Rng.from_seed(bytes(32))
+    z._block()
+    assert b"".join(w.to_bytes(4, "little") for w in z.buf)[:16].hex() == "76b8e0ada0f13d90405d6ae55386bd28"
+
+    # -- a PCG32 (Lcg64Xsh32) built from the published recipe, to check the two pieces StdRng shares with it
+    class Lcg64Xsh32:
+        def __init__(self, seed16):
+            self.inc = int.from_bytes(seed16[8:16], "little") | 1
+            self.state = (int.from_bytes(seed16[:8], "little") + self.inc) & M64
+            self.step()
+
+        def step(self):
+            self.state = (self.state * 6364136223846793005 + self.inc) & M64
+
+        def next_u32(self):
+            st = self.state
+            self.step()
+            xs, rot = (((st >> 18) ^ st) >> 27) & 0xFFFFFFFF, st >> 59
+            return ((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF
+
+        def next_u64(self):
+            lo = self.next_u32()
+            return (self.next_u32() << 32) | lo
+    assert Lcg64Xsh32(bytes(range(1, 17))).next_u64() == 1204678643940597513          # the helper itself is right
+    # seed_from_u64(0): the seed bytes come from StdRng.seed_words_from_u64 (the code recompute_constraints uses)
+    seed16 = b"".join(w.to_bytes(4, "little") for w in StdRng.seed_words_from_u64(0, 4))
+    assert Lcg64Xsh32(seed16).next_u64() == 18195738587432868099
+    # Standard f64 from rand::test::rng(0x6f44f5646c2a7334) = Pcg32::new(seed, 11634580027462260723)
+    p = Lcg64Xsh32((0x6f44f5646c2a7334).to_bytes(8, "little") + (11634580027462260723 << 1 & M64).to_bytes(8, "little"))
+    assert [StdRng.f64_from_u64(p.next_u64()) for _ in range(3)] == [0.7346051961657583, 0.20298547462974248, 0.8166436635290655]
+
+    # -- the stream the reference consumes, frozen (tests/golden/stdrng_3019.json, written by tools/make_golden.py)
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "stdrng_3019.json")))
+    r = StdRng(3019)
+    assert [r.next_u64() for _ in range(len(g["next_u64"]))] == g["next_u64"]
+    r = StdRng(3019)
+    assert [r.gen_f64().hex() for _ in range(len(g["gen_f64_hex"]))] == g["gen_f64_hex"]
     a, b = StdRng(3019), StdRng(3019)
     xs = [a.gen_f64() for _ in range(100)]
     assert xs == [b.gen_f64() for _ in range(100)] and all(0.0 <= x < 1.0 for x in xs) and len(set(xs)) == 100

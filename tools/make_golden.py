@@ -100,9 +100,24 @@ def small():
     np.savez_compressed(os.path.join(OUT, "r2_small.npz"), **r2)
 
 
+def stdrng():
+    """The stream `recompute_constraints` consumes: StdRng::seed_from_u64(3019) (viterbi_solver/utils.rs:101).  The
+    generator is pinned to the rand crates' published vectors by tests/test_cli.py; this freezes its first draws."""
+    import json
+
+    from consistent_viterbi_b200.superseq import StdRng
+    a, b = StdRng(3019), StdRng(3019)
+    json.dump({"seed": 3019, "next_u64": [a.next_u64() for _ in range(16)], "gen_f64_hex": [b.gen_f64().hex() for _ in range(16)]},
+              open(os.path.join(OUT, "stdrng_3019.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--stdrng-only" in sys.argv:
+        stdrng()
+        sys.exit(0)
     for n in "ABC":
         house(n)
     small()
+    stdrng()
     print("golden fixtures written to", OUT)
