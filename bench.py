@@ -205,52 +205,85 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU baseline: the C oracle (port of the reference loops), bounded sample
 # ----------------------------------------------------------------------------------------------
+def cpu_sample(wl, threads):
+    """The bounded sample both CPU legs (cpu_baseline of the GPU arm and --impl reference) run per pass:
+    (obs, off, cells, description).  K <= 64: the WHOLE batch when one pass takes a few seconds on this host
+    (it does at the POS shape on the GPU boxes), else the longest prefix that does.  K > 64: `threads` sequences x
+    the first 64 steps (one full sequence already costs seconds)."""
+    from oracle import pyoracle as po
+
+    off, obs, K = wl["off"], wl["obs"], wl["K"]
+    B = len(off) - 1
+    if K > 64:
+        T = int(off[1] - off[0])
+        Tc, nb = min(T, 64), min(B, threads)
+        o = np.arange(nb + 1, dtype=np.int64) * Tc
+        ob = np.concatenate([obs[off[b]: off[b] + Tc] for b in range(nb)])
+        return ob, o, float(nb) * (Tc - 1) * K * K, f"{nb} sequences x first {Tc} steps of the workload"
+    nb = max(1, min(B, 2000))
+    t0 = time.perf_counter()
+    po.decode_batch(wl["A"], wl["B"], obs[: off[nb]], off[: nb + 1], nthreads=threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    per_seq = dt / nb
+    nb2 = B if per_seq * B <= 8.0 else int(max(nb, min(B, 6.0 / per_seq)))
+    o = off[: nb2 + 1]
+    desc = f"all {B} sequences of the workload" if nb2 == B else f"first {nb2} of {B} sequences of the workload"
+    return obs[: o[-1]], o, float(((np.diff(o) - 1) * K * K).sum()), desc
+
+
 def cpu_baseline(wl, budget_s=12.0, threads=None):
+    """Times the oracle on the sample and RETURNS its output so that the caller can compare the GPU result with it
+    (bench.py "parity")."""
     from oracle import pyoracle as po
 
     threads = threads or (os.cpu_count() or 1)
-    off, obs, K = wl["off"], wl["obs"], wl["K"]
-    B = len(off) - 1
-
-    def run(nb):
-        o = off[: nb + 1]
+    ob, o, cells, desc = cpu_sample(wl, threads)
+    tot_t, reps, paths, scores = 0.0, 0, None, None
+    while tot_t < budget_s and reps < 4:          # ~10-30 s of CPU work in total
         t0 = time.perf_counter()
-        po.decode_batch(wl["A"], wl["B"], obs[: o[-1]], o, nthreads=threads)
-        dt = time.perf_counter() - t0
-        return float(((np.diff(o) - 1) * K * K).sum()), dt
+        paths, scores = po.decode_batch(wl["A"], wl["B"], ob, o, nthreads=threads)
+        tot_t += time.perf_counter() - t0
+        reps += 1
+    line = {"value": cells * reps / tot_t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{desc} x {reps} passes, {tot_t:.1f} s, C oracle (port of viterbi.rs:5-32), {threads} OpenMP threads"}
+    return line, (paths, scores, o)
 
-    nb = max(1, min(B, 64 if K > 64 else 2000))
-    if K > 64:
-        # one long sequence already costs seconds on the CPU: bound T as well
-        T = int(off[1] - off[0])
-        Tc = min(T, 64)
-        o = np.arange(min(B, threads) + 1, dtype=np.int64) * Tc
-        ob = np.concatenate([obs[off[b]: off[b] + Tc] for b in range(len(o) - 1)])
-        t0 = time.perf_counter()
-        po.decode_batch(wl["A"], wl["B"], ob, o, nthreads=threads)
-        dt = time.perf_counter() - t0
-        cells = float(len(o) - 1) * (Tc - 1) * K * K
-        return {"value": cells / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"{len(o) - 1} sequences x first {Tc} steps of the workload, {dt:.1f} s, C oracle (port of "
-                          f"viterbi.rs:5-32), {threads} OpenMP threads"}
-    cells, dt = run(nb)
-    nb2 = int(max(nb, min(B, nb * budget_s / max(dt, 1e-3))))
-    tot_c, tot_t, reps = 0.0, 0.0, 0
-    while tot_t < budget_s and reps < 8:          # ~10-30 s of CPU work in total
-        cells, dt = run(nb2)
-        tot_c += cells; tot_t += dt; reps += 1
-    return {"value": tot_c / tot_t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {nb2} sequences of the workload x {reps} passes, {tot_t:.1f} s, C oracle (port of "
-                      f"viterbi.rs:5-32), {threads} OpenMP threads"}
+
+def parity_block(ref, got_paths, got_scores, off_full):
+    """GPU result vs the oracle output of cpu_baseline on the same sequences (bit patterns for the scores)."""
+    rp, rs, o = ref
+    nb, ne = len(o) - 1, int(o[-1])
+    same_layout = bool((np.asarray(off_full[: nb + 1]) == o).all())
+    if not same_layout:                            # K > 64 sample: truncated sequences, not comparable element-wise
+        return None
+    mism = int((got_paths[:ne] != rp).sum())
+    return {"sequences": nb, "elements": ne, "path_mismatches": mism,
+            "score_bits_equal": bool(got_scores[:nb].tobytes() == rs.tobytes()),
+            "against": "C oracle (oracle/cv_oracle.c, restatement of viterbi.rs:5-32), same inputs, same run"}
 
 
 # ----------------------------------------------------------------------------------------------
-def run_other(cv, L, device):
-    """Short, bounded runs of the other BASELINE configs (reported under "other"; parity for each is in tests/)."""
+def _roof(cells, ms, peak_mix, bytes_moved, hbm_peak, note=""):
+    """Both SURVEY 8(d) views for a secondary leg: FP64 add+compare issue (2 per cell) and HBM bytes."""
+    alu = 2.0 * cells / (ms * 1e-3)
+    hbm = bytes_moved / (ms * 1e-3) / 1e9
+    r = {"fp64": {"achieved": alu / 1e12, "peak": peak_mix / 1e12, "unit": "TFLOP/s", "frac": alu / peak_mix},
+         "hbm": {"achieved": hbm, "peak": hbm_peak, "unit": "GB/s", "frac": hbm / hbm_peak}, "ms": ms}
+    r["bound"] = "latency (neither roofline above 10 %)" if max(r["fp64"]["frac"], r["hbm"]["frac"]) < 0.10 else \
+                 ("fp64_alu" if r["fp64"]["frac"] >= r["hbm"]["frac"] else "hbm")
+    if note:
+        r["note"] = note
+    return r
+
+
+def run_other(cv, L, device, peak_mix, hbm_peak, large_full=True):
+    """Short, bounded runs of the other BASELINE configs (reported under "other"; parity for each is in tests/ and,
+    where the CPU leg runs the same work, asserted here as well)."""
     from oracle import pyoracle as po
     other = {}
+    nthreads = os.cpu_count() or 1
     # configs[1]: datasets/ar, full data set, batched decode (three models, 60 day-sequences in total)
-    ar, t_gpu, t_cpu, cells = workload_ar(), 0.0, 0.0, 0.0
+    ar, t_gpu, t_cpu, cells, steps, kbytes = workload_ar(), 0.0, 0.0, 0.0, 0.0, 0.0
     for w in ar:
         hm = cv.HMM(w["A"], w["B"], w["pi"])
         cv.decode_batch(hm, w["obs"], w["off"], device=device)
@@ -260,22 +293,32 @@ def run_other(cv, L, device):
         t_gpu += (time.perf_counter() - t0) / 5
         assert (paths == w["golden"]).all()
         t0 = time.perf_counter()
-        po.decode_batch(w["A"], w["B"], w["obs"], w["off"], nthreads=os.cpu_count() or 1)
+        rp, _ = po.decode_batch(w["A"], w["B"], w["obs"], w["off"], nthreads=nthreads)
         t_cpu += time.perf_counter() - t0
+        assert (paths == rp).all()
         cells += w["cells"]
+        nst = float((np.diff(w["off"]) - 1).sum())
+        kbytes += nst * (4 + 8 * w["K"] + 2 * w["K"] + 4)       # obs + logB^T row + u8 psi row written and read + path
         hm.close()
     other["ar_full_dataset"] = {"cells": cells, "e2e_ms": 1e3 * t_gpu, "e2e_cells_per_s": cells / t_gpu,
-                                "cpu_port_cells_per_s": cells / t_cpu,
+                                "cpu_port_cells_per_s": cells / t_cpu, "paths_equal_oracle_and_golden": True,
+                                "roofline": _roof(cells, 1e3 * t_gpu, peak_mix, kbytes, hbm_peak,
+                                                  "60 sequences, 1.5e7 cells, serial in t: step latency x longest sequence bounds it; "
+                                                  "time is the whole host call (copies and three launches included)"),
                                 "note": "60 sequences, 1.5e7 cells: latency bound (serial in t), paths equal the golden fixture"}
-    # configs[3] shape at reduced batch/length (the full B=4096, T=4096 run is `--workload large`: 3.95 s/step)
+    # configs[3] shape at reduced batch/length, and (large_full) the full B=4096, T=4096 pass
     w = workload_large(0, 2048, 64)
     hm = cv.HMM(w["A"], w["B"], w["pi"])
     cv.decode_batch(hm, w["obs"], w["off"], device=device)
     t0 = time.perf_counter()
     cv.decode_batch(hm, w["obs"], w["off"], device=device)
     dt = time.perf_counter() - t0
-    other["large_K1024_B2048_T64"] = {"cells": w["cells"], "e2e_ms": 1e3 * dt, "e2e_cells_per_s": w["cells"] / dt,
-                                      "note": "full configs[3] (B=4096, T=4096, `--workload large`): 3.95 s/step = 4.45e12 cells/s, 52 % of the FP64 roofline (DESIGN.md)"}
+    other["large_K1024_B2048_T64"] = {"cells": w["cells"], "e2e_ms": 1e3 * dt, "e2e_cells_per_s": w["cells"] / dt}
+    if large_full:
+        try:
+            other["large_full"] = run_large_full(cv, L, device, hm, peak_mix, hbm_peak)
+        except Exception as e:  # noqa: BLE001
+            other["large_full"] = {"error": repr(e)}
     hm.close()
     # supervised MLE event counts (hmm.rs:35-48) at the POS shape, 1M sentences, random tags
     w = workload_pos(0, 1000000)
@@ -315,32 +358,101 @@ def run_other(cv, L, device):
                                                "(K-fold the device's work for the same tables), cells counted as K sweeps per pair",
                                  "lower_bound": r["lower_bound"]}
     hm.close()
-    # configs[0] stand-in and configs[4]: constrained decode with a node budget
-    for kind, budget, cpu_budget in (("trucks", 0, 150), ("heavy", 2000, 6)):    # trucks-like: complete search
+    # configs[0] stand-in and configs[4]: constrained decode.  First GPU and CPU at the SAME small node budget, every
+    # result compared (objective bits, solution, nodes, steps, per-node bounds); then the GPU at the full budget.
+    for kind, budget, cpu_budget in (("trucks", 0, 150), ("heavy", 2000, 20)):    # trucks-like: complete search
         w = workload_cp(kind)
         hm = cv.HMM(w["A"], w["B"], w["pi"])
-        cv.cp_solve_arrays(hm, w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=3, device=device)
+        args = (w["obs"], w["start"], w["comp"], w["ncomp"])
+        cv.cp_solve_arrays(hm, *args, max_nodes=3, device=device)
+        t0 = time.perf_counter()
+        rc = po.cp_solve(w["A"], w["B"], w["pi"], *args, max_nodes=cpu_budget, trace_nodes=cpu_budget)
+        dtc = time.perf_counter() - t0
+        g = cv.cp_solve_arrays(hm, *args, max_nodes=cpu_budget, device=device, want_ub=cpu_budget)
+        n = min(len(g["ub"]), int(rc["explored"]))
+        same = bool(g["explored"] == rc["explored"] and g["steps"] == rc["steps"] and (g["sol"] == rc["sol"]).all()
+                    and np.float64(g["obj"]).tobytes() == np.float64(rc["obj"]).tobytes()
+                    and g["ub"][:n].tobytes() == rc["ub"][:n].tobytes())
+        assert same, f"{kind}: GPU and oracle differ at max_nodes={cpu_budget}"
         L.cv_set_timing(1)
         t0 = time.perf_counter()
-        r = cv.cp_solve_arrays(hm, w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=budget, device=device)
+        r = cv.cp_solve_arrays(hm, *args, max_nodes=budget, device=device)
         dt = time.perf_counter() - t0
         loop_ms = L.cv_last_kernel_ms(hm.device_handle(device))
         L.cv_set_timing(0)
-        t0 = time.perf_counter()
-        rc = po.cp_solve(w["A"], w["B"], w["pi"], w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=cpu_budget)
-        dtc = time.perf_counter() - t0
         K = w["K"]
+        cells = float(r["steps"]) * K * K
+        # per sweep step: delta row written (8K) + psi row written (2K, u16) + previous delta row read (8K) + obs (4)
         other[w["name"]] = {"N": w["N"], "K": K, "nodes": int(r["explored"]), "sweep_steps": int(r["steps"]),
-                            "cells": float(r["steps"]) * K * K, "e2e_ms": 1e3 * dt,
-                            "e2e_cells_per_s": float(r["steps"]) * K * K / dt, "ms_per_node": 1e3 * dt / max(1, r["explored"]),
+                            "cells": cells, "e2e_ms": 1e3 * dt,
+                            "e2e_cells_per_s": cells / dt, "ms_per_node": 1e3 * dt / max(1, r["explored"]),
                             "device_loop_ms_per_node": loop_ms / max(1, r["explored"]),
                             "cpu_port_cells_per_s": float(rc["steps"]) * K * K / dtc, "cpu_nodes": int(rc["explored"]),
                             "cpu_ms_per_node": 1e3 * dtc / max(1, rc["explored"]), "objective": r["obj"],
                             "max_nodes": budget, "clamped_fraction": w["clamped"],
+                            "parity": {"max_nodes": cpu_budget, "identical_to_oracle": same,
+                                       "compared": "objective bits, solution, explored nodes, sweep steps, every node's bound"},
+                            "roofline": _roof(cells, loop_ms, peak_mix, float(r["steps"]) * (18 * K + 4), hbm_peak,
+                                              "device loop of the whole search (CUDA events); a node is a chain of short "
+                                              "dependent launches, so step latency, not a pipe, bounds it"),
                             "note": "max_nodes = 0: complete branch and bound; the CPU port (single thread, like the "
                                     "reference) runs a node-budgeted prefix of the same search"}
         hm.close()
     return other
+
+
+def run_large_full(cv, L, device, hm, peak_mix, hbm_peak):
+    """BASELINE configs[3] at full size: K = 1024, M = 4096, T = 4096, B = 4096 (1.76e13 cells, 137 GB of delta
+    history).  One warm-up pass at reduced batch (kernels and model already warm), one timed full pass with the
+    forward/backtrace kernels timed by CUDA events, and 8 sequences checked against the oracle."""
+    import torch
+    from oracle import pyoracle as po
+
+    w = workload_large(0, 4096, 4096)
+    K = w["K"]
+    h = hm.device_handle(device)
+    N, B = len(w["obs"]), len(w["off"]) - 1
+    d_obs = torch.from_numpy(w["obs"].view(np.int32)).cuda()
+    d_off = torch.from_numpy(w["off"]).cuda()
+    d_path = torch.empty(N, dtype=torch.int32, device="cuda")
+    d_score = torch.empty(B, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream()
+    L.cv_set_timing(1)
+    try:
+        t0 = time.perf_counter()
+        cv._lib.check(L.cv_decode_batch_dev(h, d_obs.data_ptr(), d_off.data_ptr(), B, N, 4096, d_path.data_ptr(),
+                                            d_score.data_ptr(), st.cuda_stream, 1))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        fwd, bt = L.cv_last_kernel_ms(h), L.cv_last_backtrace_ms(h)
+    finally:
+        L.cv_set_timing(0)
+    paths = d_path.cpu().numpy().view(np.uint32)
+    scores = d_score.cpu().numpy()
+    sel = [0, 511, 1024, 1777, 2048, 3000, 3583, 4095]
+    off = w["off"]
+    sub_obs = np.concatenate([w["obs"][off[b]:off[b + 1]] for b in sel])
+    sub_off = np.arange(len(sel) + 1, dtype=np.int64) * 4096
+    t0 = time.perf_counter()
+    rp, rs = po.decode_batch(w["A"], w["B"], sub_obs, sub_off, nthreads=os.cpu_count() or 1)
+    dtc = time.perf_counter() - t0
+    got_p = np.concatenate([paths[off[b]:off[b + 1]] for b in sel])
+    mism = int((got_p != rp).sum())
+    bits = bool(scores[sel].tobytes() == rs.tobytes())
+    steps = float(B) * 4095
+    kl = ((K + 127) // 128) * 128
+    # the delta history is what moves: one [Kl] f64 row per (sequence, step) written by the forward pass, read by the backtrace
+    out = {"cells": w["cells"], "B": B, "T": 4096, "K": K, "kernel_ms": fwd, "backtrace_ms": bt, "wall_ms": 1e3 * wall,
+           "cells_per_s": w["cells"] / (fwd * 1e-3), "cells_per_s_wall": w["cells"] / wall,
+           "roofline": _roof(w["cells"], fwd, peak_mix, steps * (4 + 8 * K + 8 * kl), hbm_peak,
+                             "forward kernel(s) alone, CUDA events on the launching stream; FP64 peak from this run's probe"),
+           "parity": {"sequences": len(sel), "path_mismatches": mism, "score_bits_equal": bits,
+                      "against": f"C oracle on sequences {sel} ({dtc:.1f} s)"},
+           "cpu_port_cells_per_s": len(sel) * 4095.0 * K * K / dtc}
+    assert mism == 0 and bits, "large_full: GPU and oracle differ"
+    del d_obs, d_off, d_path, d_score
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_cp_sharded(cv, L, spec, local, rank, world, dist, torch):
@@ -386,43 +498,43 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pos", choices=["pos", "large"])
-    ap.add_argument("--nseq", type=int, default=0, help="sequences per GPU (0 = the config's size)")
+    ap.add_argument("--nseq", type=int, default=0, help="sequences of the batch (0 = the config's size)")
     ap.add_argument("--seqlen", type=int, default=0, help="T for --workload large (0 = 4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other configs")
-    ap.add_argument("--cp-sharded", default="", metavar="KIND:NODES",
-                    help="with --gpus > 1: also time the constrained decode sharded over the ranks (csrc/cp_dist.cuh), "
-                         "e.g. heavy:2000 (configs[4]) or trucks:0; reported under \"cp_sharded\"")
+    ap.add_argument("--no-large-full", action="store_true", help="skip the full-size configs[3] pass of the `other` legs")
+    ap.add_argument("--cp-sharded", default="heavy:2000", metavar="KIND:NODES",
+                    help="with --gpus > 1: the constrained decode sharded over the ranks (csrc/cp_dist.cuh) next to the "
+                         "single-GPU solve, e.g. heavy:2000 (configs[4], the default) or trucks:0; 'off' skips it")
     return ap.parse_args()
 
 
-def build_workload(args, rank):
+def build_workload(args, rank=0):
     if args.workload == "pos":
         return workload_pos(rank, args.nseq or 1_000_000)
     return workload_large(rank, args.nseq or 4096, args.seqlen or 4096)
 
 
+def config_block(wl, world):
+    """Identical in both arms (`--impl ours` / `--impl reference`): the driver compares it."""
+    B, N = len(wl["off"]) - 1, int(wl["off"][-1])
+    return {"workload": wl["name"], "desc": wl["desc"], "sequences": B, "elements": N, "cells_per_step": wl["cells"],
+            "sharding": f"the batch cut into {world} contiguous slices by forward steps, one per GPU; decoded paths and "
+                        "scores all-gathered (ncclAllGather) inside the timed region" if world > 1 else "1 GPU, whole batch",
+            "l2": "inputs + delta history per step >> 126 MB L2 (no flush needed)"}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm (C oracle port; the Rust binary cannot be
-    built here) with all host threads, each step a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU algorithm (C oracle port; the Rust binary cannot be built here)
+    with all host threads; each step one pass over the same bounded sample cpu_baseline uses (the whole batch at the
+    POS shape on the GPU boxes)."""
     if rank != 0:
         return
     from oracle import pyoracle as po
 
-    wl = build_workload(args, 0)
+    wl = build_workload(args)
     threads = os.cpu_count() or 1
-    K, off, obs = wl["K"], wl["off"], wl["obs"]
-    if K > 64:
-        Tc, nb = 32, min(len(off) - 1, threads)
-        o = np.arange(nb + 1, dtype=np.int64) * Tc
-        ob = np.concatenate([obs[off[b]: off[b] + Tc] for b in range(nb)])
-        sample = f"{nb} sequences x first {Tc} steps per step"
-    else:
-        nb = min(len(off) - 1, 20000)
-        o = off[: nb + 1]
-        ob = obs[: o[-1]]
-        sample = f"first {nb} sequences per step"
-    cells = float(((np.diff(o) - 1) * K * K).sum())
+    ob, o, cells, desc = cpu_sample(wl, threads)
     for _ in range(args.warmup):
         po.decode_batch(wl["A"], wl["B"], ob, o, nthreads=threads)
     t0 = time.perf_counter()
@@ -432,14 +544,35 @@ def run_reference(args, rank, world):
     v = cells * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "desc": wl["desc"]},
+        "config": config_block(wl, world),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample + f", C oracle (port of viterbi.rs:5-32), {threads} OpenMP threads"},
+                         "sample": f"{desc} per step, C oracle (port of viterbi.rs:5-32), {threads} OpenMP threads"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def pin_rank_to_gpu_cpus(local, world):
+    """Keep this rank's host threads on its own share of the CPUs NVML lists as local to its GPU (its NUMA node);
+    pinned buffers allocated afterwards are first-touched there.  Returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1 and 64 * i + b < ncpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "unchanged (NVML lists no usable CPUs)"
+        n_local = max(1, world)
+        share = [c for i, c in enumerate(allowed) if i * n_local // len(allowed) == local % n_local] or allowed
+        os.sched_setaffinity(0, share)
+        return f"{len(share)} of the {len(allowed)} CPUs local to GPU {local}"
+    except Exception as e:  # noqa: BLE001
+        return f"unchanged ({type(e).__name__})"
 
 
 def main():
@@ -455,22 +588,20 @@ def main():
     import torch.distributed as dist
 
     import consistent_viterbi_b200 as cv
+    from consistent_viterbi_b200.dist import ShardedDecoder
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
+    affinity = pin_rank_to_gpu_cpus(local, world) if world > 1 else "not pinned (1 rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = cv._lib.lib()
-    if os.environ.get("CV_CHUNKS"):
-        L.cv_debug_set_chunks(int(os.environ["CV_CHUNKS"]))
-    if os.environ.get("CV_SMALL_CFG"):
-        L.cv_debug_set_small_config(int(os.environ["CV_SMALL_CFG"]))
-    wl = build_workload(args, rank)
+    wl = build_workload(args)                      # the SAME batch on every rank; rank r decodes slice r of it
     hmm = cv.HMM(wl["A"], wl["B"], wl["pi"])
     h = hmm.device_handle(local)
     obs_np, off_np = wl["obs"], wl["off"]
     B, N = len(off_np) - 1, int(off_np[-1])
-    max_len = int(np.diff(off_np).max())
+    K = wl["K"]
 
     # ---- FP64 issue peak of this GPU, measured now (roofline denominator) ----
     ops, ms = C.c_double(), C.c_double()
@@ -479,17 +610,17 @@ def main():
     cv._lib.check(L.cv_debug_probe_fp64(local, 1, 20000, C.byref(ops), C.byref(ms)))
     peak_mix = ops.value
 
-    # ---- device-resident inputs ----
-    d_obs = torch.from_numpy(obs_np.view(np.int32)).cuda()
-    d_off = torch.from_numpy(off_np).cuda()
-    d_path = torch.empty(N, dtype=torch.int32, device="cuda")
-    d_score = torch.empty(B, dtype=torch.float64, device="cuda")
+    # ---- this rank's slice, device resident; results land in the padded all-gather buffers ----
+    sd = ShardedDecoder(hmm, off_np, device=local)
+    sd.load_obs(obs_np)
+    my_cells = float(((np.diff(sd.off_l_np) - 1) * K * K).sum())
     stream = torch.cuda.current_stream()
 
-    def step_dev(timing=False):
-        rc = L.cv_decode_batch_dev(h, d_obs.data_ptr(), d_off.data_ptr(), B, N, max_len, d_path.data_ptr(),
-                                   d_score.data_ptr(), stream.cuda_stream, 0)
-        cv._lib.check(rc)
+    def step_dev():
+        sd.step()                                  # cv_decode_batch_dev (+ in-place ncclAllGather when world > 1)
+        if world > 1:
+            return sd.paths(), sd.scores()         # batch-ordered results on every rank
+        return None
 
     def barrier():
         if world > 1:
@@ -510,33 +641,64 @@ def main():
         barrier()
     launches = L.cv_launch_count() - launches0
     dev_ms = e0.elapsed_time(e1)
+    full_paths = sd.paths().cpu().numpy().view(np.uint32)
+    full_scores = sd.scores().cpu().numpy()
+
+    # ---- share of the collective: the same steps without / with only the all-gather ----
+    gather_ms = 0.0
+    if world > 1:
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        barrier()
+        g0.record(stream)
+        for _ in range(args.steps):
+            sd.decode_local()
+        g1.record(stream)
+        for _ in range(args.steps):
+            sd.gather()
+            sd.paths(); sd.scores()
+        g2.record(stream)
+        barrier()
+        local_ms, gather_ms = g0.elapsed_time(g1) / args.steps, g1.elapsed_time(g2) / args.steps
 
     # ---- dominant-kernel duration: CUDA events on the launching stream around the forward kernel ----
     L.cv_set_timing(1)
     fwd_ms, bt_ms = [], []
+    n_el, n_sq = sd.n_el[rank], sd.n_sq[rank]
     for _ in range(max(3, min(args.steps, 5))):
-        rc = L.cv_decode_batch_dev(h, d_obs.data_ptr(), d_off.data_ptr(), B, N, max_len, d_path.data_ptr(),
-                                   d_score.data_ptr(), stream.cuda_stream, 1)
+        rc = L.cv_decode_batch_dev(h, sd.obs_l.data_ptr(), sd.off_l.data_ptr(), n_sq, n_el, sd.max_len,
+                                   sd.gpaths[rank].data_ptr(), sd.gscores[rank].data_ptr(), stream.cuda_stream, 1)
         cv._lib.check(rc)
         fwd_ms.append(L.cv_last_kernel_ms(h))
         bt_ms.append(L.cv_last_backtrace_ms(h))
     L.cv_set_timing(0)
-    fwd = float(np.mean(fwd_ms))
+    fwd, bt = float(np.mean(fwd_ms)), float(np.mean(bt_ms))
 
-    # ---- end to end through the C ABI with pinned host buffers ----
+    # ---- end to end through the C ABI with pinned host buffers: this rank's slice in, its results out ----
+    e0_, e1_ = sd.e0, sd.e1
+    off_l = sd.off_l_np
+
     def pinned(arr):
-        p = L.cv_host_alloc(arr.nbytes)
+        p = L.cv_host_alloc(max(arr.nbytes, 1))
         assert p, "cv_host_alloc failed"
-        buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(arr.nbytes,))
-        buf[:] = arr.view(np.uint8).reshape(-1)
-        return p, buf
-    p_obs, _ = pinned(obs_np)
-    p_off, _ = pinned(off_np)
-    p_path = L.cv_host_alloc(4 * N)
-    p_score = L.cv_host_alloc(8 * B)
+        buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(arr.nbytes, 1),))
+        buf[: arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        return p
+    p_obs = pinned(np.ascontiguousarray(obs_np[e0_:e1_]))
+    p_off = pinned(np.ascontiguousarray(off_l))
+    p_path = L.cv_host_alloc(max(4 * n_el, 1))
+    p_score = L.cv_host_alloc(max(8 * n_sq, 1))
+    pin_path = torch.from_numpy(np.ctypeslib.as_array(C.cast(p_path, C.POINTER(C.c_int32)), shape=(max(n_el, 1),)))
+    pin_score = torch.from_numpy(np.ctypeslib.as_array(C.cast(p_score, C.POINTER(C.c_double)), shape=(max(n_sq, 1),)))
 
     def step_e2e():
-        cv._lib.check(L.cv_decode_batch(h, p_obs, p_off, B, p_path, p_score))
+        # H2D of the slice, decode, D2H of its paths / scores: one C-ABI call with host pointers
+        cv._lib.check(L.cv_decode_batch(h, p_obs, p_off, n_sq, p_path, p_score))
+        if world > 1:
+            # every rank also needs the others' paths on its device (north_star): upload own rows, all-gather on device
+            sd.gpaths[rank, :n_el].copy_(pin_path[:n_el], non_blocking=True)
+            sd.gscores[rank, :n_sq].copy_(pin_score[:n_sq], non_blocking=True)
+            sd.gather()
+            torch.cuda.current_stream().synchronize()
     for _ in range(2):
         step_e2e()
     barrier()
@@ -547,35 +709,69 @@ def main():
     barrier()
     e2e_s = (time.perf_counter() - t0) / n_e2e
     # check the end-to-end result against the device-resident one
-    host_paths = np.ctypeslib.as_array(C.cast(p_path, C.POINTER(C.c_uint32)), shape=(N,))
-    assert (host_paths == d_path.cpu().numpy().view(np.uint32)).all(), "e2e and device-resident paths differ"
+    host_paths = np.ctypeslib.as_array(C.cast(p_path, C.POINTER(C.c_uint32)), shape=(max(n_el, 1),))[:n_el]
+    assert (host_paths == full_paths[e0_:e1_]).all(), "e2e and device-resident paths differ"
 
     # ---- reduce over ranks ----
-    def allmax(x):
+    def allred(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def allsum(x):
+    def allgather_vals(xs):
+        t = torch.tensor(xs, dtype=torch.float64, device="cuda")
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+            return [xs]
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.tolist() for o in out]
+
+    MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
+
+    # ---- secondary: weak scaling (every rank decodes its OWN full-size batch, no collective), as round 1 measured ----
+    weak = None
+    if world > 1 and args.workload == "pos":
+        wlw = workload_pos(rank + 1, args.nseq or 1_000_000)
+        d_obs = torch.from_numpy(wlw["obs"].view(np.int32)).cuda()
+        d_off = torch.from_numpy(wlw["off"]).cuda()
+        Bw, Nw = len(wlw["off"]) - 1, int(wlw["off"][-1])
+        d_path = torch.empty(Nw, dtype=torch.int32, device="cuda")
+        d_score = torch.empty(Bw, dtype=torch.float64, device="cuda")
+        mlw = int(np.diff(wlw["off"]).max())
+
+        def step_weak():
+            cv._lib.check(L.cv_decode_batch_dev(h, d_obs.data_ptr(), d_off.data_ptr(), Bw, Nw, mlw, d_path.data_ptr(),
+                                                d_score.data_ptr(), stream.cuda_stream, 0))
+        for _ in range(args.warmup):
+            step_weak()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        for _ in range(args.steps):
+            step_weak()
+        w1.record(stream)
+        barrier()
+        wms = allred(w0.elapsed_time(w1), MAX)
+        wcells = allred(wlw["cells"], SUM)
+        weak = {"scaling": "weak", "value": wcells * args.steps / (wms * 1e-3), "unit": UNIT, "ms_per_step": wms / args.steps,
+                "per_gpu_sequences": Bw, "note": "every rank decodes its own batch of the config's size; no data-path collective"}
+        del d_obs, d_off, d_path, d_score
 
     cp_sharded = None
-    if args.cp_sharded and world > 1:
+    if args.cp_sharded and args.cp_sharded != "off" and world > 1:
         try:
             cp_sharded = run_cp_sharded(cv, L, args.cp_sharded, local, rank, world, dist, torch)
         except Exception as e:  # noqa: BLE001
             cp_sharded = {"error": repr(e)}
 
-    total_cells = allsum(wl["cells"])
-    dev_ms = allmax(dev_ms)
-    e2e_s = allmax(e2e_s)
-    launches = int(allsum(float(launches)))
+    per_rank = allgather_vals([dev_ms / args.steps, 1e3 * e2e_s, fwd, bt, gather_ms, float(n_sq), my_cells])
+    dev_ms = allred(dev_ms, MAX)
+    e2e_s = allred(e2e_s, MAX)
+    launches = int(allred(float(launches), SUM))
+    fwd_max = allred(fwd, MAX)
+    bt_max = allred(bt, MAX)
 
     if rank == 0:
         peaks = {}
@@ -584,7 +780,6 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        K = wl["K"]
         # algorithmic HBM bytes per step of one sequence (DESIGN.md "Roofline"): obs u32 + logB^T row +
         # delta-history row written by the forward kernel and read back by the backtrace + path u32
         if K <= 64:
@@ -592,45 +787,69 @@ def main():
         else:
             w = 1 if ((K + 127) // 128) * 128 <= 256 else 2
             bytes_per_step = 4 + 8 * K + w * K + w + 4
-        fp64_ops = 2.0 * wl["cells"]                      # 1 DADD + 1 compare per cell
-        achieved_alu = fp64_ops / (fwd * 1e-3)
-        traffic = None
+        my_steps = float((np.diff(off_l) - 1).sum())
+        achieved_alu = 2.0 * my_cells / (fwd * 1e-3)                 # 1 DADD + 1 compare per cell, rank 0's slice
+        step_ms = dev_ms / args.steps
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl["name"])
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if world == 1 and wl["name"] in tj:
+                traffic, traffic_src = tj[wl["name"]], tj.get("_source")
         except Exception:
             pass
+        hbm_ach = my_steps * bytes_per_step / ((fwd + bt) * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": total_cells * args.steps / (dev_ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "desc": wl["desc"], "per_gpu_sequences": B, "per_gpu_elements": N,
-                       "sharding": f"{world} x independent shards, no data-path collective",
-                       "l2": "inputs + delta history per step >> 126 MB L2 (no flush needed)"},
-            "e2e": {"value": total_cells / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(obs_np.nbytes + off_np.nbytes),
-                    "d2h_bytes_per_step": int(4 * N + 8 * B), "ms_per_step": 1e3 * e2e_s,
-                    "api": "cv_decode_batch (C ABI, pinned host buffers)"},
+            "metric": METRIC, "value": wl["cells"] * args.steps / (dev_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_block(wl, world),
+            "e2e": {"value": wl["cells"] / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(4 * n_el + 8 * (n_sq + 1) + (4 * n_el + 8 * n_sq if world > 1 else 0)),
+                    "d2h_bytes_per_step": int(4 * n_el + 8 * n_sq), "ms_per_step": 1e3 * e2e_s,
+                    "bytes_note": "rank 0's slice; every rank moves its own slice",
+                    "api": "cv_decode_batch (C ABI, pinned host buffers)" +
+                           (" per rank + ncclAllGather of the device copies" if world > 1 else "")},
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "roofline": {
                 "bound": "fp64_alu", "kernel": "decode_small_fwd_kernel" if K <= 64 else "decode_large_kernel",
                 "achieved": achieved_alu / 1e12, "peak": peak_mix / 1e12, "unit": "TFLOP/s",
-                "unit_note": "FP64 add+compare operations (2 per cell), not tensor FLOPs; frac = max(ALU view, HBM view) as SURVEY 8d defines",
-                "frac": achieved_alu / peak_mix, "traffic": traffic,
+                "unit_note": "FP64 add+compare operations (2 per cell, SURVEY 8d), not tensor FLOPs",
+                "frac": achieved_alu / peak_mix,
+                "frac_on_step": 2.0 * wl["cells"] / world / (step_ms * 1e-3) / peak_mix,
+                "frac_note": "frac = the forward kernel timed alone (CUDA events on its stream); frac_on_step = the same "
+                             "algorithmic operations over the whole driver-timed step (forward + concurrent backtrace"
+                             + (" + all-gather" if world > 1 else "") + ")",
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: DADD+DSETP issue rate over all SMs (cv_debug_probe_fp64 mode 1); "
                                f"DADD alone {peak_dadd / 1e12:.2f}",
-                "kernel_ms": fwd, "backtrace_ms": float(np.mean(bt_ms)),
-                "hbm": {"achieved": wl["steps"] * bytes_per_step / ((fwd + float(np.mean(bt_ms))) * 1e-3) / 1e9,
-                        "peak": hbm_peak, "unit": "GB/s", "bytes_per_step": bytes_per_step,
-                        "frac": wl["steps"] * bytes_per_step / ((fwd + float(np.mean(bt_ms))) * 1e-3) / 1e9 / hbm_peak,
+                "kernel_ms": fwd, "backtrace_ms": bt, "kernel_ms_max_over_ranks": fwd_max, "backtrace_ms_max_over_ranks": bt_max,
+                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "bytes_per_step": bytes_per_step,
+                        "frac": hbm_ach / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             },
         }
+        if world > 1:
+            line["collective"] = {"name": "ncclAllGather (torch.distributed.all_gather_into_tensor, in place) of paths (int32) "
+                                          "and scores (f64), padded to the largest slice, + un-padding concatenation",
+                                  "ms_per_step": gather_ms, "local_decode_ms_per_step": local_ms,
+                                  "share_of_step": gather_ms / max(step_ms, 1e-9),
+                                  "bytes_received_per_rank": int((world - 1) * (sd.gpaths.shape[1] * 4 + sd.gscores.shape[1] * 8))}
+            line["per_rank"] = {"columns": ["step_ms", "e2e_ms", "fwd_kernel_ms", "backtrace_ms", "gather_ms", "sequences", "cells"],
+                                "rows": per_rank, "host_affinity": affinity}
+            if weak is not None:
+                line["weak_scaling"] = weak
         if not args.no_cpu and world == 1:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            line["cpu_baseline"], ref = cpu_baseline(wl)
+            par = parity_block(ref, full_paths, full_scores, off_np)
+            if par is not None:
+                line["parity"] = par
         if not args.no_other and world == 1 and args.workload == "pos":
+            hmm.close()                                   # free the POS workspaces (9 GB of history) first
+            del sd
+            torch.cuda.empty_cache()
             try:
-                line["other"] = run_other(cv, L, local)
+                line["other"] = run_other(cv, L, local, peak_mix, hbm_peak, large_full=not args.no_large_full)
             except Exception as e:  # the headline numbers stand on their own
                 line["other"] = {"error": repr(e)}
         if cp_sharded is not None:
@@ -639,6 +858,7 @@ def main():
     for p in (p_obs, p_off, p_path, p_score):
         L.cv_host_free(p)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

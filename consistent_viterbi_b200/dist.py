@@ -1,9 +1,12 @@
-"""Multi-GPU sharding of the batched decode.
+"""Multi-GPU sharding of the batched decode (BASELINE.json north_star: "each GPU taking a
+contiguous slice ... NCCL over NVLink is used only to all-gather decoded paths").
 
-Sequences are independent units, so the batch is cut into one contiguous slice per rank, balanced by
-forward steps sum(T_b - 1); the model is replicated; no collective sits on the data path.  The only
-collectives are the optional all-gather of the decoded paths/scores (`gather=True`) over NCCL (or gloo on
-CPU-only hosts for the host-logic tests).  One process per GPU, `torch.distributed` for the plumbing."""
+Sequences are independent units (`viterbi::decode` is called once per sequence, viterbi.rs:5), so the batch is cut
+into one contiguous slice per rank, balanced by forward steps; the model is replicated.  One process per GPU,
+`torch.distributed` (NCCL) for the plumbing.  The data path never leaves the device between the decode and the
+collective: `cv_decode_batch_dev` writes this rank's paths / scores straight into its row of the padded gather
+buffers and one in-place `all_gather_into_tensor` per buffer (ncclAllGather over NVLink) completes them on every
+rank.  The collective is the only exchange; there is no reduction on this path."""
 from __future__ import annotations
 
 import numpy as np
@@ -33,40 +36,111 @@ def local_slice(obs_flat, seq_off, rank: int, world_size: int):
     return np.asarray(obs_flat)[e0:e1], seq_off[b0:b1 + 1] - e0, b0, b1
 
 
+class ShardedDecoder:
+    """The sharded batched decode of ONE batch layout (seq_off), reusable across steps with new observations.
+
+    Every rank builds it with the same `seq_off`.  Buffers (torch tensors on this rank's device):
+      obs_l   [n_el(rank)]  int32   this rank's slice of the observations (fill with `load_obs` or write in place)
+      gpaths  [world, P]    int32   padded gather buffer, P = max_r n_el(r); row r = paths of rank r's slice
+      gscores [world, S]    float64 S = max_r n_seq(r)
+    `step()` enqueues decode + all-gather on the current stream; `paths()` / `scores()` return the batch-ordered
+    results (device tensors, one concatenation of the un-padded rows).
+
+    `decode_fn(obs_np, off_np) -> (paths, scores)` replaces the GPU call in the CPU-only (gloo) host-logic tests."""
+
+    def __init__(self, hmm, seq_off, device: int = -1, decode_fn=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.hmm, self.decode_fn = hmm, decode_fn
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+        self.seq_off = seq_off
+        self.bounds = shard_bounds(seq_off, self.world)
+        self.n_el = [int(seq_off[self.bounds[r + 1]] - seq_off[self.bounds[r]]) for r in range(self.world)]
+        self.n_sq = [int(self.bounds[r + 1] - self.bounds[r]) for r in range(self.world)]
+        self.b0, self.b1 = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        self.e0, self.e1 = int(seq_off[self.b0]), int(seq_off[self.b1])
+        on_gpu = decode_fn is None
+        if on_gpu:
+            if not torch.cuda.is_available():
+                raise RuntimeError("ShardedDecoder needs a CUDA device (no CPU fallback)")
+            self.device_index = torch.cuda.current_device() if device < 0 else device
+            self.dev = torch.device("cuda", self.device_index)
+        else:
+            self.device_index, self.dev = -1, torch.device("cpu")
+        off_l = seq_off[self.b0:self.b1 + 1] - self.e0
+        self.off_l_np = off_l
+        self.max_len = int(np.diff(off_l).max()) if self.b1 > self.b0 else 0
+        P, S = max(max(self.n_el), 1), max(max(self.n_sq), 1)
+        # rows padded to 16 bytes so every rank's row is aligned for the collective
+        P, S = (P + 3) // 4 * 4, (S + 1) // 2 * 2
+        self.off_l = torch.from_numpy(off_l.copy()).to(self.dev)
+        self.obs_l = torch.zeros(max(self.n_el[self.rank], 1), dtype=torch.int32, device=self.dev)
+        self.gpaths = torch.zeros((self.world, P), dtype=torch.int32, device=self.dev)
+        self.gscores = torch.zeros((self.world, S), dtype=torch.float64, device=self.dev)
+        self.handle = hmm.device_handle(self.device_index) if on_gpu else None
+
+    # -- inputs ------------------------------------------------------------------------------------------------
+    def load_obs(self, obs_flat, non_blocking: bool = False):
+        """Copy this rank's slice of the FULL observation array (numpy u32, or a pinned torch int32 tensor)."""
+        torch = self.torch
+        if isinstance(obs_flat, np.ndarray):
+            src = torch.from_numpy(np.ascontiguousarray(obs_flat[self.e0:self.e1]).view(np.int32))
+        else:
+            src = obs_flat[self.e0:self.e1]
+        self.obs_l[: self.e1 - self.e0].copy_(src, non_blocking=non_blocking)
+
+    # -- one step ------------------------------------------------------------------------------------------------
+    def decode_local(self):
+        """This rank's slice: paths / scores land directly in row `rank` of the gather buffers."""
+        n_el, n_sq = self.n_el[self.rank], self.n_sq[self.rank]
+        if n_sq == 0:
+            return
+        if self.decode_fn is not None:
+            p, s = self.decode_fn(self.obs_l[:n_el].numpy().view(np.uint32), self.off_l_np)
+            self.gpaths[self.rank, :n_el] = self.torch.from_numpy(np.ascontiguousarray(p).view(np.int32))
+            self.gscores[self.rank, :n_sq] = self.torch.from_numpy(np.ascontiguousarray(s))
+            return
+        from . import _lib
+        st = self.torch.cuda.current_stream(self.dev)
+        rc = _lib.lib().cv_decode_batch_dev(self.handle, self.obs_l.data_ptr(), self.off_l.data_ptr(), n_sq, n_el,
+                                            self.max_len, self.gpaths[self.rank].data_ptr(),
+                                            self.gscores[self.rank].data_ptr(), st.cuda_stream, 0)
+        _lib.check(rc)
+
+    def gather(self):
+        """In-place all-gather of both buffers (ncclAllGather: row r of every rank's buffer <- rank r's row)."""
+        if self.world == 1:
+            return
+        self.dist.all_gather_into_tensor(self.gpaths.view(-1), self.gpaths[self.rank], group=self.group)
+        self.dist.all_gather_into_tensor(self.gscores.view(-1), self.gscores[self.rank], group=self.group)
+
+    def step(self):
+        self.decode_local()
+        self.gather()
+
+    # -- results ---------------------------------------------------------------------------------------------------
+    def paths(self):
+        """int32 [N] (bit patterns of the u32 states), batch order, on this rank's device."""
+        return self.torch.cat([self.gpaths[r, : self.n_el[r]] for r in range(self.world)])
+
+    def scores(self):
+        return self.torch.cat([self.gscores[r, : self.n_sq[r]] for r in range(self.world)])
+
+
 def decode_batch_sharded(hmm, obs_flat, seq_off, device: int = -1, gather: bool = True, decode_fn=None):
-    """Decode this rank's slice on its GPU; with gather=True every rank returns the full (paths, scores).
-
-    `decode_fn(hmm, obs, off)` defaults to the GPU path (`viterbi.decode_batch`); the CPU-only tests of the
-    host logic inject a stand-in."""
-    import torch
-    import torch.distributed as dist
-
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    if decode_fn is None:
-        from .viterbi import decode_batch
-
-        def decode_fn(h, o, f):
-            return decode_batch(h, o, f, device=device)
-    seq_off = np.asarray(seq_off, dtype=np.int64)
-    obs_l, off_l, b0, b1 = local_slice(obs_flat, seq_off, rank, world)
-    paths_l, scores_l = decode_fn(hmm, obs_l, off_l) if b1 > b0 else (np.zeros(0, np.uint32), np.zeros(0))
-    if not gather or world == 1:
-        return paths_l, scores_l, (b0, b1)
-    bnd = shard_bounds(seq_off, world)
-    backend = dist.get_backend()
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    # all-gather with padding to the largest slice (paths u32 as int32 bit patterns, scores f64)
-    n_el = [int(seq_off[bnd[r + 1]] - seq_off[bnd[r]]) for r in range(world)]
-    n_sq = [int(bnd[r + 1] - bnd[r]) for r in range(world)]
-    pbuf = torch.zeros(max(n_el), dtype=torch.int32, device=dev)
-    pbuf[: len(paths_l)] = torch.from_numpy(np.ascontiguousarray(paths_l).view(np.int32)).to(dev)
-    sbuf = torch.zeros(max(n_sq), dtype=torch.float64, device=dev)
-    sbuf[: len(scores_l)] = torch.from_numpy(np.ascontiguousarray(scores_l)).to(dev)
-    pall = [torch.empty_like(pbuf) for _ in range(world)]
-    sall = [torch.empty_like(sbuf) for _ in range(world)]
-    dist.all_gather(pall, pbuf)
-    dist.all_gather(sall, sbuf)
-    paths = np.concatenate([pall[r][: n_el[r]].cpu().numpy().view(np.uint32) for r in range(world)])
-    scores = np.concatenate([sall[r][: n_sq[r]].cpu().numpy() for r in range(world)])
-    return paths, scores, (b0, b1)
+    """Decode this rank's slice on its GPU; with gather=True every rank returns the full (paths, scores) as numpy
+    arrays.  One H2D of the rank's observations, one D2H of the results; everything between stays on the device
+    (see ShardedDecoder).  Returns (paths u32, scores f64, (b0, b1))."""
+    sd = ShardedDecoder(hmm, seq_off, device=device, decode_fn=decode_fn)
+    sd.load_obs(np.ascontiguousarray(obs_flat, dtype=np.uint32))
+    sd.decode_local()
+    if gather and sd.world > 1:
+        sd.gather()
+        paths, scores = sd.paths(), sd.scores()
+    else:
+        paths, scores = sd.gpaths[sd.rank, : sd.n_el[sd.rank]], sd.gscores[sd.rank, : sd.n_sq[sd.rank]]
+    return paths.cpu().numpy().view(np.uint32), scores.cpu().numpy(), (sd.b0, sd.b1)

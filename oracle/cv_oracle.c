@@ -34,6 +34,18 @@ static inline int64_t argmax_first(const double *v, int64_t n, int *nan_flag)
     return best;
 }
 
+/* Test hook: the argmax above on a caller-supplied vector, with the reference's error cases
+ * (ndarray-stats MinMaxError::{EmptyInput, UndefinedOrder}). */
+int cvo_argmax(const double *v, int64_t n, int64_t *idx_out)
+{
+    if (n <= 0) return CVO_ERR_EMPTY;
+    int nan_flag = 0;
+    int64_t i = argmax_first(v, n, &nan_flag);
+    if (nan_flag) return CVO_ERR_NAN;
+    if (idx_out) *idx_out = i;
+    return CVO_OK;
+}
+
 /* ------------------------------------------------------------------------ */
 /* R1: viterbi::decode (viterbi.rs:5-32)                                      */
 /* ------------------------------------------------------------------------ */

@@ -40,6 +40,10 @@ extern "C" {
 #define CVO_ERR_ARG       3   /* bad argument (obs out of range, comp id >= ncomp ...) */
 #define CVO_ERR_ASSERT    4   /* reference assert!(obj > best_obj) would fire (cp.rs:87) */
 
+/* ndarray-stats 0.5 QuantileExt::argmax on a 1-D f64 vector (test hook): first element that compares Greater than
+ * the running maximum; CVO_ERR_EMPTY for n == 0 (MinMaxError::EmptyInput), CVO_ERR_NAN for NaN (UndefinedOrder). */
+int cvo_argmax(const double *v, int64_t n, int64_t *idx_out);
+
 /* R1 -- viterbi::decode, src/viterbi_solver/viterbi.rs:5-32.
  * path_out[T]; *score_out = delta[T-1][end_state]. */
 int cvo_decode(int K, int64_t M, const double *logA, const double *logB,

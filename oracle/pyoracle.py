@@ -40,6 +40,8 @@ def lib() -> C.CDLL:
             C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_int64),
             C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
         )
+        L.cvo_argmax.argtypes = [dp, C.c_int64, i64p]
+        L.cvo_argmax.restype = C.c_int
         L.cvo_decode.argtypes = [C.c_int, C.c_int64, dp, dp, u32p, C.c_int64, u32p, dp]
         L.cvo_decode.restype = C.c_int
         L.cvo_decode_trace.argtypes = [C.c_int, C.c_int64, dp, dp, u32p, C.c_int64, dp, u32p]
@@ -71,6 +73,16 @@ class OracleError(RuntimeError):
     def __init__(self, code):
         super().__init__(f"oracle status {code}")
         self.code = code
+
+
+def argmax(v):
+    """ndarray-stats 0.5 `QuantileExt::argmax` of a 1-D f64 vector (OracleError on empty input / NaN)."""
+    v = _f64(np.asarray(v, dtype=np.float64).reshape(-1))
+    idx = C.c_int64(0)
+    rc = lib().cvo_argmax(_p(v, C.c_double), v.shape[0], C.byref(idx))
+    if rc:
+        raise OracleError(rc)
+    return int(idx.value)
 
 
 def decode(logA, logB, obs):

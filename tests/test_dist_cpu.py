@@ -34,12 +34,21 @@ def _worker(rank, world, port, q):
     A, B, pi = random_hmm(rng, 6, 7)
     obs, off = random_batch(rng, 301, 7, 1, 25)
 
-    def fake_gpu(hmm, o, f):
+    def fake_gpu(o, f):
         return po.decode_batch(A, B, o, f)
 
     paths, scores, (b0, b1) = cvd.decode_batch_sharded(None, obs, off, gather=True, decode_fn=fake_gpu)
     ref_p, ref_s = po.decode_batch(A, B, obs, off)
     ok = bool((paths == ref_p).all() and scores.tobytes() == ref_s.tobytes())
+    # the reusable form: same layout, new observations every step; results stay in the padded gather buffers
+    sd = cvd.ShardedDecoder(None, off, decode_fn=fake_gpu)
+    for it in range(2):
+        obs2 = rng.integers(0, 7, size=len(obs)).astype(np.uint32)          # same stream on both ranks
+        sd.load_obs(obs2)
+        sd.step()
+        rp2, rs2 = po.decode_batch(A, B, obs2, off)
+        ok = ok and bool((sd.paths().numpy().view(np.uint32) == rp2).all()) and sd.scores().numpy().tobytes() == rs2.tobytes()
+    ok = ok and sd.gpaths.shape[0] == world and (sd.b0, sd.b1) == (b0, b1)
     q.put((rank, ok, b0, b1))
     dist.barrier()
     dist.destroy_process_group()

@@ -220,3 +220,21 @@ def test_oracle_cfn_longest_path_bruteforce():
                     best = max(best, s)
                 exp = 0.0 if best == -math.inf else best          # -inf costs are not accumulated (cfn.rs:123)
                 assert r["tables"][0, 1, n1, n2] == exp and r["tables"][1, 0, n2, n1] == exp
+
+
+def test_argmax_matches_ndarray_stats_published_cases():
+    """The one third-party semantic on the path: ndarray-stats 0.5 `QuantileExt::argmax` (call sites viterbi.rs:16,24,
+    cp.rs:39,53,74,86).  The crate is not under /root/reference; these are the cases of its own test suite
+    (tests/quantile.rs::test_argmax, restated on the flattened row-major vector) plus the rule its implementation
+    documents: the running maximum starts at the first element and only a strictly Greater element replaces it."""
+    assert po.argmax([1, 5, 3, 2, 0, 6]) == 5                       # array![[1, 5, 3], [2, 0, 6]].argmax() == Ok((1, 2))
+    assert po.argmax([1., 5., 3., 2., 0., 6.]) == 5
+    with pytest.raises(po.OracleError) as e:                        # [[1., 5., 3.], [2., NAN, 6.]] -> Err(UndefinedOrder)
+        po.argmax([1., 5., 3., 2., np.nan, 6.])
+    assert e.value.code == 2
+    with pytest.raises(po.OracleError) as e:                        # array![[], []] -> Err(EmptyInput)
+        po.argmax([])
+    assert e.value.code == 1
+    assert po.argmax([3., 7., 7., 1.]) == 1                         # equal maxima: the first one stays
+    assert po.argmax([-np.inf, -np.inf, -np.inf]) == 0              # SURVEY Q7
+    assert po.argmax([-0.0, 0.0]) == 0 and po.argmax([0.0, -0.0]) == 0
