@@ -687,16 +687,16 @@ def main():
     p_off = pinned(np.ascontiguousarray(off_l))
     p_path = L.cv_host_alloc(max(4 * n_el, 1))
     p_score = L.cv_host_alloc(max(8 * n_sq, 1))
-    pin_path = torch.from_numpy(np.ctypeslib.as_array(C.cast(p_path, C.POINTER(C.c_int32)), shape=(max(n_el, 1),)))
-    pin_score = torch.from_numpy(np.ctypeslib.as_array(C.cast(p_score, C.POINTER(C.c_double)), shape=(max(n_sq, 1),)))
 
     def step_e2e():
         # H2D of the slice, decode, D2H of its paths / scores: one C-ABI call with host pointers
-        cv._lib.check(L.cv_decode_batch(h, p_obs, p_off, n_sq, p_path, p_score))
-        if world > 1:
-            # every rank also needs the others' paths on its device (north_star): upload own rows, all-gather on device
-            sd.gpaths[rank, :n_el].copy_(pin_path[:n_el], non_blocking=True)
-            sd.gscores[rank, :n_sq].copy_(pin_score[:n_sq], non_blocking=True)
+        if world == 1:
+            cv._lib.check(L.cv_decode_batch(h, p_obs, p_off, n_sq, p_path, p_score))
+        else:
+            # every rank also needs the others' paths on its device (north_star): the device copies of this rank's
+            # results stay in its row of the gather buffers (cv_decode_batch_keep), then the all-gather on device
+            cv._lib.check(L.cv_decode_batch_keep(h, p_obs, p_off, n_sq, p_path, p_score, sd.gpaths[rank].data_ptr(),
+                                                 sd.gscores[rank].data_ptr()))
             sd.gather()
             torch.cuda.current_stream().synchronize()
     for _ in range(2):
@@ -804,11 +804,11 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_block(wl, world),
             "e2e": {"value": wl["cells"] / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(4 * n_el + 8 * (n_sq + 1) + (4 * n_el + 8 * n_sq if world > 1 else 0)),
+                    "h2d_bytes_per_step": int(4 * n_el + 8 * (n_sq + 1)),
                     "d2h_bytes_per_step": int(4 * n_el + 8 * n_sq), "ms_per_step": 1e3 * e2e_s,
                     "bytes_note": "rank 0's slice; every rank moves its own slice",
-                    "api": "cv_decode_batch (C ABI, pinned host buffers)" +
-                           (" per rank + ncclAllGather of the device copies" if world > 1 else "")},
+                    "api": "cv_decode_batch (C ABI, pinned host buffers)" if world == 1 else
+                           "cv_decode_batch_keep (C ABI, pinned host buffers; device copies kept) per rank + ncclAllGather"},
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "roofline": {

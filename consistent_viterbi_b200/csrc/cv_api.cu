@@ -98,6 +98,18 @@ __global__ void build_layouts_kernel(const double *A, const double *Bm, const do
 
 extern "C" void cv_hmm_destroy(cv_hmm *h);
 
+// Slot-permuted copies for the balanced state split: column slot 8g + q of row r <- column (state) first(g) + q of the
+// natural layout when q < count(g), else -inf; first(g) = g * base + min(g, rem), count(g) = base + (g < rem).
+__global__ void permute_slots_kernel(const double *in, double *out, int64_t rows, int Kp, int base, int rem)
+{
+    const int64_t n = rows * Kp, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int64_t r = e / Kp; const int c = (int)(e % Kp), g = c >> 3, q = c & 7;
+        const int first = g * base + min(g, rem), cnt = base + (g < rem ? 1 : 0);
+        out[e] = q < cnt ? in[r * Kp + first + q] : neg_inf();
+    }
+}
+
 __global__ void transpose_kernel(const double *in, double *out, int n)
 {
     __shared__ double tile[32][33];
@@ -205,6 +217,16 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     if (K <= SMALL_K_MAX) { h->dA = pA; h->dBT = pBT; h->dPi = pPi; }
     else { h->dAl = pA; h->dBTl = pBT; h->dPi = pPi; }
     pA = pBT = pPi = nullptr;                      // owned by the handle now (cv_hmm_destroy)
+    if (K <= SMALL_K_MAX && h->TQT == 8 && K % 8 != 0 && K / h->G >= 5) {
+        // balanced state split of the forward tile kernel: no padded target states (K = 45: 8,8,8,7,7,7 instead of 5 x 8 + 5)
+        CUDA_TRY(cudaMalloc(&h->dAb, sizeof(double) * (size_t)K * Kp));
+        CUDA_TRY(cudaMalloc(&h->dBTb, sizeof(double) * (size_t)M * Kp));
+        permute_slots_kernel<<<std::max(1, h->num_sms) * 4, 256>>>(h->dA, h->dAb, K, Kp, K / h->G, K % h->G);
+        permute_slots_kernel<<<std::max(1, h->num_sms) * 4, 256>>>(h->dBT, h->dBTb, M, Kp, K / h->G, K % h->G);
+        g_launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
     if (K > SMALL_K_MAX) {
         CUDA_TRY(cudaMalloc(&h->dATl, sizeof(double) * (size_t)Kp * Kp));
         transpose_kernel<<<dim3((Kp + 31) / 32, (Kp + 31) / 32), dim3(32, 8)>>>(h->dAl, h->dATl, Kp);
@@ -222,7 +244,7 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl, h->dATl}) if (p) cudaFree(p);
+    for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl, h->dATl, h->dAb, h->dBTb}) if (p) cudaFree(p);
     for (DevBuf *b : {&h->obs, &h->seq_off, &h->path, &h->score}) b->release();
     for (auto &w : h->ws) {
         for (DevBuf *b : {&w.order, &w.keys_in, &w.keys_out, &w.vals_in, &w.cub_tmp, &w.hist, &w.tmax, &w.base, &w.misc,
@@ -399,6 +421,11 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
 
     DecodeSmallParams p;
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
+    p.At = h->dA; p.BTt = h->dBT; p.nq_base = p.nq_rem = 0;
+    p.pipe = (g_tune.fwd_variant & 1) ? 1 : 0;
+    if ((g_tune.fwd_variant & 2) && h->dAb && h->TQT == 8 && tpt == 2) {
+        p.At = h->dAb; p.BTt = h->dBTb; p.nq_base = h->K / G; p.nq_rem = h->K % G;
+    }
     p.tile_base = (const long long *)w.base.p;
     p.hist = (double *)w.hist.p; p.hist_cap_slabs = (long long)(hist_rows / (size_t)NS); p.path = d_path; p.score = d_score; p.tile_counter = d_counter; p.status = d_status;
     p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp; p.G = G; p.S = S; p.NS = NS; p.ntiles = ntiles;
@@ -646,7 +673,7 @@ static StreamWriteValue32Fn stream_write_value32()
 // (chunk, length), so the kernels consume the chunks in arrival order.  Against one launch per chunk this
 // removes the per-chunk sort / launch / ramp costs: the copies hide behind 13 ms of kernels instead of 6 x 2.3 ms.
 static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B, uint32_t *path_out,
-                           double *score_out, int nch, bool *handled)
+                           double *score_out, int nch, bool *handled, uint32_t *d_path, double *d_score)
 {
     *handled = false;
     StreamWaitValue32Fn wait32 = stream_wait_value32();
@@ -656,9 +683,8 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     const int64_t N = seq_off[B];
     DecodeWs &w = h->ws[0];
     cudaStream_t sk = w.st, s_in = h->ws[1].st, s_out = h->ws[1].st_bt;
-    uint32_t *d_obs = (uint32_t *)h->obs.p, *d_path = (uint32_t *)h->path.p;
+    uint32_t *d_obs = (uint32_t *)h->obs.p;
     int64_t *d_off = (int64_t *)h->seq_off.p;
-    double *d_score = (double *)h->score.p;
     int rc;
     if ((rc = w.order.ensure(sizeof(uint32_t) * (size_t)B)) || (rc = w.keys_in.ensure(sizeof(uint32_t) * (size_t)B)) ||
         (rc = w.keys_out.ensure(sizeof(uint32_t) * (size_t)B)) || (rc = w.vals_in.ensure(sizeof(uint32_t) * (size_t)B)) ||
@@ -683,7 +709,6 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
                                                                       (uint32_t *)w.vals_in.p, d_status, d_maxlen);
     g_launches++;
     int *hs = (int *)h->pinned_status + 8;
-    CUDA_TRY(cudaMemcpyAsync(hs, d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, sk));      // status, longest length
     CUDA_TRY(cudaStreamWaitEvent(s_in, w.ev_pre, 0));                                          // `arrived` is zeroed first
     for (int k = 0; k < nch; k++) {
         const int64_t e0 = seq_off[sio.cbs.cb[k]], e1 = seq_off[sio.cbs.cb[k + 1]];
@@ -691,11 +716,16 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
         if (e1 > e0) CUDA_TRY(cudaMemcpyAsync(d_obs + e0, obs_flat + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, s_in));
         if (write32(s_in, (unsigned long long)(uintptr_t)d_arrived, (unsigned int)(k + 1), 0x0) != 0) return fail(CV_ERR_CUDA, "cuStreamWriteValue32 failed");
     }
-    CUDA_TRY(cudaStreamSynchronize(sk));                                                       // ~0.2 ms: offsets in, lengths checked
-    if (hs[0] == CV_ERR_EMPTY) { cudaStreamSynchronize(s_in); return fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)"); }
-    if (hs[0] == CV_ERR_ARG) { cudaStreamSynchronize(s_in); return fail(CV_ERR_ARG, "seq_off not monotone"); }
-    if (hs[0]) { cudaStreamSynchronize(s_in); *handled = false; return CV_OK; }                // e.g. a sequence longer than 2^24: chunked path
-    const int64_t max_len = (int64_t)(unsigned int)hs[1];
+    // Lengths are checked and the longest one found on the HOST while the first copies fly (the forward kernel cannot
+    // start before chunk 0 has arrived anyway): no device round trip before the launch.
+    int64_t max_len = 0;
+    for (int64_t b = 0; b < B; b++) {
+        const int64_t len = seq_off[b + 1] - seq_off[b];
+        if (len <= 0) return len == 0 ? fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)")
+                                      : fail(CV_ERR_ARG, "seq_off not monotone");
+        max_len = std::max(max_len, len);
+    }
+    if (max_len > 0xffffffLL) { *handled = false; return CV_OK; }                              // does not fit the 24-bit sort key: chunked path
 
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)w.keys_in.p, (uint32_t *)w.keys_out.p,
@@ -723,8 +753,24 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     return report_status(hs, 1);
 }
 
+static int decode_batch_host(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B, uint32_t *path_out,
+                             double *score_out, uint32_t *d_path_keep, double *d_score_keep);
+
 extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B,
                                uint32_t *path_out, double *score_out)
+{
+    return decode_batch_host(h, obs_flat, seq_off, B, path_out, score_out, nullptr, nullptr);
+}
+
+extern "C" int cv_decode_batch_keep(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B,
+                                    uint32_t *path_out, double *score_out, uint32_t *d_path_keep, double *d_score_keep)
+{
+    if (!d_path_keep || !d_score_keep) return fail(CV_ERR_ARG, "NULL device buffer");
+    return decode_batch_host(h, obs_flat, seq_off, B, path_out, score_out, d_path_keep, d_score_keep);
+}
+
+static int decode_batch_host(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B, uint32_t *path_out,
+                             double *score_out, uint32_t *d_path_keep, double *d_score_keep)
 {
     if (!h) return fail(CV_ERR_ARG, "NULL model");
     if (B < 0) return fail(CV_ERR_ARG, "negative B");
@@ -736,16 +782,17 @@ extern "C" int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_
     int rc;
     if ((rc = h->obs.ensure(sizeof(uint32_t) * (size_t)N))) return rc;
     if ((rc = h->seq_off.ensure(sizeof(int64_t) * (size_t)(B + 1)))) return rc;
-    if ((rc = h->path.ensure(sizeof(uint32_t) * (size_t)N))) return rc;
-    if ((rc = h->score.ensure(sizeof(double) * (size_t)B))) return rc;
-    uint32_t *d_obs = (uint32_t *)h->obs.p, *d_path = (uint32_t *)h->path.p;
+    if (!d_path_keep && (rc = h->path.ensure(sizeof(uint32_t) * (size_t)N))) return rc;
+    if (!d_score_keep && (rc = h->score.ensure(sizeof(double) * (size_t)B))) return rc;
+    // the device copies of the results: the library's own buffers, or the caller's (cv_decode_batch_keep)
+    uint32_t *d_obs = (uint32_t *)h->obs.p, *d_path = d_path_keep ? d_path_keep : (uint32_t *)h->path.p;
     int64_t *d_off = (int64_t *)h->seq_off.p;
-    double *d_score = (double *)h->score.p;
+    double *d_score = d_score_keep ? d_score_keep : (double *)h->score.p;
     const bool timing = g_timing.load() != 0;
     const int nch = chunk_count(h, B, timing, true);
     if (!timing) {
         bool handled = false;
-        if ((rc = decode_streamed(h, obs_flat, seq_off, B, path_out, score_out, nch, &handled))) return rc;
+        if ((rc = decode_streamed(h, obs_flat, seq_off, B, path_out, score_out, nch, &handled, d_path, d_score))) return rc;
         if (handled) return CV_OK;
     }
     // Chunk k: H2D of its observations -> order/forward/backtrace -> D2H of its paths, on stream k % 2, so the

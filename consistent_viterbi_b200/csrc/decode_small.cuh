@@ -47,8 +47,9 @@
 namespace cvb {
 
 struct DecodeSmallParams {
-    const double *A;         // [K][Kp]   logA, columns >= K padded with -inf
+    const double *A;         // [K][Kp]   logA, columns >= K padded with -inf (natural column order: the backtrace)
     const double *BT;        // [M][Kp]   logB transposed (obs-major), padded -inf
+    const double *At, *BTt;  // what the forward tile kernel reads: A / BT, or their slot-permuted copies (balanced split)
     const uint32_t *obs;     // [N]
     const int64_t *seq_off;  // [B+1]
     const uint32_t *order;   // [B] sequence ids, longest first
@@ -74,6 +75,11 @@ struct DecodeSmallParams {
     int64_t cb[18];                  // chunk boundaries: chunk c = sequences [cb[c], cb[c+1])
     int64_t M, B;
     int K, Kp, G, S, NS, ntiles;   // NS = sequences per tile = 32 * TPT * S
+    // balanced state split (TQT = 8 only): state group g owns nq_base + (g < nq_rem) states starting at state
+    // g * nq_base + min(g, nq_rem); the columns of A / BT are permuted into 8-wide slots per group (slot 8g + q holds
+    // that group's q-th state, unused slots -inf).  nq_base = 0: the plain layout (group g = states 8g .. 8g+7).
+    int nq_base, nq_rem;
+    int pipe;                      // 1: software-pipelined tile loop (adds of predecessor j+1 next to the selects of j)
 };
 
 __host__ __device__ inline int em_pitch(int Kp) { return Kp + 2; }   // doubles; bank-conflict-free row pitch
@@ -86,7 +92,9 @@ __host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS)
 
 // value-only TP x TQ micro-tile: best[p][q] = max_j ( dcol[j*ldd + p] + arow[j*lda + q] )
 // (strict > keeps the first maximum's bits, e.g. the sign of a zero, as the reference does).
-template <int TQT, int UNR = 2, int TPT = TP>
+// NQ <= TQT: only the first NQ target states of the slot group are computed (balanced split: the slots behind them
+// are padding); the operand loads stay 16-byte pairs.
+template <int TQT, int UNR = 2, int TPT = TP, int NQ = TQT>
 __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol, int ldd,
                                                  const double *__restrict__ arow, int lda, int nj,
                                                  double (&best)[TPT][TQT])
@@ -101,14 +109,14 @@ __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol
         }
         double a[TQT];
 #pragma unroll
-        for (int q = 0; q < TQT / 2; q++) {
+        for (int q = 0; q < (NQ + 1) / 2; q++) {
             const double2 aa = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2 * q);
             a[2 * q] = aa.x; a[2 * q + 1] = aa.y;
         }
 #pragma unroll
         for (int p = 0; p < TPT; p++)
 #pragma unroll
-            for (int q = 0; q < TQT; q++) {
+            for (int q = 0; q < NQ; q++) {
                 const double v = dd[p] + a[q];
                 best[p][q] = v > best[p][q] ? v : best[p][q];
             }
@@ -181,6 +189,43 @@ __device__ __forceinline__ void fence_proxy_async_smem()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// One step of one thread: its TPT sequences x NQ target states.  best = max_j (delta[t-1][j] + a[j][i]) over all
+// predecessors (value only), then (.. + b) (viterbi.rs:17) into the other delta buffer.  `row0` points at the row of the
+// group's first state in that buffer, `nreal` = how many of the NQ states exist (the last group of the plain layout
+// may reach past K).
+template <int TQT, int TPT, int NQ>
+__device__ __forceinline__ void fwd_step(const double *__restrict__ dcur, double *__restrict__ row0, int NS,
+                                         const double *__restrict__ arow, int Kp, int K, const double *__restrict__ e0, int EP,
+                                         uint64_t *em_bar, uint32_t em_phase, int nreal, int pipe)
+{
+    double best[TPT][TQT];
+#pragma unroll
+    for (int q = 0; q < TPT; q++)
+#pragma unroll
+        for (int k = 0; k < TQT; k++) best[q][k] = neg_inf();
+    if (NQ == TQT && pipe) maxplus_tile_val_pipe<TQT, TPT>(dcur, NS, arow, Kp, K, best);
+    else maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT, NQ>(dcur, NS, arow, Kp, K, best);
+
+    mbar_wait(em_bar, em_phase);      // emission rows of step t have landed
+#pragma unroll
+    for (int k = 0; k < (NQ + 1) / 2; k++) {
+        double2 x[TPT];
+#pragma unroll
+        for (int q = 0; q < TPT; q++) x[q] = *reinterpret_cast<const double2 *>(e0 + (size_t)q * EP + 2 * k);
+        // (delta + a) + b (viterbi.rs:17).  Sequences that already ended compute garbage in their
+        // own column only; their last row is already in the history.
+#pragma unroll
+        for (int q = 0; q < TPT; q += 2) {
+            if (2 * k < nreal)
+                *reinterpret_cast<double2 *>(row0 + (size_t)(2 * k) * NS + q) =
+                    make_double2(best[q][2 * k] + x[q].x, best[q + 1][2 * k] + x[q + 1].x);
+            if (2 * k + 1 < NQ && 2 * k + 1 < nreal)
+                *reinterpret_cast<double2 *>(row0 + (size_t)(2 * k + 1) * NS + q) =
+                    make_double2(best[q][2 * k + 1] + x[q].y, best[q + 1][2 * k + 1] + x[q + 1].y);
+        }
+    }
+}
+
 // TQT = target states per thread (8 or 12; a warp owns TQT adjacent states); MAXT/MINB only set the register
 // budget (launch bounds).  The host picks TQT and S so that a CTA has a multiple of 4 warps: warps map to the
 // four SM sub-partitions by warp id, and with the per-step barrier an uneven split leaves sub-partitions idle.
@@ -199,7 +244,10 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = w % p.G, sg = w / p.G;
-    const int i0 = g * TQT;
+    const int i0 = g * TQT;                                  // first column slot of the group in sA / sEm
+    // first state (= delta row) of the group and how many of its TQT slots are real states
+    const int srow0 = p.nq_base ? g * p.nq_base + min(g, p.nq_rem) : i0;
+    const int nreal = p.nq_base ? p.nq_base + (g < p.nq_rem ? 1 : 0) : max(0, min(TQT, K - i0));
     const int s0 = sg * (32 * TPT) + lane * TPT;
     const uint32_t slab_bytes = (uint32_t)((size_t)K * NS * 8);
     const uint32_t row_bytes = (uint32_t)(Kp * 8);
@@ -213,7 +261,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         fence_proxy_async_smem();
         const uint32_t bytes = (uint32_t)((size_t)K * Kp * 8);
         mbar_expect_tx(sBar, bytes);
-        tma_bulk_g2s(sA, p.A, bytes, sBar);
+        tma_bulk_g2s(sA, p.At, bytes, sBar);
     }
     __syncthreads();
     mbar_wait(sBar, 0);
@@ -240,7 +288,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
             if (s < NS && t < sLen[s]) {
                 uint32_t o = o_cur[k];
                 if ((int64_t)o >= p.M) { *p.status = 3; o = 0; }   // index panic in the reference
-                tma_bulk_g2s(sEm + (size_t)s * EP, p.BT + (size_t)o * Kp, row_bytes, sBar + 1);
+                tma_bulk_g2s(sEm + (size_t)s * EP, p.BTt + (size_t)o * Kp, row_bytes, sBar + 1);
             }
         }
     };
@@ -309,35 +357,25 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         }
 
         for (int t = 1; t < Tmax; t++) {
-            double best[TPT][TQT];
-#pragma unroll
-            for (int q = 0; q < TPT; q++)
-#pragma unroll
-                for (int k = 0; k < TQT; k++) best[q][k] = neg_inf();
             const double *dcur = sD + (size_t)((t - 1) & 1) * K * NS + s0;
-            maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT>(dcur, NS, sA + i0, Kp, K, best);
-
-            mbar_wait(sBar + 1, em_phase);      // emission rows of step t have landed
-            em_phase ^= 1;
-            double *dnext = sD + (size_t)(t & 1) * K * NS + s0;
+            double *row0 = sD + (size_t)(t & 1) * K * NS + (size_t)srow0 * NS + s0;
             const double *e0 = sEm + (size_t)s0 * EP + i0;
-#pragma unroll
-            for (int k = 0; k < TQT / 2; k++) {
-                double2 x[TPT];
-#pragma unroll
-                for (int q = 0; q < TPT; q++) x[q] = *reinterpret_cast<const double2 *>(e0 + (size_t)q * EP + 2 * k);
-                // (delta + a) + b (viterbi.rs:17).  Sequences that already ended compute garbage in their
-                // own column only; their last row is already in the history.
-#pragma unroll
-                for (int q = 0; q < TPT; q += 2) {
-                    if (i0 + 2 * k < K)
-                        *reinterpret_cast<double2 *>(dnext + (size_t)(i0 + 2 * k) * NS + q) =
-                            make_double2(best[q][2 * k] + x[q].x, best[q + 1][2 * k] + x[q + 1].x);
-                    if (i0 + 2 * k + 1 < K)
-                        *reinterpret_cast<double2 *>(dnext + (size_t)(i0 + 2 * k + 1) * NS + q) =
-                            make_double2(best[q][2 * k + 1] + x[q].y, best[q + 1][2 * k + 1] + x[q + 1].y);
+            bool done = false;
+            if constexpr (TQT == 8 && TPT == 2) {
+                if (p.nq_base != 0) {
+                    // balanced split: this group's state count (warp-uniform); groups of fewer than 5 states take the
+                    // full-width path below (their unused slots hold -inf and are not stored)
+                    done = true;
+                    switch (nreal) {
+                        case 7: fwd_step<8, 2, 7>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal, 0); break;
+                        case 6: fwd_step<8, 2, 6>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal, 0); break;
+                        case 5: fwd_step<8, 2, 5>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal, 0); break;
+                        default: done = false;
+                    }
                 }
             }
+            if (!done) fwd_step<TQT, TPT, TQT>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal, p.pipe);
+            em_phase ^= 1;
             fence_proxy_async_smem();           // make this thread's delta writes visible to the TMA store
             if (tid == 0) tma_store_wait_read_all();   // slab t-1 has left the buffer step t+1 will overwrite
             __syncthreads();

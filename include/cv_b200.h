@@ -66,6 +66,14 @@ int64_t cv_hmm_nobs(const cv_hmm *h);          /* M = prod(bdims)               
 int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off,
                     int64_t B, uint32_t *path_out, double *score_out);
 
+/* Same call, and the device copies of the results are left in the caller's DEVICE buffers d_path_keep[N] /
+ * d_score_keep[B] as well (e.g. rows of an all-gather buffer: a multi-GPU caller decodes its slice from host memory
+ * and runs the device-side collective without uploading the paths again).  The device buffers are complete when the
+ * call returns. */
+int cv_decode_batch_keep(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off,
+                         int64_t B, uint32_t *path_out, double *score_out,
+                         uint32_t *d_path_keep, double *d_score_keep);
+
 /* Same, with every buffer already resident on the model's device; enqueued on
  * `stream` (a cudaStream_t, NULL = default stream) without host sync, except
  * that the status word is read back when `sync_status` != 0. */

@@ -287,3 +287,58 @@ def test_large_k_dataflow_stress():
         sc = _path_score(A, B, obs[off[b]:off[b + 1]], p[off[b]:off[b + 1]])
         assert np.float64(sc).tobytes() == np.float64(s[b]).tobytes() or (sc == -np.inf and s[b] == -np.inf)
     h.close()
+
+
+@pytest.mark.parametrize("K", [13, 37, 45, 47, 61])
+def test_forward_kernel_variants_equal_oracle(K):
+    """The forward tile kernel's variants (cv_debug_set_fwd_variant: 1 = software-pipelined loop, 2 = balanced state
+    split with slot-permuted logA / logB^T copies, 3 = both) against the oracle, ragged lengths, -inf entries."""
+    rng = np.random.default_rng(4400 + K)
+    M = 40
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.15)
+    obs, off = random_batch(rng, 9000, M, 1, 40)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        L.cv_debug_set_chain_max_batch(0)
+        for v in (0, 1, 2, 3):
+            L.cv_debug_set_fwd_variant(v)
+            p, s = cv.decode_batch(h, obs, off)
+            assert (p == rp).all() and s.tobytes() == rs.tobytes(), f"variant {v}"
+    finally:
+        L.cv_debug_set_fwd_variant(0)
+        L.cv_debug_set_chain_max_batch(-1)
+    h.close()
+
+
+def test_decode_batch_keep_leaves_device_copies():
+    """cv_decode_batch_keep: host results as cv_decode_batch, and the same results in the caller's device buffers
+    (rows of an all-gather buffer in the multi-GPU path).  Streamed and per-chunk host paths."""
+    import ctypes as C
+
+    import torch
+    rng = np.random.default_rng(31)
+    K, M = 45, 60
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    obs, off = random_batch(rng, 60000, M, 1, 30)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    hd = h.device_handle(torch.cuda.current_device())
+    N, Bn = len(obs), len(off) - 1
+    paths, scores = np.zeros(N, np.uint32), np.zeros(Bn)
+    try:
+        for chunks, streamed in ((4, 1), (3, 0), (1, 1)):
+            L.cv_debug_set_chunks(chunks)
+            L.cv_debug_set_pipeline(-1, streamed)
+            d_path = torch.full((N,), -1, dtype=torch.int32, device="cuda")
+            d_score = torch.zeros(Bn, dtype=torch.float64, device="cuda")
+            cv._lib.check(L.cv_decode_batch_keep(hd, obs.ctypes.data, off.ctypes.data, Bn, paths.ctypes.data,
+                                                 scores.ctypes.data, d_path.data_ptr(), d_score.data_ptr()))
+            assert (paths == rp).all() and scores.tobytes() == rs.tobytes()
+            assert (d_path.cpu().numpy().view(np.uint32) == rp).all() and d_score.cpu().numpy().tobytes() == rs.tobytes()
+    finally:
+        L.cv_debug_set_chunks(-1)
+        L.cv_debug_set_pipeline(1, 1)
+    h.close()
