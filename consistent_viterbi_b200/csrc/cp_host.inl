@@ -54,6 +54,16 @@ struct CpRun {
     int sweep_blocks_per_sm = 8;                 // co-resident CTAs of the sweep kernel (occupancy query)
     bool poll = true;                            // CV_CP_HOSTPOLL=0: copy + stream synchronise instead
     psi_t *d_F = nullptr; int *d_entry = nullptr; uint64_t *d_sol = nullptr;
+    // leaf batch (cp_leaf_group): the siblings of the last component evaluated together
+    bool leaf_batch = false;
+    int nleaf = 0;                               // positions of the last component (= its sweeps)
+    double *d_leaf_last = nullptr;               // [K siblings][nleaf][K] last row of every sibling's sweeps
+    psi_t *d_c2 = nullptr;                       // [K siblings][nleaf] C2 backpointers of every sibling
+    double *d_leaf_terms = nullptr, *d_leaf_ub = nullptr;   // [K][leaf_term_stride], [K]
+    long long leaf_term_stride = 0;
+    int32_t *d_prev_seg = nullptr, *d_leaf_idx = nullptr; int64_t *d_leaf_pos = nullptr;
+    SumWs leaf_ws;
+    double *h_leaf_ub = nullptr;                 // pinned, [K]
     double *h_ub = nullptr;                      // pinned
     int err = CV_OK;
     size_t smem;
@@ -61,39 +71,44 @@ struct CpRun {
 
 // ub = ((0.0 + x_0) + x_1) + ... in order (cp.rs:103-116): plain loop for short lists, the block-structured
 // exact-order kernels for long ones, the single-CTA binade scan beyond SUM_MAX_BLOCKS blocks.
+// nlists > 1: a batch of lists (leaf batch), list y at terms + y * term_stride with its block workspace at
+// + y * ws.blk_stride, result y to ub.dev[y] (ub.host must be null); every kernel runs with gridDim.y = nlists.
 int cp_launch_sum(const double *terms, int nterms, const UbSink &ub, unsigned int *counter, const SumWs &ws, bool have_stats,
-                  int force, cudaStream_t st, const PeerWait &pw)
+                  int force, cudaStream_t st, const PeerWait &pw, int nlists = 1, long long term_stride = 0)
 {
     const int nblk = (nterms + SUM_BLK - 1) / SUM_BLK;
     int kind = nterms < g_sum_parallel_min ? 0 : (nblk > SUM_MAX_BLOCKS ? 2 : 1);
     if (force >= 0) kind = (force == 1 && nblk > SUM_MAX_BLOCKS) ? 2 : force;
     if (kind == 1 && nblk == 0) kind = 0;
-    const PeerWait none{nullptr, 1, 0u, nullptr};
-    if (kind == 0) { cp_sum_kernel<<<1, 256, 0, st>>>(terms, nterms, ub, counter, pw); g_launches++; }
+    const SumBatch batch{nlists > 1 ? term_stride : 0, nlists > 1 ? ws.blk_stride : 0};
+    const unsigned ny = (unsigned)std::max(nlists, 1);
+    if (kind == 0) { cp_sum_kernel<<<dim3(1, ny), 256, 0, st>>>(terms, nterms, ub, counter, pw, batch); g_launches++; }
     else if (kind == 2) {
         if (pw.R > 1) { cp_peer_wait_kernel<<<1, 32, 0, st>>>(pw); g_launches++; }
-        cp_sum_exact_kernel<<<1, QS_THREADS, 0, st>>>(terms, nterms, ub, counter);
+        cp_sum_exact_kernel<<<dim3(1, ny), QS_THREADS, 0, st>>>(terms, nterms, ub, counter, batch);
         g_launches++;
     } else {
-        if (!have_stats || pw.R > 1) { cp_sum_stats_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bflag, pw); g_launches++; }
+        if (!have_stats || pw.R > 1) { cp_sum_stats_kernel<<<dim3(nblk, ny), SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, ws.bflag, pw, batch); g_launches++; }
         const double *bpre = nullptr;
-        if (nblk >= SUM_PREFIX_MIN) { cp_sum_prefix_kernel<<<1, 1024, 0, st>>>(ws.bsum, nblk, ws.bpre); g_launches++; bpre = ws.bpre; }
-        cp_sum_blockfn_kernel<<<nblk, SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, bpre, ws.bexp, ws.bfn);
-        cp_sum_chain_kernel<<<1, SUMC_THREADS, sum_chain_smem_bytes(nblk), st>>>(terms, nterms, nblk, ws.bflag, ws.bexp, ws.bfn, ub, counter);
+        if (nblk >= SUM_PREFIX_MIN) { cp_sum_prefix_kernel<<<dim3(1, ny), 1024, 0, st>>>(ws.bsum, nblk, ws.bpre, batch); g_launches++; bpre = ws.bpre; }
+        cp_sum_blockfn_kernel<<<dim3(nblk, ny), SUM_BLK, 0, st>>>(terms, nterms, ws.bsum, bpre, ws.bexp, ws.bfn, batch);
+        cp_sum_chain_kernel<<<dim3(1, ny), SUMC_THREADS, sum_chain_smem_bytes(nblk), st>>>(terms, nterms, nblk, ws.bflag, ws.bexp, ws.bfn, ub, counter, batch);
         g_launches += 2;
     }
-    (void)none;
     CUDA_TRY(cudaGetLastError());
     return CV_OK;
 }
 
-int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
+// leaf_nsib > 0: leaf batch -- the sweeps of siblings 0 .. leaf_nsib-1 in one launch, last rows only (cp_kernels.cuh)
+int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode, int leaf_nsib = 0)
 {
     if (nseg <= 0) return CV_OK;
     CpSweepArgs a;
     a.seg_from = r.d_seg_from + seg_begin; a.seg_len = r.d_seg_len + seg_begin;
     a.nseg = (int)nseg; a.ntiles = (int)((nseg + 63) / 64); a.node = node; a.init_mode = init_mode;
     a.tile_counter = r.d_counter;
+    a.leaf_nsib = leaf_nsib; a.leaf_last = r.d_leaf_last;
+    const int64_t ntask = nseg * std::max(leaf_nsib, 1);
     // (the segment counter is zeroed by the previous node's sum kernel / the set-up memset)
     if (r.p.K > SMALL_K_MAX) {                                  // generic path: states looped per lane, logA from L2
         const size_t smem_g = (size_t)CPG_WARPS * 2 * r.p.Kp * sizeof(double);
@@ -109,7 +124,7 @@ int cp_sweep(CpRun &r, int64_t seg_begin, int64_t nseg, int node, int init_mode)
                           (size_t)CPW_WARPS * 2 * 16 * r.p.Kp;              // up to two segments per warp
     const bool fullwarp = g_tune.cp_fullwarp != 0;    // A/B hook: one segment per warp for every K
     const int64_t segs_per_block = (int64_t)CPW_WARPS * (r.p.Kp <= 16 && !fullwarp ? 2 : 1);
-    const int grid = (int)std::min<int64_t>((nseg + segs_per_block - 1) / segs_per_block, (int64_t)r.h->num_sms * r.sweep_blocks_per_sm);
+    const int grid = (int)std::min<int64_t>((ntask + segs_per_block - 1) / segs_per_block, (int64_t)r.h->num_sms * r.sweep_blocks_per_sm);
     const bool regs = r.p.Kp == 8 * ((r.p.K + 7) / 8);       // register-resident logA column needs Kp = 4 * KQ
     const int kq = regs ? (r.p.K + 7) / 8 : 9;
     if (fullwarp && kq == 1) cp_sweep_chain_kernel<1, 2><<<grid, 32 * CPW_WARPS, smem_c, r.st>>>(r.p, a);
@@ -165,6 +180,80 @@ int cp_backtrack(CpRun &r, double obj)
     return CV_OK;
 }
 
+// ---- leaf batch ---------------------------------------------------------------------------------------------------
+// The K nodes of the last component (cp.rs:96-124 with comp = ncomp-1) are leaves: each runs its sweeps, its bound
+// and, if the bound beats best_obj, the backtrack; they all sweep the same segments and overwrite the same rows.
+// Instead of K round trips of five dependent launches, their bounds are evaluated together from one batched sweep
+// (last rows only), one batched terms launch and one batched exact-order sum; the host then walks the K bounds in
+// the reference's order (explored_nodes, pruning test, best_obj) and replays at most two siblings on the real
+// delta / psi state: the last one whose bound improved best_obj (its backtrack reads that state) and the last
+// sibling evaluated (the state the reference leaves behind).  C2 backpointers of the other siblings -- one psi
+// column each -- are written from the batch in sibling order around the replays, so every psi entry holds what
+// the sequential loop would have left at that moment.  Bit-identical to the node-by-node loop (tests/test_cp_gpu.py
+// runs both and compares the complete state).
+int cp_leaf_group(CpRun &r, int32_t comp)
+{
+    const int K = r.p.K;
+    const int64_t nseg = r.seg_off[comp + 1] - r.seg_off[comp];
+    const int nterms = (int)r.cons_off[comp + 1];
+    int nb = K;
+    if (r.max_nodes) nb = (int)std::min<uint64_t>((uint64_t)K, r.max_nodes - r.explored);
+    if (nb <= 0) return CV_OK;
+    int rc;
+    if ((rc = cp_sweep(r, r.seg_off[comp], nseg, 0, 0, nb))) return rc;
+    CpLeafArgs a;
+    a.term_pos = r.d_cons_pos; a.term_comp = r.d_term_comp; a.prev_seg = r.d_prev_seg; a.leaf_idx = r.d_leaf_idx;
+    a.leaf_last = r.d_leaf_last; a.c2_out = r.d_c2; a.terms = r.d_leaf_terms; a.bsum = r.leaf_ws.bsum; a.bflag = r.leaf_ws.bflag;
+    a.nterms = nterms; a.nseg = (int)nseg; a.nleaf = r.nleaf; a.last = comp;
+    a.term_stride = r.leaf_term_stride; a.blk_stride = r.leaf_ws.blk_stride;
+    cp_leaf_terms_kernel<<<dim3((unsigned)((nterms + SUM_BLK - 1) / SUM_BLK), (unsigned)nb), SUM_BLK, 0, r.st>>>(r.p, a);
+    g_launches++;
+    const UbSink sink{r.d_leaf_ub, nullptr, nullptr, 0ULL};
+    if ((rc = cp_launch_sum(r.d_leaf_terms, nterms, sink, r.d_counter, r.leaf_ws, true, g_sum_force, r.st,
+                            PeerWait{nullptr, 1, 0u, nullptr}, nb, r.leaf_term_stride)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(r.h_leaf_ub, r.d_leaf_ub, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, r.st));
+    CUDA_TRY(cudaStreamSynchronize(r.st));
+    // the reference's loop over the siblings, on the K bounds (cp.rs:96-123)
+    int win = -1; double best = r.best_obj, win_ub = 0.0;
+    for (int s = 0; s < nb; s++) {
+        r.explored++;
+        r.steps += r.seg_steps[comp];
+        const double ub = r.h_leaf_ub[s];
+        if (r.h->cp_ub.size() < (1u << 20)) r.h->cp_ub.push_back(ub);
+        if (std::isnan(ub)) return fail(CV_ERR_NAN, "NaN upper bound");
+        if (ub > best) { best = ub; win = s; win_ub = ub; }
+    }
+    const unsigned gl = (unsigned)((r.nleaf + 127) / 128);
+    auto apply_c2 = [&](int s0, int s1) {
+        if (s1 <= s0) return;
+        cp_leaf_apply_c2_kernel<<<gl, 128, 0, r.st>>>(r.p, r.d_leaf_pos, r.nleaf, r.d_c2, s0, s1);
+        g_launches++;
+    };
+    auto replay = [&](int s) -> int {                                  // the sibling's viterbi_from calls on the real state
+        int rc2 = cp_sweep(r, r.seg_off[comp], nseg, s, 0);
+        if (rc2) return rc2;
+        const int64_t nfix = r.fix_off[comp + 1] - r.fix_off[comp];
+        cp_fixup_kernel<<<(unsigned)((std::max<int64_t>(nfix, 1) + 127) / 128), 128, 0, r.st>>>(
+            r.p, r.d_fix_pos + r.fix_off[comp], (int)nfix, comp, s, r.lo, r.hi);
+        g_launches++;
+        return CV_OK;
+    };
+    int done = 0;                                                      // siblings whose psi columns are in place
+    if (win >= 0) {
+        apply_c2(0, win);
+        if ((rc = replay(win))) return rc;
+        if ((rc = cp_backtrack(r, win_ub))) return rc;                 // cp.rs:121
+        done = win + 1;
+    }
+    if (win != nb - 1) {
+        apply_c2(done, nb - 1);
+        if ((rc = replay(nb - 1))) return rc;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CV_OK;
+}
+
 // cp.rs:95-126
 int cp_solve_r(CpRun &r, int32_t comp)
 {
@@ -173,6 +262,7 @@ int cp_solve_r(CpRun &r, int32_t comp)
     const int64_t nfix = r.fix_off[comp + 1] - r.fix_off[comp];
     const int nterms = (int)r.cons_off[comp + 1];
     const int nlocal = (int)r.lterm_off[comp + 1];
+    if (r.leaf_batch && comp + 1 == r.ncomp && nseg > 0) return cp_leaf_group(r, comp);
     for (int state = 0; state < K; state++) {
         if (r.max_nodes && r.explored >= r.max_nodes) break;            // builder-added, deterministic budget
         r.explored++;                                                    // cp.rs:97
@@ -506,6 +596,46 @@ static int cp_solve_impl(cv_hmm *h, cv_cp_dist *dx, const uint32_t *obs, const u
     }
     CUDA_TRY(cudaMemsetAsync(r.d_sol, 0, sizeof(uint64_t) * (size_t)N, st));       // best_sol = 0 (cp.rs:29)
     if ((rc = r.sum_ws.bind(b[14], cons_pos.size()))) return rc;
+    // ---- leaf batch: scratch for the K siblings of the last component (see cp_leaf_group) ----
+    {
+        const int32_t last = ncomp - 1;
+        const int64_t nleaf = ncomp > 0 ? r.seg_off[ncomp] - r.seg_off[last] : 0;
+        const size_t scratch = (size_t)K * (size_t)nleaf * K * sizeof(double) + (size_t)K * (cons_pos.size() + 1) * sizeof(double);
+        r.leaf_batch = g_tune.cp_leaf_batch && !sharded && K <= SMALL_K_MAX && K >= 2 && nleaf > 0 &&
+                       nleaf * (int64_t)K < 0x7fffffffLL && scratch < ((size_t)4 << 30);
+        if (r.leaf_batch) {
+            const int64_t *lf = seg_from.data() + r.seg_off[last];             // the last component's sweeps, device order
+            std::vector<int32_t> seg_of_pos((size_t)N, -1);
+            for (int64_t g = 0; g < nleaf; g++) seg_of_pos[(size_t)lf[g]] = (int32_t)g;
+            // nearest clamped position at or below every row
+            std::vector<int32_t> prev_seg(cons_pos.size(), -1), leaf_idx(cons_pos.size(), -1);
+            std::vector<int64_t> below((size_t)N, -1);
+            int64_t lastc = -1;
+            for (int64_t t = 0; t < N; t++) { if (comp[t] >= 0) lastc = t; below[(size_t)t] = lastc; }
+            for (size_t k = 0; k < cons_pos.size(); k++) {
+                const int64_t t = cons_pos[k];
+                if (term_comp[k] == last) leaf_idx[k] = seg_of_pos[(size_t)t];
+                if (t > 0) {
+                    const int64_t q = below[(size_t)(t - 1)];
+                    if (q >= 0 && comp[q] == last) prev_seg[k] = seg_of_pos[(size_t)q];
+                }
+            }
+            std::vector<int32_t> both(prev_seg); both.insert(both.end(), leaf_idx.begin(), leaf_idx.end());
+            int32_t *d32 = nullptr;
+            if ((rc = upload(b[15], both, &d32, st))) return rc;
+            r.d_prev_seg = d32; r.d_leaf_idx = d32 + prev_seg.size();
+            r.nleaf = (int)nleaf;
+            r.d_leaf_pos = r.d_seg_from + r.seg_off[last];
+            r.leaf_term_stride = (long long)((cons_pos.size() + SUM_BLK) / SUM_BLK * SUM_BLK);
+            if ((rc = b[16].ensure(sizeof(double) * (size_t)K * (size_t)nleaf * K))) return rc;
+            if ((rc = b[17].ensure(sizeof(psi_t) * (size_t)K * (size_t)nleaf + 64))) return rc;
+            if ((rc = b[18].ensure(sizeof(double) * ((size_t)K * (size_t)r.leaf_term_stride + K) + 64))) return rc;
+            r.d_leaf_last = (double *)b[16].p; r.d_c2 = (psi_t *)b[17].p;
+            r.d_leaf_terms = (double *)b[18].p; r.d_leaf_ub = r.d_leaf_terms + (size_t)K * (size_t)r.leaf_term_stride;
+            if ((rc = r.leaf_ws.bind(b[19], cons_pos.size(), (size_t)K))) return rc;
+            r.h_leaf_ub = (double *)((char *)h->pinned_status + 1024);
+        }
+    }
     g_sum_force = g_tune.cp_sum;
     r.h_ub = (double *)h->pinned_status + 1;
     r.h_ub[0] = r.h_ub[1] = r.h_ub[2] = 0.0;

@@ -52,6 +52,12 @@ struct CpSweepArgs {
     int node;                 // clamped state (ignored when init_mode)
     int init_mode;            // 1: rows start from delta[seg_from] as stored (init_viterbi prefix)
     unsigned int *tile_counter;
+    // Leaf batch (cp_host.inl, cp_leaf_group): the K sibling nodes of the last component sweep the same segments
+    // and overwrite the same rows, so their bounds can be evaluated together.  leaf_nsib > 0: task r = (sibling
+    // r / nseg, segment r % nseg), clamped state = sibling; delta / psi in global memory are NOT touched, only the
+    // last delta row of each sweep is kept: leaf_last[(sibling * nseg + segment) * K + i].
+    int leaf_nsib;
+    double *leaf_last;
 };
 
 __host__ __device__ inline size_t cp_sweep_smem_bytes(int K, int Kp)
@@ -101,16 +107,19 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
     // Segments are sorted longest first and dealt to the warps round-robin (static: no claim round trip); the next
     // segment's start / length are fetched while the current one is swept.
     const int stride = (int)gridDim.x * CPW_WARPS * GP;
+    const bool leaf = a.leaf_nsib > 0;
+    const int ntask = leaf ? a.nseg * a.leaf_nsib : a.nseg;                   // host keeps nseg * nsib < 2^31
     int r = ((int)blockIdx.x * CPW_WARPS + (int)(threadIdx.x >> 5)) * GP + grp;
     int64_t from_n = 0; int len_n = -1;
-    if (r < a.nseg) { from_n = __ldg(a.seg_from + r); len_n = __ldg(a.seg_len + r); }
+    if (r < ntask) { const int g = leaf ? r % a.nseg : r; from_n = __ldg(a.seg_from + g); len_n = __ldg(a.seg_len + g); }
     for (;; r += stride) {
-        if (r - grp >= a.nseg) break;                                         // warp-uniform
-        const bool valid = r < a.nseg;
+        if (r - grp >= ntask) break;                                          // warp-uniform
+        const bool valid = r < ntask;
         const int64_t from = from_n;
         const int len = len_n;
+        const int node = leaf ? r / a.nseg : a.node;
         from_n = 0; len_n = -1;
-        if (r + stride < a.nseg) { from_n = __ldg(a.seg_from + r + stride); len_n = __ldg(a.seg_len + r + stride); }
+        if (r + stride < ntask) { const int g = leaf ? (r + stride) % a.nseg : r + stride; from_n = __ldg(a.seg_from + g); len_n = __ldg(a.seg_len + g); }
         const int lenmax = __reduce_max_sync(0xffffffffu, len);
 
         double d[NSL];
@@ -122,8 +131,8 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
                 if (a.init_mode) {
                     d[s] = (i < K) ? p.delta[(size_t)from * K + i] : neg_inf();
                 } else {
-                    d[s] = (i == a.node) ? 0.0 : neg_inf();                      // cp.rs:33-34
-                    if (i < K) p.delta[(size_t)from * K + i] = d[s];
+                    d[s] = (i == node) ? 0.0 : neg_inf();                        // cp.rs:33-34
+                    if (i < K && !leaf) p.delta[(size_t)from * K + i] = d[s];
                 }
             }
             if (i < Kp) { sdw[i] = (i < K) ? d[s] : neg_inf(); sdw[Kp + i] = neg_inf(); }
@@ -173,12 +182,20 @@ __global__ void __launch_bounds__(32 * CPW_WARPS) cp_sweep_chain_kernel(const Cp
             for (int s = 0; s < NSL; s++) {
                 const int i = sub + 32 * s;
                 if (act && i < K) {
-                    p.delta[(size_t)t * K + i] = v[s];
-                    p.psi[(size_t)t * K + i] = (psi_t)idx[s];
+                    if (!leaf) {
+                        p.delta[(size_t)t * K + i] = v[s];
+                        p.psi[(size_t)t * K + i] = (psi_t)idx[s];
+                    }
                     sdw[(k & 1) * Kp + i] = v[s];
+                    d[s] = v[s];
                 }
             }
             __syncwarp();
+        }
+        if (leaf && valid) {                                                      // the sweep's last row (the reset row when len = 0)
+            double *out = a.leaf_last + ((size_t)node * a.nseg + (size_t)(r % a.nseg)) * K;
+#pragma unroll
+            for (int s = 0; s < NSL; s++) { const int i = sub + 32 * s; if (i < K) out[i] = d[s]; }
         }
     }
 }
@@ -305,6 +322,11 @@ __device__ __forceinline__ void peer_wait_block(const PeerWait &w)
     __syncthreads();
 }
 
+// Batched form (all sum kernels): blockIdx.y selects list y of a batch -- terms + y * batch.term_stride, block
+// workspace + y * batch.blk_stride, result to ub_out.dev[y]; a single list is batch = {0, 0}, gridDim.y = 1.
+struct SumBatch { long long term_stride, blk_stride; };
+__device__ __forceinline__ UbSink ub_sink_of(const UbSink &o) { UbSink r = o; r.dev = o.dev + blockIdx.y; return r; }
+
 // ---- block statistics for the block-structured exact sum (further down) -------------------------------------
 // Every SUM_BLK consecutive terms form a block; a block's plain f64 sum (any order -- it only PREDICTS the
 // binade of the running sum) and its special-value flags (1 = positive or NaN term, 2 = -inf term).
@@ -354,10 +376,83 @@ __global__ void __launch_bounds__(SUM_BLK) cp_terms_kernel(const CpParams p, con
     sum_block_stats(term, blockIdx.x, bsum, bflag);
 }
 
+// ---- leaf batch: the bound terms of all sibling nodes of the last component in one launch ------------------------
+// Sibling s (component `last` clamped to state s; components < last as in p.choice) would, node by node, run its
+// sweeps, the C1/C2 fix-ups and cp_terms_kernel.  Here nothing is written to delta / psi: what the sibling's sweeps
+// WOULD have left in the rows a term reads comes from leaf_last (cp_sweep_chain_kernel, leaf mode):
+//   row t-1 of a clamped position t is the last row of the sweep that starts at the nearest clamped position below
+//   t; prev_seg[k] = that sweep's index when it belongs to the last component (sibling-specific), else -1 (the row
+//   in global memory is what every sibling sees);
+//   psi[t][s_c]: C2 when t itself is a position of the last component (first-argmax over row t-1, cp.rs:35-41),
+//   C1 when t-1 is one (psi[t][choice] = s, cp.rs:43-45), else the stored entry.
+// The C2 results are kept (c2_out[s * nleaf + leaf_idx[k]]) and written to psi later, sibling by sibling in the
+// reference's order (cp_leaf_apply_c2_kernel).  grid = (blocks of SUM_BLK terms, siblings).
+struct CpLeafArgs {
+    const int64_t *term_pos; const int32_t *term_comp;   // [nterms] as for cp_terms_kernel
+    const int32_t *prev_seg;                              // [nterms] leaf sweep that owns row t-1, or -1
+    const int32_t *leaf_idx;                              // [nterms] index among the last component's positions, or -1
+    const double *leaf_last;                              // [nsib][nseg][K]
+    psi_t *c2_out;                                        // [nsib][nleaf]
+    double *terms; double *bsum; int *bflag;              // [nsib][term_stride], [nsib][blk_stride] x 2
+    int nterms, nseg, nleaf, last;
+    long long term_stride, blk_stride;
+};
+
+__global__ void __launch_bounds__(SUM_BLK) cp_leaf_terms_kernel(const CpParams p, const CpLeafArgs a)
+{
+    const int k = blockIdx.x * SUM_BLK + threadIdx.x, sib = blockIdx.y;
+    double term = 0.0;
+    if (k < a.nterms) {
+        const int64_t t = a.term_pos[k];
+        const int c = a.term_comp[k];
+        const int st = c == a.last ? sib : p.choice[c];
+        const int K = p.K, Kp = p.Kp;
+        const double b = p.BT[(size_t)p.obs[t] * Kp + st];
+        if (t == 0) {
+            term = p.Pi[st] + b;
+        } else {
+            const int g = a.prev_seg[k];
+            const double *prev = g >= 0 ? a.leaf_last + ((size_t)sib * a.nseg + (size_t)g) * K : p.delta + (size_t)(t - 1) * K;
+            const bool stt = p.start[t] != 0;
+            int sf;
+            if (c == a.last) {                               // C2 (cp_fixup_kernel): psi[t][sib] = first-argmax_j(prev[j] + tr_j(sib))
+                double bv = 0.0; int bi = 0;
+                for (int j = 0; j < K; j++) {
+                    const double v = prev[j] + (stt ? p.Pi[sib] : p.A[(size_t)j * Kp + sib]);
+                    if (j == 0 || v > bv) { bv = v; bi = j; }
+                }
+                sf = bi;
+                a.c2_out[(size_t)sib * a.nleaf + a.leaf_idx[k]] = (psi_t)bi;
+            } else if (p.comp[t - 1] == a.last) {            // C1: psi[t][choice[c]] = sib, and st = choice[c]
+                sf = sib;
+            } else {
+                sf = p.psi[(size_t)t * K + st];
+            }
+            const double arc = (stt ? p.Pi[st] : p.A[(size_t)sf * Kp + st]) + b;
+            term = prev[sf] + arc;
+        }
+        a.terms[(size_t)sib * a.term_stride + k] = term;
+    }
+    sum_block_stats(term, blockIdx.x, a.bsum + (size_t)sib * a.blk_stride, a.bflag + (size_t)sib * a.blk_stride);
+}
+
+// psi[pos][s] = C2 result of sibling s for s in [s0, s1) at every position of the last component (pos != 0):
+// the entries the siblings' viterbi_from calls leave behind, one column each (cp.rs:35-41).
+__global__ void cp_leaf_apply_c2_kernel(const CpParams p, const int64_t *leaf_pos, int nleaf, const psi_t *c2, int s0, int s1)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nleaf) return;
+    const int64_t pos = leaf_pos[i];
+    if (pos == 0) return;
+    for (int s = s0; s < s1; s++) p.psi[(size_t)pos * p.K + s] = c2[(size_t)s * nleaf + i];
+}
+
 // block statistics of an existing term list (debug hook / lists not produced by cp_terms_kernel)
 __global__ void __launch_bounds__(SUM_BLK) cp_sum_stats_kernel(const double *terms, int nterms, double *bsum, int *bflag,
-                                                             const PeerWait pw)
+                                                             const PeerWait pw, const SumBatch batch)
 {
+    terms += (size_t)blockIdx.y * batch.term_stride;
+    bsum += (size_t)blockIdx.y * batch.blk_stride; bflag += (size_t)blockIdx.y * batch.blk_stride;
     peer_wait_block(pw);
     const int k = blockIdx.x * SUM_BLK + threadIdx.x;
     sum_block_stats(k < nterms ? terms[k] : 0.0, blockIdx.x, bsum, bflag);
@@ -366,9 +461,11 @@ __global__ void __launch_bounds__(SUM_BLK) cp_sum_stats_kernel(const double *ter
 // ub = ((0.0 + term_0) + term_1) + ...  exactly in order (cp.rs:103,109,114).  The order is part of the result,
 // so one thread performs the adds; the rest of the block streams the terms through a double-buffered shared
 // memory stage and the adder keeps 16 terms in registers ahead of the dependent DADD chain (8 clk per term).
-__global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, const UbSink ub_out,
-                                                     unsigned int *reset_counter, const PeerWait pw)
+__global__ void __launch_bounds__(256) cp_sum_kernel(const double *terms, int nterms, const UbSink ub_out_,
+                                                     unsigned int *reset_counter, const PeerWait pw, const SumBatch batch)
 {
+    terms += (size_t)blockIdx.y * batch.term_stride;
+    const UbSink ub_out = ub_sink_of(ub_out_);
     peer_wait_block(pw);
     if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
     constexpr int CH = 2048;
@@ -448,9 +545,11 @@ __device__ __forceinline__ QFn qfn_elem(double x, int e)
 constexpr int QS_THREADS = 1024, QS_EPT = 8;
 constexpr int QS_SERIAL_HEAD = 2048;                // leading terms summed by the plain loop
 
-__global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *terms, int nterms, const UbSink ub_out,
-                                                                  unsigned int *reset_counter)
+__global__ void __launch_bounds__(QS_THREADS) cp_sum_exact_kernel(const double *terms, int nterms, const UbSink ub_out_,
+                                                                  unsigned int *reset_counter, const SumBatch batch)
 {
+    terms += (size_t)blockIdx.y * batch.term_stride;
+    const UbSink ub_out = ub_sink_of(ub_out_);
     if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
     __shared__ double s_sh; __shared__ int pos_sh, cross_sh, mode_sh;
     __shared__ unsigned long long qbefore_sh, qend_sh;
@@ -599,8 +698,9 @@ constexpr int SUM_PREFIX_MIN = 2048;                  // from here on the approx
 
 // approximate exclusive prefix of the block sums for long lists (short ones sum the earlier blocks inside
 // cp_sum_blockfn_kernel): every thread a contiguous stretch, then a scan of the 1024 partial sums
-__global__ void __launch_bounds__(1024) cp_sum_prefix_kernel(const double *bsum, int nblk, double *bpre)
+__global__ void __launch_bounds__(1024) cp_sum_prefix_kernel(const double *bsum, int nblk, double *bpre, const SumBatch batch)
 {
+    bsum += (size_t)blockIdx.y * batch.blk_stride; bpre += (size_t)blockIdx.y * batch.blk_stride;
     __shared__ double part[1024];
     const int tid = threadIdx.x, per = (nblk + 1023) / 1024, lo = min(tid * per, nblk), hi = min(lo + per, nblk);
     double acc = 0.0;
@@ -618,8 +718,11 @@ __global__ void __launch_bounds__(1024) cp_sum_prefix_kernel(const double *bsum,
 }
 
 __global__ void __launch_bounds__(SUM_BLK) cp_sum_blockfn_kernel(const double *terms, int nterms, const double *bsum,
-                                                               const double *bpre, int *bexp, QFn *bfn)
+                                                               const double *bpre, int *bexp, QFn *bfn, const SumBatch batch)
 {
+    terms += (size_t)blockIdx.y * batch.term_stride;
+    bsum += (size_t)blockIdx.y * batch.blk_stride; bexp += (size_t)blockIdx.y * batch.blk_stride; bfn += (size_t)blockIdx.y * batch.blk_stride;
+    if (bpre) bpre += (size_t)blockIdx.y * batch.blk_stride;
     __shared__ double ws[SUM_BLK / 32]; __shared__ int e_sh; __shared__ QFn wagg[SUM_BLK / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     double acc = 0.0;
@@ -677,12 +780,14 @@ __device__ __forceinline__ bool qfn_try(double &s, int e, const QFn f)
 // workspace of the block-structured sum, carved out of one device buffer
 struct SumWs {
     double *bsum = nullptr, *bpre = nullptr; QFn *bfn = nullptr; int *bflag = nullptr, *bexp = nullptr;
-    template <class Buf> int bind(Buf &b, size_t nterms)
+    long long blk_stride = 0;                           // entries per list when the workspace holds a batch of lists
+    template <class Buf> int bind(Buf &b, size_t nterms, size_t nlists = 1)
     {
-        const size_t nblk = (nterms + SUM_BLK - 1) / SUM_BLK + 1;
+        const size_t per = (nterms + SUM_BLK - 1) / SUM_BLK + 1, nblk = per * nlists;
         const int rc = b.ensure(nblk * (2 * sizeof(double) + sizeof(QFn) + 2 * sizeof(int)) + 64);
         if (rc) return rc;
         bfn = (QFn *)b.p; bsum = (double *)(bfn + nblk); bpre = bsum + nblk; bflag = (int *)(bpre + nblk); bexp = bflag + nblk;
+        blk_stride = (long long)per;
         return 0;
     }
 };
@@ -699,8 +804,12 @@ __host__ __device__ inline size_t sum_chain_smem_bytes(int nblk)
 // Lists longer than SUM_TILE_BLOCKS blocks go through in tiles, the running sum carried from tile to tile.
 __global__ void __launch_bounds__(SUMC_THREADS) cp_sum_chain_kernel(const double *terms, int nterms, int nblk,
                                                                    const int *bflag, const int *bexp, const QFn *bfn,
-                                                                   const UbSink ub_out, unsigned int *reset_counter)
+                                                                   const UbSink ub_out_, unsigned int *reset_counter,
+                                                                   const SumBatch batch)
 {
+    terms += (size_t)blockIdx.y * batch.term_stride;
+    bflag += (size_t)blockIdx.y * batch.blk_stride; bexp += (size_t)blockIdx.y * batch.blk_stride; bfn += (size_t)blockIdx.y * batch.blk_stride;
+    const UbSink ub_out = ub_sink_of(ub_out_);
     if (threadIdx.x == 0 && reset_counter) *reset_counter = 0u;
     constexpr int MAXG = SUM_TILE_BLOCKS / 32;
     extern __shared__ __align__(16) unsigned char sumc_raw[];

@@ -184,7 +184,7 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     CUDA_TRY(cudaEventCreate(&h->ev0));
     CUDA_TRY(cudaEventCreate(&h->ev1));
     CUDA_TRY(cudaEventCreate(&h->ev2));
-    CUDA_TRY(cudaMallocHost(&h->pinned_status, 64));
+    CUDA_TRY(cudaMallocHost(&h->pinned_status, 2048));     // [0, 64): status / bound words, [1024, 2048): leaf-batch bounds
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     for (auto &w : h->ws) {
         CUDA_TRY(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
@@ -377,7 +377,9 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     int tpt = g_tune.tp;
     if (h->TQT != 8) tpt = 2;
     while (S > 1 && (B + 32 * tpt * S - 1) / (32 * tpt * S) < 4 * (int64_t)h->num_sms) S--;
-    size_t smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S);
+    // fwd_variant bit 2: emissions read straight from L2 (no shared-memory stage): three CTAs per SM at the POS shape
+    const int emd = ((g_tune.fwd_variant & 4) && h->TQT == 8 && tpt == 2 && S == 1 && 32 * G <= 192) ? 1 : 0;
+    size_t smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S, emd);
     while (smem > 220 * 1024 && S > 1) { S--; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
     if (smem > 220 * 1024 && tpt == 4) { tpt = 2; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
     const int NS = 32 * tpt * S;
@@ -440,6 +442,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     else if (h->TQT == 6) kern = variant == 1 ? decode_small_fwd_kernel<6, 512, 1> : decode_small_fwd_kernel<6, 256, 2>;
     else if (tpt == 4 && threads <= 256) kern = decode_small_fwd_kernel<8, 256, 1, 4>;
     else if (tpt == 4) kern = decode_small_fwd_kernel<8, 512, 1, 4>;
+    else if (emd) kern = decode_small_fwd_kernel<8, 192, 3, 2, 1>;
     else kern = variant == 1 ? decode_small_fwd_kernel<8, 512, 1>
               : variant == 2 ? decode_small_fwd_kernel<8, 384, 2> : decode_small_fwd_kernel<8, 256, 3>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -112,7 +112,7 @@ struct cv_hmm {
         cudaEvent_t ev_pre = nullptr, ev_bt = nullptr;
     } ws[2];
     cudaEvent_t ev_fork = nullptr;
-    cvb::DevBuf cpb[16];     // constrained-solver state (kept after cv_cp_solve for the parity hooks)
+    cvb::DevBuf cpb[24];     // constrained-solver state (kept after cv_cp_solve for the parity hooks)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     double last_ms = 0.0, last_bt_ms = 0.0;   // forward kernel / backtrace kernel

@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
 
         for (int t = 1; t < len; t++) {
             double e[NSL];
-#pragma unroll
             const uint32_t on = checked(oq[0]);
 #pragma unroll
             for (int s = 0; s < NSL; s++) { e[s] = e_next[s]; e_next[s] = bt[(size_t)on * Kp + col[s]]; }

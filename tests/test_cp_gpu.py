@@ -135,3 +135,38 @@ def test_cp_dense_deep_search():
     import bench
     w = bench.workload_cp("trucks")
     _check(w["A"], w["B"], w["pi"], w["obs"], w["start"], w["comp"], w["ncomp"], max_nodes=400)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cp_leaf_batch_equals_node_by_node(seed):
+    """The K sibling leaves of the last component evaluated as one batch (cp_leaf_group) against the node-by-node
+    loop and the oracle: complete delta / psi state, every bound, counters -- with node budgets that stop inside a
+    leaf group, adjacent clamped positions, ties and -inf entries, 1 to 4 components."""
+    rng = np.random.default_rng(9100 + seed)
+    L = cv._lib.lib()
+    try:
+        for it in range(10):
+            K = int(rng.integers(2, 10)); M = int(rng.integers(2, 7))
+            A, B, pi = random_hmm(rng, K, M, ties=(it % 4 == 0), zero_frac=0.15)
+            obs, start, comp, ncomp = random_superseq(rng, int(rng.integers(2, 10)), M, int(rng.integers(1, 5)),
+                                                      float(rng.choice([0.1, 0.3, 0.6])), 1, 14)
+            budget = int(rng.choice([0, 0, 7, 23, 61]))
+            for on in (1, 0):
+                L.cv_debug_set_cp_leaf_batch(on)
+                _check(A, B, pi, obs, start, comp, ncomp, max_nodes=budget)
+    finally:
+        L.cv_debug_set_cp_leaf_batch(1)
+
+
+def test_cp_leaf_batch_mid_size():
+    rng = np.random.default_rng(77)
+    L = cv._lib.lib()
+    try:
+        for K in (12, 16, 33):
+            A, B, pi = random_hmm(rng, K, 20, zero_frac=0.05)
+            obs, start, comp, ncomp = random_superseq(rng, 40, 20, 3, 0.15, 20, 120)
+            for on in (1, 0):
+                L.cv_debug_set_cp_leaf_batch(on)
+                _check(A, B, pi, obs, start, comp, ncomp, max_nodes=150)
+    finally:
+        L.cv_debug_set_cp_leaf_batch(1)

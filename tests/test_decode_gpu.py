@@ -292,7 +292,8 @@ def test_large_k_dataflow_stress():
 @pytest.mark.parametrize("K", [13, 37, 45, 47, 61])
 def test_forward_kernel_variants_equal_oracle(K):
     """The forward tile kernel's variants (cv_debug_set_fwd_variant: 1 = software-pipelined loop, 2 = balanced state
-    split with slot-permuted logA / logB^T copies, 3 = both) against the oracle, ragged lengths, -inf entries."""
+    split with slot-permuted logA / logB^T copies, 4 = emissions read from L2 without the shared-memory stage; bits
+    combine) against the oracle, ragged lengths, -inf entries."""
     rng = np.random.default_rng(4400 + K)
     M = 40
     A, B, pi = random_hmm(rng, K, M, zero_frac=0.15)
@@ -302,7 +303,7 @@ def test_forward_kernel_variants_equal_oracle(K):
     L = cv._lib.lib()
     try:
         L.cv_debug_set_chain_max_batch(0)
-        for v in (0, 1, 2, 3):
+        for v in (0, 1, 2, 3, 4, 6):
             L.cv_debug_set_fwd_variant(v)
             p, s = cv.decode_batch(h, obs, off)
             assert (p == rp).all() and s.tobytes() == rs.tobytes(), f"variant {v}"
