@@ -44,7 +44,7 @@ static Tuning tuning_from_env()
     t.streamed = geti("CV_STREAMED", t.streamed);
     if (const char *e = getenv("CV_TQ")) t.tq = !strcmp(e, "auto") ? 0 : (atoi(e) == 12 ? 12 : atoi(e) == 6 ? 6 : 8);
     t.tp = geti("CV_TP", 2) == 4 ? 4 : 2;
-    t.fwd_variant = geti("CV_FWD", t.fwd_variant);
+    t.balanced_split = geti("CV_BALANCED", t.balanced_split);
     t.debug = getenv("CV_DEBUG") != nullptr;
     t.bt_prof = getenv("CV_BT_PROF") != nullptr;
     t.e2e_prof = getenv("CV_E2E_PROF") != nullptr;
@@ -377,9 +377,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     int tpt = g_tune.tp;
     if (h->TQT != 8) tpt = 2;
     while (S > 1 && (B + 32 * tpt * S - 1) / (32 * tpt * S) < 4 * (int64_t)h->num_sms) S--;
-    // fwd_variant bit 2: emissions read straight from L2 (no shared-memory stage): three CTAs per SM at the POS shape
-    const int emd = ((g_tune.fwd_variant & 4) && h->TQT == 8 && tpt == 2 && S == 1 && 32 * G <= 192) ? 1 : 0;
-    size_t smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S, emd);
+    size_t smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S);
     while (smem > 220 * 1024 && S > 1) { S--; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
     if (smem > 220 * 1024 && tpt == 4) { tpt = 2; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
     const int NS = 32 * tpt * S;
@@ -424,8 +422,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     DecodeSmallParams p;
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
     p.At = h->dA; p.BTt = h->dBT; p.nq_base = p.nq_rem = 0;
-    p.pipe = (g_tune.fwd_variant & 1) ? 1 : 0;
-    if ((g_tune.fwd_variant & 2) && h->dAb && h->TQT == 8 && tpt == 2) {
+    if (g_tune.balanced_split && h->dAb && h->TQT == 8 && tpt == 2) {
         p.At = h->dAb; p.BTt = h->dBTb; p.nq_base = h->K / G; p.nq_rem = h->K % G;
     }
     p.tile_base = (const long long *)w.base.p;
@@ -442,7 +439,6 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     else if (h->TQT == 6) kern = variant == 1 ? decode_small_fwd_kernel<6, 512, 1> : decode_small_fwd_kernel<6, 256, 2>;
     else if (tpt == 4 && threads <= 256) kern = decode_small_fwd_kernel<8, 256, 1, 4>;
     else if (tpt == 4) kern = decode_small_fwd_kernel<8, 512, 1, 4>;
-    else if (emd) kern = decode_small_fwd_kernel<8, 192, 3, 2, 1>;
     else kern = variant == 1 ? decode_small_fwd_kernel<8, 512, 1>
               : variant == 2 ? decode_small_fwd_kernel<8, 384, 2> : decode_small_fwd_kernel<8, 256, 3>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

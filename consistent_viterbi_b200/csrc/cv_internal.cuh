@@ -48,7 +48,7 @@ struct Tuning {
     int streamed = 1;              // host copies streamed past one launch                        (CV_STREAMED)
     int tq = 8;                    // target states per warp of the forward tile kernel: 6, 8, 12, 0 = auto (CV_TQ)
     int tp = 2;                    // sequences per lane: 2 or 4                                  (CV_TP)
-    int fwd_variant = 0;           // forward tile kernel: bit 0 = software-pipelined loop, bit 1 = balanced state split (CV_FWD)
+    int balanced_split = 1;        // forward tile kernel: state groups of near-equal size, no padded states (CV_BALANCED)
     int debug = 0;                 // print launch shapes                                         (CV_DEBUG)
     int bt_prof = 0, e2e_prof = 0; // print pipeline timelines                                    (CV_BT_PROF, CV_E2E_PROF)
     long long large_group_rb = 0;  // row blocks per group of the large-K kernel, 0 = automatic    (CV_LARGE_GROUP_RB)

@@ -79,16 +79,14 @@ struct DecodeSmallParams {
     // g * nq_base + min(g, nq_rem); the columns of A / BT are permuted into 8-wide slots per group (slot 8g + q holds
     // that group's q-th state, unused slots -inf).  nq_base = 0: the plain layout (group g = states 8g .. 8g+7).
     int nq_base, nq_rem;
-    int pipe;                      // 1: software-pipelined tile loop (adds of predecessor j+1 next to the selects of j)
 };
 
 __host__ __device__ inline int em_pitch(int Kp) { return Kp + 2; }   // doubles; bank-conflict-free row pitch
 
 // dynamic smem: [A][delta x2][em][off i64][len i32][mbarA, mbarEm][tile]
-// em_direct: no emission stage -- every thread reads its emission values straight from logB^T (L2) in the epilogue
-__host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS, int em_direct = 0)
+__host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS)
 {
-    return (size_t)K * Kp * 8 + (size_t)2 * K * NS * 8 + (em_direct ? 0 : (size_t)NS * em_pitch(Kp) * 8) + (size_t)NS * (8 + 4) + 32 + 16;
+    return (size_t)K * Kp * 8 + (size_t)2 * K * NS * 8 + (size_t)NS * em_pitch(Kp) * 8 + (size_t)NS * (8 + 4) + 32 + 16;
 }
 
 // value-only TP x TQ micro-tile: best[p][q] = max_j ( dcol[j*ldd + p] + arow[j*lda + q] )
@@ -125,50 +123,6 @@ __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol
 }
 
 
-// Software-pipelined variant: the adds of predecessor j+1 are issued next to the compare/selects of j, so the
-// FP64 adds never wait behind a batch of selects in the in-order issue stream.
-template <int TQT, int TPT = TP>
-__device__ __forceinline__ void maxplus_tile_val_pipe(const double *__restrict__ dcol, int ldd,
-                                                      const double *__restrict__ arow, int lda, int nj,
-                                                      double (&best)[TPT][TQT])
-{
-    double v[TPT][TQT];
-    auto load_add = [&](int j, double (&out)[TPT][TQT]) {
-        double dd[TPT], a[TQT];
-#pragma unroll
-        for (int p = 0; p < TPT / 2; p++) {
-            const double2 d = *reinterpret_cast<const double2 *>(dcol + (size_t)j * ldd + 2 * p);
-            dd[2 * p] = d.x; dd[2 * p + 1] = d.y;
-        }
-#pragma unroll
-        for (int q = 0; q < TQT / 2; q++) {
-            const double2 aa = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2 * q);
-            a[2 * q] = aa.x; a[2 * q + 1] = aa.y;
-        }
-#pragma unroll
-        for (int p = 0; p < TPT; p++)
-#pragma unroll
-            for (int q = 0; q < TQT; q++) out[p][q] = dd[p] + a[q];
-    };
-    load_add(0, v);
-#pragma unroll 2
-    for (int j = 1; j < nj; j++) {
-        double vn[TPT][TQT];
-        load_add(j, vn);
-#pragma unroll
-        for (int p = 0; p < TPT; p++)
-#pragma unroll
-            for (int q = 0; q < TQT; q++) {
-                best[p][q] = v[p][q] > best[p][q] ? v[p][q] : best[p][q];
-                v[p][q] = vn[p][q];
-            }
-    }
-#pragma unroll
-    for (int p = 0; p < TPT; p++)
-#pragma unroll
-        for (int q = 0; q < TQT; q++) best[p][q] = v[p][q] > best[p][q] ? v[p][q] : best[p][q];
-}
-
 __device__ __forceinline__ void tma_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
@@ -194,29 +148,24 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 // predecessors (value only), then (.. + b) (viterbi.rs:17) into the other delta buffer.  `row0` points at the row of the
 // group's first state in that buffer, `nreal` = how many of the NQ states exist (the last group of the plain layout
 // may reach past K).
-// EMD = 1: e0 is unused, the emission values of sequence q come from global memory at eg[q] (logB^T row of its
-// observation + the group's first slot) and there is no mbarrier to wait for.
-template <int TQT, int TPT, int NQ, int EMD = 0>
+template <int TQT, int TPT, int NQ>
 __device__ __forceinline__ void fwd_step(const double *__restrict__ dcur, double *__restrict__ row0, int NS,
                                          const double *__restrict__ arow, int Kp, int K, const double *__restrict__ e0, int EP,
-                                         uint64_t *em_bar, uint32_t em_phase, int nreal, int pipe,
-                                         const double *const *eg = nullptr)
+                                         uint64_t *em_bar, uint32_t em_phase, int nreal)
 {
     double best[TPT][TQT];
 #pragma unroll
     for (int q = 0; q < TPT; q++)
 #pragma unroll
         for (int k = 0; k < TQT; k++) best[q][k] = neg_inf();
-    if (NQ == TQT && pipe) maxplus_tile_val_pipe<TQT, TPT>(dcur, NS, arow, Kp, K, best);
-    else maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT, NQ>(dcur, NS, arow, Kp, K, best);
+    maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT, NQ>(dcur, NS, arow, Kp, K, best);
 
-    if (!EMD) mbar_wait(em_bar, em_phase);      // emission rows of step t have landed
+    mbar_wait(em_bar, em_phase);      // emission rows of step t have landed
 #pragma unroll
     for (int k = 0; k < (NQ + 1) / 2; k++) {
         double2 x[TPT];
 #pragma unroll
-        for (int q = 0; q < TPT; q++)
-            x[q] = EMD ? __ldg(reinterpret_cast<const double2 *>(eg[q]) + k) : *reinterpret_cast<const double2 *>(e0 + (size_t)q * EP + 2 * k);
+        for (int q = 0; q < TPT; q++) x[q] = *reinterpret_cast<const double2 *>(e0 + (size_t)q * EP + 2 * k);
         // (delta + a) + b (viterbi.rs:17).  Sequences that already ended compute garbage in their
         // own column only; their last row is already in the history.
 #pragma unroll
@@ -234,9 +183,7 @@ __device__ __forceinline__ void fwd_step(const double *__restrict__ dcur, double
 // TQT = target states per thread (8 or 12; a warp owns TQT adjacent states); MAXT/MINB only set the register
 // budget (launch bounds).  The host picks TQT and S so that a CTA has a multiple of 4 warps: warps map to the
 // four SM sub-partitions by warp id, and with the per-step barrier an uneven split leaves sub-partitions idle.
-// EMD = 1 ("emissions direct"): no shared-memory stage for the emission rows (25 KB at K = 45), every thread reads its
-// 2 x 8 emission values from logB^T in L2 right before the epilogue; three CTAs fit an SM then.
-template <int TQT, int MAXT, int MINB, int TPT = TP, int EMD = 0>
+template <int TQT, int MAXT, int MINB, int TPT = TP>
 __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -244,7 +191,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     double *sA = reinterpret_cast<double *>(smem_raw);
     double *sD = sA + (size_t)K * Kp;
     double *sEm = sD + (size_t)2 * K * NS;
-    int64_t *sOff = reinterpret_cast<int64_t *>(sEm + (EMD ? 0 : (size_t)NS * EP));
+    int64_t *sOff = reinterpret_cast<int64_t *>(sEm + (size_t)NS * EP);
     int *sLen = reinterpret_cast<int *>(sOff + NS);
     uint64_t *sBar = reinterpret_cast<uint64_t *>(sLen + NS);   // [0] logA, [1] emissions
     int *sTile = reinterpret_cast<int *>(sBar + 4);
@@ -351,14 +298,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         if (tid == 0 && Tmax > 0) tma_bulk_s2g(slab, sD, slab_bytes);   // history slab 0 = delta(0)
 
         uint32_t o_nxt[EMK];                                                  // obs of the NEXT step to fetch
-        uint32_t od_cur[TPT], od_nxt[TPT];                                    // EMD: observations of this thread's own sequences
-        if constexpr (EMD) {
-#pragma unroll
-            for (int q = 0; q < TPT; q++) {
-                od_cur[q] = (1 < sLen[s0 + q]) ? ld_obs(p.obs + sOff[s0 + q] + 1) : 0u;
-                od_nxt[q] = (2 < sLen[s0 + q]) ? ld_obs(p.obs + sOff[s0 + q] + 2) : 0u;
-            }
-        } else {
+        {
             uint32_t o1[EMK];
 #pragma unroll
             for (int k = 0; k < EMK; k++) {
@@ -374,17 +314,6 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
             const double *dcur = sD + (size_t)((t - 1) & 1) * K * NS + s0;
             double *row0 = sD + (size_t)(t & 1) * K * NS + (size_t)srow0 * NS + s0;
             const double *e0 = sEm + (size_t)s0 * EP + i0;
-            const double *eg[TPT];
-            if constexpr (EMD) {
-#pragma unroll
-                for (int q = 0; q < TPT; q++) {
-                    uint32_t o = od_cur[q];
-                    if ((int64_t)o >= p.M) { *p.status = 3; o = 0; }          // index panic in the reference
-                    eg[q] = p.BTt + (size_t)o * Kp + i0;
-                    od_cur[q] = od_nxt[q];
-                    od_nxt[q] = (t + 2 < sLen[s0 + q]) ? ld_obs(p.obs + sOff[s0 + q] + t + 2) : 0u;
-                }
-            }
             bool done = false;
             if constexpr (TQT == 8 && TPT == 2) {
                 if (p.nq_base != 0) {
@@ -392,27 +321,25 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
                     // full-width path below (their unused slots hold -inf and are not stored)
                     done = true;
                     switch (nreal) {
-                        case 7: fwd_step<8, 2, 7, EMD>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal, 0, eg); break;
-                        case 6: fwd_step<8, 2, 6, EMD>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal, 0, eg); break;
-                        case 5: fwd_step<8, 2, 5, EMD>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal, 0, eg); break;
+                        case 7: fwd_step<8, 2, 7>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal); break;
+                        case 6: fwd_step<8, 2, 6>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal); break;
+                        case 5: fwd_step<8, 2, 5>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal); break;
                         default: done = false;
                     }
                 }
             }
-            if (!done) fwd_step<TQT, TPT, TQT, EMD>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal, p.pipe, eg);
+            if (!done) fwd_step<TQT, TPT, TQT>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal);
             em_phase ^= 1;
             fence_proxy_async_smem();           // make this thread's delta writes visible to the TMA store
             if (tid == 0) tma_store_wait_read_all();   // slab t-1 has left the buffer step t+1 will overwrite
             __syncthreads();
             if (tid == 0) tma_bulk_s2g(slab + (size_t)t * K * NS, sD + (size_t)(t & 1) * K * NS, slab_bytes);
-            if constexpr (!EMD) {
-                if (t + 1 < Tmax) {
-                    issue_emissions(t + 1, o_nxt);
+            if (t + 1 < Tmax) {
+                issue_emissions(t + 1, o_nxt);
 #pragma unroll
-                    for (int k = 0; k < EMK; k++) {
-                        const int s = w + nw * (lane + 32 * k);
-                        o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? ld_obs(p.obs + sOff[s] + t + 2) : 0u;
-                    }
+                for (int k = 0; k < EMK; k++) {
+                    const int s = w + nw * (lane + 32 * k);
+                    o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? ld_obs(p.obs + sOff[s] + t + 2) : 0u;
                 }
             }
         }

@@ -7,6 +7,51 @@
 
 namespace cvb {
 
+// (probe only) Software-pipelined variant: the adds of predecessor j+1 are issued next to the compare/selects of j, so the
+// FP64 adds never wait behind a batch of selects in the in-order issue stream.
+template <int TQT, int TPT = TP>
+__device__ __forceinline__ void maxplus_tile_val_pipe(const double *__restrict__ dcol, int ldd,
+                                                      const double *__restrict__ arow, int lda, int nj,
+                                                      double (&best)[TPT][TQT])
+{
+    double v[TPT][TQT];
+    auto load_add = [&](int j, double (&out)[TPT][TQT]) {
+        double dd[TPT], a[TQT];
+#pragma unroll
+        for (int p = 0; p < TPT / 2; p++) {
+            const double2 d = *reinterpret_cast<const double2 *>(dcol + (size_t)j * ldd + 2 * p);
+            dd[2 * p] = d.x; dd[2 * p + 1] = d.y;
+        }
+#pragma unroll
+        for (int q = 0; q < TQT / 2; q++) {
+            const double2 aa = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2 * q);
+            a[2 * q] = aa.x; a[2 * q + 1] = aa.y;
+        }
+#pragma unroll
+        for (int p = 0; p < TPT; p++)
+#pragma unroll
+            for (int q = 0; q < TQT; q++) out[p][q] = dd[p] + a[q];
+    };
+    load_add(0, v);
+#pragma unroll 2
+    for (int j = 1; j < nj; j++) {
+        double vn[TPT][TQT];
+        load_add(j, vn);
+#pragma unroll
+        for (int p = 0; p < TPT; p++)
+#pragma unroll
+            for (int q = 0; q < TQT; q++) {
+                best[p][q] = v[p][q] > best[p][q] ? v[p][q] : best[p][q];
+                v[p][q] = vn[p][q];
+            }
+    }
+#pragma unroll
+    for (int p = 0; p < TPT; p++)
+#pragma unroll
+        for (int q = 0; q < TQT; q++) best[p][q] = v[p][q] > best[p][q] ? v[p][q] : best[p][q];
+}
+
+
 // mode 0: independent DADD chains; mode 1: DADD + DSETP (predicate OR-chained, no selects)
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) probe_fp64_kernel(double *out, int iters, double seed)

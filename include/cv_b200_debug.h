@@ -27,8 +27,9 @@ void cv_debug_set_chain_max_batch(long long b);
 /* bt_concurrent = 1 runs the backtrace kernel next to the forward kernel (tile by tile), streamed = 1 lets
  * cv_decode_batch stream its copies past ONE launch instead of launching once per chunk; -1 = leave as is */
 void cv_debug_set_pipeline(int bt_concurrent, int streamed);
-/* forward-kernel variant of the small-K tile kernel (see csrc/decode_small.cuh); 0 = default */
-void cv_debug_set_fwd_variant(int v);
+/* forward tile kernel: 1 (default) = balanced state split (state groups of near-equal size over slot-permuted copies
+ * of logA / logB^T, no padded target states), 0 = groups of 8 states with the last one padded */
+void cv_debug_set_balanced_split(int on);
 /* row blocks per group of the large-K kernel (0 = automatic: as many as the delta history fits) */
 void cv_debug_set_large_group_rb(long long rb);
 /* constrained solver: 1 = the K sibling leaves of the last component are evaluated by one batched launch, 0 = node by node */

@@ -290,10 +290,10 @@ def test_large_k_dataflow_stress():
 
 
 @pytest.mark.parametrize("K", [13, 37, 45, 47, 61])
-def test_forward_kernel_variants_equal_oracle(K):
-    """The forward tile kernel's variants (cv_debug_set_fwd_variant: 1 = software-pipelined loop, 2 = balanced state
-    split with slot-permuted logA / logB^T copies, 4 = emissions read from L2 without the shared-memory stage; bits
-    combine) against the oracle, ragged lengths, -inf entries."""
+def test_forward_kernel_state_splits_equal_oracle(K):
+    """The forward tile kernel with the balanced state split (default: groups of near-equal size over slot-permuted
+    copies of logA / logB^T, e.g. 8,8,8,7,7,7 for K = 45) and with plain groups of 8 (last one padded), against the
+    oracle; ragged lengths, -inf entries."""
     rng = np.random.default_rng(4400 + K)
     M = 40
     A, B, pi = random_hmm(rng, K, M, zero_frac=0.15)
@@ -303,12 +303,12 @@ def test_forward_kernel_variants_equal_oracle(K):
     L = cv._lib.lib()
     try:
         L.cv_debug_set_chain_max_batch(0)
-        for v in (0, 1, 2, 3, 4, 6):
-            L.cv_debug_set_fwd_variant(v)
+        for on in (1, 0):
+            L.cv_debug_set_balanced_split(on)
             p, s = cv.decode_batch(h, obs, off)
-            assert (p == rp).all() and s.tobytes() == rs.tobytes(), f"variant {v}"
+            assert (p == rp).all() and s.tobytes() == rs.tobytes(), f"balanced_split={on}"
     finally:
-        L.cv_debug_set_fwd_variant(0)
+        L.cv_debug_set_balanced_split(1)
         L.cv_debug_set_chain_max_batch(-1)
     h.close()
 

@@ -1,9 +1,8 @@
 """Times the forward tile kernel variants on the POS shape (BASELINE configs[2]) and checks each against variant 0.
 
-    python tools/fwd_variants.py [nseq] [variants...]        e.g.  python tools/fwd_variants.py 1000000 0 1 2 3
+    python tools/fwd_variants.py [nseq] [variants...]        e.g.  python tools/fwd_variants.py 1000000 1 0
 
-fwd_variant bits (include/cv_b200_debug.h, csrc/decode_small.cuh): 1 = software-pipelined tile loop, 2 = balanced
-state split.  Prints the forward kernel alone (CUDA events, timing mode), and the device-resident step (forward +
+variant = cv_debug_set_balanced_split value: 1 = balanced state split (default), 0 = groups of 8 states, last padded.  Prints the forward kernel alone (CUDA events, timing mode), and the device-resident step (forward +
 concurrent backtrace) for each variant, plus the extra `CV_*` launch-shape settings given in the environment."""
 import ctypes as C
 import json
@@ -19,7 +18,7 @@ import bench  # noqa: E402
 import consistent_viterbi_b200 as cv  # noqa: E402
 
 nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-variants = [int(v) for v in sys.argv[2:]] or [0, 1, 2, 3]
+variants = [int(v) for v in sys.argv[2:]] or [1, 0]
 wl = bench.workload_pos(0, nseq)
 L = cv._lib.lib()
 hmm = cv.HMM(wl["A"], wl["B"], wl["pi"])
@@ -44,7 +43,7 @@ def run(sync):
 ref = None
 out = []
 for v in variants:
-    L.cv_debug_set_fwd_variant(v)
+    L.cv_debug_set_balanced_split(v)
     for _ in range(3):
         run(0)
     torch.cuda.synchronize()
@@ -70,5 +69,5 @@ for v in variants:
            "same_as_first": same}
     out.append(rec)
     print(json.dumps(rec), flush=True)
-L.cv_debug_set_fwd_variant(0)
+L.cv_debug_set_balanced_split(1)
 print(json.dumps({"peak_fp64_ops": peak, "env": {k: v for k, v in os.environ.items() if k.startswith("CV_")}}))
