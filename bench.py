@@ -641,7 +641,8 @@ def main():
         barrier()
     launches = L.cv_launch_count() - launches0
     dev_ms = e0.elapsed_time(e1)
-    full_paths = sd.paths().cpu().numpy().view(np.uint32)
+    full_paths = sd.paths().cpu().numpy()
+    full_paths = full_paths.astype(np.uint32) if sd.narrow_paths else full_paths.view(np.uint32)
     full_scores = sd.scores().cpu().numpy()
 
     # ---- share of the collective: the same steps without / with only the all-gather ----
@@ -664,9 +665,10 @@ def main():
     L.cv_set_timing(1)
     fwd_ms, bt_ms = [], []
     n_el, n_sq = sd.n_el[rank], sd.n_sq[rank]
+    dec_fn = L.cv_decode_batch_dev_u8 if sd.narrow_paths else L.cv_decode_batch_dev
     for _ in range(max(3, min(args.steps, 5))):
-        rc = L.cv_decode_batch_dev(h, sd.obs_l.data_ptr(), sd.off_l.data_ptr(), n_sq, n_el, sd.max_len,
-                                   sd.gpaths[rank].data_ptr(), sd.gscores[rank].data_ptr(), stream.cuda_stream, 1)
+        rc = dec_fn(h, sd.obs_l.data_ptr(), sd.off_l.data_ptr(), n_sq, n_el, sd.max_len,
+                    sd.gpaths[rank].data_ptr(), sd.gscores[rank].data_ptr(), stream.cuda_stream, 1)
         cv._lib.check(rc)
         fwd_ms.append(L.cv_last_kernel_ms(h))
         bt_ms.append(L.cv_last_backtrace_ms(h))
@@ -688,6 +690,8 @@ def main():
     p_path = L.cv_host_alloc(max(4 * n_el, 1))
     p_score = L.cv_host_alloc(max(8 * n_sq, 1))
 
+    keep_path = torch.empty(max(n_el, 1), dtype=torch.int32, device="cuda") if world > 1 else None
+
     def step_e2e():
         # H2D of the slice, decode, D2H of its paths / scores: one C-ABI call with host pointers
         if world == 1:
@@ -695,8 +699,9 @@ def main():
         else:
             # every rank also needs the others' paths on its device (north_star): the device copies of this rank's
             # results stay in its row of the gather buffers (cv_decode_batch_keep), then the all-gather on device
-            cv._lib.check(L.cv_decode_batch_keep(h, p_obs, p_off, n_sq, p_path, p_score, sd.gpaths[rank].data_ptr(),
+            cv._lib.check(L.cv_decode_batch_keep(h, p_obs, p_off, n_sq, p_path, p_score, keep_path.data_ptr(),
                                                  sd.gscores[rank].data_ptr()))
+            sd.gpaths[rank, :n_el].copy_(keep_path[:n_el])            # u32 -> the gather buffer's element type (u8 for K <= 64)
             sd.gather()
             torch.cuda.current_stream().synchronize()
     for _ in range(2):
@@ -711,6 +716,26 @@ def main():
     # check the end-to-end result against the device-resident one
     host_paths = np.ctypeslib.as_array(C.cast(p_path, C.POINTER(C.c_uint32)), shape=(max(n_el, 1),))[:n_el]
     assert (host_paths == full_paths[e0_:e1_]).all(), "e2e and device-resident paths differ"
+
+    # ---- the same call with narrow host formats (u16 observations in, u8 states out): a third of the PCIe bytes ----
+    narrow_s = None
+    if K <= 64 and wl["M"] <= 65536:
+        p_obs16 = pinned(np.ascontiguousarray(obs_np[e0_:e1_].astype(np.uint16)))
+        p_path8 = L.cv_host_alloc(max(n_el, 1))
+
+        def step_narrow():
+            cv._lib.check(L.cv_decode_batch_u16u8(h, p_obs16, p_off, n_sq, p_path8, p_score))
+        for _ in range(2):
+            step_narrow()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            step_narrow()
+        barrier()
+        narrow_s = (time.perf_counter() - t0) / n_e2e
+        host_paths8 = np.ctypeslib.as_array(C.cast(p_path8, C.POINTER(C.c_uint8)), shape=(max(n_el, 1),))[:n_el]
+        assert (host_paths8 == full_paths[e0_:e1_]).all(), "narrow-format and device-resident paths differ"
+        L.cv_host_free(p_obs16); L.cv_host_free(p_path8)
 
     # ---- reduce over ranks ----
     def allred(x, op):
@@ -769,6 +794,8 @@ def main():
     per_rank = allgather_vals([dev_ms / args.steps, 1e3 * e2e_s, fwd, bt, gather_ms, float(n_sq), my_cells])
     dev_ms = allred(dev_ms, MAX)
     e2e_s = allred(e2e_s, MAX)
+    if narrow_s is not None:
+        narrow_s = allred(narrow_s, MAX)
     launches = int(allred(float(launches), SUM))
     fwd_max = allred(fwd, MAX)
     bt_max = allred(bt, MAX)
@@ -829,12 +856,18 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             },
         }
+        if narrow_s is not None:
+            line["e2e_narrow"] = {"value": wl["cells"] / narrow_s, "unit": UNIT, "ms_per_step": 1e3 * narrow_s,
+                                  "h2d_bytes_per_step": int(2 * n_el + 8 * (n_sq + 1)), "d2h_bytes_per_step": int(n_el + 8 * n_sq),
+                                  "api": "cv_decode_batch_u16u8 (u16 observations, u8 states; per rank, no collective)",
+                                  "note": "secondary: the reference-shaped u32 call above is the headline e2e"}
         if world > 1:
-            line["collective"] = {"name": "ncclAllGather (torch.distributed.all_gather_into_tensor, in place) of paths (int32) "
-                                          "and scores (f64), padded to the largest slice, + un-padding concatenation",
+            line["collective"] = {"name": "ncclAllGather (torch.distributed.all_gather_into_tensor, in place) of paths (u8 states for "
+                                          "K <= 64, else u32) and scores (f64), padded to the largest slice, + un-padding concatenation",
                                   "ms_per_step": gather_ms, "local_decode_ms_per_step": local_ms,
                                   "share_of_step": gather_ms / max(step_ms, 1e-9),
-                                  "bytes_received_per_rank": int((world - 1) * (sd.gpaths.shape[1] * 4 + sd.gscores.shape[1] * 8))}
+                                  "path_element_bytes": int(sd.gpaths.element_size()),
+                                  "bytes_received_per_rank": int((world - 1) * (sd.gpaths.shape[1] * sd.gpaths.element_size() + sd.gscores.shape[1] * 8))}
             line["per_rank"] = {"columns": ["step_ms", "e2e_ms", "fwd_kernel_ms", "backtrace_ms", "gather_ms", "sequences", "cells"],
                                 "rows": per_rank, "host_affinity": affinity}
             if weak is not None:

@@ -54,9 +54,12 @@ SIGNATURES = {
     "cv_hmm_nstates": (C.c_int, [C.c_void_p]),
     "cv_hmm_nobs": (C.c_int64, [C.c_void_p]),
     "cv_decode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "cv_decode_batch_u16u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "cv_decode_batch_keep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cv_decode_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "cv_decode_batch_dev_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "cv_cp_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
                               C.c_void_p, _dp, _u64p, _u64p]),
     "cv_cp_dist_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),

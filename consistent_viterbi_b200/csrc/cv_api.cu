@@ -422,6 +422,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     DecodeSmallParams p;
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
     p.At = h->dA; p.BTt = h->dBT; p.nq_base = p.nq_rem = 0;
+    p.obs16 = h->obs16; p.path8 = h->path8;
     if (g_tune.balanced_split && h->dAb && h->TQT == 8 && tpt == 2) {
         p.At = h->dAb; p.BTt = h->dBTb; p.nq_base = h->K / G; p.nq_rem = h->K % G;
     }
@@ -541,6 +542,7 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
         p.psi = (uint8_t *)w.hist.p; p.path = d_path; p.score = d_score; p.counter = d_counter; p.status = d_status;
         p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp;
         p.bt_in_smem = ((size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
+        p.obs16 = h->obs16; p.path8 = h->path8;
         const size_t smem = (size_t)h->K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) +
                             (size_t)DC_WARPS * (16 * h->Kp + 32 * h->Kp + 128);
         const int grid = (int)std::min<int64_t>((B + DC_WARPS - 1) / DC_WARPS, (int64_t)h->num_sms * 8);
@@ -600,8 +602,28 @@ static int report_status(const int *status_words, int n)
     return CV_OK;
 }
 
+static int decode_batch_dev_impl(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
+                                 int64_t max_len, uint32_t *d_path, double *d_score, void *stream, int sync_status);
+
 extern "C" int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
                                    int64_t max_len, uint32_t *d_path, double *d_score, void *stream, int sync_status)
+{
+    return decode_batch_dev_impl(h, d_obs, d_off, B, N, max_len, d_path, d_score, stream, sync_status);
+}
+
+extern "C" int cv_decode_batch_dev_u8(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
+                                      int64_t max_len, uint8_t *d_path, double *d_score, void *stream, int sync_status)
+{
+    if (!h) return fail(CV_ERR_ARG, "NULL model");
+    if (h->K > SMALL_K_MAX) return fail(CV_ERR_UNSUPPORTED, "u8 paths are implemented for K <= %d", SMALL_K_MAX);
+    h->path8 = 1;
+    const int rc = decode_batch_dev_impl(h, d_obs, d_off, B, N, max_len, reinterpret_cast<uint32_t *>(d_path), d_score, stream, sync_status);
+    h->path8 = 0;
+    return rc;
+}
+
+static int decode_batch_dev_impl(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
+                                 int64_t max_len, uint32_t *d_path, double *d_score, void *stream, int sync_status)
 {
     if (!h) return fail(CV_ERR_ARG, "NULL model");
     if (B < 0 || N < 0) return fail(CV_ERR_ARG, "negative size");
@@ -675,6 +697,7 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
                            double *score_out, int nch, bool *handled, uint32_t *d_path, double *d_score)
 {
     *handled = false;
+    const size_t ob = h->obs16 ? 2 : 4, pb = h->path8 ? 1 : 4;       // bytes per observation / per path element on the host side
     StreamWaitValue32Fn wait32 = stream_wait_value32();
     StreamWriteValue32Fn write32 = stream_write_value32();
     if (!g_tune.streamed || !g_tune.bt_concurrent || !wait32 || !write32 || nch < 2 || nch > STREAM_MAX_CHUNKS) return CV_OK;
@@ -712,7 +735,7 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     for (int k = 0; k < nch; k++) {
         const int64_t e0 = seq_off[sio.cbs.cb[k]], e1 = seq_off[sio.cbs.cb[k + 1]];
         if (e1 < e0 || e1 > N) return fail(CV_ERR_ARG, "seq_off not monotone");
-        if (e1 > e0) CUDA_TRY(cudaMemcpyAsync(d_obs + e0, obs_flat + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, s_in));
+        if (e1 > e0) CUDA_TRY(cudaMemcpyAsync((char *)d_obs + ob * e0, (const char *)obs_flat + ob * e0, ob * (size_t)(e1 - e0), cudaMemcpyHostToDevice, s_in));
         if (write32(s_in, (unsigned long long)(uintptr_t)d_arrived, (unsigned int)(k + 1), 0x0) != 0) return fail(CV_ERR_CUDA, "cuStreamWriteValue32 failed");
     }
     // Lengths are checked and the longest one found on the HOST while the first copies fly (the forward kernel cannot
@@ -740,7 +763,7 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
         if (b1 == b0) continue;
         if (wait32(s_out, (unsigned long long)(uintptr_t)(d_chunk_done + k), (unsigned int)(b1 - b0), 0x0 /* GEQ */) != 0)
             return fail(CV_ERR_CUDA, "cuStreamWaitValue32 failed");
-        CUDA_TRY(cudaMemcpyAsync(path_out + e0, d_path + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, s_out));
+        CUDA_TRY(cudaMemcpyAsync((char *)path_out + pb * e0, (const char *)d_path + pb * e0, pb * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, s_out));
         if (score_out) CUDA_TRY(cudaMemcpyAsync(score_out + b0, d_score + b0, sizeof(double) * (size_t)(b1 - b0), cudaMemcpyDeviceToHost, s_out));
     }
     CUDA_TRY(cudaMemcpyAsync(hs, d_status, sizeof(int), cudaMemcpyDeviceToHost, sk));
@@ -768,6 +791,20 @@ extern "C" int cv_decode_batch_keep(cv_hmm *h, const uint32_t *obs_flat, const i
     return decode_batch_host(h, obs_flat, seq_off, B, path_out, score_out, d_path_keep, d_score_keep);
 }
 
+extern "C" int cv_decode_batch_u16u8(cv_hmm *h, const uint16_t *obs_flat, const int64_t *seq_off, int64_t B,
+                                     uint8_t *path_out, double *score_out)
+{
+    if (!h) return fail(CV_ERR_ARG, "NULL model");
+    if (h->M > 65536) return fail(CV_ERR_UNSUPPORTED, "u16 observations need M <= 65536 (M = %lld)", (long long)h->M);
+    if (h->K > 256) return fail(CV_ERR_UNSUPPORTED, "u8 paths need K <= 256 (K = %d)", h->K);
+    if (h->K > SMALL_K_MAX) return fail(CV_ERR_UNSUPPORTED, "the narrow host formats are implemented for K <= %d", SMALL_K_MAX);
+    h->obs16 = 1; h->path8 = 1;
+    const int rc = decode_batch_host(h, reinterpret_cast<const uint32_t *>(obs_flat), seq_off, B,
+                                     reinterpret_cast<uint32_t *>(path_out), score_out, nullptr, nullptr);
+    h->obs16 = 0; h->path8 = 0;
+    return rc;
+}
+
 static int decode_batch_host(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B, uint32_t *path_out,
                              double *score_out, uint32_t *d_path_keep, double *d_score_keep)
 {
@@ -789,6 +826,7 @@ static int decode_batch_host(cv_hmm *h, const uint32_t *obs_flat, const int64_t 
     double *d_score = d_score_keep ? d_score_keep : (double *)h->score.p;
     const bool timing = g_timing.load() != 0;
     const int nch = chunk_count(h, B, timing, true);
+    const size_t ob = h->obs16 ? 2 : 4, pb = h->path8 ? 1 : 4;
     if (!timing) {
         bool handled = false;
         if ((rc = decode_streamed(h, obs_flat, seq_off, B, path_out, score_out, nch, &handled, d_path, d_score))) return rc;
@@ -817,11 +855,11 @@ static int decode_batch_host(cv_hmm *h, const uint32_t *obs_flat, const int64_t 
         const int64_t e0 = seq_off[b0], e1 = seq_off[b1];
         CUDA_TRY(cudaMemcpyAsync(d_off + b0, seq_off + b0, sizeof(int64_t) * (size_t)(b1 - b0 + 1), cudaMemcpyHostToDevice, st));
         mark(st);
-        CUDA_TRY(cudaMemcpyAsync(d_obs + e0, obs_flat + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync((char *)d_obs + ob * e0, (const char *)obs_flat + ob * e0, ob * (size_t)(e1 - e0), cudaMemcpyHostToDevice, st));
         mark(st);
         if ((rc = decode_chunk(h, w, d_obs, d_off + b0, b1 - b0, e1 - e0, max_len, d_path, d_score + b0, st, timing))) return rc;
         mark(st);
-        CUDA_TRY(cudaMemcpyAsync(path_out + e0, d_path + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync((char *)path_out + pb * e0, (const char *)d_path + pb * e0, pb * (size_t)(e1 - e0), cudaMemcpyDeviceToHost, st));
         if (score_out)
             CUDA_TRY(cudaMemcpyAsync(score_out + b0, d_score + b0, sizeof(double) * (size_t)(b1 - b0), cudaMemcpyDeviceToHost, st));
         mark(st);

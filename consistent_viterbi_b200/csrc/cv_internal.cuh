@@ -116,6 +116,7 @@ struct cv_hmm {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     double last_ms = 0.0, last_bt_ms = 0.0;   // forward kernel / backtrace kernel
+    int obs16 = 0, path8 = 0;                 // host formats of the call in progress (cv_decode_batch_u16u8), else 0
     // CP debug state
     int64_t cp_N = 0;
     std::vector<double> cp_ub;

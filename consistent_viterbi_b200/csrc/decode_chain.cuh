@@ -24,6 +24,7 @@ struct DecodeChainParams {
     int64_t M, B;
     int K, Kp;
     int bt_in_smem;          // logB^T fits shared memory (M * Kp * 8 bytes after logA)
+    int obs16, path8;        // narrow host formats (cv_decode_batch_u16u8): u16 observations in, u8 states out
 };
 
 constexpr int DC_WARPS = 4;
@@ -78,7 +79,13 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
             if (lane + 32 * s < Kp) { sdw[lane + 32 * s] = (lane + 32 * s < K) ? 0.0 : neg_inf(); sdw[Kp + lane + 32 * s] = neg_inf(); }
         }
         __syncwarp();
-        auto load_obs = [&](int t) -> uint32_t { return (t < len) ? __ldg(p.obs + off + t) : 0u; };
+        auto load_obs = [&](int t) -> uint32_t {
+            if (t >= len) return 0u;
+            return p.obs16 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(p.obs) + off + t) : __ldg(p.obs + off + t);
+        };
+        auto store_path = [&](int64_t idx, uint32_t st) {
+            if (p.path8) reinterpret_cast<uint8_t *>(p.path)[idx] = (uint8_t)st; else p.path[idx] = st;
+        };
         auto checked = [&](uint32_t o) -> uint32_t {                                             // index panic
             if ((int64_t)o >= p.M) { *p.status = 3; return 0u; }
             return o;
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
         warp_argmax(bv, cur);
         if (lane == 0) {
             if (p.score) p.score[b] = bv;
-            p.path[off + len - 1] = (uint32_t)cur;
+            store_path(off + len - 1, (uint32_t)cur);
         }
         // backtrace (viterbi.rs:27-30): 32 backpointer rows at a time through shared memory
         __syncwarp();
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
             }
             __syncwarp();
             cur = __shfl_sync(0xffffffffu, cur, 0);
-            if (lane < nrows) p.path[off + thi - lane - 1] = pbuf[lane];
+            if (lane < nrows) store_path(off + thi - lane - 1, pbuf[lane]);
             __syncwarp();
         }
     }

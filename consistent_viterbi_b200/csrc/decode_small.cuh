@@ -79,7 +79,25 @@ struct DecodeSmallParams {
     // g * nq_base + min(g, nq_rem); the columns of A / BT are permuted into 8-wide slots per group (slot 8g + q holds
     // that group's q-th state, unused slots -inf).  nq_base = 0: the plain layout (group g = states 8g .. 8g+7).
     int nq_base, nq_rem;
+    // narrow host formats (cv_decode_batch_u16u8): obs holds u16 observations, path receives u8 states
+    int obs16, path8;
 };
+
+// element `idx` of the observation array (u32, or u16 when obs16); `coherent`: the copy engine is still writing the
+// buffer (streamed host path), so the read-only path and L1 must not be used
+__device__ __forceinline__ uint32_t load_obs_at(const DecodeSmallParams &p, int64_t idx, bool coherent)
+{
+    if (p.obs16) {
+        const uint16_t *q = reinterpret_cast<const uint16_t *>(p.obs) + idx;
+        return coherent ? (uint32_t)__ldcg(q) : (uint32_t)__ldg(q);
+    }
+    return coherent ? __ldcg(p.obs + idx) : __ldg(p.obs + idx);
+}
+__device__ __forceinline__ void store_path_at(const DecodeSmallParams &p, int64_t idx, uint32_t state)
+{
+    if (p.path8) reinterpret_cast<uint8_t *>(p.path)[idx] = (uint8_t)state;
+    else p.path[idx] = state;
+}
 
 __host__ __device__ inline int em_pitch(int Kp) { return Kp + 2; }   // doubles; bank-conflict-free row pitch
 
@@ -252,7 +270,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     // boundary could be served stale.  ld.global.cg reads through to L2, where the copy engine's writes land before
     // the `arrived` word that releases the chunk.
     const bool obs_streamed = p.arrived != nullptr;
-    auto ld_obs = [&](const uint32_t *q) -> uint32_t { return obs_streamed ? __ldcg(q) : __ldg(q); };
+    auto ld_obs = [&](int64_t idx) -> uint32_t { return load_obs_at(p, idx, obs_streamed); };
 
     for (;;) {
         if (tid == 0) *sTile = (int)atomicAdd(p.tile_counter, 1u);
@@ -304,8 +322,8 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
             for (int k = 0; k < EMK; k++) {
                 const int s = w + nw * (lane + 32 * k);
                 const bool in = s < NS;
-                o1[k] = (in && 1 < sLen[s]) ? ld_obs(p.obs + sOff[s] + 1) : 0u;
-                o_nxt[k] = (in && 2 < sLen[s]) ? ld_obs(p.obs + sOff[s] + 2) : 0u;
+                o1[k] = (in && 1 < sLen[s]) ? ld_obs(sOff[s] + 1) : 0u;
+                o_nxt[k] = (in && 2 < sLen[s]) ? ld_obs(sOff[s] + 2) : 0u;
             }
             if (Tmax > 1) issue_emissions(1, o1);
         }
@@ -339,7 +357,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 #pragma unroll
                 for (int k = 0; k < EMK; k++) {
                     const int s = w + nw * (lane + 32 * k);
-                    o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? ld_obs(p.obs + sOff[s] + t + 2) : 0u;
+                    o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? ld_obs(sOff[s] + t + 2) : 0u;
                 }
             }
         }
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
             if (v > bv) { bv = v; cur = j; }
         }
         if (p.score) p.score[b] = bv;
-        p.path[off + len - 1] = (uint32_t)cur;
+        store_path_at(p, off + len - 1, (uint32_t)cur);
         if (len == 1) { bt_mark_done(p, b); continue; }
 
         // walk back (viterbi.rs:27-30): steps tt = len-1 .. 1, each a scan of row tt-1 in chunks of BT_CHUNK predecessors;
@@ -446,7 +464,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         double dcur = bv;                                     // delta[tt][cur]
         double bufA[BT_CHUNK], bufB[BT_CHUNK];                // two chunk buffers used alternately: no register copies
         const double *rowp = col + (size_t)(len - 2) * sl;    // row tt-1
-        uint32_t *pout = p.path + off + (len - 2);
+        int64_t pout = off + (len - 2);
         auto load_chunk = [&](const double *prow, int c, double (&dst)[BT_CHUNK]) {
             const double *q = prow + (size_t)c * (BT_CHUNK * (size_t)NS);
             if (c < nfull) {
@@ -499,7 +517,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
             // psi = 0 when delta[tt][cur] = -inf (emission -inf or all candidates -inf; see header comment)
             cur = (dcur > neg_inf()) ? mi : 0;
             dcur = __ldcg(rowp + (size_t)cur * NS);              // delta[tt-1][cur]
-            *pout = (uint32_t)cur;
+            store_path_at(p, pout, (uint32_t)cur);
             pout--; rowp -= sl;
         };
         load_chunk(rowp, 0, bufA);

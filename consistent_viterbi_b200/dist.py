@@ -41,14 +41,15 @@ class ShardedDecoder:
 
     Every rank builds it with the same `seq_off`.  Buffers (torch tensors on this rank's device):
       obs_l   [n_el(rank)]  int32   this rank's slice of the observations (fill with `load_obs` or write in place)
-      gpaths  [world, P]    int32   padded gather buffer, P = max_r n_el(r); row r = paths of rank r's slice
+      gpaths  [world, P]    uint8 / int32  padded gather buffer, P = max_r n_el(r); row r = paths of rank r's slice
+                            (u8 states when K <= 64 -- a quarter of the all-gather bytes -- else u32 bit patterns)
       gscores [world, S]    float64 S = max_r n_seq(r)
     `step()` enqueues decode + all-gather on the current stream; `paths()` / `scores()` return the batch-ordered
     results (device tensors, one concatenation of the un-padded rows).
 
     `decode_fn(obs_np, off_np) -> (paths, scores)` replaces the GPU call in the CPU-only (gloo) host-logic tests."""
 
-    def __init__(self, hmm, seq_off, device: int = -1, decode_fn=None, group=None):
+    def __init__(self, hmm, seq_off, device: int = -1, decode_fn=None, group=None, narrow_paths=None):
         import torch
         import torch.distributed as dist
 
@@ -74,12 +75,15 @@ class ShardedDecoder:
         off_l = seq_off[self.b0:self.b1 + 1] - self.e0
         self.off_l_np = off_l
         self.max_len = int(np.diff(off_l).max()) if self.b1 > self.b0 else 0
+        if narrow_paths is None:
+            narrow_paths = on_gpu and hmm.nstates() <= 64
+        self.narrow_paths = bool(narrow_paths)
         P, S = max(max(self.n_el), 1), max(max(self.n_sq), 1)
         # rows padded to 16 bytes so every rank's row is aligned for the collective
-        P, S = (P + 3) // 4 * 4, (S + 1) // 2 * 2
+        P, S = (P + 15) // 16 * 16, (S + 1) // 2 * 2
         self.off_l = torch.from_numpy(off_l.copy()).to(self.dev)
         self.obs_l = torch.zeros(max(self.n_el[self.rank], 1), dtype=torch.int32, device=self.dev)
-        self.gpaths = torch.zeros((self.world, P), dtype=torch.int32, device=self.dev)
+        self.gpaths = torch.zeros((self.world, P), dtype=torch.uint8 if self.narrow_paths else torch.int32, device=self.dev)
         self.gscores = torch.zeros((self.world, S), dtype=torch.float64, device=self.dev)
         self.handle = hmm.device_handle(self.device_index) if on_gpu else None
 
@@ -101,14 +105,15 @@ class ShardedDecoder:
             return
         if self.decode_fn is not None:
             p, s = self.decode_fn(self.obs_l[:n_el].numpy().view(np.uint32), self.off_l_np)
-            self.gpaths[self.rank, :n_el] = self.torch.from_numpy(np.ascontiguousarray(p).view(np.int32))
+            pp = np.ascontiguousarray(p)
+            self.gpaths[self.rank, :n_el] = self.torch.from_numpy(pp.astype(np.uint8) if self.narrow_paths else pp.view(np.int32))
             self.gscores[self.rank, :n_sq] = self.torch.from_numpy(np.ascontiguousarray(s))
             return
         from . import _lib
         st = self.torch.cuda.current_stream(self.dev)
-        rc = _lib.lib().cv_decode_batch_dev(self.handle, self.obs_l.data_ptr(), self.off_l.data_ptr(), n_sq, n_el,
-                                            self.max_len, self.gpaths[self.rank].data_ptr(),
-                                            self.gscores[self.rank].data_ptr(), st.cuda_stream, 0)
+        fn = _lib.lib().cv_decode_batch_dev_u8 if self.narrow_paths else _lib.lib().cv_decode_batch_dev
+        rc = fn(self.handle, self.obs_l.data_ptr(), self.off_l.data_ptr(), n_sq, n_el, self.max_len,
+                self.gpaths[self.rank].data_ptr(), self.gscores[self.rank].data_ptr(), st.cuda_stream, 0)
         _lib.check(rc)
 
     def gather(self):
@@ -124,7 +129,7 @@ class ShardedDecoder:
 
     # -- results ---------------------------------------------------------------------------------------------------
     def paths(self):
-        """int32 [N] (bit patterns of the u32 states), batch order, on this rank's device."""
+        """[N] states in batch order on this rank's device: uint8, or int32 bit patterns of u32 when not narrow."""
         return self.torch.cat([self.gpaths[r, : self.n_el[r]] for r in range(self.world)])
 
     def scores(self):
@@ -143,4 +148,5 @@ def decode_batch_sharded(hmm, obs_flat, seq_off, device: int = -1, gather: bool 
         paths, scores = sd.paths(), sd.scores()
     else:
         paths, scores = sd.gpaths[sd.rank, : sd.n_el[sd.rank]], sd.gscores[sd.rank, : sd.n_sq[sd.rank]]
-    return paths.cpu().numpy().view(np.uint32), scores.cpu().numpy(), (sd.b0, sd.b1)
+    pn = paths.cpu().numpy()
+    return (pn.astype(np.uint32) if sd.narrow_paths else pn.view(np.uint32)), scores.cpu().numpy(), (sd.b0, sd.b1)

@@ -33,6 +33,24 @@ def decode_batch(hmm: HMM, obs_flat, seq_off, device: int = -1, want_scores: boo
     return paths, scores
 
 
+def decode_batch_narrow(hmm: HMM, obs_flat, seq_off, device: int = -1):
+    """decode_batch with narrow host formats (cv_decode_batch_u16u8): observations cross PCIe as u16 (M <= 65536),
+    states come back as u8 (K <= 64 here).  Same results; returns (paths u8[N], scores f64[B])."""
+    obs16 = np.ascontiguousarray(obs_flat, dtype=np.uint16)
+    if (np.asarray(obs_flat) != obs16).any():
+        raise ValueError("observation does not fit u16")
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    B, N = seq_off.shape[0] - 1, obs16.shape[0]
+    if B > 0 and int(seq_off[-1]) != N:
+        raise ValueError("seq_off[-1] != len(obs_flat)")
+    paths = np.zeros(N, dtype=np.uint8)
+    scores = np.zeros(max(B, 0), dtype=np.float64)
+    rc = _lib.lib().cv_decode_batch_u16u8(hmm.device_handle(device), obs16.ctypes.data, seq_off.ctypes.data, B,
+                                          paths.ctypes.data, scores.ctypes.data)
+    _lib.check(rc)
+    return paths, scores
+
+
 def decode(sequence, hmm: HMM, device: int = -1) -> np.ndarray:
     """viterbi::decode(sequence, hmm) -> Array1<usize> (viterbi.rs:5). `sequence` is a
     list of D-dimensional observations (Vec<[usize; D]>)."""

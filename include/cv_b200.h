@@ -66,6 +66,12 @@ int64_t cv_hmm_nobs(const cv_hmm *h);          /* M = prod(bdims)               
 int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off,
                     int64_t B, uint32_t *path_out, double *score_out);
 
+/* Same call with narrow HOST formats: u16 observations (needs M <= 65536) and u8 states (needs K <= 256; implemented
+ * for K <= 64).  A third of the bytes cross PCIe (POS shape: 216 MB -> 75 MB per million sentences); the kernels read
+ * and write the narrow types directly.  cv_decode_batch stays the reference-shaped entry. */
+int cv_decode_batch_u16u8(cv_hmm *h, const uint16_t *obs_flat, const int64_t *seq_off,
+                          int64_t B, uint8_t *path_out, double *score_out);
+
 /* Same call, and the device copies of the results are left in the caller's DEVICE buffers d_path_keep[N] /
  * d_score_keep[B] as well (e.g. rows of an all-gather buffer: a multi-GPU caller decodes its slice from host memory
  * and runs the device-side collective without uploading the paths again).  The device buffers are complete when the
@@ -80,6 +86,12 @@ int cv_decode_batch_keep(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq
 int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs_flat, const int64_t *d_seq_off,
                         int64_t B, int64_t N, int64_t max_len, uint32_t *d_path_out,
                         double *d_score_out, void *stream, int sync_status);
+
+/* cv_decode_batch_dev with u8 states in d_path_out[N] (K <= 64): a quarter of the bytes for a following all-gather of
+ * the decoded paths across GPUs. */
+int cv_decode_batch_dev_u8(cv_hmm *h, const uint32_t *d_obs_flat, const int64_t *d_seq_off,
+                           int64_t B, int64_t N, int64_t max_len, uint8_t *d_path_out,
+                           double *d_score_out, void *stream, int sync_status);
 
 /* ---- constrained decode ----------------------------------------------------
  * Replaces: CPSolver::new(&hmm, &super_seq) + Solver::solve + get_solution +

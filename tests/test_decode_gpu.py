@@ -343,3 +343,32 @@ def test_decode_batch_keep_leaves_device_copies():
         L.cv_debug_set_chunks(-1)
         L.cv_debug_set_pipeline(1, 1)
     h.close()
+
+
+@pytest.mark.parametrize("K,Bn", [(45, 70000), (20, 500), (64, 30000)])
+def test_narrow_host_formats_equal_oracle(K, Bn):
+    """cv_decode_batch_u16u8 (u16 observations in, u8 states out): same paths and score bits as the oracle on the
+    tile kernel (streamed and per-chunk host paths) and on the warp-per-sequence kernel; error codes as documented."""
+    rng = np.random.default_rng(808 + K)
+    M = 300
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    obs, off = random_batch(rng, Bn, M, 1, 30)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        for chunks, streamed in ((-1, 1), (3, 0), (4, 1)):
+            L.cv_debug_set_chunks(chunks)
+            L.cv_debug_set_pipeline(-1, streamed)
+            p, s = cv.decode_batch_narrow(h, obs, off)
+            assert p.dtype == np.uint8 and (p == rp).all() and s.tobytes() == rs.tobytes()
+    finally:
+        L.cv_debug_set_chunks(-1)
+        L.cv_debug_set_pipeline(1, 1)
+    h.close()
+    A2, B2, pi2 = random_hmm(rng, 70, 5)
+    h2 = cv.HMM(A2, B2, pi2)
+    with pytest.raises(cv.CvError) as e:                              # K > 64: not implemented for the narrow formats
+        cv.decode_batch_narrow(h2, np.zeros(4, np.uint32), np.array([0, 4], np.int64))
+    assert e.value.code == cv._lib.ERR_UNSUPPORTED
+    h2.close()
