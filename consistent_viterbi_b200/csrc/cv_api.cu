@@ -6,6 +6,8 @@
 // entry points return CV_ERR_CUDA.
 #include "cv_internal.cuh"
 
+#include <chrono>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -588,7 +590,9 @@ static int chunk_count(const cv_hmm *h, int64_t B, bool timing, bool host_buffer
     // Host buffers, streamed past one launch (decode_streamed): 4 chunks measured best (2: 14.8 ms, 3: 14.3, 4: 14.2-14.3,
     // 6: 14.4, 10: 14.8, 16: 15.0 -- every chunk restarts the longest-first tile order); one launch per chunk: 6.
     const bool can_stream = g_tune.streamed && g_tune.bt_concurrent && stream_wait_value32() != nullptr;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? (can_stream ? 4 : 6) : dev_chunks, B / per_chunk));
+    if (host_buffers && can_stream)        // streamed: the copies hide behind one launch; two chunks already pay for a short batch
+        return (int)std::max<int64_t>(B >= 2 * 8192 ? 2 : 1, std::min<int64_t>(4, B / per_chunk));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 6 : dev_chunks, B / per_chunk));
 }
 
 static int report_status(const int *status_words, int n)
@@ -723,6 +727,13 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     // From here on copies from / to the caller's host buffers are in flight: every return (error or not) first drains
     // the three streams, so the caller may free or reuse its buffers as soon as this function returns.
     struct Drain { cudaStream_t s[3]; ~Drain() { for (cudaStream_t x : s) cudaStreamSynchronize(x); cudaGetLastError(); } } drain{{sk, s_in, s_out}};
+    // CV_E2E_PROF=1: a timeline of this call (host clock for the enqueue / wait phases, events for the device phases)
+    const bool prof = g_tune.e2e_prof != 0;
+    cudaEvent_t pe[6] = {};
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    double hm_scan = 0.0, hm_enq = 0.0;
+    if (prof) { for (auto &e : pe) cudaEventCreate(&e); cudaEventRecord(pe[0], sk); }
     // offsets first (the ordering needs nothing else), then the observations chunk by chunk on the copy stream
     CUDA_TRY(cudaMemsetAsync(w.misc.p, 0, 256, sk));
     CUDA_TRY(cudaEventRecord(w.ev_pre, sk));
@@ -738,16 +749,28 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
         if (e1 > e0) CUDA_TRY(cudaMemcpyAsync((char *)d_obs + ob * e0, (const char *)obs_flat + ob * e0, ob * (size_t)(e1 - e0), cudaMemcpyHostToDevice, s_in));
         if (write32(s_in, (unsigned long long)(uintptr_t)d_arrived, (unsigned int)(k + 1), 0x0) != 0) return fail(CV_ERR_CUDA, "cuStreamWriteValue32 failed");
     }
-    // Lengths are checked and the longest one found on the HOST while the first copies fly (the forward kernel cannot
-    // start before chunk 0 has arrived anyway): no device round trip before the launch.
+    // Lengths are checked and the longest one is found before the launch (the history is sized from it).  Small
+    // batches (a slice of a sharded batch): on the HOST while the first copies fly -- 0.1 ms per 100 k sequences and no
+    // device round trip.  Large ones: by the keys kernel, read back with one ~0.2 ms synchronisation (a single host
+    // thread would need ~0.7 ms for a million offsets, which delays the launch past the arrival of chunk 0).
     int64_t max_len = 0;
-    for (int64_t b = 0; b < B; b++) {
-        const int64_t len = seq_off[b + 1] - seq_off[b];
-        if (len <= 0) return len == 0 ? fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)")
-                                      : fail(CV_ERR_ARG, "seq_off not monotone");
-        max_len = std::max(max_len, len);
+    if (B <= (1 << 18)) {
+        for (int64_t b = 0; b < B; b++) {
+            const int64_t len = seq_off[b + 1] - seq_off[b];
+            if (len <= 0) return len == 0 ? fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)")
+                                          : fail(CV_ERR_ARG, "seq_off not monotone");
+            max_len = std::max(max_len, len);
+        }
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(hs, d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, sk));  // status, longest length
+        CUDA_TRY(cudaStreamSynchronize(sk));
+        if (hs[0] == CV_ERR_EMPTY) return fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)");
+        if (hs[0] == CV_ERR_ARG) return fail(CV_ERR_ARG, "seq_off not monotone");
+        if (hs[0]) { *handled = false; return CV_OK; }                                         // e.g. a sequence longer than 2^24: chunked path
+        max_len = (int64_t)(unsigned int)hs[1];
     }
     if (max_len > 0xffffffLL) { *handled = false; return CV_OK; }                              // does not fit the 24-bit sort key: chunked path
+    if (prof) { hm_scan = host_ms(); cudaEventRecord(pe[1], sk); cudaEventRecord(pe[4], s_in); }
 
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)w.keys_in.p, (uint32_t *)w.keys_out.p,
@@ -755,7 +778,9 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     if ((rc = w.cub_tmp.ensure(tmp_bytes))) return rc;
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p, (uint32_t *)w.keys_out.p,
                                                        (uint32_t *)w.vals_in.p, (uint32_t *)w.order.p, (int)B, 0, 32, sk));
+    if (prof) cudaEventRecord(pe[2], sk);
     if ((rc = launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, sk, false, &sio))) return rc;
+    if (prof) cudaEventRecord(pe[3], sk);
     // paths / scores of chunk c leave as soon as the backtrace has counted all its sequences
     CUDA_TRY(cudaStreamWaitEvent(s_out, w.ev_pre, 0));
     for (int k = 0; k < nch; k++) {
@@ -768,9 +793,19 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     }
     CUDA_TRY(cudaMemcpyAsync(hs, d_status, sizeof(int), cudaMemcpyDeviceToHost, sk));
     hs[1] = 0;
+    if (prof) { hm_enq = host_ms(); cudaEventRecord(pe[5], s_out); }
     CUDA_TRY(cudaStreamSynchronize(sk));
     CUDA_TRY(cudaStreamSynchronize(s_out));
     CUDA_TRY(cudaStreamSynchronize(s_in));
+    if (prof) {
+        const double hm_end = host_ms();
+        float t[6] = {};
+        for (int i = 1; i < 6; i++) cudaEventElapsedTime(&t[i], pe[0], pe[i]);
+        fprintf(stderr, "[cv] streamed B=%lld nch=%d | host: lengths known %.2f, all enqueued %.2f, done %.2f ms | device (from first enqueue): "
+                        "offsets+keys %.2f, sorted %.2f, forward+backtrace done %.2f, last chunk in %.2f, last copy out %.2f ms\n",
+                (long long)B, nch, hm_scan, hm_enq, hm_end, t[1], t[2], t[3], t[4], t[5]);
+        for (auto &e : pe) cudaEventDestroy(e);
+    }
     *handled = true;
     return report_status(hs, 1);
 }
