@@ -47,6 +47,7 @@ static Tuning tuning_from_env()
     if (const char *e = getenv("CV_TQ")) t.tq = !strcmp(e, "auto") ? 0 : (atoi(e) == 12 ? 12 : atoi(e) == 6 ? 6 : 8);
     t.tp = geti("CV_TP", 2) == 4 ? 4 : 2;
     t.balanced_split = geti("CV_BALANCED", t.balanced_split);
+    t.long_split = geti("CV_LONG_SPLIT", t.long_split);
     t.debug = getenv("CV_DEBUG") != nullptr;
     t.bt_prof = getenv("CV_BT_PROF") != nullptr;
     t.e2e_prof = getenv("CV_E2E_PROF") != nullptr;
@@ -188,6 +189,10 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
     CUDA_TRY(cudaEventCreate(&h->ev2));
     CUDA_TRY(cudaMallocHost(&h->pinned_status, 2048));     // [0, 64): status / bound words, [1024, 2048): leaf-batch bounds
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->st_long, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_long_dep, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_long_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_all_in, cudaEventDisableTiming));
     for (auto &w : h->ws) {
         CUDA_TRY(cudaStreamCreateWithFlags(&w.st, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
@@ -250,7 +255,7 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
     for (DevBuf *b : {&h->obs, &h->seq_off, &h->path, &h->score}) b->release();
     for (auto &w : h->ws) {
         for (DevBuf *b : {&w.order, &w.keys_in, &w.keys_out, &w.vals_in, &w.cub_tmp, &w.hist, &w.tmax, &w.base, &w.misc,
-                          &w.lg_arr, &w.lg_start, &w.lg_done, &w.delta_g})
+                          &w.lg_arr, &w.lg_start, &w.lg_done, &w.delta_g, &w.is_long, &w.long_list, &w.long_psi})
             b->release();
         if (w.st) cudaStreamDestroy(w.st);
         if (w.done) cudaEventDestroy(w.done);
@@ -259,6 +264,8 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
         if (w.ev_bt) cudaEventDestroy(w.ev_bt);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->st_long) cudaStreamDestroy(h->st_long);
+    for (cudaEvent_t e : {h->ev_long_dep, h->ev_long_done, h->ev_all_in}) if (e) cudaEventDestroy(e);
     for (auto &b : h->cpb) b.release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -284,13 +291,36 @@ extern "C" void cv_host_free(void *p) { if (p) cudaFreeHost(p); }
 // ---------------------------------------------------------------------------
 // batched plain Viterbi
 // ---------------------------------------------------------------------------
-__global__ void seq_len_keys_kernel(const int64_t *seq_off, int64_t B, uint32_t *keys, uint32_t *vals, int *status)
+// Long-sequence split (launch_decode_small): the tile kernel runs a tile in lock step for as many steps as its longest
+// sequence has, ~8 us per step, so in a SHORT batch (a slice of a sharded batch) a handful of very long sequences
+// are the critical path of the whole launch.  Sequences longer than `lstar` are taken out of the tiles: they get
+// sort key 0 (they sit in a tile of the shortest sequences as inactive slots), are flagged in is_long[] and
+// appended to long_list, and the warp-per-sequence kernel decodes them next to the tile kernel (0.3-0.5 us per
+// step).  lstar = 0: no split.  At most cap_long sequences are moved (the rest stay in the tiles: still correct).
+struct LongSplit {
+    uint32_t lstar, cap_long;
+    uint8_t *is_long;            // [B], zeroed by the host
+    uint32_t *long_list;         // [cap_long]
+    unsigned int *n_long;        // appended so far (may exceed cap_long)
+};
+__device__ __forceinline__ bool take_long(const LongSplit &ls, int64_t b, int64_t len)
+{
+    if (ls.lstar == 0 || len <= (int64_t)ls.lstar) return false;
+    const unsigned int idx = atomicAdd(ls.n_long, 1u);
+    if (idx >= ls.cap_long) return false;
+    ls.long_list[idx] = (uint32_t)b;
+    ls.is_long[b] = 1;
+    return true;
+}
+
+__global__ void seq_len_keys_kernel(const int64_t *seq_off, int64_t B, uint32_t *keys, uint32_t *vals, int *status, const LongSplit ls)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int64_t len = seq_off[b + 1] - seq_off[b];
     if (len <= 0) *status = CV_ERR_EMPTY;          // reference: sequence.len()-1 underflow panic
-    keys[b] = (uint32_t)(len < 0 ? 0 : (len > 0xffffffffLL ? 0xffffffffLL : len));
+    const bool lng = take_long(ls, b, len);
+    keys[b] = lng ? 0u : (uint32_t)(len < 0 ? 0 : (len > 0xffffffffLL ? 0xffffffffLL : len));
     vals[b] = (uint32_t)b;
 }
 
@@ -307,7 +337,7 @@ constexpr int STREAM_MAX_CHUNKS = 16;
 struct ChunkBounds { int nch; int64_t cb[STREAM_MAX_CHUNKS + 2]; };
 
 __global__ void seq_chunk_keys_kernel(const int64_t *seq_off, int64_t B, const ChunkBounds cbs, uint32_t *keys, uint32_t *vals,
-                                      int *status, unsigned int *max_len)
+                                      int *status, unsigned int *max_len, const LongSplit ls)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -319,7 +349,7 @@ __global__ void seq_chunk_keys_kernel(const int64_t *seq_off, int64_t B, const C
     atomicMax(max_len, l);
     int c = 0;
     while (c + 1 < cbs.nch && b >= cbs.cb[c + 1]) c++;
-    keys[b] = ((uint32_t)(cbs.nch - 1 - c) << 24) | l;
+    keys[b] = ((uint32_t)(cbs.nch - 1 - c) << 24) | (take_long(ls, b, len) ? 0u : l);
     vals[b] = (uint32_t)b;
 }
 
@@ -344,7 +374,38 @@ struct StreamedIO {
     ChunkBounds cbs;
     unsigned int *d_arrived;        // chunks whose observations have arrived
     unsigned int *d_chunk_done;     // [nch] finished sequences per chunk
+    cudaEvent_t all_in;             // recorded on the copy stream behind the last chunk of observations
 };
+
+// Threshold of the long-sequence split (see LongSplit): a tile should not run longer than ~70 % of the tile-steps an
+// average resident CTA executes in this launch; never below 64 steps; 0 = no split (nothing is that long).
+static uint32_t long_threshold(const cv_hmm *h, int64_t N, int64_t max_len)
+{
+    if (!g_tune.long_split || max_len <= 0 || h->K > SMALL_K_MAX) return 0;
+    const int64_t per_cta = (N / 64) / std::max<int64_t>(1, (int64_t)h->num_sms * 2);
+    const int64_t l = std::max<int64_t>(64, per_cta * 7 / 10);
+    return l >= max_len ? 0u : (uint32_t)std::min<int64_t>(l, 0xffffff);
+}
+constexpr uint32_t LONG_CAP = 4096;
+
+// binds the split's buffers for one launch (workspace set w) and zeroes the flags; ls.lstar = 0 when there is no split
+static int long_split_setup(cv_hmm *h, cv_hmm::DecodeWs &w, int64_t B, int64_t N, int64_t max_len, cudaStream_t st, LongSplit &ls)
+{
+    ls = LongSplit{0u, 0u, nullptr, nullptr, nullptr};
+    const uint32_t lstar = long_threshold(h, N, max_len);
+    if (!lstar) return CV_OK;
+    int rc;
+    const size_t row = (size_t)max_len * h->Kp;
+    const uint32_t cap = (uint32_t)std::max<size_t>(1, std::min<size_t>(LONG_CAP, ((size_t)512 << 20) / std::max<size_t>(row, 1)));
+    if ((rc = w.is_long.ensure((size_t)B))) return rc;
+    if ((rc = w.long_list.ensure(sizeof(uint32_t) * cap))) return rc;
+    if ((rc = w.long_psi.ensure(row * cap + 64))) return rc;
+    CUDA_TRY(cudaMemsetAsync(w.is_long.p, 0, (size_t)B, st));
+    ls.lstar = lstar; ls.cap_long = cap;
+    ls.is_long = (uint8_t *)w.is_long.p; ls.long_list = (uint32_t *)w.long_list.p;
+    ls.n_long = (unsigned int *)w.misc.p + 9;                // misc is zeroed by the caller before the keys kernel
+    return CV_OK;
+}
 
 typedef cv_hmm::DecodeWs DecodeWs;
 #include "decode_large_host.inl"
@@ -367,9 +428,35 @@ static StreamWaitValue32Fn stream_wait_value32()
 }
 
 
+// the warp-per-sequence kernel with the instantiation that fits K (register-resident logA column for K <= 32)
+static int launch_chain_kernel(const cv_hmm *h, const DecodeChainParams &p, int grid, cudaStream_t st)
+{
+    const size_t smem = (size_t)h->K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) +
+                        (size_t)DC_WARPS * (16 * h->Kp + 32 * h->Kp + 128);
+    auto go = [&](auto kern) -> int {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 32 * DC_WARPS, smem, st>>>(p);
+        return CV_OK;
+    };
+    const bool regs = h->Kp == 8 * ((h->K + 7) / 8);     // register-resident logA column needs Kp = 4 * KQ
+    int rc;
+    switch (regs ? (h->K + 7) / 8 : 9) {
+        case 1: rc = go(decode_chain_kernel<1, 2>); break;
+        case 2: rc = go(decode_chain_kernel<1, 4>); break;
+        case 3: rc = go(decode_chain_kernel<1, 6>); break;
+        case 4: rc = go(decode_chain_kernel<1, 8>); break;
+        default: rc = h->K <= 32 ? go(decode_chain_kernel<1, 0>) : go(decode_chain_kernel<2, 0>);
+    }
+    if (rc) return rc;
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CV_OK;
+}
+
 static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int64_t *d_off, int64_t B,
                                int64_t N, uint32_t *d_path, double *d_score, unsigned int *d_counter, int *d_status,
-                               int64_t max_len, cudaStream_t st, bool timing, const StreamedIO *sio = nullptr)
+                               int64_t max_len, cudaStream_t st, bool timing, const StreamedIO *sio = nullptr,
+                               const LongSplit *ls = nullptr)
 {
     const int G = h->G;
     const uint32_t *d_order = (const uint32_t *)w.order.p, *d_sorted_len = (const uint32_t *)w.keys_out.p;
@@ -425,6 +512,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
     p.At = h->dA; p.BTt = h->dBT; p.nq_base = p.nq_rem = 0;
     p.obs16 = h->obs16; p.path8 = h->path8;
+    p.is_long = (ls && ls->lstar) ? ls->is_long : nullptr;
     if (g_tune.balanced_split && h->dAb && h->TQT == 8 && tpt == 2) {
         p.At = h->dAb; p.BTt = h->dBTb; p.nq_base = h->K / G; p.nq_rem = h->K % G;
     }
@@ -468,6 +556,28 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
         p.started = (unsigned int *)w.lg_done.p + ntiles;
         CUDA_TRY(cudaEventRecord(w.ev_pre, st));
     }
+    // Long-sequence split: the flagged sequences run on the warp-per-sequence kernel next to the tile kernels, on a
+    // stream of its own; it is launched first so that its few CTAs are resident before the persistent forward CTAs.
+    bool long_launched = false;
+    if (ls && ls->lstar) {
+        DecodeChainParams q;
+        q.A = h->dA; q.BT = h->dBT; q.obs = d_obs; q.seq_off = d_off; q.order = ls->long_list;
+        q.psi = (uint8_t *)w.long_psi.p; q.path = d_path; q.score = d_score;
+        q.counter = (unsigned int *)w.misc.p + 8; q.status = d_status;
+        q.M = h->M; q.B = (int64_t)ls->cap_long; q.K = h->K; q.Kp = h->Kp;
+        q.bt_in_smem = ((size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
+        q.obs16 = h->obs16; q.path8 = h->path8;
+        q.B_dev = ls->n_long; q.psi_stride = max_len;
+        q.chunk_done = sio ? sio->d_chunk_done : nullptr; q.nch = sio ? sio->cbs.nch : 0;
+        if (sio) for (int c = 0; c <= sio->cbs.nch; c++) q.cb[c] = sio->cbs.cb[c];
+        CUDA_TRY(cudaEventRecord(h->ev_long_dep, st));                        // keys kernel (list, count) and the offsets are done
+        CUDA_TRY(cudaStreamWaitEvent(h->st_long, h->ev_long_dep, 0));
+        if (sio) CUDA_TRY(cudaStreamWaitEvent(h->st_long, sio->all_in, 0));   // streamed: all observations on the device
+        const int grid_l = (int)std::min<int64_t>((ls->cap_long + DC_WARPS - 1) / DC_WARPS, (int64_t)h->num_sms);
+        if ((rc = launch_chain_kernel(h, q, grid_l, h->st_long))) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_long_done, h->st_long));
+        long_launched = true;
+    }
     const bool bt_prof = g_tune.bt_prof != 0;   // prints forward / forward+backtrace times of the concurrent mode
     if (timing || bt_prof) CUDA_TRY(cudaEventRecord(h->ev0, st));
     kern<<<std::max(1, grid), threads, smem, st>>>(p);
@@ -492,6 +602,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(w.ev_bt, w.st_bt));
         CUDA_TRY(cudaStreamWaitEvent(st, w.ev_bt, 0));
+        if (long_launched) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_long_done, 0));
         if (bt_prof) {
             CUDA_TRY(cudaEventRecord(h->ev2, st));
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -506,6 +617,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (timing) CUDA_TRY(cudaEventRecord(h->ev2, st));
+    if (long_launched) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_long_done, 0));
     return CV_OK;
 }
 
@@ -524,9 +636,12 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
     unsigned int *d_counter = (unsigned int *)w.misc.p;
     int *d_status = (int *)w.misc.p + 16;
     CUDA_TRY(cudaMemsetAsync(w.misc.p, 0, 256, st));
+    const bool chain_all = h->K <= SMALL_K_MAX && (g_tune.chain_max_b < 0 ? B <= 8192 : B <= g_tune.chain_max_b);
+    LongSplit ls{0u, 0u, nullptr, nullptr, nullptr};
+    if (!chain_all && (rc = long_split_setup(h, w, B, N, max_len, st, ls))) return rc;
     // order sequences by length, longest first (stable radix sort => deterministic)
     seq_len_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_off, B, (uint32_t *)w.keys_in.p,
-                                                                    (uint32_t *)w.vals_in.p, d_status);
+                                                                    (uint32_t *)w.vals_in.p, d_status, ls);
     g_launches++;
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)w.keys_in.p,
@@ -536,7 +651,7 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p,
                                                        (uint32_t *)w.keys_out.p, (uint32_t *)w.vals_in.p,
                                                        (uint32_t *)w.order.p, (int)B, 0, 32, st));
-    if (h->K <= SMALL_K_MAX && (g_tune.chain_max_b < 0 ? B <= 8192 : B <= g_tune.chain_max_b)) {
+    if (chain_all) {
         // few sequences: one warp per sequence (latency-oriented), backpointers as u8 rows
         if ((rc = w.hist.ensure((size_t)N * h->Kp + 64))) return rc;
         DecodeChainParams p;
@@ -545,31 +660,15 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
         p.M = h->M; p.B = B; p.K = h->K; p.Kp = h->Kp;
         p.bt_in_smem = ((size_t)h->M * h->Kp * 8 <= CHAIN_BT_SMEM_MAX) ? 1 : 0;
         p.obs16 = h->obs16; p.path8 = h->path8;
-        const size_t smem = (size_t)h->K * h->Kp * 8 + (p.bt_in_smem ? (size_t)h->M * h->Kp * 8 : 0) +
-                            (size_t)DC_WARPS * (16 * h->Kp + 32 * h->Kp + 128);
+        p.B_dev = nullptr; p.psi_stride = 0; p.chunk_done = nullptr; p.nch = 0;
         const int grid = (int)std::min<int64_t>((B + DC_WARPS - 1) / DC_WARPS, (int64_t)h->num_sms * 8);
         if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
-        auto go = [&](auto kern) -> int {
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, 32 * DC_WARPS, smem, st>>>(p);
-            return CV_OK;
-        };
-        const bool regs = h->Kp == 8 * ((h->K + 7) / 8);     // register-resident logA column needs Kp = 4 * KQ
-        switch (regs ? (h->K + 7) / 8 : 9) {
-            case 1: rc = go(decode_chain_kernel<1, 2>); break;
-            case 2: rc = go(decode_chain_kernel<1, 4>); break;
-            case 3: rc = go(decode_chain_kernel<1, 6>); break;
-            case 4: rc = go(decode_chain_kernel<1, 8>); break;
-            default: rc = h->K <= 32 ? go(decode_chain_kernel<1, 0>) : go(decode_chain_kernel<2, 0>);
-        }
-        if (rc) return rc;
-        g_launches++;
-        CUDA_TRY(cudaGetLastError());
+        if ((rc = launch_chain_kernel(h, p, grid, st))) return rc;
         if (timing) { CUDA_TRY(cudaEventRecord(h->ev1, st)); CUDA_TRY(cudaEventRecord(h->ev2, st)); }
         return CV_OK;
     }
     if (h->K <= SMALL_K_MAX)
-        return launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, st, timing);
+        return launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, st, timing, nullptr, &ls);
     if (timing) CUDA_TRY(cudaEventRecord(h->ev0, st));
     if ((rc = launch_decode_large(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, st))) return rc;
     if (timing) { CUDA_TRY(cudaEventRecord(h->ev1, st)); CUDA_TRY(cudaEventRecord(h->ev2, st)); }
@@ -721,7 +820,17 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     unsigned int *d_maxlen = (unsigned int *)w.misc.p + 17, *d_arrived = (unsigned int *)w.misc.p + 32, *d_chunk_done = d_arrived + 1;
     StreamedIO sio;
     sio.cbs.nch = nch;
-    for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
+    // Chunk sizes: the forward kernel cannot start before chunk 0 is on the device, and the last chunk's paths leave
+    // after the kernels have ended -- both sit outside the overlap.  With four or more chunks the first and the last
+    // one are made small (1/16 of the batch each) and the middle ones carry the rest.
+    if (nch >= 4) {
+        static const int w6[7] = {0, 1, 4, 8, 12, 15, 16};
+        nch = 6;
+        sio.cbs.nch = nch;
+        for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * w6[k] / 16;
+    } else {
+        for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
+    }
     sio.d_arrived = d_arrived; sio.d_chunk_done = d_chunk_done;
 
     // From here on copies from / to the caller's host buffers are in flight: every return (error or not) first drains
@@ -738,9 +847,6 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     CUDA_TRY(cudaMemsetAsync(w.misc.p, 0, 256, sk));
     CUDA_TRY(cudaEventRecord(w.ev_pre, sk));
     CUDA_TRY(cudaMemcpyAsync(d_off, seq_off, sizeof(int64_t) * (size_t)(B + 1), cudaMemcpyHostToDevice, sk));
-    seq_chunk_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, sk>>>(d_off, B, sio.cbs, (uint32_t *)w.keys_in.p,
-                                                                      (uint32_t *)w.vals_in.p, d_status, d_maxlen);
-    g_launches++;
     int *hs = (int *)h->pinned_status + 8;
     CUDA_TRY(cudaStreamWaitEvent(s_in, w.ev_pre, 0));                                          // `arrived` is zeroed first
     for (int k = 0; k < nch; k++) {
@@ -749,19 +855,30 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
         if (e1 > e0) CUDA_TRY(cudaMemcpyAsync((char *)d_obs + ob * e0, (const char *)obs_flat + ob * e0, ob * (size_t)(e1 - e0), cudaMemcpyHostToDevice, s_in));
         if (write32(s_in, (unsigned long long)(uintptr_t)d_arrived, (unsigned int)(k + 1), 0x0) != 0) return fail(CV_ERR_CUDA, "cuStreamWriteValue32 failed");
     }
-    // Lengths are checked and the longest one is found before the launch (the history is sized from it).  Small
-    // batches (a slice of a sharded batch): on the HOST while the first copies fly -- 0.1 ms per 100 k sequences and no
-    // device round trip.  Large ones: by the keys kernel, read back with one ~0.2 ms synchronisation (a single host
-    // thread would need ~0.7 ms for a million offsets, which delays the launch past the arrival of chunk 0).
-    int64_t max_len = 0;
+    CUDA_TRY(cudaEventRecord(h->ev_all_in, s_in));
+    sio.all_in = h->ev_all_in;
+    // the long-sequence split needs the longest length before the keys kernel: small batches only (host scan below
+    // is moved up for them); large batches have nothing that long relative to their size
+    LongSplit ls{0u, 0u, nullptr, nullptr, nullptr};
+    int64_t max_len_host = 0;
     if (B <= (1 << 18)) {
         for (int64_t b = 0; b < B; b++) {
             const int64_t len = seq_off[b + 1] - seq_off[b];
             if (len <= 0) return len == 0 ? fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)")
                                           : fail(CV_ERR_ARG, "seq_off not monotone");
-            max_len = std::max(max_len, len);
+            max_len_host = std::max(max_len_host, len);
         }
-    } else {
+        if (max_len_host <= 0xffffffLL && (rc = long_split_setup(h, w, B, N, max_len_host, sk, ls))) return rc;
+    }
+    seq_chunk_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, sk>>>(d_off, B, sio.cbs, (uint32_t *)w.keys_in.p,
+                                                                      (uint32_t *)w.vals_in.p, d_status, d_maxlen, ls);
+    g_launches++;
+    // Lengths are checked and the longest one is found before the launch (the history is sized from it).  Small
+    // batches (a slice of a sharded batch): on the HOST while the first copies fly -- 0.1 ms per 100 k sequences and no
+    // device round trip.  Large ones: by the keys kernel, read back with one ~0.2 ms synchronisation (a single host
+    // thread would need ~0.7 ms for a million offsets, which delays the launch past the arrival of chunk 0).
+    int64_t max_len = max_len_host;
+    if (B > (1 << 18)) {
         CUDA_TRY(cudaMemcpyAsync(hs, d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, sk));  // status, longest length
         CUDA_TRY(cudaStreamSynchronize(sk));
         if (hs[0] == CV_ERR_EMPTY) return fail(CV_ERR_EMPTY, "empty sequence in batch (reference: usize underflow panic)");
@@ -779,7 +896,7 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p, (uint32_t *)w.keys_out.p,
                                                        (uint32_t *)w.vals_in.p, (uint32_t *)w.order.p, (int)B, 0, 32, sk));
     if (prof) cudaEventRecord(pe[2], sk);
-    if ((rc = launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, sk, false, &sio))) return rc;
+    if ((rc = launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, sk, false, &sio, &ls))) return rc;
     if (prof) cudaEventRecord(pe[3], sk);
     // paths / scores of chunk c leave as soon as the backtrace has counted all its sequences
     CUDA_TRY(cudaStreamWaitEvent(s_out, w.ev_pre, 0));

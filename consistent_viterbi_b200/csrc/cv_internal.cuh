@@ -49,6 +49,7 @@ struct Tuning {
     int tq = 8;                    // target states per warp of the forward tile kernel: 6, 8, 12, 0 = auto (CV_TQ)
     int tp = 2;                    // sequences per lane: 2 or 4                                  (CV_TP)
     int balanced_split = 1;        // forward tile kernel: state groups of near-equal size, no padded states (CV_BALANCED)
+    int long_split = 1;            // very long sequences of a short batch go to the warp-per-sequence kernel (CV_LONG_SPLIT)
     int debug = 0;                 // print launch shapes                                         (CV_DEBUG)
     int bt_prof = 0, e2e_prof = 0; // print pipeline timelines                                    (CV_BT_PROF, CV_E2E_PROF)
     long long large_group_rb = 0;  // row blocks per group of the large-K kernel, 0 = automatic    (CV_LARGE_GROUP_RB)
@@ -106,12 +107,15 @@ struct cv_hmm {
     // backtrace / copies of chunk k) on two internal streams
     struct DecodeWs {
         cvb::DevBuf order, keys_in, keys_out, vals_in, cub_tmp, hist, tmax, base, misc, lg_arr, lg_start, lg_done, delta_g;
+        cvb::DevBuf is_long, long_list, long_psi;          // long-sequence split of the tile path (cv_api.cu)
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
         cudaStream_t st_bt = nullptr;                      // concurrent backtrace (launch_decode_small)
         cudaEvent_t ev_pre = nullptr, ev_bt = nullptr;
     } ws[2];
     cudaEvent_t ev_fork = nullptr;
+    cudaStream_t st_long = nullptr;                        // warp-per-sequence kernel for the long sequences of a tile launch
+    cudaEvent_t ev_long_dep = nullptr, ev_long_done = nullptr, ev_all_in = nullptr;
     cvb::DevBuf cpb[24];     // constrained-solver state (kept after cv_cp_solve for the parity hooks)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;

@@ -25,6 +25,14 @@ struct DecodeChainParams {
     int K, Kp;
     int bt_in_smem;          // logB^T fits shared memory (M * Kp * 8 bytes after logA)
     int obs16, path8;        // narrow host formats (cv_decode_batch_u16u8): u16 observations in, u8 states out
+    // long-sequence split of the tile path (cv_api.cu): `order` is the list of long sequences, their number is read on
+    // the device (min(*B_dev, B)); backpointer rows of list entry r start at row r * psi_stride; on the streamed host
+    // path every finished sequence is counted in chunk_done[chunk of the sequence].  B_dev = nullptr: plain batch.
+    const unsigned int *B_dev;
+    int64_t psi_stride;
+    unsigned int *chunk_done;
+    int nch;
+    int64_t cb[18];
 };
 
 constexpr int DC_WARPS = 4;
@@ -55,6 +63,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
     const double *bt = p.bt_in_smem ? sBT : p.BT;
     const bool pf = !p.bt_in_smem;
     const int64_t psi_base = p.seq_off[0];      // offsets are absolute into obs / path; the psi buffer is chunk-local
+    const int64_t nseq = p.B_dev ? min((int64_t)*p.B_dev, p.B) : p.B;
 
     const double zero_pi[NSL] = {};
     double acol[KQ > 0 ? 4 * KQ : 1];
@@ -66,10 +75,11 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
         unsigned int r = 0;
         if (lane == 0) r = atomicAdd(p.counter, 1u);
         r = __shfl_sync(0xffffffffu, r, 0);
-        if ((int64_t)r >= p.B) break;
+        if ((int64_t)r >= nseq) break;
         const uint32_t b = p.order[r];
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
+        const int64_t prow = p.B_dev ? (int64_t)r * p.psi_stride : off - psi_base;    // first backpointer row of this sequence
 
         double d[NSL], e_next[NSL];
         int col[NSL];
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
                 int ix = idx[s];
                 if (!(e[s] > neg_inf())) { v = neg_inf(); ix = 0; }                              // viterbi.rs:19-21
                 const int i = lane + 32 * s;
-                if (i < K) p.psi[(size_t)(off - psi_base + t) * Kp + i] = (uint8_t)ix;                      // viterbi.rs:18
+                if (i < K) p.psi[(size_t)(prow + t) * Kp + i] = (uint8_t)ix;                      // viterbi.rs:18
                 d[s] = (i < K) ? v : neg_inf();
                 if (i < K) sdw[(t & 1) * Kp + i] = v;
             }
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
         for (int thi = len - 1; thi >= 1; thi -= 32) {
             const int nrows = min(32, thi);                       // rows thi, thi-1, ..., thi-nrows+1
             if (lane < nrows) {
-                const uint2 *src = reinterpret_cast<const uint2 *>(p.psi + (size_t)(off - psi_base + thi - lane) * Kp);
+                const uint2 *src = reinterpret_cast<const uint2 *>(p.psi + (size_t)(prow + thi - lane) * Kp);
                 uint2 *dst = reinterpret_cast<uint2 *>(stage + (size_t)lane * Kp);
                 for (int k = 0; k < Kp / 8; k++) dst[k] = __ldcg(src + k);
             }
@@ -155,6 +165,15 @@ __global__ void __launch_bounds__(32 * DC_WARPS) decode_chain_kernel(const Decod
             cur = __shfl_sync(0xffffffffu, cur, 0);
             if (lane < nrows) store_path(off + thi - lane - 1, pbuf[lane]);
             __syncwarp();
+        }
+        if (p.chunk_done) {                                          // streamed host path: this sequence's results may leave
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                int c = 0;
+                while (c + 1 < p.nch && (int64_t)b >= p.cb[c + 1]) c++;
+                atomicAdd(p.chunk_done + c, 1u);
+            }
         }
     }
 }

@@ -81,6 +81,9 @@ struct DecodeSmallParams {
     int nq_base, nq_rem;
     // narrow host formats (cv_decode_batch_u16u8): obs holds u16 observations, path receives u8 states
     int obs16, path8;
+    // long-sequence split: sequences flagged here are decoded by the warp-per-sequence kernel, the tile kernels treat
+    // them as inactive slots (nullptr: no split)
+    const uint8_t *is_long;
 };
 
 // element `idx` of the observation array (u32, or u16 when obs16); `coherent`: the copy engine is still writing the
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
                 const uint32_t b = p.order[r];
                 off = p.seq_off[b];
                 len = (int)(p.seq_off[b + 1] - off);
+                if (p.is_long && p.is_long[b]) len = 0;              // decoded by the warp-per-sequence kernel
             }
             sOff[s] = off; sLen[s] = len;
         }
@@ -442,6 +446,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
             __threadfence();                                   // the leader's acquire, extended to the lanes that waited
         }
         const uint32_t b = p.order[r];
+        if (p.is_long && p.is_long[b]) continue;                      // the warp-per-sequence kernel owns this sequence
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
         if (p.tile_base[tile] + (long long)len > p.hist_cap_slabs) { bt_mark_done(p, b); continue; }   // tile refused by the forward kernel (status 7)

@@ -372,3 +372,48 @@ def test_narrow_host_formats_equal_oracle(K, Bn):
         cv.decode_batch_narrow(h2, np.zeros(4, np.uint32), np.array([0, 4], np.int64))
     assert e.value.code == cv._lib.ERR_UNSUPPORTED
     h2.close()
+
+
+@pytest.mark.parametrize("K", [45, 24])
+def test_long_sequence_split_equals_oracle(K):
+    """Short batch with a few very long sequences: the tile path hands sequences longer than its threshold to the
+    warp-per-sequence kernel (LongSplit, cv_api.cu).  Host path (streamed, two chunks, long sequences in both chunks),
+    narrow formats, the per-chunk host path and the device-resident path, all against the oracle."""
+    import torch
+    rng = np.random.default_rng(5100 + K)
+    M = 80
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    Bn = 40000
+    lens = rng.integers(1, 30, size=Bn)
+    for b in rng.integers(0, Bn, size=25):
+        lens[b] = rng.integers(200, 1500)
+    off = np.zeros(Bn + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    obs = rng.integers(0, M, size=int(off[-1])).astype(np.uint32)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        for streamed in (1, 0):
+            L.cv_debug_set_pipeline(-1, streamed)
+            p, s = cv.decode_batch(h, obs, off)
+            assert (p == rp).all() and s.tobytes() == rs.tobytes(), f"streamed={streamed}"
+            p8, s8 = cv.decode_batch_narrow(h, obs, off)
+            assert (p8 == rp).all() and s8.tobytes() == rs.tobytes()
+    finally:
+        L.cv_debug_set_pipeline(1, 1)
+    hd = h.device_handle(torch.cuda.current_device())
+    N = len(obs)
+    d_obs = torch.from_numpy(obs.view(np.int32)).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    for fn, dt in ((L.cv_decode_batch_dev, torch.int32), (L.cv_decode_batch_dev_u8, torch.uint8)):
+        d_path = torch.zeros(N, dtype=dt, device="cuda")
+        d_score = torch.zeros(Bn, dtype=torch.float64, device="cuda")
+        for _ in range(2):                                            # twice: the flags / lists are rebuilt every call
+            cv._lib.check(fn(hd, d_obs.data_ptr(), d_off.data_ptr(), Bn, N, int(lens.max()), d_path.data_ptr(),
+                             d_score.data_ptr(), torch.cuda.current_stream().cuda_stream, 1))
+        torch.cuda.synchronize()
+        got = d_path.cpu().numpy()
+        got = got.astype(np.uint32) if dt == torch.uint8 else got.view(np.uint32)
+        assert (got == rp).all() and d_score.cpu().numpy().tobytes() == rs.tobytes()
+    h.close()
