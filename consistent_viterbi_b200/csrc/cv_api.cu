@@ -820,17 +820,9 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     unsigned int *d_maxlen = (unsigned int *)w.misc.p + 17, *d_arrived = (unsigned int *)w.misc.p + 32, *d_chunk_done = d_arrived + 1;
     StreamedIO sio;
     sio.cbs.nch = nch;
-    // Chunk sizes: the forward kernel cannot start before chunk 0 is on the device, and the last chunk's paths leave
-    // after the kernels have ended -- both sit outside the overlap.  With four or more chunks the first and the last
-    // one are made small (1/16 of the batch each) and the middle ones carry the rest.
-    if (nch >= 4) {
-        static const int w6[7] = {0, 1, 4, 8, 12, 15, 16};
-        nch = 6;
-        sio.cbs.nch = nch;
-        for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * w6[k] / 16;
-    } else {
-        for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
-    }
+    // (equal chunks: making the first and the last chunk small -- 1/16 of the batch each, six chunks -- was measured
+    // slower at 1 M sentences, 13.9 vs 13.4 ms: every chunk restarts the longest-first tile order)
+    for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
     sio.d_arrived = d_arrived; sio.d_chunk_done = d_chunk_done;
 
     // From here on copies from / to the caller's host buffers are in flight: every return (error or not) first drains

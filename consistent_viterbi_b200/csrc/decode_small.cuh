@@ -60,8 +60,11 @@ struct DecodeSmallParams {
     double *score;           // [B] or nullptr
     unsigned int *tile_counter;
     int *status;             // 0 ok, else CV_ERR_*
-    // concurrent backtrace (nullptr = the backtrace runs after the forward kernel): tile_done[tile] is raised when
-    // the tile's history is complete in global memory, *started counts the forward CTAs that have begun
+    // concurrent backtrace (nullptr = the backtrace runs after the forward kernel): tile_done is a QUEUE of finished
+    // tiles in completion order -- a forward CTA appends tile + 1 (slot = atomicAdd(started + 1)) once the tile's
+    // history is complete in global memory, backtrace warp q / 2 takes queue slot q.  (Indexed by tile id the first
+    // backtrace CTAs would sit on the longest tiles, which finish last, while hundreds of short tiles queue up behind
+    // them.)  started[0] counts the forward CTAs that have begun.
     int *tile_done;
     unsigned int *started;
     // streamed host path (nullptr / 0 otherwise): one launch over the whole batch while the observations still
@@ -371,7 +374,8 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
                 tma_store_wait_all();
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __threadfence();
-                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_done + tile), "r"(1) : "memory");
+                const unsigned int slot = atomicAdd(p.started + 1, 1u);
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_done + slot), "r"(tile + 1) : "memory");
             } else {
                 tma_store_wait_read_all();         // last slab read out before the buffers are reused
             }
@@ -425,27 +429,29 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t total = (int64_t)p.ntiles * NS;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += nthreads) {
-        if (r >= p.B) continue;
-        const int tile = (int)(r / NS), s = (int)(r % NS);
+        int tile = (int)(r / NS);
+        const int s = (int)(r % NS);
         if (p.tile_done) {
-            // concurrent mode: the forward kernel is still running; wait for this tile (bounded: ~17 s -- a tile of
-            // a million steps takes ~3 s --, then error).  One lane per warp polls (a warp = 32 sequences of one
-            // tile), about once a microsecond: tens of thousands of threads polling L2 would slow the forward kernel.
-            const unsigned int am = __activemask();
-            if ((int)(threadIdx.x & 31) == __ffs(am) - 1) {
+            // concurrent mode: the forward kernel is still running; this warp (32 sequences of one tile) takes queue
+            // slot r / NS and waits until a finished tile is published there (bounded: ~17 s -- a tile of a million
+            // steps takes ~3 s --, then error).  One lane polls, about once a microsecond: tens of thousands of
+            // threads polling L2 would slow the forward kernel.
+            int v = 0;
+            if ((threadIdx.x & 31) == 0) {
                 const long long t0 = clock64();
                 for (;;) {
-                    int v;
                     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.tile_done + tile) : "memory");
                     if (v) break;
-                    if (clock64() - t0 > (1LL << 35)) { *p.status = 5; break; }
+                    if (clock64() - t0 > (1LL << 35)) { *p.status = 5; v = tile + 1; break; }
                     __nanosleep(1000);
                 }
             }
-            __syncwarp(am);
+            tile = __shfl_sync(0xffffffffu, v, 0) - 1;
             __threadfence();                                   // the leader's acquire, extended to the lanes that waited
         }
-        const uint32_t b = p.order[r];
+        const int64_t rr = (int64_t)tile * NS + s;                     // rank in the length-sorted order
+        if (rr >= p.B) continue;
+        const uint32_t b = p.order[rr];
         if (p.is_long && p.is_long[b]) continue;                      // the warp-per-sequence kernel owns this sequence
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
