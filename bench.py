@@ -503,6 +503,10 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other configs")
     ap.add_argument("--no-large-full", action="store_true", help="skip the full-size configs[3] pass of the `other` legs")
+    ap.add_argument("--depth", type=int, default=2,
+                    help="batches in flight on the device-resident leg: consecutive steps alternate between this many "
+                         "streams / model handles, so one step's sort and launch ramp overlap the previous step's backtrace "
+                         "tail and all-gather (1 = strictly one after the other)")
     ap.add_argument("--cp-sharded", default="heavy:2000", metavar="KIND:NODES",
                     help="with --gpus > 1: the constrained decode sharded over the ranks (csrc/cp_dist.cuh) next to the "
                          "single-GPU solve, e.g. heavy:2000 (configs[4], the default) or trucks:0; 'off' skips it")
@@ -521,6 +525,8 @@ def config_block(wl, world):
     return {"workload": wl["name"], "desc": wl["desc"], "sequences": B, "elements": N, "cells_per_step": wl["cells"],
             "sharding": f"the batch cut into {world} contiguous slices by forward steps, one per GPU; decoded paths and "
                         "scores all-gathered (ncclAllGather) inside the timed region" if world > 1 else "1 GPU, whole batch",
+            "batches_in_flight": "2 on the device-resident leg (consecutive steps alternate between two streams / model handles; "
+                                 "ms_per_step_depth1 = strictly one after the other), 1 on the e2e leg",
             "l2": "inputs + delta history per step >> 126 MB L2 (no flush needed)"}
 
 
@@ -611,36 +617,73 @@ def main():
     peak_mix = ops.value
 
     # ---- this rank's slice, device resident; results land in the padded all-gather buffers ----
-    sd = ShardedDecoder(hmm, off_np, device=local)
-    sd.load_obs(obs_np)
+    # `depth` independent pipelines (own model handle = own workspaces, own buffers, own stream): step i runs on
+    # pipeline i % depth, so consecutive batches overlap at their edges -- what a throughput-oriented caller does
+    depth = max(1, args.depth)
+    hmms = [hmm] + [cv.HMM(wl["A"], wl["B"], wl["pi"]) for _ in range(depth - 1)]
+    sds = [ShardedDecoder(hm, off_np, device=local) for hm in hmms]
+    for x in sds:
+        x.load_obs(obs_np)
+    sd = sds[0]
     my_cells = float(((np.diff(sd.off_l_np) - 1) * K * K).sum())
     stream = torch.cuda.current_stream()
+    pipes = [torch.cuda.Stream() for _ in range(depth)] if depth > 1 else [stream]
+    step_no = [0]
 
     def step_dev():
-        sd.step()                                  # cv_decode_batch_dev (+ in-place ncclAllGather when world > 1)
-        if world > 1:
-            return sd.paths(), sd.scores()         # batch-ordered results on every rank
+        i = step_no[0] % depth
+        step_no[0] += 1
+        with torch.cuda.stream(pipes[i]):
+            sds[i].step()                          # cv_decode_batch_dev (+ in-place ncclAllGather when world > 1)
+            if world > 1:
+                return sds[i].paths(), sds[i].scores()     # batch-ordered results on every rank
         return None
+
+    def fork():                                    # the pipelines start behind everything enqueued on the main stream
+        if depth > 1:
+            for ps in pipes:
+                ps.wait_stream(stream)
+
+    def join():                                    # ... and the main stream continues behind all of them
+        if depth > 1:
+            for ps in pipes:
+                stream.wait_stream(ps)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    fork()
     for _ in range(args.warmup):
         step_dev()
+    join()
     barrier()
     launches0 = L.cv_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
         e0.record(stream)
+        fork()
         for _ in range(args.steps):
             step_dev()
+        join()
         e1.record(stream)
         barrier()
     launches = L.cv_launch_count() - launches0
     dev_ms = e0.elapsed_time(e1)
+    # the same steps strictly one after the other on one stream (no overlap between consecutive batches)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        sd.step()
+        if world > 1:
+            sd.paths(); sd.scores()
+    e1.record(stream)
+    barrier()
+    serial_ms = e0.elapsed_time(e1) / args.steps
+    for x in sds[1:]:                              # every pipeline computed the same batch
+        assert torch.equal(x.gpaths, sd.gpaths) and torch.equal(x.gscores, sd.gscores), "pipelines disagree"
     full_paths = sd.paths().cpu().numpy()
     full_paths = full_paths.astype(np.uint32) if sd.narrow_paths else full_paths.view(np.uint32)
     full_scores = sd.scores().cpu().numpy()
@@ -791,7 +834,8 @@ def main():
         except Exception as e:  # noqa: BLE001
             cp_sharded = {"error": repr(e)}
 
-    per_rank = allgather_vals([dev_ms / args.steps, 1e3 * e2e_s, fwd, bt, gather_ms, float(n_sq), my_cells])
+    per_rank = allgather_vals([dev_ms / args.steps, serial_ms, 1e3 * e2e_s, fwd, bt, gather_ms, float(n_sq), my_cells])
+    serial_ms = allred(serial_ms, MAX)
     dev_ms = allred(dev_ms, MAX)
     e2e_s = allred(e2e_s, MAX)
     if narrow_s is not None:
@@ -830,6 +874,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_block(wl, world),
+            "ms_per_step_depth1": serial_ms, "value_depth1": wl["cells"] / (serial_ms * 1e-3),
             "e2e": {"value": wl["cells"] / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(4 * n_el + 8 * (n_sq + 1)),
                     "d2h_bytes_per_step": int(4 * n_el + 8 * n_sq), "ms_per_step": 1e3 * e2e_s,
@@ -845,7 +890,7 @@ def main():
                 "frac": achieved_alu / peak_mix,
                 "frac_on_step": 2.0 * wl["cells"] / world / (step_ms * 1e-3) / peak_mix,
                 "frac_note": "frac = the forward kernel timed alone (CUDA events on its stream); frac_on_step = the same "
-                             "algorithmic operations over the whole driver-timed step (forward + concurrent backtrace"
+                             "algorithmic operations over the whole driver-timed step (forward + concurrent backtrace, two batches in flight"
                              + (" + all-gather" if world > 1 else "") + ")",
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: DADD+DSETP issue rate over all SMs (cv_debug_probe_fp64 mode 1); "
@@ -868,7 +913,7 @@ def main():
                                   "share_of_step": gather_ms / max(step_ms, 1e-9),
                                   "path_element_bytes": int(sd.gpaths.element_size()),
                                   "bytes_received_per_rank": int((world - 1) * (sd.gpaths.shape[1] * sd.gpaths.element_size() + sd.gscores.shape[1] * 8))}
-            line["per_rank"] = {"columns": ["step_ms", "e2e_ms", "fwd_kernel_ms", "backtrace_ms", "gather_ms", "sequences", "cells"],
+            line["per_rank"] = {"columns": ["step_ms", "step_ms_depth1", "e2e_ms", "fwd_kernel_ms", "backtrace_ms", "gather_ms", "sequences", "cells"],
                                 "rows": per_rank, "host_affinity": affinity}
             if weak is not None:
                 line["weak_scaling"] = weak
@@ -878,8 +923,9 @@ def main():
             if par is not None:
                 line["parity"] = par
         if not args.no_other and world == 1 and args.workload == "pos":
-            hmm.close()                                   # free the POS workspaces (9 GB of history) first
-            del sd
+            for hm in hmms:                               # free the POS workspaces (9 GB of history each) first
+                hm.close()
+            del sd, sds
             torch.cuda.empty_cache()
             try:
                 line["other"] = run_other(cv, L, local, peak_mix, hbm_peak, large_full=not args.no_large_full)
