@@ -503,10 +503,6 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other configs")
     ap.add_argument("--no-large-full", action="store_true", help="skip the full-size configs[3] pass of the `other` legs")
-    ap.add_argument("--depth", type=int, default=2,
-                    help="batches in flight on the device-resident leg: consecutive steps alternate between this many "
-                         "streams / model handles, so one step's sort and launch ramp overlap the previous step's backtrace "
-                         "tail and all-gather (1 = strictly one after the other)")
     ap.add_argument("--cp-sharded", default="heavy:2000", metavar="KIND:NODES",
                     help="with --gpus > 1: the constrained decode sharded over the ranks (csrc/cp_dist.cuh) next to the "
                          "single-GPU solve, e.g. heavy:2000 (configs[4], the default) or trucks:0; 'off' skips it")
@@ -525,8 +521,7 @@ def config_block(wl, world):
     return {"workload": wl["name"], "desc": wl["desc"], "sequences": B, "elements": N, "cells_per_step": wl["cells"],
             "sharding": f"the batch cut into {world} contiguous slices by forward steps, one per GPU; decoded paths and "
                         "scores all-gathered (ncclAllGather) inside the timed region" if world > 1 else "1 GPU, whole batch",
-            "batches_in_flight": "2 on the device-resident leg (consecutive steps alternate between two streams / model handles; "
-                                 "ms_per_step_depth1 = strictly one after the other), 1 on the e2e leg",
+
             "l2": "inputs + delta history per step >> 126 MB L2 (no flush needed)"}
 
 
@@ -617,73 +612,28 @@ def main():
     peak_mix = ops.value
 
     # ---- this rank's slice, device resident; results land in the padded all-gather buffers ----
-    # `depth` independent pipelines (own model handle = own workspaces, own buffers, own stream): step i runs on
-    # pipeline i % depth, so consecutive batches overlap at their edges -- what a throughput-oriented caller does
-    depth = max(1, args.depth)
-    hmms = [hmm] + [cv.HMM(wl["A"], wl["B"], wl["pi"]) for _ in range(depth - 1)]
-    sds = [ShardedDecoder(hm, off_np, device=local) for hm in hmms]
-    for x in sds:
-        x.load_obs(obs_np)
-    sd = sds[0]
+    sd = ShardedDecoder(hmm, off_np, device=local)
+    sd.load_obs(obs_np)
     my_cells = float(((np.diff(sd.off_l_np) - 1) * K * K).sum())
     stream = torch.cuda.current_stream()
-    pipes = [torch.cuda.Stream() for _ in range(depth)] if depth > 1 else [stream]
-    step_no = [0]
 
     def step_dev():
-        i = step_no[0] % depth
-        step_no[0] += 1
-        with torch.cuda.stream(pipes[i]):
-            sds[i].step()                          # cv_decode_batch_dev (+ in-place ncclAllGather when world > 1)
-            if world > 1:
-                return sds[i].paths(), sds[i].scores()     # batch-ordered results on every rank
-        return None
+        sd.step()      # cv_decode_batch_dev(_u8) into this rank's row of the gather buffer (+ one in-place ncclAllGather when world > 1)
 
-    def fork():                                    # the pipelines start behind everything enqueued on the main stream
-        if depth > 1:
-            for ps in pipes:
-                ps.wait_stream(stream)
-
-    def join():                                    # ... and the main stream continues behind all of them
-        if depth > 1:
-            for ps in pipes:
-                stream.wait_stream(ps)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    fork()
     for _ in range(args.warmup):
         step_dev()
-    join()
     barrier()
     launches0 = L.cv_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
         e0.record(stream)
-        fork()
         for _ in range(args.steps):
             step_dev()
-        join()
         e1.record(stream)
         barrier()
     launches = L.cv_launch_count() - launches0
     dev_ms = e0.elapsed_time(e1)
-    # the same steps strictly one after the other on one stream (no overlap between consecutive batches)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        sd.step()
-        if world > 1:
-            sd.paths(); sd.scores()
-    e1.record(stream)
-    barrier()
-    serial_ms = e0.elapsed_time(e1) / args.steps
-    for x in sds[1:]:                              # every pipeline computed the same batch
-        assert torch.equal(x.gpaths, sd.gpaths) and torch.equal(x.gscores, sd.gscores), "pipelines disagree"
     full_paths = sd.paths().cpu().numpy()
     full_paths = full_paths.astype(np.uint32) if sd.narrow_paths else full_paths.view(np.uint32)
     full_scores = sd.scores().cpu().numpy()
@@ -699,7 +649,6 @@ def main():
         g1.record(stream)
         for _ in range(args.steps):
             sd.gather()
-            sd.paths(); sd.scores()
         g2.record(stream)
         barrier()
         local_ms, gather_ms = g0.elapsed_time(g1) / args.steps, g1.elapsed_time(g2) / args.steps
@@ -834,8 +783,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             cp_sharded = {"error": repr(e)}
 
-    per_rank = allgather_vals([dev_ms / args.steps, serial_ms, 1e3 * e2e_s, fwd, bt, gather_ms, float(n_sq), my_cells])
-    serial_ms = allred(serial_ms, MAX)
+    per_rank = allgather_vals([dev_ms / args.steps, 1e3 * e2e_s, fwd, bt, gather_ms, float(n_sq), my_cells])
     dev_ms = allred(dev_ms, MAX)
     e2e_s = allred(e2e_s, MAX)
     if narrow_s is not None:
@@ -874,7 +822,6 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_block(wl, world),
-            "ms_per_step_depth1": serial_ms, "value_depth1": wl["cells"] / (serial_ms * 1e-3),
             "e2e": {"value": wl["cells"] / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(4 * n_el + 8 * (n_sq + 1)),
                     "d2h_bytes_per_step": int(4 * n_el + 8 * n_sq), "ms_per_step": 1e3 * e2e_s,
@@ -890,7 +837,7 @@ def main():
                 "frac": achieved_alu / peak_mix,
                 "frac_on_step": 2.0 * wl["cells"] / world / (step_ms * 1e-3) / peak_mix,
                 "frac_note": "frac = the forward kernel timed alone (CUDA events on its stream); frac_on_step = the same "
-                             "algorithmic operations over the whole driver-timed step (forward + concurrent backtrace, two batches in flight"
+                             "algorithmic operations over the whole driver-timed step (forward + concurrent backtrace"
                              + (" + all-gather" if world > 1 else "") + ")",
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: DADD+DSETP issue rate over all SMs (cv_debug_probe_fp64 mode 1); "
@@ -907,13 +854,13 @@ def main():
                                   "api": "cv_decode_batch_u16u8 (u16 observations, u8 states; per rank, no collective)",
                                   "note": "secondary: the reference-shaped u32 call above is the headline e2e"}
         if world > 1:
-            line["collective"] = {"name": "ncclAllGather (torch.distributed.all_gather_into_tensor, in place) of paths (u8 states for "
-                                          "K <= 64, else u32) and scores (f64), padded to the largest slice, + un-padding concatenation",
+            line["collective"] = {"name": "one in-place ncclAllGather (torch.distributed.all_gather_into_tensor) of the [world][scores f64 | "
+                                          "paths u8 (K <= 64, else u32)] buffer, rows padded to the largest slice",
                                   "ms_per_step": gather_ms, "local_decode_ms_per_step": local_ms,
                                   "share_of_step": gather_ms / max(step_ms, 1e-9),
                                   "path_element_bytes": int(sd.gpaths.element_size()),
-                                  "bytes_received_per_rank": int((world - 1) * (sd.gpaths.shape[1] * sd.gpaths.element_size() + sd.gscores.shape[1] * 8))}
-            line["per_rank"] = {"columns": ["step_ms", "step_ms_depth1", "e2e_ms", "fwd_kernel_ms", "backtrace_ms", "gather_ms", "sequences", "cells"],
+                                  "bytes_received_per_rank": int((world - 1) * sd.gbuf.shape[1])}
+            line["per_rank"] = {"columns": ["step_ms", "e2e_ms", "fwd_kernel_ms", "backtrace_ms", "gather_ms", "sequences", "cells"],
                                 "rows": per_rank, "host_affinity": affinity}
             if weak is not None:
                 line["weak_scaling"] = weak
@@ -923,9 +870,8 @@ def main():
             if par is not None:
                 line["parity"] = par
         if not args.no_other and world == 1 and args.workload == "pos":
-            for hm in hmms:                               # free the POS workspaces (9 GB of history each) first
-                hm.close()
-            del sd, sds
+            hmm.close()                                   # free the POS workspaces (9 GB of history) first
+            del sd
             torch.cuda.empty_cache()
             try:
                 line["other"] = run_other(cv, L, local, peak_mix, hbm_peak, large_full=not args.no_large_full)

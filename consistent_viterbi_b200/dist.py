@@ -4,9 +4,11 @@ contiguous slice ... NCCL over NVLink is used only to all-gather decoded paths")
 Sequences are independent units (`viterbi::decode` is called once per sequence, viterbi.rs:5), so the batch is cut
 into one contiguous slice per rank, balanced by forward steps; the model is replicated.  One process per GPU,
 `torch.distributed` (NCCL) for the plumbing.  The data path never leaves the device between the decode and the
-collective: `cv_decode_batch_dev` writes this rank's paths / scores straight into its row of the padded gather
-buffers and one in-place `all_gather_into_tensor` per buffer (ncclAllGather over NVLink) completes them on every
-rank.  The collective is the only exchange; there is no reduction on this path."""
+collective: `cv_decode_batch_dev(_u8)` writes this rank's scores and paths straight into its row of ONE padded
+gather buffer and one in-place `all_gather_into_tensor` (ncclAllGather over NVLink) completes it on every rank.  The
+collective is the only exchange; there is no reduction on this path.  The gathered product is the padded buffer
+(row r = rank r's slice: `gscores[r, :n_sq[r]]`, `gpaths[r, :n_el[r]]`); `paths()` / `scores()` concatenate the rows
+into batch order for callers that want one flat array."""
 from __future__ import annotations
 
 import numpy as np
@@ -41,11 +43,12 @@ class ShardedDecoder:
 
     Every rank builds it with the same `seq_off`.  Buffers (torch tensors on this rank's device):
       obs_l   [n_el(rank)]  int32   this rank's slice of the observations (fill with `load_obs` or write in place)
-      gpaths  [world, P]    uint8 / int32  padded gather buffer, P = max_r n_el(r); row r = paths of rank r's slice
+      gbuf    [world, 8*S + P*e] uint8  the gather buffer, one row per rank: scores first, then paths
+      gscores [world, S]    float64 view of gbuf, S = max_r n_seq(r)
+      gpaths  [world, P]    uint8 / int32 view of gbuf, P = max_r n_el(r); row r = paths of rank r's slice
                             (u8 states when K <= 64 -- a quarter of the all-gather bytes -- else u32 bit patterns)
-      gscores [world, S]    float64 S = max_r n_seq(r)
-    `step()` enqueues decode + all-gather on the current stream; `paths()` / `scores()` return the batch-ordered
-    results (device tensors, one concatenation of the un-padded rows).
+    `step()` enqueues decode + ONE in-place all-gather on the current stream; `paths()` / `scores()` return the
+    batch-ordered results (device tensors, one concatenation of the un-padded rows).
 
     `decode_fn(obs_np, off_np) -> (paths, scores)` replaces the GPU call in the CPU-only (gloo) host-logic tests."""
 
@@ -83,8 +86,10 @@ class ShardedDecoder:
         P, S = (P + 15) // 16 * 16, (S + 1) // 2 * 2
         self.off_l = torch.from_numpy(off_l.copy()).to(self.dev)
         self.obs_l = torch.zeros(max(self.n_el[self.rank], 1), dtype=torch.int32, device=self.dev)
-        self.gpaths = torch.zeros((self.world, P), dtype=torch.uint8 if self.narrow_paths else torch.int32, device=self.dev)
-        self.gscores = torch.zeros((self.world, S), dtype=torch.float64, device=self.dev)
+        pbytes = P * (1 if self.narrow_paths else 4)
+        self.gbuf = torch.zeros((self.world, 8 * S + pbytes), dtype=torch.uint8, device=self.dev)
+        self.gscores = self.gbuf[:, : 8 * S].view(torch.float64)
+        self.gpaths = self.gbuf[:, 8 * S:] if self.narrow_paths else self.gbuf[:, 8 * S:].view(torch.int32)
         self.handle = hmm.device_handle(self.device_index) if on_gpu else None
 
     # -- inputs ------------------------------------------------------------------------------------------------
@@ -117,11 +122,10 @@ class ShardedDecoder:
         _lib.check(rc)
 
     def gather(self):
-        """In-place all-gather of both buffers (ncclAllGather: row r of every rank's buffer <- rank r's row)."""
+        """In-place all-gather of the buffer (ncclAllGather: row r of every rank's buffer <- rank r's row)."""
         if self.world == 1:
             return
-        self.dist.all_gather_into_tensor(self.gpaths.view(-1), self.gpaths[self.rank], group=self.group)
-        self.dist.all_gather_into_tensor(self.gscores.view(-1), self.gscores[self.rank], group=self.group)
+        self.dist.all_gather_into_tensor(self.gbuf.view(-1), self.gbuf[self.rank], group=self.group)
 
     def step(self):
         self.decode_local()
