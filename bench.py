@@ -620,6 +620,11 @@ def main():
     def step_dev():
         sd.step()      # cv_decode_batch_dev(_u8) into this rank's row of the gather buffer (+ one in-place ncclAllGather when world > 1)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(args.warmup):
         step_dev()
     barrier()

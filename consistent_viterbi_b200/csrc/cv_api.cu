@@ -689,8 +689,10 @@ static int chunk_count(const cv_hmm *h, int64_t B, bool timing, bool host_buffer
     // Host buffers, streamed past one launch (decode_streamed): 4 chunks measured best (2: 14.8 ms, 3: 14.3, 4: 14.2-14.3,
     // 6: 14.4, 10: 14.8, 16: 15.0 -- every chunk restarts the longest-first tile order); one launch per chunk: 6.
     const bool can_stream = g_tune.streamed && g_tune.bt_concurrent && stream_wait_value32() != nullptr;
-    if (host_buffers && can_stream)        // streamed: the copies hide behind one launch; two chunks already pay for a short batch
-        return (int)std::max<int64_t>(B >= 2 * 8192 ? 2 : 1, std::min<int64_t>(4, B / per_chunk));
+    // Streaming pays from ~450 k sequences: below, every chunk's restart of the longest-first tile order costs more
+    // than the copies it hides (measured: 250 k sequences 4.2 ms streamed in two chunks vs 3.0 ms on the device; one
+    // H2D -> decode -> D2H pass is 3.7 ms), so shorter batches go through in one piece.
+    if (host_buffers && can_stream) return B / per_chunk >= 4 ? 4 : 1;
     return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 6 : dev_chunks, B / per_chunk));
 }
 
