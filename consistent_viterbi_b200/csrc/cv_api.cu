@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "decode_small.cuh"
+#include "decode_prefilter.cuh"
 #include "decode_chain.cuh"
 #include "decode_large.cuh"
 
@@ -48,6 +49,7 @@ static Tuning tuning_from_env()
     t.tp = geti("CV_TP", 2) == 4 ? 4 : 2;
     t.balanced_split = geti("CV_BALANCED", t.balanced_split);
     t.long_split = geti("CV_LONG_SPLIT", t.long_split);
+    t.prefilter = geti("CV_PREFILTER", t.prefilter);
     t.debug = getenv("CV_DEBUG") != nullptr;
     t.bt_prof = getenv("CV_BT_PROF") != nullptr;
     t.e2e_prof = getenv("CV_E2E_PROF") != nullptr;
@@ -122,6 +124,24 @@ __global__ void transpose_kernel(const double *in, double *out, int n)
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8)
         if (bx + r < n && by + threadIdx.x < n) out[(size_t)(bx + r) * n + by + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+// Operands of the pre-filter forward kernel (decode_prefilter.cuh) from the natural layout A [K][Kp]:
+//   A32 [Kp][Kp] f32: row = predecessor j, column = slot c -> rn32(logA[j][state(c)]), clamped to PF_NEG; padding PF_NEG
+//   A64T [Kp][Kp] f64: row = slot c, column = predecessor j -> logA[j][state(c)]; padding -inf
+// state(c) = first(g) + q for slot c = 8 g + q of the balanced split (base, rem), or c itself when base = 0.
+__global__ void build_prefilter_kernel(const double *A, int K, int Kp, int base, int rem, float *A32, double *A64T)
+{
+    const int n = Kp * Kp;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int j = e / Kp, c = e % Kp, g = c >> 3, q = c & 7;
+        int st = c;
+        if (base) { const int first = g * base + min(g, rem), cnt = base + (g < rem ? 1 : 0); st = q < cnt ? first + q : -1; }
+        const bool real = j < K && st >= 0 && st < K;
+        const double v = real ? A[(size_t)j * Kp + st] : neg_inf();
+        A32[(size_t)j * Kp + c] = fmaxf(__double2float_rn(v), PF_NEG);
+        A64T[(size_t)c * Kp + j] = v;
+    }
 }
 
 extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *logA, const double *logB,
@@ -234,6 +254,19 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
     }
+    // every finite entry of logA / logB <= 0 (log-probabilities): the f32 pre-filter's error bound needs it
+    h->nonpositive = true;
+    for (int64_t i = 0; i < (int64_t)K * K && h->nonpositive; i++) if (logA[i] > 0.0) h->nonpositive = false;
+    for (int64_t i = 0; i < (int64_t)K * M && h->nonpositive; i++) if (logB[i] > 0.0) h->nonpositive = false;
+    if (K <= SMALL_K_MAX && h->TQT == 8 && h->nonpositive && K >= 17 && Kp % 8 == 0) {
+        CUDA_TRY(cudaMalloc(&h->dA32, sizeof(float) * (size_t)Kp * Kp));
+        CUDA_TRY(cudaMalloc(&h->dA64T, sizeof(double) * (size_t)Kp * Kp));
+        const bool bal = h->dAb != nullptr;
+        build_prefilter_kernel<<<32, 256>>>(h->dA, K, Kp, bal ? K / h->G : 0, bal ? K % h->G : 0, h->dA32, h->dA64T);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
     if (K > SMALL_K_MAX) {
         CUDA_TRY(cudaMalloc(&h->dATl, sizeof(double) * (size_t)Kp * Kp));
         transpose_kernel<<<dim3((Kp + 31) / 32, (Kp + 31) / 32), dim3(32, 8)>>>(h->dAl, h->dATl, Kp);
@@ -251,7 +284,8 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl, h->dATl, h->dAb, h->dBTb}) if (p) cudaFree(p);
+    for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl, h->dATl, h->dAb, h->dBTb, h->dA64T}) if (p) cudaFree(p);
+    if (h->dA32) cudaFree(h->dA32);
     for (DevBuf *b : {&h->obs, &h->seq_off, &h->path, &h->score}) b->release();
     for (auto &w : h->ws) {
         for (DevBuf *b : {&w.order, &w.keys_in, &w.keys_out, &w.vals_in, &w.cub_tmp, &w.hist, &w.tmax, &w.base, &w.misc,
@@ -465,8 +499,12 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     if (g_tune.small_cfg >= 0) { S = std::max(1, std::min(4, g_tune.small_cfg / 10)); variant = std::max(1, g_tune.small_cfg % 10); }
     int tpt = g_tune.tp;
     if (h->TQT != 8) tpt = 2;
+    // forward kernel with the f32 pre-filter (decode_prefilter.cuh): non-positive models, 64 sequences per tile
+    const bool pf = g_tune.prefilter && h->dA32 && h->TQT == 8 && g_tune.small_cfg < 0 && tpt == 2 && 32 * G <= 256 &&
+                    decode_pf_smem_bytes(h->Kp) <= 113 * 1024;
+    if (pf) S = 1;
     while (S > 1 && (B + 32 * tpt * S - 1) / (32 * tpt * S) < 4 * (int64_t)h->num_sms) S--;
-    size_t smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S);
+    size_t smem = pf ? decode_pf_smem_bytes(h->Kp) : decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S);
     while (smem > 220 * 1024 && S > 1) { S--; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
     if (smem > 220 * 1024 && tpt == 4) { tpt = 2; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
     const int NS = 32 * tpt * S;
@@ -492,7 +530,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     // also checks every tile against hist_cap_rows and reports CV_ERR_UNSUPPORTED instead of storing past the end.
     const size_t stairs = sio ? 2 * (size_t)sio->cbs.nch - 1 : 1;
     const size_t hist_rows = (size_t)N + (size_t)NS * (size_t)max_len * stairs;     // in units of K doubles
-    const size_t hist_elems = hist_rows * (size_t)h->K;
+    const size_t hist_elems = hist_rows * (size_t)(pf ? pf_pitch(h->Kp) : h->K);    // pre-filter kernel: rows of Kp + 2 doubles
     if ((rc = w.hist.ensure(hist_elems * sizeof(double)))) return rc;
     if ((rc = w.tmax.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
     if ((rc = w.base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
@@ -513,7 +551,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     p.At = h->dA; p.BTt = h->dBT; p.nq_base = p.nq_rem = 0;
     p.obs16 = h->obs16; p.path8 = h->path8;
     p.is_long = (ls && ls->lstar) ? ls->is_long : nullptr;
-    if (g_tune.balanced_split && h->dAb && h->TQT == 8 && tpt == 2) {
+    p.A32s = h->dA32; p.A64Ts = h->dA64T;
+    if ((pf || g_tune.balanced_split) && h->dAb && h->TQT == 8 && tpt == 2) {     // (the pre-filter operands are built for the balanced split)
         p.At = h->dAb; p.BTt = h->dBTb; p.nq_base = h->K / G; p.nq_rem = h->K % G;
     }
     p.tile_base = (const long long *)w.base.p;
@@ -526,7 +565,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
         for (int c = 0; c <= sio->cbs.nch; c++) p.cb[c] = sio->cbs.cb[c];
     }
     void (*kern)(DecodeSmallParams);
-    if (h->TQT == 12) kern = variant == 1 ? decode_small_fwd_kernel<12, 512, 1> : decode_small_fwd_kernel<12, 256, 2>;
+    if (pf) kern = decode_pf_fwd_kernel;
+    else if (h->TQT == 12) kern = variant == 1 ? decode_small_fwd_kernel<12, 512, 1> : decode_small_fwd_kernel<12, 256, 2>;
     else if (h->TQT == 6) kern = variant == 1 ? decode_small_fwd_kernel<6, 512, 1> : decode_small_fwd_kernel<6, 256, 2>;
     else if (tpt == 4 && threads <= 256) kern = decode_small_fwd_kernel<8, 256, 1, 4>;
     else if (tpt == 4) kern = decode_small_fwd_kernel<8, 512, 1, 4>;
@@ -539,8 +579,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     occ = std::max(1, occ);
     const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * occ, ntiles);
     if (g_tune.debug)
-        fprintf(stderr, "[cv] decode_small: K=%d TQ=%d TP=%d G=%d S=%d variant=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
-                h->K, h->TQT, tpt, G, S, variant, threads, smem, occ, grid, ntiles);
+        fprintf(stderr, "[cv] decode_small: K=%d TQ=%d TP=%d G=%d S=%d variant=%d prefilter=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",
+                h->K, h->TQT, tpt, G, S, variant, (int)pf, threads, smem, occ, grid, ntiles);
     // Concurrent backtrace: the backtrace kernel runs next to the forward kernel on a second stream and follows
     // it tile by tile (tile_done flags).  It is released only when every forward CTA is resident (stream wait on
     // the `started` counter), so its spinning CTAs can never keep a forward CTA off an SM; it then lives on the
@@ -586,8 +626,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     if (timing || bt_prof) CUDA_TRY(cudaEventRecord(h->ev1, st));
     // end state + backtrace with lazy backpointers: one thread per sequence
     const size_t smem_bt = (size_t)h->K * (h->K | 1) * 8 + 16 * 8;      // + one chunk of padding behind the last row
-    void (*bt_seq)(DecodeSmallParams) = NS == 64 ? backtrace_small_kernel<16, 4, 64> : backtrace_small_kernel<16, 4, 0>;
-    void (*bt_con)(DecodeSmallParams) = NS == 64 ? backtrace_small_kernel<8, 8, 64> : backtrace_small_kernel<8, 8, 0>;
+    void (*bt_seq)(DecodeSmallParams) = pf ? backtrace_small_kernel<16, 4, 64, 1> : NS == 64 ? backtrace_small_kernel<16, 4, 64> : backtrace_small_kernel<16, 4, 0>;
+    void (*bt_con)(DecodeSmallParams) = pf ? backtrace_small_kernel<8, 8, 64, 1> : NS == 64 ? backtrace_small_kernel<8, 8, 64> : backtrace_small_kernel<8, 8, 0>;
     CUDA_TRY(cudaFuncSetAttribute(bt_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
     CUDA_TRY(cudaFuncSetAttribute(bt_con, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
     // same shared-memory carve-out as the forward kernel, or the two kernels cannot share an SM

@@ -49,6 +49,7 @@ struct Tuning {
     int tq = 8;                    // target states per warp of the forward tile kernel: 6, 8, 12, 0 = auto (CV_TQ)
     int tp = 2;                    // sequences per lane: 2 or 4                                  (CV_TP)
     int balanced_split = 1;        // forward tile kernel: state groups of near-equal size, no padded states (CV_BALANCED)
+    int prefilter = 0;             // forward tile kernel with the f32 pre-filter (decode_prefilter.cuh) when the model allows it (CV_PREFILTER)
     int long_split = 1;            // very long sequences of a short batch go to the warp-per-sequence kernel (CV_LONG_SPLIT)
     int debug = 0;                 // print launch shapes                                         (CV_DEBUG)
     int bt_prof = 0, e2e_prof = 0; // print pipeline timelines                                    (CV_BT_PROF, CV_E2E_PROF)
@@ -94,6 +95,8 @@ struct cv_hmm {
     double *dPi = nullptr;   // [Kp]
     // slot-permuted copies for the balanced state split of the forward tile kernel (TQT = 8, K % 8 != 0), else null
     double *dAb = nullptr, *dBTb = nullptr;
+    // pre-filter forward kernel (decode_prefilter.cuh): f32 logA with slot-permuted columns, f64 logA transposed per slot
+    float *dA32 = nullptr; double *dA64T = nullptr;
     // large-K layout
     int Kl = 0;              // K padded to a multiple of LARGE_BN
     double *dAl = nullptr;   // [Kl][Kl]

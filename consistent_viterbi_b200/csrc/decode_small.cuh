@@ -50,6 +50,8 @@ struct DecodeSmallParams {
     const double *A;         // [K][Kp]   logA, columns >= K padded with -inf (natural column order: the backtrace)
     const double *BT;        // [M][Kp]   logB transposed (obs-major), padded -inf
     const double *At, *BTt;  // what the forward tile kernel reads: A / BT, or their slot-permuted copies (balanced split)
+    const float *A32s;       // pre-filter kernel (decode_prefilter.cuh): [Kp][Kp] f32, rows = predecessors, slot-permuted columns
+    const double *A64Ts;     //                                           [Kp][Kp] f64, rows = slots, columns = predecessors
     const uint32_t *obs;     // [N]
     const int64_t *seq_off;  // [B+1]
     const uint32_t *order;   // [B] sequence ids, longest first
@@ -410,11 +412,15 @@ __device__ __forceinline__ void bt_mark_done(const DecodeSmallParams &p, uint32_
 }
 
 // NSC = sequences per tile when known at compile time (64: the load offsets become immediates), 0 = p.NS
-template <int BT_CHUNK, int MINB, int NSC>
+// LAYOUT = 0: history slabs [K][NS] (decode_small_fwd_kernel); 1: [NS][Kp + 2] (decode_pf_fwd_kernel: a sequence's
+// row is contiguous and read as 16-byte vectors)
+template <int BT_CHUNK, int MINB, int NSC, int LAYOUT = 0>
 __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, Kp = p.Kp, NS = NSC ? NSC : p.NS;
+    const size_t JS = LAYOUT ? 1 : (size_t)NS;                // distance between consecutive states of one sequence
+    const size_t SS = LAYOUT ? (size_t)(Kp + 2) : 1;          // distance between consecutive sequences of one state
     const int ATP = K | 1;                                   // odd pitch: rows of different states spread over banks
     double *sAT = reinterpret_cast<double *>(smem_raw);     // sAT[s*ATP + j] = logA[j][s]
     for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) {
@@ -423,7 +429,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
     }
     __syncthreads();
 
-    const size_t sl = (size_t)K * NS;
+    const size_t sl = LAYOUT ? (size_t)NS * (Kp + 2) : (size_t)K * NS;
     const int nfull = K / BT_CHUNK, ktail = K - nfull * BT_CHUNK;   // full chunks, predecessors of the partial last chunk
     const int nchunk = nfull + (ktail ? 1 : 0);
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -456,13 +462,13 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
         if (p.tile_base[tile] + (long long)len > p.hist_cap_slabs) { bt_mark_done(p, b); continue; }   // tile refused by the forward kernel (status 7)
-        const double *col = p.hist + (size_t)p.tile_base[tile] * sl + s;   // column s of slab 0
+        const double *col = p.hist + (size_t)p.tile_base[tile] * sl + (size_t)s * SS;   // sequence s of slab 0
 
         // end state: argmax of the last row (viterbi.rs:24)
         const double *row = col + (size_t)(len - 1) * sl;
         double bv = __ldcs(row); int cur = 0;
         for (int j = 1; j < K; j++) {
-            const double v = __ldcs(row + (size_t)j * NS);
+            const double v = __ldcs(row + (size_t)j * JS);
             if (v > bv) { bv = v; cur = j; }
         }
         if (p.score) p.score[b] = bv;
@@ -477,13 +483,19 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         const double *rowp = col + (size_t)(len - 2) * sl;    // row tt-1
         int64_t pout = off + (len - 2);
         auto load_chunk = [&](const double *prow, int c, double (&dst)[BT_CHUNK]) {
-            const double *q = prow + (size_t)c * (BT_CHUNK * (size_t)NS);
-            if (c < nfull) {
+            const double *q = prow + (size_t)c * (BT_CHUNK * JS);
+            if (LAYOUT && c < nfull) {
 #pragma unroll
-                for (int k = 0; k < BT_CHUNK; k++) dst[k] = __ldcs(q + (size_t)k * NS);
+                for (int k = 0; k < BT_CHUNK; k += 2) {
+                    const double2 v = __ldcs(reinterpret_cast<const double2 *>(q + k));
+                    dst[k] = v.x; dst[k + 1] = v.y;
+                }
+            } else if (c < nfull) {
+#pragma unroll
+                for (int k = 0; k < BT_CHUNK; k++) dst[k] = __ldcs(q + (size_t)k * JS);
             } else {
 #pragma unroll
-                for (int k = 0; k < BT_CHUNK; k++) dst[k] = (k < ktail) ? __ldcs(q + (size_t)k * NS) : neg_inf();
+                for (int k = 0; k < BT_CHUNK; k++) dst[k] = (k < ktail) ? __ldcs(q + (size_t)k * JS) : neg_inf();
             }
         };
         double mv = 0.0; int mi = 0;
@@ -527,7 +539,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
             }
             // psi = 0 when delta[tt][cur] = -inf (emission -inf or all candidates -inf; see header comment)
             cur = (dcur > neg_inf()) ? mi : 0;
-            dcur = __ldcg(rowp + (size_t)cur * NS);              // delta[tt-1][cur]
+            dcur = __ldcg(rowp + (size_t)cur * JS);              // delta[tt-1][cur]
             store_path_at(p, pout, (uint32_t)cur);
             pout--; rowp -= sl;
         };

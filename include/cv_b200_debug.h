@@ -30,6 +30,9 @@ void cv_debug_set_pipeline(int bt_concurrent, int streamed);
 /* forward tile kernel: 1 (default) = balanced state split (state groups of near-equal size over slot-permuted copies
  * of logA / logB^T, no padded target states), 0 = groups of 8 states with the last one padded */
 void cv_debug_set_balanced_split(int on);
+/* forward tile kernel with the f32 pre-filter (csrc/decode_prefilter.cuh) for models whose entries are all <= 0:
+ * 1 = on, 0 = the plain f64 tile kernel */
+void cv_debug_set_prefilter(int on);
 /* row blocks per group of the large-K kernel (0 = automatic: as many as the delta history fits) */
 void cv_debug_set_large_group_rb(long long rb);
 /* constrained solver: 1 = the K sibling leaves of the last component are evaluated by one batched launch, 0 = node by node */

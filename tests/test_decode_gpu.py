@@ -1,5 +1,7 @@
 """GPU parity tests (mode R1): cv_decode_batch through the C ABI against the C
 oracle, bit-exact on paths (u32) and scores (f64 bit patterns)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -416,4 +418,59 @@ def test_long_sequence_split_equals_oracle(K):
         got = d_path.cpu().numpy()
         got = got.astype(np.uint32) if dt == torch.uint8 else got.view(np.uint32)
         assert (got == rp).all() and d_score.cpu().numpy().tobytes() == rs.tobytes()
+    h.close()
+
+
+@pytest.mark.parametrize("K,ties,zero_frac", [(45, False, 0.15), (45, True, 0.0), (24, True, 0.0), (33, False, 0.5), (64, False, 0.05), (17, False, 0.1), (61, True, 0.0)])
+def test_prefilter_forward_kernel_equals_oracle(K, ties, zero_frac):
+    """decode_pf_fwd_kernel (f32 pre-filter + exact f64 pass over the winning block of predecessors) against the
+    oracle: models full of exact ties / +-0.0 / -inf (the "runner-up too close" full-scan path), sparse models (half
+    of the entries -inf), long sequences (delta grows, so does the f32 error), streamed and device-resident paths."""
+    rng = np.random.default_rng(6600 + K)
+    M = 40
+    A, B, pi = random_hmm(rng, K, M, zero_frac=zero_frac, ties=ties)
+    lens = rng.integers(1, 60, size=7000)
+    lens[:6] = rng.integers(2000, 6000, size=6)              # |delta| in the thousands
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    obs = rng.integers(0, M, size=int(off[-1])).astype(np.uint32)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        L.cv_debug_set_chain_max_batch(0)
+        for split in (1, 0):                                      # with and without the long-sequence split
+            L.cv_debug_set_prefilter(1)
+            os.environ  # noqa: B018
+            p, s = cv.decode_batch(h, obs, off)
+            assert (p == rp).all(), "paths"
+            assert s.tobytes() == rs.tobytes(), "score bits"
+            p8, s8 = cv.decode_batch_narrow(h, obs, off)
+            assert (p8 == rp).all() and s8.tobytes() == rs.tobytes()
+    finally:
+        L.cv_debug_set_prefilter(0)
+        L.cv_debug_set_chain_max_batch(-1)
+    h.close()
+
+
+def test_prefilter_is_skipped_for_models_with_positive_entries():
+    """The pre-filter's error bound needs every entry <= 0; a model with a positive log-score takes the plain kernel
+    (and still equals the oracle)."""
+    rng = np.random.default_rng(12)
+    K, M = 40, 30
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    A[3, 5] = 0.75
+    B[7, 2] = 1.5
+    obs, off = random_batch(rng, 9000, M, 1, 40)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        L.cv_debug_set_chain_max_batch(0)
+        L.cv_debug_set_prefilter(1)
+        p, s = cv.decode_batch(h, obs, off)
+        assert (p == rp).all() and s.tobytes() == rs.tobytes()
+    finally:
+        L.cv_debug_set_prefilter(0)
+        L.cv_debug_set_chain_max_batch(-1)
     h.close()

@@ -2,7 +2,8 @@
 
     python tools/fwd_variants.py [nseq] [variants...]        e.g.  python tools/fwd_variants.py 1000000 1 0
 
-variant = cv_debug_set_balanced_split value: 1 = balanced state split (default), 0 = groups of 8 states, last padded.  Prints the forward kernel alone (CUDA events, timing mode), and the device-resident step (forward +
+variant: 1 = balanced state split (default), 0 = groups of 8 states (last one padded), 2 = the pre-filter kernel
+(decode_prefilter.cuh).  Prints the forward kernel alone (CUDA events, timing mode), and the device-resident step (forward +
 concurrent backtrace) for each variant, plus the extra `CV_*` launch-shape settings given in the environment."""
 import ctypes as C
 import json
@@ -43,7 +44,8 @@ def run(sync):
 ref = None
 out = []
 for v in variants:
-    L.cv_debug_set_balanced_split(v)
+    L.cv_debug_set_balanced_split(1 if v else 0)
+    L.cv_debug_set_prefilter(1 if v == 2 else 0)
     for _ in range(3):
         run(0)
     torch.cuda.synchronize()
@@ -70,4 +72,5 @@ for v in variants:
     out.append(rec)
     print(json.dumps(rec), flush=True)
 L.cv_debug_set_balanced_split(1)
+L.cv_debug_set_prefilter(0)
 print(json.dumps({"peak_fp64_ops": peak, "env": {k: v for k, v in os.environ.items() if k.startswith("CV_")}}))
