@@ -474,3 +474,22 @@ def test_prefilter_is_skipped_for_models_with_positive_entries():
         L.cv_debug_set_prefilter(0)
         L.cv_debug_set_chain_max_batch(-1)
     h.close()
+
+
+def test_long_sequence_split_beyond_its_capacity():
+    """More sequences above the split threshold than the warp-per-sequence list holds (4096): the surplus stays in
+    the tiles with its full length -- still the oracle's result."""
+    rng = np.random.default_rng(5300)
+    K, M, Bn = 45, 60, 40000
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    lens = rng.integers(1, 30, size=Bn)
+    lens[rng.choice(Bn, size=5000, replace=False)] = rng.integers(250, 320, size=5000)
+    off = np.zeros(Bn + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    obs = rng.integers(0, M, size=int(off[-1])).astype(np.uint32)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    for _ in range(2):
+        p, s = cv.decode_batch(h, obs, off)
+        assert (p == rp).all() and s.tobytes() == rs.tobytes()
+    h.close()
