@@ -50,7 +50,6 @@ static Tuning tuning_from_env()
     t.balanced_split = geti("CV_BALANCED", t.balanced_split);
     t.long_split = geti("CV_LONG_SPLIT", t.long_split);
     t.prefilter = geti("CV_PREFILTER", t.prefilter);
-    t.uneven_chunks = geti("CV_UNEVEN_CHUNKS", t.uneven_chunks);
     t.debug = getenv("CV_DEBUG") != nullptr;
     t.bt_prof = getenv("CV_BT_PROF") != nullptr;
     t.e2e_prof = getenv("CV_E2E_PROF") != nullptr;
@@ -863,16 +862,11 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     unsigned int *d_maxlen = (unsigned int *)w.misc.p + 17, *d_arrived = (unsigned int *)w.misc.p + 32, *d_chunk_done = d_arrived + 1;
     StreamedIO sio;
     sio.cbs.nch = nch;
-    // Chunk sizes: the forward kernel cannot start before chunk 0 is on the device and the last chunk's paths leave
-    // after the kernels have ended, so with four chunks the outer two are small (1/8 of the batch) and the inner two
-    // carry 3/8 each -- CV_UNEVEN_CHUNKS=0 makes them equal.  (Six chunks with 1/16 at both ends were slower, 13.9 vs
-    // 13.4 ms at 1 M sentences: every chunk restarts the longest-first tile order.)
-    if (nch == 4 && g_tune.uneven_chunks) {
-        static const int w4[5] = {0, 2, 8, 14, 16};
-        for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * w4[k] / 16;
-    } else {
-        for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
-    }
+    // Equal chunks.  Small outer chunks (the forward kernel cannot start before chunk 0 is on the device, the last
+    // chunk's paths leave after the kernels have ended) were measured and lost at 1 M sentences: four chunks of
+    // 1/8, 3/8, 3/8, 1/8 13.45 vs 13.24 ms, six chunks with 1/16 at both ends 13.9 ms -- the uneven middle chunks
+    // restart the longest-first tile order with more work behind them.
+    for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
     sio.d_arrived = d_arrived; sio.d_chunk_done = d_chunk_done;
 
     // From here on copies from / to the caller's host buffers are in flight: every return (error or not) first drains

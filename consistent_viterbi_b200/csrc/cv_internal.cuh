@@ -50,7 +50,6 @@ struct Tuning {
     int tp = 2;                    // sequences per lane: 2 or 4                                  (CV_TP)
     int balanced_split = 1;        // forward tile kernel: state groups of near-equal size, no padded states (CV_BALANCED)
     int prefilter = 0;             // forward tile kernel with the f32 pre-filter (decode_prefilter.cuh) when the model allows it (CV_PREFILTER)
-    int uneven_chunks = 1;         // streamed host path: small first / last chunk (CV_UNEVEN_CHUNKS)
     int long_split = 1;            // very long sequences of a short batch go to the warp-per-sequence kernel (CV_LONG_SPLIT)
     int debug = 0;                 // print launch shapes                                         (CV_DEBUG)
     int bt_prof = 0, e2e_prof = 0; // print pipeline timelines                                    (CV_BT_PROF, CV_E2E_PROF)
