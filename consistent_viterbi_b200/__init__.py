@@ -7,9 +7,9 @@ include/cv_b200.h) and the host-side mirror of the reference's solver interface.
 from . import _lib
 from ._lib import CvError
 from .hmm import HMM
-from .viterbi import decode, decode_batch, decode_batch_narrow
+from .viterbi import decode, decode_batch, decode_batch_f32, decode_batch_narrow
 from .cp import CPSolver, CpDistGroup, Solver, cfn_tables, cp_solve_arrays, plan_cuts
 from .superseq import Constraints, SuperSequence, load_sequences, load_tags
 
-__all__ = ["HMM", "decode", "decode_batch", "decode_batch_narrow", "CPSolver", "Solver", "cp_solve_arrays", "CpDistGroup", "plan_cuts", "cfn_tables", "Constraints",
+__all__ = ["HMM", "decode", "decode_batch", "decode_batch_narrow", "decode_batch_f32", "CPSolver", "Solver", "cp_solve_arrays", "CpDistGroup", "plan_cuts", "cfn_tables", "Constraints",
            "SuperSequence", "load_sequences", "load_tags", "CvError", "_lib"]

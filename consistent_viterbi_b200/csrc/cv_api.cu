@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "decode_small.cuh"
 #include "decode_prefilter.cuh"
+#include "decode_f32.cuh"
 #include "decode_chain.cuh"
 #include "decode_large.cuh"
 
@@ -124,6 +125,19 @@ __global__ void transpose_kernel(const double *in, double *out, int n)
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8)
         if (bx + r < n && by + threadIdx.x < n) out[(size_t)(bx + r) * n + by + threadIdx.x] = tile[threadIdx.x][r];
+}
+
+// f32 copies for the optional f32 mode (decode_f32.cuh): out[r][c] = rn32(in[r][state(c)]) with the slot permutation of
+// the balanced split (base = 0: identity), -inf padding.
+__global__ void build_f32_kernel(const double *in, float *out, int64_t rows, int K, int Kp, int base, int rem)
+{
+    const int64_t n = rows * Kp, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int64_t r = e / Kp; const int c = (int)(e % Kp), g = c >> 3, q = c & 7;
+        int st = c;
+        if (base) { const int first = g * base + min(g, rem), cnt = base + (g < rem ? 1 : 0); st = q < cnt ? first + q : -1; }
+        out[e] = (st >= 0 && st < K) ? __double2float_rn(in[r * Kp + st]) : __int_as_float(0xff800000);
+    }
 }
 
 // Operands of the pre-filter forward kernel (decode_prefilter.cuh) from the natural layout A [K][Kp]:
@@ -254,6 +268,20 @@ extern "C" int cv_hmm_create(int K, int D, const uint64_t *bdims, const double *
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
     }
+    if (K <= SMALL_K_MAX && h->TQT == 8 && Kp % 8 == 0) {
+        // optional f32 mode (cv_decode_batch_f32): f32 copies of the model
+        const bool bal = h->dAb != nullptr;
+        const int base = bal ? K / h->G : 0, rem = bal ? K % h->G : 0;
+        CUDA_TRY(cudaMalloc(&h->dA32n, sizeof(float) * (size_t)K * Kp));
+        CUDA_TRY(cudaMalloc(&h->dA32f, sizeof(float) * (size_t)K * Kp));
+        CUDA_TRY(cudaMalloc(&h->dBT32, sizeof(float) * (size_t)M * Kp));
+        build_f32_kernel<<<32, 256>>>(h->dA, h->dA32n, K, K, Kp, 0, 0);
+        build_f32_kernel<<<32, 256>>>(h->dA, h->dA32f, K, K, Kp, base, rem);
+        build_f32_kernel<<<std::max(1, h->num_sms) * 4, 256>>>(h->dBT, h->dBT32, M, K, Kp, base, rem);
+        g_launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
     // every finite entry of logA / logB <= 0 (log-probabilities): the f32 pre-filter's error bound needs it
     h->nonpositive = true;
     for (int64_t i = 0; i < (int64_t)K * K && h->nonpositive; i++) if (logA[i] > 0.0) h->nonpositive = false;
@@ -285,7 +313,7 @@ extern "C" void cv_hmm_destroy(cv_hmm *h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (double *p : {h->dA, h->dBT, h->dPi, h->dAl, h->dBTl, h->dATl, h->dAb, h->dBTb, h->dA64T}) if (p) cudaFree(p);
-    if (h->dA32) cudaFree(h->dA32);
+    for (float *p : {h->dA32, h->dA32n, h->dA32f, h->dBT32}) if (p) cudaFree(p);
     for (DevBuf *b : {&h->obs, &h->seq_off, &h->path, &h->score}) b->release();
     for (auto &w : h->ws) {
         for (DevBuf *b : {&w.order, &w.keys_in, &w.keys_out, &w.vals_in, &w.cub_tmp, &w.hist, &w.tmax, &w.base, &w.misc,
@@ -415,7 +443,7 @@ struct StreamedIO {
 // average resident CTA executes in this launch; never below 64 steps; 0 = no split (nothing is that long).
 static uint32_t long_threshold(const cv_hmm *h, int64_t N, int64_t max_len)
 {
-    if (!g_tune.long_split || max_len <= 0 || h->K > SMALL_K_MAX) return 0;
+    if (!g_tune.long_split || max_len <= 0 || h->K > SMALL_K_MAX || h->f32mode) return 0;   // (the warp-per-sequence kernel is f64)
     const int64_t per_cta = (N / 64) / std::max<int64_t>(1, (int64_t)h->num_sms * 2);
     const int64_t l = std::max<int64_t>(64, per_cta * 7 / 10);
     return l >= max_len ? 0u : (uint32_t)std::min<int64_t>(l, 0xffffff);
@@ -500,11 +528,14 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     int tpt = g_tune.tp;
     if (h->TQT != 8) tpt = 2;
     // forward kernel with the f32 pre-filter (decode_prefilter.cuh): non-positive models, 64 sequences per tile
-    const bool pf = g_tune.prefilter && h->dA32 && h->TQT == 8 && g_tune.small_cfg < 0 && tpt == 2 && 32 * G <= 256 &&
+    const bool pf = !h->f32mode && g_tune.prefilter && h->dA32 && h->TQT == 8 && g_tune.small_cfg < 0 && tpt == 2 && 32 * G <= 256 &&
                     decode_pf_smem_bytes(h->Kp) <= 113 * 1024;
-    if (pf) S = 1;
+    // optional f32 mode (decode_f32.cuh): its own forward kernel, f32 history, f32 backtrace
+    const bool f32 = h->f32mode && h->dA32f && h->TQT == 8 && g_tune.small_cfg < 0 && tpt == 2 && 32 * G <= 256;
+    if (h->f32mode && !f32) return fail(CV_ERR_UNSUPPORTED, "the f32 mode needs the default tile shape (K <= 64)");
+    if (pf || f32) S = 1;
     while (S > 1 && (B + 32 * tpt * S - 1) / (32 * tpt * S) < 4 * (int64_t)h->num_sms) S--;
-    size_t smem = pf ? decode_pf_smem_bytes(h->Kp) : decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S);
+    size_t smem = f32 ? decode_f32_smem_bytes(h->K, h->Kp) : pf ? decode_pf_smem_bytes(h->Kp) : decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S);
     while (smem > 220 * 1024 && S > 1) { S--; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
     if (smem > 220 * 1024 && tpt == 4) { tpt = 2; smem = decode_small_smem_bytes(h->K, h->Kp, 32 * tpt * S); }
     const int NS = 32 * tpt * S;
@@ -531,7 +562,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     const size_t stairs = sio ? 2 * (size_t)sio->cbs.nch - 1 : 1;
     const size_t hist_rows = (size_t)N + (size_t)NS * (size_t)max_len * stairs;     // in units of K doubles
     const size_t hist_elems = hist_rows * (size_t)(pf ? pf_pitch(h->Kp) : h->K);    // pre-filter kernel: rows of Kp + 2 doubles
-    if ((rc = w.hist.ensure(hist_elems * sizeof(double)))) return rc;
+    if ((rc = w.hist.ensure(hist_elems * (f32 ? sizeof(float) : sizeof(double))))) return rc;
     if ((rc = w.tmax.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
     if ((rc = w.base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
     if (sio) {
@@ -551,8 +582,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     p.At = h->dA; p.BTt = h->dBT; p.nq_base = p.nq_rem = 0;
     p.obs16 = h->obs16; p.path8 = h->path8;
     p.is_long = (ls && ls->lstar) ? ls->is_long : nullptr;
-    p.A32s = h->dA32; p.A64Ts = h->dA64T;
-    if ((pf || g_tune.balanced_split) && h->dAb && h->TQT == 8 && tpt == 2) {     // (the pre-filter operands are built for the balanced split)
+    p.A32s = f32 ? h->dA32f : h->dA32; p.A64Ts = h->dA64T; p.A32n = h->dA32n; p.BT32 = h->dBT32;
+    if ((pf || f32 || g_tune.balanced_split) && h->dAb && h->TQT == 8 && tpt == 2) {     // (the pre-filter operands are built for the balanced split)
         p.At = h->dAb; p.BTt = h->dBTb; p.nq_base = h->K / G; p.nq_rem = h->K % G;
     }
     p.tile_base = (const long long *)w.base.p;
@@ -565,7 +596,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
         for (int c = 0; c <= sio->cbs.nch; c++) p.cb[c] = sio->cbs.cb[c];
     }
     void (*kern)(DecodeSmallParams);
-    if (pf) kern = decode_pf_fwd_kernel;
+    if (f32) kern = decode_f32_fwd_kernel;
+    else if (pf) kern = decode_pf_fwd_kernel;
     else if (h->TQT == 12) kern = variant == 1 ? decode_small_fwd_kernel<12, 512, 1> : decode_small_fwd_kernel<12, 256, 2>;
     else if (h->TQT == 6) kern = variant == 1 ? decode_small_fwd_kernel<6, 512, 1> : decode_small_fwd_kernel<6, 256, 2>;
     else if (tpt == 4 && threads <= 256) kern = decode_small_fwd_kernel<8, 256, 1, 4>;
@@ -626,8 +658,8 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     if (timing || bt_prof) CUDA_TRY(cudaEventRecord(h->ev1, st));
     // end state + backtrace with lazy backpointers: one thread per sequence
     const size_t smem_bt = (size_t)h->K * (h->K | 1) * 8 + 16 * 8;      // + one chunk of padding behind the last row
-    void (*bt_seq)(DecodeSmallParams) = pf ? backtrace_small_kernel<16, 4, 64, 1> : NS == 64 ? backtrace_small_kernel<16, 4, 64> : backtrace_small_kernel<16, 4, 0>;
-    void (*bt_con)(DecodeSmallParams) = pf ? backtrace_small_kernel<8, 8, 64, 1> : NS == 64 ? backtrace_small_kernel<8, 8, 64> : backtrace_small_kernel<8, 8, 0>;
+    void (*bt_seq)(DecodeSmallParams) = f32 ? backtrace_small_kernel<16, 4, 64, 0, float> : pf ? backtrace_small_kernel<16, 4, 64, 1> : NS == 64 ? backtrace_small_kernel<16, 4, 64> : backtrace_small_kernel<16, 4, 0>;
+    void (*bt_con)(DecodeSmallParams) = f32 ? backtrace_small_kernel<8, 8, 64, 0, float> : pf ? backtrace_small_kernel<8, 8, 64, 1> : NS == 64 ? backtrace_small_kernel<8, 8, 64> : backtrace_small_kernel<8, 8, 0>;
     CUDA_TRY(cudaFuncSetAttribute(bt_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
     CUDA_TRY(cudaFuncSetAttribute(bt_con, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
     // same shared-memory carve-out as the forward kernel, or the two kernels cannot share an SM
@@ -764,6 +796,17 @@ extern "C" int cv_decode_batch_dev_u8(cv_hmm *h, const uint32_t *d_obs, const in
     h->path8 = 1;
     const int rc = decode_batch_dev_impl(h, d_obs, d_off, B, N, max_len, reinterpret_cast<uint32_t *>(d_path), d_score, stream, sync_status);
     h->path8 = 0;
+    return rc;
+}
+
+extern "C" int cv_decode_batch_dev_f32(cv_hmm *h, const uint32_t *d_obs, const int64_t *d_off, int64_t B, int64_t N,
+                                       int64_t max_len, uint32_t *d_path, double *d_score, void *stream, int sync_status)
+{
+    if (!h) return fail(CV_ERR_ARG, "NULL model");
+    if (!h->dA32f) return fail(CV_ERR_UNSUPPORTED, "the f32 mode is implemented for K <= %d", SMALL_K_MAX);
+    h->f32mode = 1;
+    const int rc = decode_batch_dev_impl(h, d_obs, d_off, B, N, max_len, d_path, d_score, stream, sync_status);
+    h->f32mode = 0;
     return rc;
 }
 
@@ -977,6 +1020,17 @@ extern "C" int cv_decode_batch_keep(cv_hmm *h, const uint32_t *obs_flat, const i
 {
     if (!d_path_keep || !d_score_keep) return fail(CV_ERR_ARG, "NULL device buffer");
     return decode_batch_host(h, obs_flat, seq_off, B, path_out, score_out, d_path_keep, d_score_keep);
+}
+
+extern "C" int cv_decode_batch_f32(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off, int64_t B,
+                                   uint32_t *path_out, double *score_out)
+{
+    if (!h) return fail(CV_ERR_ARG, "NULL model");
+    if (!h->dA32f) return fail(CV_ERR_UNSUPPORTED, "the f32 mode is implemented for K <= %d", SMALL_K_MAX);
+    h->f32mode = 1;
+    const int rc = decode_batch_host(h, obs_flat, seq_off, B, path_out, score_out, nullptr, nullptr);
+    h->f32mode = 0;
+    return rc;
 }
 
 extern "C" int cv_decode_batch_u16u8(cv_hmm *h, const uint16_t *obs_flat, const int64_t *seq_off, int64_t B,

@@ -97,6 +97,9 @@ struct cv_hmm {
     double *dAb = nullptr, *dBTb = nullptr;
     // pre-filter forward kernel (decode_prefilter.cuh): f32 logA with slot-permuted columns, f64 logA transposed per slot
     float *dA32 = nullptr; double *dA64T = nullptr;
+    // f32 mode (decode_f32.cuh): rn32(logA) natural [K][Kp] and slot-permuted [K][Kp], rn32(logB^T) slot-permuted [M][Kp]
+    float *dA32n = nullptr, *dA32f = nullptr, *dBT32 = nullptr;
+    int f32mode = 0;                          // the call in progress is cv_decode_batch_f32 / cv_decode_batch_dev_f32
     // large-K layout
     int Kl = 0;              // K padded to a multiple of LARGE_BN
     double *dAl = nullptr;   // [Kl][Kl]

@@ -50,6 +50,8 @@ struct DecodeSmallParams {
     const double *A;         // [K][Kp]   logA, columns >= K padded with -inf (natural column order: the backtrace)
     const double *BT;        // [M][Kp]   logB transposed (obs-major), padded -inf
     const double *At, *BTt;  // what the forward tile kernel reads: A / BT, or their slot-permuted copies (balanced split)
+    const float *A32n;       // f32 mode (decode_f32.cuh): rn32(logA) [K][Kp], natural columns (backtrace); A32s/BT32 below for its forward kernel
+    const float *BT32;       //                            rn32(logB^T) [M][Kp], slot-permuted like BTt
     const float *A32s;       // pre-filter kernel (decode_prefilter.cuh): [Kp][Kp] f32, rows = predecessors, slot-permuted columns
     const double *A64Ts;     //                                           [Kp][Kp] f64, rows = slots, columns = predecessors
     const uint32_t *obs;     // [N]
@@ -414,18 +416,21 @@ __device__ __forceinline__ void bt_mark_done(const DecodeSmallParams &p, uint32_
 // NSC = sequences per tile when known at compile time (64: the load offsets become immediates), 0 = p.NS
 // LAYOUT = 0: history slabs [K][NS] (decode_small_fwd_kernel); 1: [NS][Kp + 2] (decode_pf_fwd_kernel: a sequence's
 // row is contiguous and read as 16-byte vectors)
-template <int BT_CHUNK, int MINB, int NSC, int LAYOUT = 0>
+// T = double (exact, the reference's arithmetic) or float (cv_decode_batch_f32: the f32 history of decode_f32.cuh and
+// rn32(logA), same first-maximum rule on fl32 sums)
+template <int BT_CHUNK, int MINB, int NSC, int LAYOUT = 0, typename T = double>
 __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const DecodeSmallParams p)
 {
+    const T NEG = (T)neg_inf();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K, Kp = p.Kp, NS = NSC ? NSC : p.NS;
     const size_t JS = LAYOUT ? 1 : (size_t)NS;                // distance between consecutive states of one sequence
     const size_t SS = LAYOUT ? (size_t)(Kp + 2) : 1;          // distance between consecutive sequences of one state
     const int ATP = K | 1;                                   // odd pitch: rows of different states spread over banks
-    double *sAT = reinterpret_cast<double *>(smem_raw);     // sAT[s*ATP + j] = logA[j][s]
+    T *sAT = reinterpret_cast<T *>(smem_raw);               // sAT[s*ATP + j] = logA[j][s]
     for (int e = threadIdx.x; e < K * Kp; e += blockDim.x) {
         const int j = e / Kp, s = e % Kp;
-        if (s < K) sAT[(size_t)s * ATP + j] = p.A[e];
+        if (s < K) sAT[(size_t)s * ATP + j] = sizeof(T) == 4 ? (T)p.A32n[e] : (T)p.A[e];
     }
     __syncthreads();
 
@@ -462,68 +467,68 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
         if (p.tile_base[tile] + (long long)len > p.hist_cap_slabs) { bt_mark_done(p, b); continue; }   // tile refused by the forward kernel (status 7)
-        const double *col = p.hist + (size_t)p.tile_base[tile] * sl + (size_t)s * SS;   // sequence s of slab 0
+        const T *col = reinterpret_cast<const T *>(p.hist) + (size_t)p.tile_base[tile] * sl + (size_t)s * SS;   // sequence s of slab 0
 
         // end state: argmax of the last row (viterbi.rs:24)
-        const double *row = col + (size_t)(len - 1) * sl;
-        double bv = __ldcs(row); int cur = 0;
+        const T *row = col + (size_t)(len - 1) * sl;
+        T bv = __ldcs(row); int cur = 0;
         for (int j = 1; j < K; j++) {
-            const double v = __ldcs(row + (size_t)j * JS);
+            const T v = __ldcs(row + (size_t)j * JS);
             if (v > bv) { bv = v; cur = j; }
         }
-        if (p.score) p.score[b] = bv;
+        if (p.score) p.score[b] = (double)bv;
         store_path_at(p, off + len - 1, (uint32_t)cur);
         if (len == 1) { bt_mark_done(p, b); continue; }
 
         // walk back (viterbi.rs:27-30): steps tt = len-1 .. 1, each a scan of row tt-1 in chunks of BT_CHUNK predecessors;
         // the next chunk (of this step, or the first of the next step -- rows do not depend on the path) is always
         // in flight while the current one is reduced.  Pointers advance by constants: no division in the loop.
-        double dcur = bv;                                     // delta[tt][cur]
-        double bufA[BT_CHUNK], bufB[BT_CHUNK];                // two chunk buffers used alternately: no register copies
-        const double *rowp = col + (size_t)(len - 2) * sl;    // row tt-1
+        T dcur = bv;                                          // delta[tt][cur]
+        T bufA[BT_CHUNK], bufB[BT_CHUNK];                     // two chunk buffers used alternately: no register copies
+        const T *rowp = col + (size_t)(len - 2) * sl;         // row tt-1
         int64_t pout = off + (len - 2);
-        auto load_chunk = [&](const double *prow, int c, double (&dst)[BT_CHUNK]) {
-            const double *q = prow + (size_t)c * (BT_CHUNK * JS);
-            if (LAYOUT && c < nfull) {
+        auto load_chunk = [&](const T *prow, int c, T (&dst)[BT_CHUNK]) {
+            const T *q = prow + (size_t)c * (BT_CHUNK * JS);
+            if (LAYOUT && sizeof(T) == 8 && c < nfull) {
 #pragma unroll
                 for (int k = 0; k < BT_CHUNK; k += 2) {
                     const double2 v = __ldcs(reinterpret_cast<const double2 *>(q + k));
-                    dst[k] = v.x; dst[k + 1] = v.y;
+                    dst[k] = (T)v.x; dst[k + 1] = (T)v.y;
                 }
             } else if (c < nfull) {
 #pragma unroll
                 for (int k = 0; k < BT_CHUNK; k++) dst[k] = __ldcs(q + (size_t)k * JS);
             } else {
 #pragma unroll
-                for (int k = 0; k < BT_CHUNK; k++) dst[k] = (k < ktail) ? __ldcs(q + (size_t)k * JS) : neg_inf();
+                for (int k = 0; k < BT_CHUNK; k++) dst[k] = (k < ktail) ? __ldcs(q + (size_t)k * JS) : NEG;
             }
         };
-        double mv = 0.0; int mi = 0;
-        const double *at = sAT;
+        T mv = 0; int mi = 0;
+        const T *at = sAT;
         // chunk c of the current step: candidates fl(delta[tt-1][j] + logA[j][cur]), first maximum (viterbi.rs:15-16);
         // predecessors >= K hold -inf and can never be strictly greater (logA is read up to BT_CHUNK-1 doubles past
         // K: padded)
-        auto reduce_chunk = [&](const double (&cu)[BT_CHUNK], int c) {
-            const double *ac = at + c * BT_CHUNK;
+        auto reduce_chunk = [&](const T (&cu)[BT_CHUNK], int c) {
+            const T *ac = at + c * BT_CHUNK;
             if (c == 0) {
                 mv = cu[0] + ac[0]; mi = 0;
 #pragma unroll
                 for (int k = 1; k < BT_CHUNK; k++) {
-                    const double v = cu[k] + ac[k];
+                    const T v = cu[k] + ac[k];
                     if (v > mv) { mv = v; mi = k; }
                 }
             } else {
                 const int j0 = c * BT_CHUNK;
 #pragma unroll
                 for (int k = 0; k < BT_CHUNK; k++) {
-                    const double v = cu[k] + ac[k];
+                    const T v = cu[k] + ac[k];
                     if (v > mv) { mv = v; mi = j0 + k; }
                 }
             }
         };
         // one step: X holds chunk 0 on entry; the chunk after the one being reduced is always in flight (the next
         // chunk of this step, or chunk 0 of the next step -- rows do not depend on the path)
-        auto step = [&](double (&X)[BT_CHUNK], double (&Y)[BT_CHUNK], int tt) {
+        auto step = [&](T (&X)[BT_CHUNK], T (&Y)[BT_CHUNK], int tt) {
             at = sAT + (size_t)cur * ATP;
             int c = 0;
             for (; c + 1 < nchunk; c += 2) {
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
                 reduce_chunk(X, c);
             }
             // psi = 0 when delta[tt][cur] = -inf (emission -inf or all candidates -inf; see header comment)
-            cur = (dcur > neg_inf()) ? mi : 0;
+            cur = (dcur > NEG) ? mi : 0;
             dcur = __ldcg(rowp + (size_t)cur * JS);              // delta[tt-1][cur]
             store_path_at(p, pout, (uint32_t)cur);
             pout--; rowp -= sl;

@@ -33,6 +33,21 @@ def decode_batch(hmm: HMM, obs_flat, seq_off, device: int = -1, want_scores: boo
     return paths, scores
 
 
+def decode_batch_f32(hmm: HMM, obs_flat, seq_off, device: int = -1):
+    """OPTIONAL f32 mode (cv_decode_batch_f32): the recurrence in IEEE binary32, scores within 1e-5 relative of the
+    exact mode, paths = the optimum of the f32 recurrence (may differ from the f64 path at near-ties).  Not the
+    parity path."""
+    obs_flat = np.ascontiguousarray(obs_flat, dtype=np.uint32)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    B, N = seq_off.shape[0] - 1, obs_flat.shape[0]
+    paths = np.zeros(N, dtype=np.uint32)
+    scores = np.zeros(max(B, 0), dtype=np.float64)
+    rc = _lib.lib().cv_decode_batch_f32(hmm.device_handle(device), obs_flat.ctypes.data, seq_off.ctypes.data, B,
+                                        paths.ctypes.data, scores.ctypes.data)
+    _lib.check(rc)
+    return paths, scores
+
+
 def decode_batch_narrow(hmm: HMM, obs_flat, seq_off, device: int = -1):
     """decode_batch with narrow host formats (cv_decode_batch_u16u8): observations cross PCIe as u16 (M <= 65536),
     states come back as u8 (K <= 64 here).  Same results; returns (paths u8[N], scores f64[B])."""

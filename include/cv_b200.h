@@ -72,6 +72,18 @@ int cv_decode_batch(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off,
 int cv_decode_batch_u16u8(cv_hmm *h, const uint16_t *obs_flat, const int64_t *seq_off,
                           int64_t B, uint8_t *path_out, double *score_out);
 
+/* OPTIONAL f32 mode -- not the parity path.  The same recurrence with the model rounded to f32 once and every add an
+ * IEEE binary32 add; the returned path is the exact optimum of that f32 recurrence (first-maximum backpointers),
+ * score_out[b] its f32 score widened to double: within 1e-5 relative of the f64 score of cv_decode_batch, and the
+ * path can differ from the f64 path where candidates are within f32 rounding of each other.  About 3-4x the
+ * throughput of the exact mode (packed FADD2 / 3-input FMNMX3).  K <= 64; batches of <= 8192 sequences are decoded
+ * by the exact f64 warp-per-sequence kernel.  HOST pointers / DEVICE pointers as for cv_decode_batch(_dev). */
+int cv_decode_batch_f32(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq_off,
+                        int64_t B, uint32_t *path_out, double *score_out);
+int cv_decode_batch_dev_f32(cv_hmm *h, const uint32_t *d_obs_flat, const int64_t *d_seq_off,
+                            int64_t B, int64_t N, int64_t max_len, uint32_t *d_path_out,
+                            double *d_score_out, void *stream, int sync_status);
+
 /* Same call, and the device copies of the results are left in the caller's DEVICE buffers d_path_keep[N] /
  * d_score_keep[B] as well (e.g. rows of an all-gather buffer: a multi-GPU caller decodes its slice from host memory
  * and runs the device-side collective without uploading the paths again).  The device buffers are complete when the

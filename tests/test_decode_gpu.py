@@ -493,3 +493,42 @@ def test_long_sequence_split_beyond_its_capacity():
         p, s = cv.decode_batch(h, obs, off)
         assert (p == rp).all() and s.tobytes() == rs.tobytes()
     h.close()
+
+
+@pytest.mark.parametrize("K,zero_frac", [(45, 0.05), (24, 0.3), (61, 0.0)])
+def test_f32_mode_within_tolerance(K, zero_frac):
+    """cv_decode_batch_f32 (optional, not the parity path): scores within 1e-5 relative of the f64 oracle
+    (BASELINE.json north_star's tolerance for an f32 mode), -inf exactly where the oracle has -inf, and every
+    returned path is a valid witness: re-scored in f64 with the f64 model it is within 1e-5 relative of the optimum.
+    Most paths equal the oracle's; they may differ only at near-ties."""
+    import torch
+    rng = np.random.default_rng(7700 + K)
+    M = 50
+    A, B, pi = random_hmm(rng, K, M, zero_frac=zero_frac)
+    obs, off = random_batch(rng, 20000, M, 1, 80)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    p, s = cv.decode_batch_f32(h, obs, off)
+    fin = np.isfinite(rs)
+    assert (np.isneginf(s) == np.isneginf(rs)).all()
+    rel = np.abs(s[fin] - rs[fin]) / np.maximum(np.abs(rs[fin]), 1.0)
+    assert rel.max() <= 1e-5, rel.max()
+    same = np.array([(p[off[b]:off[b + 1]] == rp[off[b]:off[b + 1]]).all() for b in range(len(off) - 1)])
+    assert same[fin].mean() > 0.97, same[fin].mean()
+    for b in np.flatnonzero(fin & ~same)[:200]:                      # a different path must be (nearly) as good
+        sc = _path_score(A, B, obs[off[b]:off[b + 1]], p[off[b]:off[b + 1]])
+        assert abs(sc - rs[b]) <= 1e-5 * max(abs(rs[b]), 1.0), (b, sc, rs[b])
+    # device-resident entry, deterministic
+    hd = h.device_handle(torch.cuda.current_device())
+    L = cv._lib.lib()
+    N, Bn = len(obs), len(off) - 1
+    d_obs = torch.from_numpy(obs.view(np.int32)).cuda(); d_off = torch.from_numpy(off).cuda()
+    d_path = torch.zeros(N, dtype=torch.int32, device="cuda"); d_score = torch.zeros(Bn, dtype=torch.float64, device="cuda")
+    cv._lib.check(L.cv_decode_batch_dev_f32(hd, d_obs.data_ptr(), d_off.data_ptr(), Bn, N, int(np.diff(off).max()),
+                                            d_path.data_ptr(), d_score.data_ptr(), torch.cuda.current_stream().cuda_stream, 1))
+    torch.cuda.synchronize()
+    assert (d_path.cpu().numpy().view(np.uint32) == p).all() and d_score.cpu().numpy().tobytes() == s.tobytes()
+    # and the exact mode is untouched by it
+    p64, s64 = cv.decode_batch(h, obs, off)
+    assert (p64 == rp).all() and s64.tobytes() == rs.tobytes()
+    h.close()

@@ -3,7 +3,7 @@
     python tools/fwd_variants.py [nseq] [variants...]        e.g.  python tools/fwd_variants.py 1000000 1 0
 
 variant: 1 = balanced state split (default), 0 = groups of 8 states (last one padded), 2 = the pre-filter kernel
-(decode_prefilter.cuh).  Prints the forward kernel alone (CUDA events, timing mode), and the device-resident step (forward +
+(decode_prefilter.cuh), 3 = the optional f32 mode (cv_decode_batch_dev_f32; results differ by design).  Prints the forward kernel alone (CUDA events, timing mode), and the device-resident step (forward +
 concurrent backtrace) for each variant, plus the extra `CV_*` launch-shape settings given in the environment."""
 import ctypes as C
 import json
@@ -36,9 +36,12 @@ cv._lib.check(L.cv_debug_probe_fp64(0, 1, 20000, C.byref(ops), C.byref(ms)))
 peak = ops.value
 
 
+FN = [L.cv_decode_batch_dev]
+
+
 def run(sync):
-    cv._lib.check(L.cv_decode_batch_dev(h, d_obs.data_ptr(), d_off.data_ptr(), B, N, ml, d_path.data_ptr(),
-                                        d_score.data_ptr(), st.cuda_stream, sync))
+    cv._lib.check(FN[0](h, d_obs.data_ptr(), d_off.data_ptr(), B, N, ml, d_path.data_ptr(),
+                        d_score.data_ptr(), st.cuda_stream, sync))
 
 
 ref = None
@@ -46,6 +49,7 @@ out = []
 for v in variants:
     L.cv_debug_set_balanced_split(1 if v else 0)
     L.cv_debug_set_prefilter(1 if v == 2 else 0)
+    FN[0] = L.cv_decode_batch_dev_f32 if v == 3 else L.cv_decode_batch_dev        # 3 = the optional f32 mode
     for _ in range(3):
         run(0)
     torch.cuda.synchronize()
