@@ -734,6 +734,37 @@ def main():
         assert (host_paths8 == full_paths[e0_:e1_]).all(), "narrow-format and device-resident paths differ"
         L.cv_host_free(p_obs16); L.cv_host_free(p_path8)
 
+    # ---- optional f32 mode (cv_decode_batch_dev_f32; not the parity path): throughput and distance from the exact result ----
+    f32_mode = None
+    if world == 1 and K <= 64:
+        d_p32 = torch.empty(max(n_el, 1), dtype=torch.int32, device="cuda")
+        d_s32 = torch.empty(max(n_sq, 1), dtype=torch.float64, device="cuda")
+
+        def step_f32():
+            cv._lib.check(L.cv_decode_batch_dev_f32(h, sd.obs_l.data_ptr(), sd.off_l.data_ptr(), n_sq, n_el, sd.max_len,
+                                                    d_p32.data_ptr(), d_s32.data_ptr(), stream.cuda_stream, 0))
+        for _ in range(3):
+            step_f32()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            step_f32()
+        f1.record(stream)
+        torch.cuda.synchronize()
+        f32_ms = f0.elapsed_time(f1) / args.steps
+        s32, p32 = d_s32.cpu().numpy(), d_p32.cpu().numpy().view(np.uint32)
+        fin = np.isfinite(full_scores)
+        rel = np.abs(s32[fin] - full_scores[fin]) / np.maximum(np.abs(full_scores[fin]), 1.0)
+        same_el = float((p32 == full_paths).mean())
+        f32_mode = {"ms_per_step": f32_ms, "value": wl["cells"] / (f32_ms * 1e-3), "unit": UNIT, "dtype": "f32",
+                    "max_rel_score_error_vs_f64": float(rel.max()) if rel.size else 0.0, "tolerance": 1e-5,
+                    "neg_inf_scores_match": bool((np.isneginf(s32) == np.isneginf(full_scores)).all()),
+                    "path_elements_equal_to_f64": same_el,
+                    "note": "optional mode of BASELINE.json's north_star (f32 recurrence, FADD2 + FMNMX3); NOT the parity path -- "
+                            "the headline value / parity / roofline above are the exact f64 mode"}
+        del d_p32, d_s32
+
     # ---- reduce over ranks ----
     def allred(x, op):
         if world == 1:
@@ -853,6 +884,8 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             },
         }
+        if f32_mode is not None:
+            line["f32_mode"] = f32_mode
         if narrow_s is not None:
             line["e2e_narrow"] = {"value": wl["cells"] / narrow_s, "unit": UNIT, "ms_per_step": 1e3 * narrow_s,
                                   "h2d_bytes_per_step": int(2 * n_el + 8 * (n_sq + 1)), "d2h_bytes_per_step": int(n_el + 8 * n_sq),
