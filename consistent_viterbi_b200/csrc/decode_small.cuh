@@ -121,25 +121,39 @@ __host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS)
 // (strict > keeps the first maximum's bits, e.g. the sign of a zero, as the reference does).
 // NQ <= TQT: only the first NQ target states of the slot group are computed (balanced split: the slots behind them
 // are padding); the operand loads stay 16-byte pairs.
-template <int TQT, int UNR = 2, int TPT = TP, int NQ = TQT>
+template <int TQT, int UNR = 2, int TPT = TP, int NQ = TQT, bool FIRST = false>
 __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol, int ldd,
                                                  const double *__restrict__ arow, int lda, int nj,
                                                  double (&best)[TPT][TQT])
 {
-#pragma unroll UNR
-    for (int j = 0; j < nj; j++) {
-        double dd[TPT];
+    auto load = [&](int j, double (&dd)[TPT], double (&a)[TQT]) {
 #pragma unroll
         for (int p = 0; p < TPT / 2; p++) {
             const double2 d = *reinterpret_cast<const double2 *>(dcol + (size_t)j * ldd + 2 * p);
             dd[2 * p] = d.x; dd[2 * p + 1] = d.y;
         }
-        double a[TQT];
 #pragma unroll
         for (int q = 0; q < (NQ + 1) / 2; q++) {
             const double2 aa = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2 * q);
             a[2 * q] = aa.x; a[2 * q + 1] = aa.y;
         }
+    };
+    int j = 0;
+    if (FIRST) {
+        // predecessor 0 starts the running maximum: `best = -inf; if (v > best) best = v` leaves best = v for every v
+        // that can occur (v is never NaN), so the initialisation and the first compare/select are dropped
+        double dd[TPT], a[TQT];
+        load(0, dd, a);
+#pragma unroll
+        for (int p = 0; p < TPT; p++)
+#pragma unroll
+            for (int q = 0; q < NQ; q++) best[p][q] = dd[p] + a[q];
+        j = 1;
+    }
+#pragma unroll UNR
+    for (; j < nj; j++) {
+        double dd[TPT], a[TQT];
+        load(j, dd, a);
 #pragma unroll
         for (int p = 0; p < TPT; p++)
 #pragma unroll
@@ -149,7 +163,6 @@ __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol
             }
     }
 }
-
 
 __device__ __forceinline__ void tma_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
 {
@@ -182,11 +195,7 @@ __device__ __forceinline__ void fwd_step(const double *__restrict__ dcur, double
                                          uint64_t *em_bar, uint32_t em_phase, int nreal)
 {
     double best[TPT][TQT];
-#pragma unroll
-    for (int q = 0; q < TPT; q++)
-#pragma unroll
-        for (int k = 0; k < TQT; k++) best[q][k] = neg_inf();
-    maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT, NQ>(dcur, NS, arow, Kp, K, best);
+    maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT, NQ, true>(dcur, NS, arow, Kp, K, best);     // K >= 1: predecessor 0 exists
 
     mbar_wait(em_bar, em_phase);      // emission rows of step t have landed
 #pragma unroll
@@ -234,6 +243,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     const uint32_t slab_bytes = (uint32_t)((size_t)K * NS * 8);
     const uint32_t row_bytes = (uint32_t)(Kp * 8);
     constexpr int EMK = 2 * TPT;   // emission slots a lane may serve: NS / (32 * warps) <= 32 * TPT * S / (32 * S) = TPT, x2 slack
+    const int emk = (NS + 32 * ((int)blockDim.x >> 5) - 1) / (32 * ((int)blockDim.x >> 5));   // ... and how many exist (1 at the POS shape)
 
     // ---- stage logA once per CTA (TMA bulk copy, UBLKCP) ----
     if (tid == 0) {
@@ -258,6 +268,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         int nact = 0;
 #pragma unroll
         for (int k = 0; k < EMK; k++) {
+            if (k >= emk) break;
             const int s = w + nw * (lane + 32 * k);
             if (s < NS && t < sLen[s]) nact++;
         }
@@ -266,6 +277,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < EMK; k++) {
+            if (k >= emk) break;
             const int s = w + nw * (lane + 32 * k);
             if (s < NS && t < sLen[s]) {
                 uint32_t o = o_cur[k];
@@ -367,6 +379,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
                 issue_emissions(t + 1, o_nxt);
 #pragma unroll
                 for (int k = 0; k < EMK; k++) {
+                    if (k >= emk) break;
                     const int s = w + nw * (lane + 32 * k);
                     o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? ld_obs(sOff[s] + t + 2) : 0u;
                 }
