@@ -41,7 +41,11 @@
 #include "common.cuh"
 
 #ifndef CVB_FWD_UNROLL
-#define CVB_FWD_UNROLL 2      // predecessors per unrolled iteration of the forward tile loop
+// predecessors per unrolled iteration of the forward tile loop.  Measured at the POS shape (K = 45: predecessor 0 is
+// peeled, 44 remain), forward kernel alone / whole step: 2: 10.94 / 11.49 ms, 4: 10.63 / 11.36 ms, 11: 10.27 / 12.64 ms
+// -- the loop-carried register moves at the back edge (22 IMAD.MOV per iteration) amortise with the unroll factor, but
+// the 13 KB loop bodies (one per state-group width) then fight the concurrent backtrace for the instruction cache.
+#define CVB_FWD_UNROLL 4
 #endif
 
 namespace cvb {
