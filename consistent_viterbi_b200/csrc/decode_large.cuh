@@ -57,12 +57,15 @@ struct DecodeLargeParams {
     int K, Kl, NCB, NRB, Tmax;
 };
 
+// NJ > 0: the chunk's predecessor count at compile time (full chunks: the loop is unrolled completely, no loop
+// overhead and no loop-carried register moves inside a chunk); NJ = 0: run-time count (the last, partial chunk)
+template <int NJ = 0>
 __device__ __forceinline__ void maxplus_accum_val(const double *__restrict__ dcol, int ldd,
                                                   const double *__restrict__ arow, int lda, int nj,
                                                   double (&best)[TP][TQ])
 {
-#pragma unroll 2
-    for (int jj = 0; jj < nj; jj++) {
+#pragma unroll (NJ > 0 ? NJ : 2)
+    for (int jj = 0; jj < (NJ > 0 ? NJ : nj); jj++) {
         const double2 d = *reinterpret_cast<const double2 *>(dcol + jj * ldd);
         const double2 a01 = *reinterpret_cast<const double2 *>(arow + jj * lda);
         const double2 a23 = *reinterpret_cast<const double2 *>(arow + jj * lda + 2);
@@ -178,8 +181,12 @@ __global__ void __maxnreg__(96) decode_large_kernel(const DecodeLargeParams p)
                 const int s = g % LG_STAGES;
                 mbar_wait(full + s, (g / LG_STAGES) & 1);
                 const int nj = min(LG_BK, K - c * LG_BK);
-                maxplus_accum_val(sD + (size_t)s * LG_STAGE_D + lane * TP, LG_BM,
-                                  sA + (size_t)s * LG_STAGE_A + w * TQ, LARGE_BN, nj, best);
+                if (nj == LG_BK)
+                    maxplus_accum_val<LG_BK>(sD + (size_t)s * LG_STAGE_D + lane * TP, LG_BM,
+                                             sA + (size_t)s * LG_STAGE_A + w * TQ, LARGE_BN, nj, best);
+                else
+                    maxplus_accum_val<0>(sD + (size_t)s * LG_STAGE_D + lane * TP, LG_BM,
+                                         sA + (size_t)s * LG_STAGE_A + w * TQ, LARGE_BN, nj, best);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + s);
             }
