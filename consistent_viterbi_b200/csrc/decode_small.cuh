@@ -45,7 +45,11 @@
 // peeled, 44 remain), forward kernel alone / whole step: 2: 10.94 / 11.49 ms, 4: 10.63 / 11.36 ms, 11: 10.27 / 12.64 ms
 // -- the loop-carried register moves at the back edge (22 IMAD.MOV per iteration) amortise with the unroll factor, but
 // the 13 KB loop bodies (one per state-group width) then fight the concurrent backtrace for the instruction cache.
+// With CVB_FWD_TREE (default) the loop takes the predecessors in pairs, two pairs per iteration: 10.60 / 11.30 ms.
 #define CVB_FWD_UNROLL 4
+#endif
+#ifndef CVB_FWD_TREE
+#define CVB_FWD_TREE 1        // 1: two predecessors are reduced before they meet the running maximum (see maxplus_tile_val)
 #endif
 
 namespace cvb {
@@ -154,8 +158,28 @@ __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol
             for (int q = 0; q < NQ; q++) best[p][q] = dd[p] + a[q];
         j = 1;
     }
+#if CVB_FWD_TREE
+    // two predecessors are reduced before they meet the running maximum: the dependent chain on `best` is one
+    // compare/select per two predecessors.  `b > a ? b : a` keeps the EARLIER value on a tie at
+    // every level, so the result carries the bits of the first maximum exactly as the sequential scan does.
+#pragma unroll 2
+    for (; j + 1 < nj; j += 2) {
+        double d0[TPT], d1[TPT], a0[TQT], a1[TQT];
+        load(j, d0, a0); load(j + 1, d1, a1);
+#pragma unroll
+        for (int p = 0; p < TPT; p++)
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const double v0 = d0[p] + a0[q], v1 = d1[p] + a1[q];
+                const double m = v1 > v0 ? v1 : v0;
+                best[p][q] = m > best[p][q] ? m : best[p][q];
+            }
+    }
+#pragma unroll 1
+#else
 #pragma unroll UNR
-    for (; j < nj; j++) {
+#endif
+    for (; j < nj; j++) {                       // (with the pair loop above: at most one predecessor is left)
         double dd[TPT], a[TQT];
         load(j, dd, a);
 #pragma unroll
