@@ -532,3 +532,22 @@ def test_f32_mode_within_tolerance(K, zero_frac):
     p64, s64 = cv.decode_batch(h, obs, off)
     assert (p64 == rp).all() and s64.tobytes() == rs.tobytes()
     h.close()
+
+
+def test_f32_mode_small_batches_take_the_exact_kernel():
+    """Batches of <= 8192 sequences go to the warp-per-sequence kernel, which is f64: in f32 mode they simply return the
+    exact result (documented in include/cv_b200.h)."""
+    rng = np.random.default_rng(41)
+    K, M = 30, 20
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    obs, off = random_batch(rng, 500, M, 1, 50)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=4)
+    h = cv.HMM(A, B, pi)
+    p, s = cv.decode_batch_f32(h, obs, off)
+    assert (p == rp).all() and s.tobytes() == rs.tobytes()
+    A2, B2, pi2 = random_hmm(rng, 70, 5)
+    h2 = cv.HMM(A2, B2, pi2)
+    with pytest.raises(cv.CvError) as e:                              # K > 64: no f32 mode
+        cv.decode_batch_f32(h2, np.zeros(4, np.uint32), np.array([0, 4], np.int64))
+    assert e.value.code == cv._lib.ERR_UNSUPPORTED
+    h.close(); h2.close()
