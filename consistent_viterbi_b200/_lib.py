@@ -95,6 +95,7 @@ DEBUG_SIGNATURES = {
     "cv_debug_set_pipeline": (None, [C.c_int, C.c_int]),
     "cv_debug_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "cv_debug_set_balanced_split": (None, [C.c_int]),
+    "cv_debug_set_fwd_ldc": (None, [C.c_int]),
     "cv_debug_set_prefilter": (None, [C.c_int]),
     "cv_debug_set_large_group_rb": (None, [C.c_longlong]),
     "cv_debug_set_cp_leaf_batch": (None, [C.c_int]),

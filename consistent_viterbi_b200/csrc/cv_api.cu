@@ -49,6 +49,7 @@ static Tuning tuning_from_env()
     if (const char *e = getenv("CV_TQ")) t.tq = !strcmp(e, "auto") ? 0 : (atoi(e) == 12 ? 12 : atoi(e) == 6 ? 6 : 8);
     t.tp = geti("CV_TP", 2) == 4 ? 4 : 2;
     t.balanced_split = geti("CV_BALANCED", t.balanced_split);
+    t.fwd_ldc = geti("CV_FWD_LDC", t.fwd_ldc);
     t.long_split = geti("CV_LONG_SPLIT", t.long_split);
     t.prefilter = geti("CV_PREFILTER", t.prefilter);
     t.debug = getenv("CV_DEBUG") != nullptr;
@@ -609,6 +610,19 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     occ = std::max(1, occ);
+    if (!f32 && !pf && h->TQT == 8 && tpt == 2 && S == 1 && variant == 1 && g_tune.fwd_ldc) {
+        // Default shape: the same kernel with compile-time row pitches (tiles of 64 sequences, logA rows at a pitch of
+        // 64 doubles in shared memory) -- unless the wider logA costs a resident CTA per SM.
+        void (*kc)(DecodeSmallParams) = decode_small_fwd_kernel<8, 512, 1, 2, FWD_LDC>;
+        const size_t smem_c = decode_small_smem_bytes(h->K, h->Kp, NS, FWD_LDC);
+        int occ_c = 0;
+        if (smem_c <= 220 * 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+            CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, kc, threads, smem_c));
+        }
+        if (occ_c >= occ) { kern = kc; smem = smem_c; }
+    }
     const int grid = (int)std::min<int64_t>((int64_t)h->num_sms * occ, ntiles);
     if (g_tune.debug)
         fprintf(stderr, "[cv] decode_small: K=%d TQ=%d TP=%d G=%d S=%d variant=%d prefilter=%d threads=%d smem=%zu occ=%d grid=%d tiles=%d\n",

@@ -120,52 +120,60 @@ __device__ __forceinline__ void store_path_at(const DecodeSmallParams &p, int64_
 __host__ __device__ inline int em_pitch(int Kp) { return Kp + 2; }   // doubles; bank-conflict-free row pitch
 
 // dynamic smem: [A][delta x2][em][off i64][len i32][mbarA, mbarEm][tile]
-__host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS)
+// lda = row pitch of logA in shared memory, in doubles: Kp, or FWD_LDC for the constant-stride kernel
+__host__ __device__ inline size_t decode_small_smem_bytes(int K, int Kp, int NS, int lda = 0)
 {
-    return (size_t)K * Kp * 8 + (size_t)2 * K * NS * 8 + (size_t)NS * em_pitch(Kp) * 8 + (size_t)NS * (8 + 4) + 32 + 16;
+    return (size_t)K * (lda ? lda : Kp) * 8 + (size_t)2 * K * NS * 8 + (size_t)NS * em_pitch(Kp) * 8 + (size_t)NS * (8 + 4) + 32 + 16;
 }
 
 // value-only TP x TQ micro-tile: best[p][q] = max_j ( dcol[j*ldd + p] + arow[j*lda + q] )
 // (strict > keeps the first maximum's bits, e.g. the sign of a zero, as the reference does).
 // NQ <= TQT: only the first NQ target states of the slot group are computed (balanced split: the slots behind them
 // are padding); the operand loads stay 16-byte pairs.
-template <int TQT, int UNR = 2, int TPT = TP, int NQ = TQT, bool FIRST = false>
-__device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol, int ldd,
-                                                 const double *__restrict__ arow, int lda, int nj,
+// LDC > 0: both row pitches are the compile-time constant LDC (doubles) -- every operand load of an unrolled iteration is
+// base + immediate off two pointers that advance once per iteration (with run-time pitches: two IMADs per predecessor)
+template <int TQT, int UNR = 2, int TPT = TP, int NQ = TQT, bool FIRST = false, int LDC = 0>
+__device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol, int ldd_rt,
+                                                 const double *__restrict__ arow, int lda_rt, int nj,
                                                  double (&best)[TPT][TQT])
 {
-    auto load = [&](int j, double (&dd)[TPT], double (&a)[TQT]) {
+    const int ldd = LDC ? LDC : ldd_rt, lda = LDC ? LDC : lda_rt;
+    // operands of one predecessor: dp / ap point at its delta row and its logA row
+    auto load = [&](const double *dp, const double *ap, double (&dd)[TPT], double (&a)[TQT]) {
 #pragma unroll
         for (int p = 0; p < TPT / 2; p++) {
-            const double2 d = *reinterpret_cast<const double2 *>(dcol + (size_t)j * ldd + 2 * p);
+            const double2 d = *reinterpret_cast<const double2 *>(dp + 2 * p);
             dd[2 * p] = d.x; dd[2 * p + 1] = d.y;
         }
 #pragma unroll
         for (int q = 0; q < (NQ + 1) / 2; q++) {
-            const double2 aa = *reinterpret_cast<const double2 *>(arow + (size_t)j * lda + 2 * q);
+            const double2 aa = *reinterpret_cast<const double2 *>(ap + 2 * q);
             a[2 * q] = aa.x; a[2 * q + 1] = aa.y;
         }
     };
-    int j = 0;
+    // the two row pointers walk the predecessors (no index arithmetic in the loop)
+    const double *dp = dcol, *ap = arow;
+    const double *const dend = dcol + (size_t)nj * ldd;
     if (FIRST) {
         // predecessor 0 starts the running maximum: `best = -inf; if (v > best) best = v` leaves best = v for every v
         // that can occur (v is never NaN), so the initialisation and the first compare/select are dropped
         double dd[TPT], a[TQT];
-        load(0, dd, a);
+        load(dp, ap, dd, a);
 #pragma unroll
         for (int p = 0; p < TPT; p++)
 #pragma unroll
             for (int q = 0; q < NQ; q++) best[p][q] = dd[p] + a[q];
-        j = 1;
+        dp += ldd; ap += lda;
     }
 #if CVB_FWD_TREE
     // two predecessors are reduced before they meet the running maximum: the dependent chain on `best` is one
     // compare/select per two predecessors.  `b > a ? b : a` keeps the EARLIER value on a tie at
     // every level, so the result carries the bits of the first maximum exactly as the sequential scan does.
+    const double *const dend2 = dp + (size_t)((nj - (FIRST ? 1 : 0)) & ~1) * ldd;      // an even number of predecessors
 #pragma unroll 2
-    for (; j + 1 < nj; j += 2) {
+    for (; dp != dend2; dp += 2 * ldd, ap += 2 * lda) {
         double d0[TPT], d1[TPT], a0[TQT], a1[TQT];
-        load(j, d0, a0); load(j + 1, d1, a1);
+        load(dp, ap, d0, a0); load(dp + ldd, ap + lda, d1, a1);
 #pragma unroll
         for (int p = 0; p < TPT; p++)
 #pragma unroll
@@ -179,9 +187,9 @@ __device__ __forceinline__ void maxplus_tile_val(const double *__restrict__ dcol
 #else
 #pragma unroll UNR
 #endif
-    for (; j < nj; j++) {                       // (with the pair loop above: at most one predecessor is left)
+    for (; dp != dend; dp += ldd, ap += lda) {                       // (with the pair loop above: at most one predecessor is left)
         double dd[TPT], a[TQT];
-        load(j, dd, a);
+        load(dp, ap, dd, a);
 #pragma unroll
         for (int p = 0; p < TPT; p++)
 #pragma unroll
@@ -217,13 +225,14 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 // predecessors (value only), then (.. + b) (viterbi.rs:17) into the other delta buffer.  `row0` points at the row of the
 // group's first state in that buffer, `nreal` = how many of the NQ states exist (the last group of the plain layout
 // may reach past K).
-template <int TQT, int TPT, int NQ>
-__device__ __forceinline__ void fwd_step(const double *__restrict__ dcur, double *__restrict__ row0, int NS,
-                                         const double *__restrict__ arow, int Kp, int K, const double *__restrict__ e0, int EP,
+template <int TQT, int TPT, int NQ, int LDC = 0>
+__device__ __forceinline__ void fwd_step(const double *__restrict__ dcur, double *__restrict__ row0, int NS_rt,
+                                         const double *__restrict__ arow, int lda, int K, const double *__restrict__ e0, int EP,
                                          uint64_t *em_bar, uint32_t em_phase, int nreal)
 {
+    const int NS = LDC ? LDC : NS_rt;
     double best[TPT][TQT];
-    maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT, NQ, true>(dcur, NS, arow, Kp, K, best);     // K >= 1: predecessor 0 exists
+    maxplus_tile_val<TQT, CVB_FWD_UNROLL, TPT, NQ, true, LDC>(dcur, NS, arow, lda, K, best);     // K >= 1: predecessor 0 exists
 
     mbar_wait(em_bar, em_phase);      // emission rows of step t have landed
 #pragma unroll
@@ -248,13 +257,17 @@ __device__ __forceinline__ void fwd_step(const double *__restrict__ dcur, double
 // TQT = target states per thread (8 or 12; a warp owns TQT adjacent states); MAXT/MINB only set the register
 // budget (launch bounds).  The host picks TQT and S so that a CTA has a multiple of 4 warps: warps map to the
 // four SM sub-partitions by warp id, and with the per-step barrier an uneven split leaves sub-partitions idle.
-template <int TQT, int MAXT, int MINB, int TPT = TP>
+// LDC > 0 (= FWD_LDC = 64): tiles of exactly LDC sequences and logA rows at a pitch of LDC doubles in shared memory,
+// both known at compile time (see maxplus_tile_val); 0: run-time NS and pitch Kp.
+constexpr int FWD_LDC = 64;
+template <int TQT, int MAXT, int MINB, int TPT = TP, int LDC = 0>
 __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const DecodeSmallParams p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = p.K, Kp = p.Kp, NS = p.NS, EP = em_pitch(Kp);
+    const int K = p.K, Kp = p.Kp, NS = LDC ? LDC : p.NS, EP = em_pitch(Kp);
+    const int lda = LDC ? LDC : Kp;
     double *sA = reinterpret_cast<double *>(smem_raw);
-    double *sD = sA + (size_t)K * Kp;
+    double *sD = sA + (size_t)K * lda;
     double *sEm = sD + (size_t)2 * K * NS;
     int64_t *sOff = reinterpret_cast<int64_t *>(sEm + (size_t)NS * EP);
     int *sLen = reinterpret_cast<int *>(sOff + NS);
@@ -281,7 +294,11 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         fence_proxy_async_smem();
         const uint32_t bytes = (uint32_t)((size_t)K * Kp * 8);
         mbar_expect_tx(sBar, bytes);
-        tma_bulk_g2s(sA, p.At, bytes, sBar);
+        if (LDC && lda != Kp) {
+            for (int r = 0; r < K; r++) tma_bulk_g2s(sA + (size_t)r * lda, p.At + (size_t)r * Kp, row_bytes, sBar);   // row by row into the wider pitch
+        } else {
+            tma_bulk_g2s(sA, p.At, bytes, sBar);
+        }
     }
     __syncthreads();
     mbar_wait(sBar, 0);
@@ -390,14 +407,14 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
                     // full-width path below (their unused slots hold -inf and are not stored)
                     done = true;
                     switch (nreal) {
-                        case 7: fwd_step<8, 2, 7>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal); break;
-                        case 6: fwd_step<8, 2, 6>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal); break;
-                        case 5: fwd_step<8, 2, 5>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal); break;
+                        case 7: fwd_step<8, 2, 7, LDC>(dcur, row0, NS, sA + i0, lda, K, e0, EP, sBar + 1, em_phase, nreal); break;
+                        case 6: fwd_step<8, 2, 6, LDC>(dcur, row0, NS, sA + i0, lda, K, e0, EP, sBar + 1, em_phase, nreal); break;
+                        case 5: fwd_step<8, 2, 5, LDC>(dcur, row0, NS, sA + i0, lda, K, e0, EP, sBar + 1, em_phase, nreal); break;
                         default: done = false;
                     }
                 }
             }
-            if (!done) fwd_step<TQT, TPT, TQT>(dcur, row0, NS, sA + i0, Kp, K, e0, EP, sBar + 1, em_phase, nreal);
+            if (!done) fwd_step<TQT, TPT, TQT, LDC>(dcur, row0, NS, sA + i0, lda, K, e0, EP, sBar + 1, em_phase, nreal);
             em_phase ^= 1;
             fence_proxy_async_smem();           // make this thread's delta writes visible to the TMA store
             if (tid == 0) tma_store_wait_read_all();   // slab t-1 has left the buffer step t+1 will overwrite

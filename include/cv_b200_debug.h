@@ -30,6 +30,9 @@ void cv_debug_set_pipeline(int bt_concurrent, int streamed);
 /* forward tile kernel: 1 (default) = balanced state split (state groups of near-equal size over slot-permuted copies
  * of logA / logB^T, no padded target states), 0 = groups of 8 states with the last one padded */
 void cv_debug_set_balanced_split(int on);
+/* forward tile kernel: 1 (default) = the instantiation with compile-time row pitches (tiles of 64 sequences, logA rows
+ * at a pitch of 64 doubles in shared memory) whenever it keeps the occupancy, 0 = run-time pitches */
+void cv_debug_set_fwd_ldc(int on);
 /* forward tile kernel with the f32 pre-filter (csrc/decode_prefilter.cuh) for models whose entries are all <= 0:
  * 1 = on, 0 = the plain f64 tile kernel */
 void cv_debug_set_prefilter(int on);
