@@ -12,7 +12,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libcv_b200.so")
+# CV_B200_SO: development override (tools/ A/B runs of differently compiled builds); the product is the in-tree library
+SO_PATH = os.environ.get("CV_B200_SO") or os.path.join(CSRC, "libcv_b200.so")
 
 OK, ERR_EMPTY, ERR_NAN, ERR_ARG, ERR_ASSERT, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = range(8)
 _NAMES = {1: "EMPTY", 2: "NAN", 3: "ARG", 4: "ASSERT", 5: "CUDA", 6: "OOM", 7: "UNSUPPORTED"}
@@ -96,6 +97,7 @@ DEBUG_SIGNATURES = {
     "cv_debug_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "cv_debug_set_balanced_split": (None, [C.c_int]),
     "cv_debug_set_fwd_ldc": (None, [C.c_int]),
+    "cv_debug_set_em_light": (None, [C.c_int]),
     "cv_debug_set_prefilter": (None, [C.c_int]),
     "cv_debug_set_large_group_rb": (None, [C.c_longlong]),
     "cv_debug_set_cp_leaf_batch": (None, [C.c_int]),

@@ -50,6 +50,7 @@ static Tuning tuning_from_env()
     t.tp = geti("CV_TP", 2) == 4 ? 4 : 2;
     t.balanced_split = geti("CV_BALANCED", t.balanced_split);
     t.fwd_ldc = geti("CV_FWD_LDC", t.fwd_ldc);
+    t.em_light = geti("CV_EM_LIGHT", t.em_light);
     t.long_split = geti("CV_LONG_SPLIT", t.long_split);
     t.prefilter = geti("CV_PREFILTER", t.prefilter);
     t.debug = getenv("CV_DEBUG") != nullptr;
@@ -581,7 +582,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     DecodeSmallParams p;
     p.A = h->dA; p.BT = h->dBT; p.obs = d_obs; p.seq_off = d_off; p.order = d_order;
     p.At = h->dA; p.BTt = h->dBT; p.nq_base = p.nq_rem = 0;
-    p.obs16 = h->obs16; p.path8 = h->path8;
+    p.obs16 = h->obs16; p.path8 = h->path8; p.em_light = g_tune.em_light;
     p.is_long = (ls && ls->lstar) ? ls->is_long : nullptr;
     p.A32s = f32 ? h->dA32f : h->dA32; p.A64Ts = h->dA64T; p.A32n = h->dA32n; p.BT32 = h->dBT32;
     if ((pf || f32 || g_tune.balanced_split) && h->dAb && h->TQT == 8 && tpt == 2) {     // (the pre-filter operands are built for the balanced split)

@@ -94,6 +94,7 @@ struct DecodeSmallParams {
     // g * nq_base + min(g, nq_rem); the columns of A / BT are permuted into 8-wide slots per group (slot 8g + q holds
     // that group's q-th state, unused slots -inf).  nq_base = 0: the plain layout (group g = states 8g .. 8g+7).
     int nq_base, nq_rem;
+    int em_light;   // 1: with an uneven balanced split the lighter state groups fetch more of the emission rows
     // narrow host formats (cv_decode_batch_u16u8): obs holds u16 observations, path receives u8 states
     int obs16, path8;
     // long-sequence split: sequences flagged here are decoded by the warp-per-sequence kernel, the tile kernels treat
@@ -284,13 +285,36 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     const uint32_t slab_bytes = (uint32_t)((size_t)K * NS * 8);
     const uint32_t row_bytes = (uint32_t)(Kp * 8);
     constexpr int EMK = 2 * TPT;   // emission slots a lane may serve: NS / (32 * warps) <= 32 * TPT * S / (32 * S) = TPT, x2 slack
-    const int emk = (NS + 32 * ((int)blockDim.x >> 5) - 1) / (32 * ((int)blockDim.x >> 5));   // ... and how many exist (1 at the POS shape)
 
+    // Who fetches the emission rows.  The per-step barrier makes the slowest warp's step the CTA's, so the fetch work
+    // (one elected-lane TMA issue per row, ~10 instructions) is dealt out by how much tile work a warp has: with an
+    // uneven balanced split the groups behind the first nq_rem own one state less -- K predecessors x 2 cells per lane
+    // x ~4.5 instructions = ~9 K instructions per step less, worth ~0.9 K rows -- and take that many more rows each
+    // (K = 45: the three 7-state warps fetch all 64 rows, the 8-state warps none).  Warp w owns the slots
+    // [em_beg, em_beg + em_cnt); lane l serves em_beg + l + 32 k.  Otherwise every warp takes an equal share.
+    const int nwarps = (int)blockDim.x >> 5;
+    int em_beg = 0, em_cnt = 0, n_fetch = 0;
+    {
+        const bool uneven = p.em_light && p.nq_base && p.nq_rem && p.S == 1;
+        const int nlight = uneven ? p.G - p.nq_rem : 0;
+        const int extra = uneven ? min(NS / nlight, (9 * K + 5) / 10) : 0;      // additional rows per lighter warp
+        const int rest = NS - extra * nlight, base = rest / nwarps, left = rest - base * nwarps;
+        // the `left` rows that remain go one each to the last warps (the lighter ones, if any)
+        int beg = 0;
+        for (int v = 0; v < nwarps; v++) {
+            const int c = base + ((uneven && v % p.G >= p.nq_rem) ? extra : 0) + (v >= nwarps - left ? 1 : 0);
+            if (v == w) { em_beg = beg; em_cnt = c; }
+            if (c > 0) n_fetch++;
+            beg += c;
+        }
+    }
+    const int emk = (em_cnt + 31) / 32;                                                            // slots per lane that exist
+    const int st_tid = (p.em_light && p.nq_base && p.nq_rem && p.S == 1) ? 32 * p.nq_rem : 0;      // the thread that issues (and waits for) the history slab stores: one of a lighter warp
     // ---- stage logA once per CTA (TMA bulk copy, UBLKCP) ----
     if (tid == 0) {
         if (p.started) atomicAdd(p.started, 1u);   // the backtrace kernel is released once every forward CTA is resident
         mbar_init(sBar, 1);
-        mbar_init(sBar + 1, blockDim.x >> 5);      // one arrival per warp and step
+        mbar_init(sBar + 1, n_fetch);              // one arrival per fetching warp and step
         fence_proxy_async_smem();
         const uint32_t bytes = (uint32_t)((size_t)K * Kp * 8);
         mbar_expect_tx(sBar, bytes);
@@ -304,18 +328,15 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     mbar_wait(sBar, 0);
     uint32_t em_phase = 0;
 
-    // Emission rows of step t for every sequence still running.  EVERY warp fetches a share of the slots (slot s
-    // belongs to warp s % nw, lane (s / nw) % 32): the per-step barrier makes the slowest warp's step time the
-    // CTA's, so the producer work is spread instead of sitting on one warp.  Each warp arrives once on the
-    // emission mbarrier with the byte count of its share.
-    const int nw = (int)blockDim.x >> 5;
+    // Emission rows of step t for every sequence still running: each fetching warp issues one TMA row copy per slot of
+    // its share (see em_beg / em_cnt above) and arrives once on the emission mbarrier with the byte count of that share.
     auto issue_emissions = [&](int t, const uint32_t (&o_cur)[EMK]) {
         int nact = 0;
 #pragma unroll
         for (int k = 0; k < EMK; k++) {
             if (k >= emk) break;
-            const int s = w + nw * (lane + 32 * k);
-            if (s < NS && t < sLen[s]) nact++;
+            const int s = em_beg + lane + 32 * k;
+            if (lane + 32 * k < em_cnt && t < sLen[s]) nact++;
         }
         const int total = __reduce_add_sync(0xffffffffu, nact);
         if (lane == 0) mbar_expect_tx(sBar + 1, (uint32_t)total * row_bytes);   // arrive + expected bytes (0 is fine)
@@ -323,8 +344,8 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 #pragma unroll
         for (int k = 0; k < EMK; k++) {
             if (k >= emk) break;
-            const int s = w + nw * (lane + 32 * k);
-            if (s < NS && t < sLen[s]) {
+            const int s = em_beg + lane + 32 * k;
+            if (lane + 32 * k < em_cnt && t < sLen[s]) {
                 uint32_t o = o_cur[k];
                 if ((int64_t)o >= p.M) { *p.status = 3; o = 0; }   // index panic in the reference
                 tma_bulk_g2s(sEm + (size_t)s * EP, p.BTt + (size_t)o * Kp, row_bytes, sBar + 1);
@@ -381,19 +402,19 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
             Tmax = 0;
         }
         double *slab = p.hist + (size_t)p.tile_base[tile] * K * NS;
-        if (tid == 0 && Tmax > 0) tma_bulk_s2g(slab, sD, slab_bytes);   // history slab 0 = delta(0)
+        if (tid == st_tid && Tmax > 0) tma_bulk_s2g(slab, sD, slab_bytes);   // history slab 0 = delta(0)
 
         uint32_t o_nxt[EMK];                                                  // obs of the NEXT step to fetch
         {
             uint32_t o1[EMK];
 #pragma unroll
             for (int k = 0; k < EMK; k++) {
-                const int s = w + nw * (lane + 32 * k);
-                const bool in = s < NS;
+                const int s = em_beg + lane + 32 * k;
+                const bool in = lane + 32 * k < em_cnt;
                 o1[k] = (in && 1 < sLen[s]) ? ld_obs(sOff[s] + 1) : 0u;
                 o_nxt[k] = (in && 2 < sLen[s]) ? ld_obs(sOff[s] + 2) : 0u;
             }
-            if (Tmax > 1) issue_emissions(1, o1);
+            if (Tmax > 1 && em_cnt > 0) issue_emissions(1, o1);
         }
 
         for (int t = 1; t < Tmax; t++) {
@@ -417,20 +438,20 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
             if (!done) fwd_step<TQT, TPT, TQT, LDC>(dcur, row0, NS, sA + i0, lda, K, e0, EP, sBar + 1, em_phase, nreal);
             em_phase ^= 1;
             fence_proxy_async_smem();           // make this thread's delta writes visible to the TMA store
-            if (tid == 0) tma_store_wait_read_all();   // slab t-1 has left the buffer step t+1 will overwrite
+            if (tid == st_tid) tma_store_wait_read_all();   // slab t-1 has left the buffer step t+1 will overwrite
             __syncthreads();
-            if (tid == 0) tma_bulk_s2g(slab + (size_t)t * K * NS, sD + (size_t)(t & 1) * K * NS, slab_bytes);
-            if (t + 1 < Tmax) {
+            if (tid == st_tid) tma_bulk_s2g(slab + (size_t)t * K * NS, sD + (size_t)(t & 1) * K * NS, slab_bytes);
+            if (t + 1 < Tmax && em_cnt > 0) {
                 issue_emissions(t + 1, o_nxt);
 #pragma unroll
                 for (int k = 0; k < EMK; k++) {
                     if (k >= emk) break;
-                    const int s = w + nw * (lane + 32 * k);
-                    o_nxt[k] = (s < NS && t + 2 < sLen[s]) ? ld_obs(sOff[s] + t + 2) : 0u;
+                    const int s = em_beg + lane + 32 * k;
+                    o_nxt[k] = (lane + 32 * k < em_cnt && t + 2 < sLen[s]) ? ld_obs(sOff[s] + t + 2) : 0u;
                 }
             }
         }
-        if (tid == 0) {
+        if (tid == st_tid) {
             if (p.tile_done) {
                 // the tile's history is complete in global memory: hand it to the concurrent backtrace
                 tma_store_wait_all();

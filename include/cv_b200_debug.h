@@ -33,6 +33,9 @@ void cv_debug_set_balanced_split(int on);
 /* forward tile kernel: 1 (default) = the instantiation with compile-time row pitches (tiles of 64 sequences, logA rows
  * at a pitch of 64 doubles in shared memory) whenever it keeps the occupancy, 0 = run-time pitches */
 void cv_debug_set_fwd_ldc(int on);
+/* forward tile kernel, balanced split with a remainder: 1 (default) = only the state groups that own one state less
+ * fetch the emission rows (they are the ones that wait at the step barrier), 0 = every warp fetches a share */
+void cv_debug_set_em_light(int on);
 /* forward tile kernel with the f32 pre-filter (csrc/decode_prefilter.cuh) for models whose entries are all <= 0:
  * 1 = on, 0 = the plain f64 tile kernel */
 void cv_debug_set_prefilter(int on);
