@@ -51,6 +51,7 @@ static Tuning tuning_from_env()
     t.balanced_split = geti("CV_BALANCED", t.balanced_split);
     t.fwd_ldc = geti("CV_FWD_LDC", t.fwd_ldc);
     t.em_light = geti("CV_EM_LIGHT", t.em_light);
+    t.bt_split = geti("CV_BT_SPLIT", t.bt_split);
     t.long_split = geti("CV_LONG_SPLIT", t.long_split);
     t.prefilter = geti("CV_PREFILTER", t.prefilter);
     t.debug = getenv("CV_DEBUG") != nullptr;
@@ -675,16 +676,30 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     const size_t smem_bt = (size_t)h->K * (h->K | 1) * 8 + 16 * 8;      // + one chunk of padding behind the last row
     void (*bt_seq)(DecodeSmallParams) = f32 ? backtrace_small_kernel<16, 4, 64, 0, float> : pf ? backtrace_small_kernel<16, 4, 64, 1> : NS == 64 ? backtrace_small_kernel<16, 4, 64> : backtrace_small_kernel<16, 4, 0>;
     void (*bt_con)(DecodeSmallParams) = f32 ? backtrace_small_kernel<8, 8, 64, 0, float> : pf ? backtrace_small_kernel<8, 8, 64, 1> : NS == 64 ? backtrace_small_kernel<8, 8, 64> : backtrace_small_kernel<8, 8, 0>;
-    CUDA_TRY(cudaFuncSetAttribute(bt_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
-    CUDA_TRY(cudaFuncSetAttribute(bt_con, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt));
+    // Four lanes per sequence (backtrace_split_kernel): f64, history layout 0, tiles of 64 sequences -- for batches that do
+    // not fill the GPU for long (a rank's slice of a sharded batch): there the one-thread-per-sequence kernel is latency
+    // bound and most of its work is still open when the forward kernel ends.  Measured, device step with the concurrent
+    // backtrace, split vs. one thread per sequence: 125 k sentences 1.51 vs 1.74 ms, 250 k 2.83 vs 2.79 ms, 500 k 5.59 vs
+    // 5.29 ms, 1 M 11.20 vs 10.56 ms (four times the threads re-stage logA four times as often and execute ~15 % more
+    // instructions next to an issue-bound forward kernel).  bt_split = 2 forces it for every size.
+    bool bt_split = g_tune.bt_split && !f32 && !pf && NS == 64 && (g_tune.bt_split >= 2 || B <= (int64_t)1300 * h->num_sms);
+    size_t smem_bt_use = smem_bt;
+    if (bt_split) {
+        const int JP = h->K <= 16 ? 4 : h->K <= 32 ? 8 : h->K <= 48 ? 12 : 16;
+        bt_seq = bt_con = JP == 4 ? backtrace_split_kernel<4, 8> : JP == 8 ? backtrace_split_kernel<8, 8>
+                        : JP == 12 ? backtrace_split_kernel<12, 8> : backtrace_split_kernel<16, 8>;
+        smem_bt_use = ((size_t)(h->K + 1) * (h->K | 1) + 4 * JP) * 8;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(bt_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt_use));
+    CUDA_TRY(cudaFuncSetAttribute(bt_con, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bt_use));
     // same shared-memory carve-out as the forward kernel, or the two kernels cannot share an SM
     CUDA_TRY(cudaFuncSetAttribute(bt_con, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    const int64_t nblk = ((int64_t)ntiles * NS + 127) / 128;
+    const int64_t nblk = ((int64_t)ntiles * NS * (bt_split ? 4 : 1) + 127) / 128;
     if (concurrent) {
         CUDA_TRY(cudaStreamWaitEvent(w.st_bt, w.ev_pre, 0));
         if (wait32(w.st_bt, (unsigned long long)(uintptr_t)p.started, (unsigned int)std::max(1, grid), 0x0 /* GEQ */) != 0)
             return fail(CV_ERR_CUDA, "cuStreamWaitValue32 failed");
-        bt_con<<<(unsigned)std::max<int64_t>(1, nblk), 128, smem_bt, w.st_bt>>>(p);   // blocks in tile order
+        bt_con<<<(unsigned)std::max<int64_t>(1, nblk), 128, smem_bt_use, w.st_bt>>>(p);   // blocks in tile order
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(w.ev_bt, w.st_bt));
@@ -700,7 +715,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
         return CV_OK;
     }
     const int grid_bt = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, (int64_t)h->num_sms * 12));
-    bt_seq<<<grid_bt, 128, smem_bt, st>>>(p);
+    bt_seq<<<grid_bt, 128, smem_bt_use, st>>>(p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (timing) CUDA_TRY(cudaEventRecord(h->ev2, st));
@@ -939,10 +954,12 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     if (prof) { for (auto &e : pe) cudaEventCreate(&e); cudaEventRecord(pe[0], sk); }
     // offsets first (the ordering needs nothing else), then the observations chunk by chunk on the copy stream
     CUDA_TRY(cudaMemsetAsync(w.misc.p, 0, 256, sk));
-    CUDA_TRY(cudaEventRecord(w.ev_pre, sk));
     CUDA_TRY(cudaMemcpyAsync(d_off, seq_off, sizeof(int64_t) * (size_t)(B + 1), cudaMemcpyHostToDevice, sk));
+    CUDA_TRY(cudaEventRecord(w.ev_pre, sk));
     int *hs = (int *)h->pinned_status + 8;
-    CUDA_TRY(cudaStreamWaitEvent(s_in, w.ev_pre, 0));                                          // `arrived` is zeroed first
+    // `arrived` is zeroed first -- and the offsets have the link to themselves: the ordering (keys, sort) waits for them,
+    // and two host-to-device copies in flight share the bandwidth (offsets + keys done at 0.5 instead of 0.25 ms)
+    CUDA_TRY(cudaStreamWaitEvent(s_in, w.ev_pre, 0));
     for (int k = 0; k < nch; k++) {
         const int64_t e0 = seq_off[sio.cbs.cb[k]], e1 = seq_off[sio.cbs.cb[k + 1]];
         if (e1 < e0 || e1 > N) return fail(CV_ERR_ARG, "seq_off not monotone");

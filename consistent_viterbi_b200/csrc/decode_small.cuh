@@ -639,4 +639,112 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same end state + backtrace with FOUR lanes per sequence (history layout 0, tiles of 64 sequences, f64).
+//
+// One thread per sequence is bound by memory latency: a lane has one chunk of 8 predecessors in flight and a step costs
+// six dependent round trips (6-10 us per step; 0.41 ms for the 125 k sentences a rank of an 8-GPU run decodes, most of
+// it left over when the forward kernel ends).  Here lane (part, sl) of a warp owns the predecessors
+// [part * JP, (part + 1) * JP) of sequence sl -- a warp holds 8 sequences, the loads of one predecessor are 64-byte
+// runs -- so a whole row is in flight at once (JP loads per lane), the dependent chain of a step is JP compares plus
+// two shuffle rounds, and no load depends on the decoded state: the delta value of the winning predecessor (the
+// `dcur` of the next step) is carried through the reduction instead of being fetched.  The first maximum survives the
+// cross-lane combine because parts are ordered by predecessor index: a later part wins only if strictly greater.
+// The end state (viterbi.rs:24) is the same scan against a column of zeros (delta + 0.0 = delta bit for bit: no delta is -0.0).
+// ---------------------------------------------------------------------------
+template <int JP, int MINB>
+__global__ void __launch_bounds__(128, MINB) backtrace_split_kernel(const DecodeSmallParams p)
+{
+    constexpr int NS = 64, LPS = 4;
+    const double NEG = neg_inf();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = p.K, Kp = p.Kp;
+    const int ATP = K | 1;                                     // odd pitch: rows of different states spread over banks
+    // sAT[s*ATP + j] = logA[j][s]; row K = zeros (+ padding: a part may read up to LPS * JP - K entries past a row's end --
+    // whatever it finds there is added to a -inf operand)
+    double *sAT = reinterpret_cast<double *>(smem_raw);
+    for (int e = threadIdx.x; e < (K + 1) * ATP + LPS * JP; e += blockDim.x) {
+        const int s = e / ATP, j = e % ATP;
+        sAT[e] = (s >= K || j >= K) ? 0.0 : p.A[(size_t)j * Kp + s];
+    }
+    __syncthreads();
+
+    const size_t sl = (size_t)K * NS;
+    const int lane = threadIdx.x & 31, part = lane >> 3;
+    const unsigned int grp_mask = 0x01010101u << (lane & 7);  // the four lanes of this sequence
+    const int j0 = part * JP;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total = (int64_t)p.ntiles * NS * LPS;
+    for (int64_t r4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r4 < total; r4 += nthreads) {
+        // warp = 8 adjacent sequences of one tile: sequence index r = (warp index) * 8 + (lane & 7)
+        const int64_t r = (r4 >> 5) * 8 + (lane & 7);
+        int tile = (int)(r / NS);
+        const int s = (int)(r % NS);
+        if (p.tile_done) {
+            // concurrent mode: queue slot `tile` holds a finished tile (see backtrace_small_kernel)
+            int v = 0;
+            if (lane == 0) {
+                const long long t0 = clock64();
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.tile_done + tile) : "memory");
+                    if (v) break;
+                    if (clock64() - t0 > (1LL << 35)) { *p.status = 5; v = tile + 1; break; }
+                    __nanosleep(1000);
+                }
+            }
+            tile = __shfl_sync(0xffffffffu, v, 0) - 1;
+            __threadfence();
+        }
+        const int64_t rr = (int64_t)tile * NS + s;
+        if (rr >= p.B) continue;
+        const uint32_t b = p.order[rr];
+        if (p.is_long && p.is_long[b]) continue;
+        const int64_t off = p.seq_off[b];
+        const int len = (int)(p.seq_off[b + 1] - off);
+        if (len <= 0 || p.tile_base[tile] + (long long)len > p.hist_cap_slabs) { if (part == 0) bt_mark_done(p, b); continue; }
+        // this lane's predecessors of row len-1 of sequence s
+        const double *rowp = p.hist + (size_t)p.tile_base[tile] * sl + (size_t)(len - 1) * sl + (size_t)j0 * NS + s;
+        double buf[JP];
+        auto load_row = [&](const double *q) {
+#pragma unroll
+            for (int k = 0; k < JP; k++) buf[k] = (j0 + k < K) ? __ldcs(q + (size_t)k * NS) : NEG;
+        };
+        load_row(rowp);
+        const double *at = sAT + (size_t)K * ATP + j0;         // the column of zeros: the end state is a plain argmax
+        double dcur = 0.0;
+        int64_t pout = off + (len - 1);
+        for (int tt = len - 1; tt >= 0; tt--) {
+            // candidates fl(delta[tt][j] + logA[j][state(tt+1)]) of this lane's part, first maximum, with the delta operand
+            double mv = buf[0] + at[0], md = buf[0];
+            int mi = j0;
+#pragma unroll
+            for (int k = 1; k < JP; k++) {
+                const double v = buf[k] + at[k];
+                if (v > mv) { mv = v; md = buf[k]; mi = j0 + k; }
+            }
+            // the row below is path independent: fetch it while the four parts are combined
+            if (tt > 0) { rowp -= sl; load_row(rowp); }
+#pragma unroll
+            for (int d = 8; d <= 16; d <<= 1) {
+                const double ov = __shfl_xor_sync(grp_mask, mv, d), od = __shfl_xor_sync(grp_mask, md, d);
+                const int oi = __shfl_xor_sync(grp_mask, mi, d);
+                // the other lane holds later predecessors iff its index is higher: later wins only if strictly greater
+                const bool take = oi > mi ? ov > mv : !(mv > ov);
+                if (take) { mv = ov; md = od; mi = oi; }
+            }
+            // psi = 0 when delta[tt+1][state(tt+1)] = -inf (emission -inf or all candidates -inf; see header comment)
+            const int cur = (dcur > NEG) ? mi : 0;
+            if (part == 0) {
+                if (tt == len - 1 && p.score) p.score[b] = mv;
+                store_path_at(p, pout, (uint32_t)cur);
+            }
+            pout--;
+            // delta[tt][cur]: the winning operand, unless the -inf rule replaced the argmax by state 0
+            dcur = (cur == mi) ? md : __ldcg(p.hist + (size_t)p.tile_base[tile] * sl + (size_t)tt * sl + (size_t)cur * NS + s);
+            at = sAT + (size_t)cur * ATP + j0;
+        }
+        if (part == 0) bt_mark_done(p, b);
+    }
+}
+
 }  // namespace cvb

@@ -36,6 +36,10 @@ void cv_debug_set_fwd_ldc(int on);
 /* forward tile kernel, balanced split with a remainder: 1 (default) = only the state groups that own one state less
  * fetch the emission rows (they are the ones that wait at the step barrier), 0 = every warp fetches a share */
 void cv_debug_set_em_light(int on);
+/* backtrace of the tile path: 1 (default) = four lanes per sequence (a whole history row in flight per step, no load
+ * that depends on the decoded state) for batches of up to ~1300 sequences per SM, 2 = for every batch size,
+ * 0 = always one thread per sequence */
+void cv_debug_set_bt_split(int on);
 /* forward tile kernel with the f32 pre-filter (csrc/decode_prefilter.cuh) for models whose entries are all <= 0:
  * 1 = on, 0 = the plain f64 tile kernel */
 void cv_debug_set_prefilter(int on);

@@ -5,7 +5,8 @@
 variant: 1 = balanced state split (default), 0 = groups of 8 states (last one padded), 2 = the pre-filter kernel
 (decode_prefilter.cuh), 3 = the optional f32 mode (cv_decode_batch_dev_f32; results differ by design), 4 = default but
 run-time row pitches in the forward kernel (cv_debug_set_fwd_ldc(0)), 5 = default but every warp fetches emission rows
-(cv_debug_set_em_light(0)).  Prints the forward kernel alone (CUDA events, timing mode), and the device-resident step (forward +
+(cv_debug_set_em_light(0)), 6 = default but the one-thread-per-sequence backtrace (cv_debug_set_bt_split(0)), 7 = the four-lane backtrace at
+every batch size (cv_debug_set_bt_split(2); the default uses it up to ~1300 sequences per SM).  Prints the forward kernel alone (CUDA events, timing mode), and the device-resident step (forward +
 concurrent backtrace) for each variant, plus the extra `CV_*` launch-shape settings given in the environment."""
 import ctypes as C
 import json
@@ -53,6 +54,7 @@ for v in variants:
     L.cv_debug_set_prefilter(1 if v == 2 else 0)
     L.cv_debug_set_fwd_ldc(0 if v == 4 else 1)
     L.cv_debug_set_em_light(0 if v == 5 else 1)
+    L.cv_debug_set_bt_split(0 if v == 6 else 2 if v == 7 else 1)
     FN[0] = L.cv_decode_batch_dev_f32 if v == 3 else L.cv_decode_batch_dev        # 3 = the optional f32 mode
     for _ in range(3):
         run(0)
@@ -83,4 +85,5 @@ L.cv_debug_set_balanced_split(1)
 L.cv_debug_set_prefilter(0)
 L.cv_debug_set_fwd_ldc(1)
 L.cv_debug_set_em_light(1)
+L.cv_debug_set_bt_split(1)
 print(json.dumps({"peak_fp64_ops": peak, "env": {k: v for k, v in os.environ.items() if k.startswith("CV_")}}))
