@@ -483,13 +483,23 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
 // the next chunk of 16 predecessors is always in flight while the current one is reduced; the only dependent
 // chain per step is 16 x (DADD, DSETP, select) x ceil(K/16).
 // streamed host path: sequence b is decoded -- its path and score may be copied out once its whole chunk is
-__device__ __forceinline__ void bt_mark_done(const DecodeSmallParams &p, uint32_t b)
+__device__ __forceinline__ int bt_chunk_of(const DecodeSmallParams &p, uint32_t b)
 {
-    if (!p.chunk_done) return;
     int c = 0;
     while (c + 1 < p.nch && (int64_t)b >= p.cb[c + 1]) c++;
-    __threadfence_system();                                  // path / score stores before the count the copy stream waits for
-    atomicAdd(p.chunk_done + c, 1u);
+    return c;
+}
+// Called by ALL 32 lanes of a warp once their sequences of this round are decoded (c = chunk of the lane's sequence,
+// -1 = none): one system-scope fence and one atomic per warp and chunk instead of one per sequence.  The lanes' path /
+// score stores are ordered before the leader's fence by the warp-level synchronisation of the match.
+__device__ __forceinline__ void bt_mark_done_warp(const DecodeSmallParams &p, int c)
+{
+    if (!p.chunk_done) return;
+    const unsigned int same = __match_any_sync(0xffffffffu, c);
+    if (c >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) {
+        __threadfence_system();                              // path / score stores before the count the copy stream waits for
+        atomicAdd(p.chunk_done + c, (unsigned int)__popc(same));
+    }
 }
 
 // NSC = sequences per tile when known at compile time (64: the load offsets become immediates), 0 = p.NS
@@ -539,13 +549,16 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
             tile = __shfl_sync(0xffffffffu, v, 0) - 1;
             __threadfence();                                   // the leader's acquire, extended to the lanes that waited
         }
+        // the lane's sequence; returns the chunk it belongs to on the streamed host path (-1: nothing to report)
+        const int done_chunk = [&]() -> int {
         const int64_t rr = (int64_t)tile * NS + s;                     // rank in the length-sorted order
-        if (rr >= p.B) continue;
+        if (rr >= p.B) return -1;
         const uint32_t b = p.order[rr];
-        if (p.is_long && p.is_long[b]) continue;                      // the warp-per-sequence kernel owns this sequence
+        if (p.is_long && p.is_long[b]) return -1;                     // the warp-per-sequence kernel owns this sequence
+        const int my_chunk = p.chunk_done ? bt_chunk_of(p, b) : -1;
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
-        if (p.tile_base[tile] + (long long)len > p.hist_cap_slabs) { bt_mark_done(p, b); continue; }   // tile refused by the forward kernel (status 7)
+        if (len <= 0 || p.tile_base[tile] + (long long)len > p.hist_cap_slabs) return my_chunk;   // tile refused by the forward kernel (status 7)
         const T *col = reinterpret_cast<const T *>(p.hist) + (size_t)p.tile_base[tile] * sl + (size_t)s * SS;   // sequence s of slab 0
 
         // end state: argmax of the last row (viterbi.rs:24)
@@ -557,7 +570,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         }
         if (p.score) p.score[b] = (double)bv;
         store_path_at(p, off + len - 1, (uint32_t)cur);
-        if (len == 1) { bt_mark_done(p, b); continue; }
+        if (len == 1) return my_chunk;
 
         // walk back (viterbi.rs:27-30): steps tt = len-1 .. 1, each a scan of row tt-1 in chunks of BT_CHUNK predecessors;
         // the next chunk (of this step, or the first of the next step -- rows do not depend on the path) is always
@@ -635,7 +648,9 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
         } else {
             for (int tt = len - 1; tt >= 1; tt--) step(bufA, bufB, tt);
         }
-        bt_mark_done(p, b);
+        return my_chunk;
+        }();
+        bt_mark_done_warp(p, done_chunk);
     }
 }
 
@@ -695,13 +710,15 @@ __global__ void __launch_bounds__(128, MINB) backtrace_split_kernel(const Decode
             tile = __shfl_sync(0xffffffffu, v, 0) - 1;
             __threadfence();
         }
+        const int done_chunk = [&]() -> int {
         const int64_t rr = (int64_t)tile * NS + s;
-        if (rr >= p.B) continue;
+        if (rr >= p.B) return -1;
         const uint32_t b = p.order[rr];
-        if (p.is_long && p.is_long[b]) continue;
+        if (p.is_long && p.is_long[b]) return -1;
+        const int my_chunk = (p.chunk_done && part == 0) ? bt_chunk_of(p, b) : -1;    // one report per sequence
         const int64_t off = p.seq_off[b];
         const int len = (int)(p.seq_off[b + 1] - off);
-        if (len <= 0 || p.tile_base[tile] + (long long)len > p.hist_cap_slabs) { if (part == 0) bt_mark_done(p, b); continue; }
+        if (len <= 0 || p.tile_base[tile] + (long long)len > p.hist_cap_slabs) return my_chunk;
         // this lane's predecessors of row len-1 of sequence s
         const double *rowp = p.hist + (size_t)p.tile_base[tile] * sl + (size_t)(len - 1) * sl + (size_t)j0 * NS + s;
         double buf[JP];
@@ -743,7 +760,9 @@ __global__ void __launch_bounds__(128, MINB) backtrace_split_kernel(const Decode
             dcur = (cur == mi) ? md : __ldcg(p.hist + (size_t)p.tile_base[tile] * sl + (size_t)tt * sl + (size_t)cur * NS + s);
             at = sAT + (size_t)cur * ATP + j0;
         }
-        if (part == 0) bt_mark_done(p, b);
+        return my_chunk;
+        }();
+        bt_mark_done_warp(p, done_chunk);
     }
 }
 
