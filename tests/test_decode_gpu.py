@@ -139,6 +139,68 @@ def test_pos_shape_sample_and_properties():
         assert (p2[off2[k]:off2[k + 1]] == paths[off[b]:off[b + 1]]).all()
 
 
+@pytest.mark.parametrize("K", [9, 20, 33, 45, 47, 64])
+def test_tile_kernel_variants_equal_oracle(K):
+    """Every launch-time variant of the tile path against the oracle on one ragged batch with -inf entries, many
+    length-1 sequences and two chunked host modes: compile-time row pitches on / off (cv_debug_set_fwd_ldc), emission-row
+    fetch dealt out by tile work / evenly (cv_debug_set_em_light), backtrace with four lanes per sequence / one thread per
+    sequence (cv_debug_set_bt_split; 2 = at every size)."""
+    rng = np.random.default_rng(7700 + K)
+    M = 35
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.2, ties=(K % 2 == 0))      # even K: dyadic values, exact ties, +-0.0
+    obs, off = random_batch(rng, 7000, M, 1, 45)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        L.cv_debug_set_chain_max_batch(0)
+        for ldc in (1, 0):
+            for light in (1, 0):
+                for split in (2, 0):
+                    for chunks in (1, 3):
+                        L.cv_debug_set_fwd_ldc(ldc); L.cv_debug_set_em_light(light); L.cv_debug_set_bt_split(split)
+                        L.cv_debug_set_chunks(chunks)
+                        p, s = cv.decode_batch(h, obs, off)
+                        assert (p == rp).all() and s.tobytes() == rs.tobytes(), (ldc, light, split, chunks)
+        # backtrace after the forward kernel (timing mode of the device API runs the kernels one after the other)
+        L.cv_debug_set_pipeline(0, 0)
+        for split in (2, 0):
+            L.cv_debug_set_bt_split(split)
+            p, s = cv.decode_batch(h, obs, off)
+            assert (p == rp).all() and s.tobytes() == rs.tobytes(), ("sequential", split)
+    finally:
+        L.cv_debug_set_fwd_ldc(1); L.cv_debug_set_em_light(1); L.cv_debug_set_bt_split(1)
+        L.cv_debug_set_pipeline(1, 1)
+        L.cv_debug_set_chunks(-1)
+        L.cv_debug_set_chain_max_batch(-1)
+    h.close()
+
+
+def test_split_backtrace_all_neg_inf_and_single_steps():
+    """The four-lane backtrace on the cases its end-state / -inf rules exist for: every emission -inf (all paths are
+    state 0 from the first -inf on), length-1 and length-2 sequences, K below / at the lane split (K = 3, 4, 5)."""
+    L = cv._lib.lib()
+    try:
+        L.cv_debug_set_chain_max_batch(0)
+        L.cv_debug_set_bt_split(2)
+        for K in (3, 4, 5, 17):
+            rng = np.random.default_rng(880 + K)
+            M = 6
+            A, B, pi = random_hmm(rng, K, M, zero_frac=0.5)
+            B[:, 0] = -np.inf                                    # observation 0 is impossible in every state
+            lens = rng.integers(1, 4, size=3000)
+            off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+            obs = rng.integers(0, M, size=int(off[-1])).astype(np.uint32)
+            rp, rs = po.decode_batch(A, B, obs, off, nthreads=4)
+            h = cv.HMM(A, B, pi)
+            p, s = cv.decode_batch(h, obs, off)
+            assert (p == rp).all() and s.tobytes() == rs.tobytes(), K
+            h.close()
+    finally:
+        L.cv_debug_set_bt_split(1)
+        L.cv_debug_set_chain_max_batch(-1)
+
+
 def test_chunked_pipeline_and_device_api():
     """cv_decode_batch cuts large batches into chunks on two internal streams and cv_decode_batch_dev takes
     device-resident buffers (torch tensors here, plain pointers at the ABI): force 3 chunks on a mid-size batch
