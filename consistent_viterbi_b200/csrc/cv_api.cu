@@ -378,15 +378,27 @@ __device__ __forceinline__ bool take_long(const LongSplit &ls, int64_t b, int64_
     return true;
 }
 
-__global__ void seq_len_keys_kernel(const int64_t *seq_off, int64_t B, uint32_t *keys, uint32_t *vals, int *status, const LongSplit ls)
+// max_len > 0: the caller's bound on the lengths -- the sort then looks only at the bits a length can have, so a longer
+// sequence must be an error (CV_ERR_ARG), not a mis-sorted batch
+__global__ void seq_len_keys_kernel(const int64_t *seq_off, int64_t B, uint32_t *keys, uint32_t *vals, int *status, const LongSplit ls,
+                                    int64_t max_len)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int64_t len = seq_off[b + 1] - seq_off[b];
     if (len <= 0) *status = CV_ERR_EMPTY;          // reference: sequence.len()-1 underflow panic
+    else if (max_len > 0 && len > max_len) *status = CV_ERR_ARG;
     const bool lng = take_long(ls, b, len);
     keys[b] = lng ? 0u : (uint32_t)(len < 0 ? 0 : (len > 0xffffffffLL ? 0xffffffffLL : len));
     vals[b] = (uint32_t)b;
+}
+
+// bits of the sort key that a length <= max_len can set
+static int key_bits(int64_t max_len)
+{
+    int b = 1;
+    while (b < 32 && (max_len >> b) != 0) b++;
+    return b;
 }
 
 // longest length of every tile of NS sequences (lengths are sorted descending)
@@ -399,7 +411,7 @@ __global__ void tile_tmax_kernel(const uint32_t *sorted_len, int ntiles, int NS,
 // ---- streamed host path: keys = (chunk descending-coded, length) so that one descending sort orders the batch by
 // chunk (ascending) and, inside a chunk, by length (longest first); lengths must fit 24 bits
 constexpr int STREAM_MAX_CHUNKS = 16;
-struct ChunkBounds { int nch; int64_t cb[STREAM_MAX_CHUNKS + 2]; };
+struct ChunkBounds { int nch; int shift; int64_t cb[STREAM_MAX_CHUNKS + 2]; };   // key = chunk field << shift | length
 
 __global__ void seq_chunk_keys_kernel(const int64_t *seq_off, int64_t B, const ChunkBounds cbs, uint32_t *keys, uint32_t *vals,
                                       int *status, unsigned int *max_len, const LongSplit ls)
@@ -414,12 +426,12 @@ __global__ void seq_chunk_keys_kernel(const int64_t *seq_off, int64_t B, const C
     atomicMax(max_len, l);
     int c = 0;
     while (c + 1 < cbs.nch && b >= cbs.cb[c + 1]) c++;
-    keys[b] = ((uint32_t)(cbs.nch - 1 - c) << 24) | (take_long(ls, b, len) ? 0u : l);
+    keys[b] = ((uint32_t)(cbs.nch - 1 - c) << cbs.shift) | (take_long(ls, b, len) ? 0u : l);
     vals[b] = (uint32_t)b;
 }
 
 // per tile of NS sorted sequences: the longest length and the last chunk it takes sequences from
-__global__ void tile_meta_kernel(const uint32_t *sorted_keys, int ntiles, int NS, int64_t B, int nch, long long *tmax, int *tchunk)
+__global__ void tile_meta_kernel(const uint32_t *sorted_keys, int ntiles, int NS, int64_t B, int nch, int shift, long long *tmax, int *tchunk)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
@@ -428,8 +440,8 @@ __global__ void tile_meta_kernel(const uint32_t *sorted_keys, int ntiles, int NS
         const int64_t r = (int64_t)t * NS + s;
         if (r >= B) break;
         const uint32_t k = sorted_keys[r];
-        lmax = max(lmax, k & 0xffffffu);
-        cmax = max(cmax, nch - 1 - (int)(k >> 24));
+        lmax = max(lmax, k & ((1u << shift) - 1u));
+        cmax = max(cmax, nch - 1 - (int)(k >> shift));
     }
     tmax[t] = (long long)lmax; tchunk[t] = cmax;
 }
@@ -570,7 +582,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     if ((rc = w.base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
     if (sio) {
         if ((rc = w.delta_g.ensure(sizeof(int) * (size_t)ntiles + 64))) return rc;     // tile -> chunk (buffer unused for K <= 64)
-        tile_meta_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(d_sorted_len, ntiles, NS, B, sio->cbs.nch, (long long *)w.tmax.p, (int *)w.delta_g.p);
+        tile_meta_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(d_sorted_len, ntiles, NS, B, sio->cbs.nch, sio->cbs.shift, (long long *)w.tmax.p, (int *)w.delta_g.p);
     } else {
         tile_tmax_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_sorted_len, ntiles, NS, (long long *)w.tmax.p);
     }
@@ -743,16 +755,18 @@ static int decode_chunk(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, const int
     if (!chain_all && (rc = long_split_setup(h, w, B, N, max_len, st, ls))) return rc;
     // order sequences by length, longest first (stable radix sort => deterministic)
     seq_len_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_off, B, (uint32_t *)w.keys_in.p,
-                                                                    (uint32_t *)w.vals_in.p, d_status, ls);
+                                                                    (uint32_t *)w.vals_in.p, d_status, ls, max_len);
     g_launches++;
+    // the radix sort only visits the bits a length can have (one 8-bit pass for lengths up to 255 instead of four)
+    const int end_bit = max_len > 0 ? key_bits(max_len) : 32;
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)w.keys_in.p,
                                                        (uint32_t *)w.keys_out.p, (uint32_t *)w.vals_in.p,
-                                                       (uint32_t *)w.order.p, (int)B, 0, 32, st));
+                                                       (uint32_t *)w.order.p, (int)B, 0, end_bit, st));
     if ((rc = w.cub_tmp.ensure(tmp_bytes))) return rc;
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p,
                                                        (uint32_t *)w.keys_out.p, (uint32_t *)w.vals_in.p,
-                                                       (uint32_t *)w.order.p, (int)B, 0, 32, st));
+                                                       (uint32_t *)w.order.p, (int)B, 0, end_bit, st));
     if (chain_all) {
         // few sequences: one warp per sequence (latency-oriented), backpointers as u8 rows
         if ((rc = w.hist.ensure((size_t)N * h->Kp + 64))) return rc;
@@ -981,6 +995,9 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
         }
         if (max_len_host <= 0xffffffLL && (rc = long_split_setup(h, w, B, N, max_len_host, sk, ls))) return rc;
     }
+    // sort key = chunk field << shift | length: 24 bits of length when the longest one is not known yet, else just the
+    // bits it needs (the sort then takes one or two 8-bit passes instead of four)
+    sio.cbs.shift = (max_len_host > 0 && max_len_host <= 0xffffffLL) ? key_bits(max_len_host) : 24;
     seq_chunk_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, sk>>>(d_off, B, sio.cbs, (uint32_t *)w.keys_in.p,
                                                                       (uint32_t *)w.vals_in.p, d_status, d_maxlen, ls);
     g_launches++;
@@ -1000,12 +1017,13 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     if (max_len > 0xffffffLL) { *handled = false; return CV_OK; }                              // does not fit the 24-bit sort key: chunked path
     if (prof) { hm_scan = host_ms(); cudaEventRecord(pe[1], sk); cudaEventRecord(pe[4], s_in); }
 
+    const int end_bit = std::min(32, sio.cbs.shift + key_bits(nch - 1));
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, (uint32_t *)w.keys_in.p, (uint32_t *)w.keys_out.p,
-                                                       (uint32_t *)w.vals_in.p, (uint32_t *)w.order.p, (int)B, 0, 32, sk));
+                                                       (uint32_t *)w.vals_in.p, (uint32_t *)w.order.p, (int)B, 0, end_bit, sk));
     if ((rc = w.cub_tmp.ensure(tmp_bytes))) return rc;
     CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp.p, tmp_bytes, (uint32_t *)w.keys_in.p, (uint32_t *)w.keys_out.p,
-                                                       (uint32_t *)w.vals_in.p, (uint32_t *)w.order.p, (int)B, 0, 32, sk));
+                                                       (uint32_t *)w.vals_in.p, (uint32_t *)w.order.p, (int)B, 0, end_bit, sk));
     if (prof) cudaEventRecord(pe[2], sk);
     if ((rc = launch_decode_small(h, w, d_obs, d_off, B, N, d_path, d_score, d_counter, d_status, max_len, sk, false, &sio, &ls))) return rc;
     if (prof) cudaEventRecord(pe[3], sk);

@@ -377,6 +377,35 @@ def test_forward_kernel_state_splits_equal_oracle(K):
     h.close()
 
 
+def test_device_api_rejects_a_max_len_that_is_too_small():
+    """cv_decode_batch_dev sorts by the bits a length <= max_len can have: a longer sequence must be CV_ERR_ARG, never a
+    silently mis-ordered batch; a generous max_len is fine."""
+    import torch
+    rng = np.random.default_rng(31)
+    K, M, Bn = 21, 30, 12000
+    A, B, pi = random_hmm(rng, K, M)
+    obs, off = random_batch(rng, Bn, M, 1, 70)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    d_obs = torch.from_numpy(obs.view(np.int32)).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    d_path = torch.zeros(len(obs), dtype=torch.int32, device="cuda")
+    d_score = torch.zeros(Bn, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream()
+    true_max = int(np.diff(off).max())
+    for ml, ok in ((true_max, True), (4 * true_max + 3, True), (0, True), (true_max - 1, False), (15, False)):
+        rc = L.cv_decode_batch_dev(h.device_handle(), d_obs.data_ptr(), d_off.data_ptr(), Bn, len(obs), ml,
+                                   d_path.data_ptr(), d_score.data_ptr(), st.cuda_stream, 1)
+        torch.cuda.synchronize()
+        if ok:
+            cv._lib.check(rc)
+            assert (d_path.cpu().numpy().view(np.uint32) == rp).all() and d_score.cpu().numpy().tobytes() == rs.tobytes(), ml
+        else:
+            assert rc == cv._lib.ERR_ARG, (ml, rc)
+    h.close()
+
+
 def test_decode_batch_keep_leaves_device_copies():
     """cv_decode_batch_keep: host results as cv_decode_batch, and the same results in the caller's device buffers
     (rows of an all-gather buffer in the multi-GPU path).  Streamed and per-chunk host paths."""
