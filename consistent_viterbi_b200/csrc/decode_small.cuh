@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
     const bool obs_streamed = p.arrived != nullptr;
     auto ld_obs = [&](int64_t idx) -> uint32_t { return load_obs_at(p, idx, obs_streamed); };
 
+    unsigned int arrived_seen = 0;      // (thread 0) chunks of observations known to be on the device
     for (;;) {
         if (tid == 0) *sTile = (int)atomicAdd(p.tile_counter, 1u);
         __syncthreads();
@@ -380,13 +381,13 @@ __global__ void __launch_bounds__(MAXT, MINB) decode_small_fwd_kernel(const Deco
         }
         for (int e = tid; e < K * NS; e += blockDim.x) sD[e] = 0.0;
         if (p.arrived && tid == 0) {
-            // streamed input: the tile's observations must have arrived (bounded wait, then error)
+            // streamed input: the tile's observations must have arrived (bounded wait, then error).  The count only
+            // grows, so the system-scope load is skipped once this thread has seen enough chunks arrive.
             const unsigned int need = (unsigned int)p.tile_chunk[tile] + 1u;
             const long long t0 = clock64();
-            for (;;) {
-                unsigned int v;
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.arrived) : "memory");
-                if (v >= need) break;
+            while (arrived_seen < need) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(arrived_seen) : "l"(p.arrived) : "memory");
+                if (arrived_seen >= need) break;
                 if (clock64() - t0 > (1LL << 32)) { *p.status = 5; break; }
                 __nanosleep(128);
             }
