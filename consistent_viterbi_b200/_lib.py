@@ -99,6 +99,7 @@ DEBUG_SIGNATURES = {
     "cv_debug_set_fwd_ldc": (None, [C.c_int]),
     "cv_debug_set_em_light": (None, [C.c_int]),
     "cv_debug_set_bt_split": (None, [C.c_int]),
+    "cv_debug_set_uneven_chunks": (None, [C.c_int]),
     "cv_debug_set_prefilter": (None, [C.c_int]),
     "cv_debug_set_large_group_rb": (None, [C.c_longlong]),
     "cv_debug_set_cp_leaf_batch": (None, [C.c_int]),

@@ -52,6 +52,7 @@ static Tuning tuning_from_env()
     t.fwd_ldc = geti("CV_FWD_LDC", t.fwd_ldc);
     t.em_light = geti("CV_EM_LIGHT", t.em_light);
     t.bt_split = geti("CV_BT_SPLIT", t.bt_split);
+    t.uneven_chunks = geti("CV_UNEVEN_CHUNKS", t.uneven_chunks);
     t.long_split = geti("CV_LONG_SPLIT", t.long_split);
     t.prefilter = geti("CV_PREFILTER", t.prefilter);
     t.debug = getenv("CV_DEBUG") != nullptr;
@@ -411,7 +412,10 @@ __global__ void tile_tmax_kernel(const uint32_t *sorted_len, int ntiles, int NS,
 // ---- streamed host path: keys = (chunk descending-coded, length) so that one descending sort orders the batch by
 // chunk (ascending) and, inside a chunk, by length (longest first); lengths must fit 24 bits
 constexpr int STREAM_MAX_CHUNKS = 16;
-struct ChunkBounds { int nch; int shift; int64_t cb[STREAM_MAX_CHUNKS + 2]; };   // key = chunk field << shift | length
+// key = ordering group << shift | length.  promote_len > 0: the sequences of the chunks behind promote_to that are longer
+// than this are ordered with chunk promote_to (all observations have long arrived when that group is reached): every
+// group starts with its longest tiles, and a late, small group must not start tiles that outlast everything else.
+struct ChunkBounds { int nch; int shift; int promote_len, promote_to; int64_t cb[STREAM_MAX_CHUNKS + 2]; };
 
 __global__ void seq_chunk_keys_kernel(const int64_t *seq_off, int64_t B, const ChunkBounds cbs, uint32_t *keys, uint32_t *vals,
                                       int *status, unsigned int *max_len, const LongSplit ls)
@@ -426,12 +430,14 @@ __global__ void seq_chunk_keys_kernel(const int64_t *seq_off, int64_t B, const C
     atomicMax(max_len, l);
     int c = 0;
     while (c + 1 < cbs.nch && b >= cbs.cb[c + 1]) c++;
+    if (cbs.promote_len > 0 && c > cbs.promote_to && len > (int64_t)cbs.promote_len) c = cbs.promote_to;
     keys[b] = ((uint32_t)(cbs.nch - 1 - c) << cbs.shift) | (take_long(ls, b, len) ? 0u : l);
     vals[b] = (uint32_t)b;
 }
 
 // per tile of NS sorted sequences: the longest length and the last chunk it takes sequences from
-__global__ void tile_meta_kernel(const uint32_t *sorted_keys, int ntiles, int NS, int64_t B, int nch, int shift, long long *tmax, int *tchunk)
+// promote_to >= 0: tiles of that ordering group may hold sequences of any later chunk (ChunkBounds::promote_len)
+__global__ void tile_meta_kernel(const uint32_t *sorted_keys, int ntiles, int NS, int64_t B, int nch, int shift, int promote_to, long long *tmax, int *tchunk)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
@@ -443,6 +449,7 @@ __global__ void tile_meta_kernel(const uint32_t *sorted_keys, int ntiles, int NS
         lmax = max(lmax, k & ((1u << shift) - 1u));
         cmax = max(cmax, nch - 1 - (int)(k >> shift));
     }
+    if (promote_to >= 0 && cmax == promote_to) cmax = nch - 1;
     tmax[t] = (long long)lmax; tchunk[t] = cmax;
 }
 
@@ -582,7 +589,7 @@ static int launch_decode_small(cv_hmm *h, DecodeWs &w, const uint32_t *d_obs, co
     if ((rc = w.base.ensure(sizeof(long long) * (size_t)ntiles))) return rc;
     if (sio) {
         if ((rc = w.delta_g.ensure(sizeof(int) * (size_t)ntiles + 64))) return rc;     // tile -> chunk (buffer unused for K <= 64)
-        tile_meta_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(d_sorted_len, ntiles, NS, B, sio->cbs.nch, sio->cbs.shift, (long long *)w.tmax.p, (int *)w.delta_g.p);
+        tile_meta_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(d_sorted_len, ntiles, NS, B, sio->cbs.nch, sio->cbs.shift, sio->cbs.promote_len > 0 ? sio->cbs.promote_to : -1, (long long *)w.tmax.p, (int *)w.delta_g.p);
     } else {
         tile_tmax_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(d_sorted_len, ntiles, NS, (long long *)w.tmax.p);
     }
@@ -949,11 +956,27 @@ static int decode_streamed(cv_hmm *h, const uint32_t *obs_flat, const int64_t *s
     unsigned int *d_maxlen = (unsigned int *)w.misc.p + 17, *d_arrived = (unsigned int *)w.misc.p + 32, *d_chunk_done = d_arrived + 1;
     StreamedIO sio;
     sio.cbs.nch = nch;
-    // Equal chunks.  Small outer chunks (the forward kernel cannot start before chunk 0 is on the device, the last
-    // chunk's paths leave after the kernels have ended) were measured and lost at 1 M sentences: four chunks of
-    // 1/8, 3/8, 3/8, 1/8 13.45 vs 13.24 ms, six chunks with 1/16 at both ends 13.9 ms -- the uneven middle chunks
-    // restart the longest-first tile order with more work behind them.
-    for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
+    // Chunk sizes.  The forward kernel cannot start before chunk 0 is on the device and the last chunk's paths leave after
+    // the kernels have ended, so both should be small -- but tiles are ordered by (chunk, length): every chunk starts with
+    // its longest, most ragged tiles, and a small late chunk starts them when everything else is about to end (measured
+    // with plain uneven chunks: 1/8, 3/8, 3/8, 1/8 13.45 vs 13.24 ms for four equal ones; six tapering chunks end the
+    // kernels 0.5 ms later than five).  The automatic choice for large batches therefore cuts 10 / 25 / 25 / 20 / 12 / 8 %
+    // and orders the LONG sequences of chunks 3.. with chunk 2 (ChunkBounds::promote_len): the late groups hold short,
+    // even tiles only, a chunk's copy out fits into the work ordered behind it, and 8 % of the paths are copied after
+    // the kernels.  A forced chunk count (cv_debug_set_chunks) gives equal chunks.
+    sio.cbs.promote_len = 0; sio.cbs.promote_to = 0;
+    if ((g_tune.chunks <= 0 && nch == 4 && g_tune.uneven_chunks) || (g_tune.uneven_chunks >= 2 && B >= 100)) {     // (2: forced, for tests)
+        nch = 6;
+        sio.cbs.nch = nch;
+        static const int pct[7] = {0, 10, 35, 60, 80, 92, 100};
+        for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * pct[k] / 100;
+        // a tile of a late group should take at most a quarter of the tile-steps a resident CTA runs for the last chunk
+        const int64_t steps_per_cta = (seq_off[B] - seq_off[sio.cbs.cb[nch - 1]]) / ((int64_t)64 * 2 * h->num_sms);
+        sio.cbs.promote_len = (int)std::max<int64_t>(4, std::min<int64_t>(steps_per_cta / 4, 1 << 20));
+        sio.cbs.promote_to = 2;
+    } else {
+        for (int k = 0; k <= nch; k++) sio.cbs.cb[k] = B * k / nch;
+    }
     sio.d_arrived = d_arrived; sio.d_chunk_done = d_chunk_done;
 
     // From here on copies from / to the caller's host buffers are in flight: every return (error or not) first drains

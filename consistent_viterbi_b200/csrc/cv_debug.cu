@@ -19,6 +19,7 @@ extern "C" void cv_debug_set_balanced_split(int on) { g_tune.balanced_split = on
 extern "C" void cv_debug_set_fwd_ldc(int on) { g_tune.fwd_ldc = on; }
 extern "C" void cv_debug_set_em_light(int on) { g_tune.em_light = on; }
 extern "C" void cv_debug_set_bt_split(int on) { g_tune.bt_split = on; }
+extern "C" void cv_debug_set_uneven_chunks(int on) { g_tune.uneven_chunks = on; }
 extern "C" void cv_debug_set_prefilter(int on) { g_tune.prefilter = on; }
 extern "C" void cv_debug_set_large_group_rb(long long rb) { g_tune.large_group_rb = rb; }
 extern "C" void cv_debug_set_cp_leaf_batch(int on) { g_tune.cp_leaf_batch = on; }

@@ -52,6 +52,7 @@ struct Tuning {
     int fwd_ldc = 1;               // forward tile kernel with compile-time row pitches (tiles of 64, logA pitch 64) when it costs no occupancy (CV_FWD_LDC)
     int em_light = 1;              // uneven balanced split: only the lighter state groups fetch the emission rows (CV_EM_LIGHT)
     int bt_split = 1;              // backtrace with four lanes per sequence (backtrace_split_kernel) where it applies (CV_BT_SPLIT)
+    int uneven_chunks = 1;         // streamed host path, automatic chunking: 10/25/25/20/12/8 % with the last chunk's long sequences promoted (CV_UNEVEN_CHUNKS)
     int prefilter = 0;             // forward tile kernel with the f32 pre-filter (decode_prefilter.cuh) when the model allows it (CV_PREFILTER)
     int long_split = 1;            // very long sequences of a short batch go to the warp-per-sequence kernel (CV_LONG_SPLIT)
     int debug = 0;                 // print launch shapes                                         (CV_DEBUG)

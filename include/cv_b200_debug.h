@@ -40,6 +40,10 @@ void cv_debug_set_em_light(int on);
  * that depends on the decoded state) for batches of up to ~1300 sequences per SM, 2 = for every batch size,
  * 0 = always one thread per sequence */
 void cv_debug_set_bt_split(int on);
+/* streamed host path: 1 (default) = large batches with automatic chunking are cut 10 / 25 / 25 / 20 / 12 / 8 % and the long
+ * sequences of the last chunk are ordered with the chunk before it, 0 = equal chunks, 2 = the uneven cut for every
+ * streamed call (tests) */
+void cv_debug_set_uneven_chunks(int on);
 /* forward tile kernel with the f32 pre-filter (csrc/decode_prefilter.cuh) for models whose entries are all <= 0:
  * 1 = on, 0 = the plain f64 tile kernel */
 void cv_debug_set_prefilter(int on);

@@ -377,6 +377,38 @@ def test_forward_kernel_state_splits_equal_oracle(K):
     h.close()
 
 
+def test_streamed_uneven_chunks_with_promotion_equal_oracle():
+    """The streamed host path with its automatic cut for large batches (10 / 25 / 25 / 20 / 12 / 8 %, long sequences of the last
+    chunk ordered with the chunk before it), forced here on a batch the oracle decodes in seconds: ragged lengths with a
+    few very long sequences in the last chunk, u32 and u16/u8 host formats, repeated calls."""
+    rng = np.random.default_rng(515)
+    K, M, Bn = 45, 70, 40000
+    A, B, pi = random_hmm(rng, K, M, zero_frac=0.1)
+    obs, off = random_batch(rng, Bn, M, 1, 30)
+    lens = np.diff(off)
+    lens[-50:] = rng.integers(200, 400, size=50)                  # long sequences at the very end: all get promoted
+    lens[-2000:-1900] = 1
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    obs = rng.integers(0, M, size=int(off[-1])).astype(np.uint32)
+    rp, rs = po.decode_batch(A, B, obs, off, nthreads=8)
+    h = cv.HMM(A, B, pi)
+    L = cv._lib.lib()
+    try:
+        L.cv_debug_set_chain_max_batch(0)
+        L.cv_debug_set_chunks(4)                                   # take the streamed path at this size ...
+        for uneven in (2, 0, 2):
+            L.cv_debug_set_uneven_chunks(uneven)                   # ... with the uneven cut forced / equal chunks
+            p, s = cv.decode_batch(h, obs, off)
+            assert (p == rp).all() and s.tobytes() == rs.tobytes(), uneven
+            p8, s8 = cv.decode_batch_narrow(h, obs.astype(np.uint16), off)
+            assert (np.asarray(p8, dtype=np.uint32) == rp).all() and s8.tobytes() == rs.tobytes(), uneven
+    finally:
+        L.cv_debug_set_uneven_chunks(1)
+        L.cv_debug_set_chunks(-1)
+        L.cv_debug_set_chain_max_batch(-1)
+    h.close()
+
+
 def test_device_api_rejects_a_max_len_that_is_too_small():
     """cv_decode_batch_dev sorts by the bits a length <= max_len can have: a longer sequence must be CV_ERR_ARG, never a
     silently mis-ordered batch; a generous max_len is fine."""
