@@ -503,6 +503,12 @@ __device__ __forceinline__ void bt_mark_done_warp(const DecodeSmallParams &p, in
     }
 }
 
+// History rows are read with the default L2 policy (ld.global.cg), not evict-first (ld.global.cs): the one value of the
+// row that a step reads again -- delta[tt-1][state], a per-lane gather -- then still hits L2.  With evict-first the
+// backtrace read 11.6 GB from DRAM for a 9.0 GB history and took 2.1 ms alone; now 1.03x the history and 1.7 ms.
+template <typename T>
+__device__ __forceinline__ T bt_ld(const T *q) { return __ldcg(q); }
+
 // NSC = sequences per tile when known at compile time (64: the load offsets become immediates), 0 = p.NS
 // LAYOUT = 0: history slabs [K][NS] (decode_small_fwd_kernel); 1: [NS][Kp + 2] (decode_pf_fwd_kernel: a sequence's
 // row is contiguous and read as 16-byte vectors)
@@ -564,9 +570,9 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
 
         // end state: argmax of the last row (viterbi.rs:24)
         const T *row = col + (size_t)(len - 1) * sl;
-        T bv = __ldcs(row); int cur = 0;
+        T bv = bt_ld(row); int cur = 0;
         for (int j = 1; j < K; j++) {
-            const T v = __ldcs(row + (size_t)j * JS);
+            const T v = bt_ld(row + (size_t)j * JS);
             if (v > bv) { bv = v; cur = j; }
         }
         if (p.score) p.score[b] = (double)bv;
@@ -590,10 +596,10 @@ __global__ void __launch_bounds__(128, MINB) backtrace_small_kernel(const Decode
                 }
             } else if (c < nfull) {
 #pragma unroll
-                for (int k = 0; k < BT_CHUNK; k++) dst[k] = __ldcs(q + (size_t)k * JS);
+                for (int k = 0; k < BT_CHUNK; k++) dst[k] = bt_ld(q + (size_t)k * JS);
             } else {
 #pragma unroll
-                for (int k = 0; k < BT_CHUNK; k++) dst[k] = (k < ktail) ? __ldcs(q + (size_t)k * JS) : NEG;
+                for (int k = 0; k < BT_CHUNK; k++) dst[k] = (k < ktail) ? bt_ld(q + (size_t)k * JS) : NEG;
             }
         };
         T mv = 0; int mi = 0;
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(128, MINB) backtrace_split_kernel(const Decode
         double buf[JP];
         auto load_row = [&](const double *q) {
 #pragma unroll
-            for (int k = 0; k < JP; k++) buf[k] = (j0 + k < K) ? __ldcs(q + (size_t)k * NS) : NEG;
+            for (int k = 0; k < JP; k++) buf[k] = (j0 + k < K) ? bt_ld(q + (size_t)k * NS) : NEG;
         };
         load_row(rowp);
         const double *at = sAT + (size_t)K * ATP + j0;         // the column of zeros: the end state is a plain argmax
