@@ -815,7 +815,9 @@ static int chunk_count(const cv_hmm *h, int64_t B, bool timing, bool host_buffer
     // Streaming pays from ~450 k sequences: below, every chunk's restart of the longest-first tile order costs more
     // than the copies it hides (measured: 250 k sequences 4.2 ms streamed in two chunks vs 3.0 ms on the device; one
     // H2D -> decode -> D2H pass is 3.7 ms), so shorter batches go through in one piece.
-    if (host_buffers && can_stream) return B / per_chunk >= 4 ? 4 : 1;
+    // With the tapering chunks of decode_streamed the crossover is lower: 350 k sequences 5.05 ms streamed vs 5.62 ms in
+    // one piece, 250 k 4.27 vs 4.03 ms.
+    if (host_buffers && can_stream) return (g_tune.uneven_chunks ? B >= (int64_t)2000 * h->num_sms : B / per_chunk >= 4) ? 4 : 1;
     return (int)std::max<int64_t>(1, std::min<int64_t>(host_buffers ? 6 : dev_chunks, B / per_chunk));
 }
 
