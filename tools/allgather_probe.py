@@ -1,0 +1,33 @@
+"""Times the one collective of the sharded decode in isolation: an in-place all_gather_into_tensor of a
+[world][bytes] buffer with the row size of a 1 M-sentence POS batch cut into `world` slices.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/allgather_probe.py
+
+Prints the time per collective for NCCL as configured by the environment (NCCL_ALGO, NCCL_PROTO, NCCL_NVLS_ENABLE ...)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+row = (1_000_000 // world) * 8 + (25_006_022 // world) + 64          # scores f64 + paths u8 of one slice
+row = (row + 255) // 256 * 256
+buf = torch.zeros(world, row, dtype=torch.uint8, device="cuda")
+for _ in range(10):
+    dist.all_gather_into_tensor(buf.view(-1), buf[rank])
+torch.cuda.synchronize()
+dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50):
+    dist.all_gather_into_tensor(buf.view(-1), buf[rank])
+e1.record()
+torch.cuda.synchronize()
+t = torch.tensor([e0.elapsed_time(e1) / 50], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    env = {k: v for k, v in os.environ.items() if k.startswith("NCCL_")}
+    print(f"world {world} row {row} B: all_gather_into_tensor {t.item():.4f} ms  env {env}", flush=True)
+dist.destroy_process_group()
