@@ -10,8 +10,22 @@ import torch
 import torch.distributed as dist
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-dist.init_process_group("nccl")
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+if os.environ.get("PROBE_EAGER"):          # as bench.py does: eager communicator bound to the device
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+else:
+    dist.init_process_group("nccl")
+if os.environ.get("PROBE_LIB"):            # a decode through the library first (its streams, carve-out settings, workspaces)
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import consistent_viterbi_b200 as cv
+    wl = bench.workload_pos(0, 250_000)
+    hmm = cv.HMM(wl["A"], wl["B"], wl["pi"])
+    for _ in range(3):
+        cv.decode_batch(hmm, wl["obs"], wl["off"], device=local)
 row = (1_000_000 // world) * 8 + (25_006_022 // world) + 64          # scores f64 + paths u8 of one slice
 row = (row + 255) // 256 * 256
 buf = torch.zeros(world, row, dtype=torch.uint8, device="cuda")
