@@ -94,7 +94,10 @@ int cv_decode_batch_keep(cv_hmm *h, const uint32_t *obs_flat, const int64_t *seq
 
 /* Same, with every buffer already resident on the model's device; enqueued on
  * `stream` (a cudaStream_t, NULL = default stream) without host sync, except
- * that the status word is read back when `sync_status` != 0. */
+ * that the status word is read back when `sync_status` != 0.
+ * N = d_seq_off[B]; max_len = an upper bound on the sequence lengths (sizes the workspace, and the ordering of the
+ * batch by length only looks at the bits such a length can have), <= 0 = not known (one extra synchronisation reads it
+ * back).  A sequence longer than a positive max_len is CV_ERR_ARG. */
 int cv_decode_batch_dev(cv_hmm *h, const uint32_t *d_obs_flat, const int64_t *d_seq_off,
                         int64_t B, int64_t N, int64_t max_len, uint32_t *d_path_out,
                         double *d_score_out, void *stream, int sync_status);
