@@ -54,6 +54,7 @@ static Tuning tuning_from_env()
     t.bt_split = geti("CV_BT_SPLIT", t.bt_split);
     t.uneven_chunks = geti("CV_UNEVEN_CHUNKS", t.uneven_chunks);
     t.long_split = geti("CV_LONG_SPLIT", t.long_split);
+    t.long_pct = geti("CV_LONG_PCT", t.long_pct);
     t.prefilter = geti("CV_PREFILTER", t.prefilter);
     t.debug = getenv("CV_DEBUG") != nullptr;
     t.bt_prof = getenv("CV_BT_PROF") != nullptr;
@@ -463,11 +464,15 @@ struct StreamedIO {
 
 // Threshold of the long-sequence split (see LongSplit): a tile should not run longer than ~70 % of the tile-steps an
 // average resident CTA executes in this launch; never below 64 steps; 0 = no split (nothing is that long).
-static uint32_t long_threshold(const cv_hmm *h, int64_t N, int64_t max_len)
+// Batches above the four-lane backtrace's range (launch_decode_small) are backtraced by one thread per sequence at
+// 6-9 us per step -- about as long again as the sequence's forward pass in a tile -- so there the limit is 45 %: at
+// 250 k sentences (a rank of a 4-GPU run) the slice holding a 191-step sentence ended 0.18 ms after the others.
+static uint32_t long_threshold(const cv_hmm *h, int64_t B, int64_t N, int64_t max_len)
 {
     if (!g_tune.long_split || max_len <= 0 || h->K > SMALL_K_MAX || h->f32mode) return 0;   // (the warp-per-sequence kernel is f64)
     const int64_t per_cta = (N / 64) / std::max<int64_t>(1, (int64_t)h->num_sms * 2);
-    const int64_t l = std::max<int64_t>(64, per_cta * 7 / 10);
+    const int pct = g_tune.long_pct > 0 ? g_tune.long_pct : (g_tune.bt_split && B <= (int64_t)1300 * h->num_sms) ? 70 : 45;
+    const int64_t l = std::max<int64_t>(64, per_cta * pct / 100);
     return l >= max_len ? 0u : (uint32_t)std::min<int64_t>(l, 0xffffff);
 }
 constexpr uint32_t LONG_CAP = 4096;
@@ -476,7 +481,7 @@ constexpr uint32_t LONG_CAP = 4096;
 static int long_split_setup(cv_hmm *h, cv_hmm::DecodeWs &w, int64_t B, int64_t N, int64_t max_len, cudaStream_t st, LongSplit &ls)
 {
     ls = LongSplit{0u, 0u, nullptr, nullptr, nullptr};
-    const uint32_t lstar = long_threshold(h, N, max_len);
+    const uint32_t lstar = long_threshold(h, B, N, max_len);
     if (!lstar) return CV_OK;
     int rc;
     const size_t row = (size_t)max_len * h->Kp;

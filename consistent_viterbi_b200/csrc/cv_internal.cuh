@@ -53,6 +53,7 @@ struct Tuning {
     int em_light = 1;              // uneven balanced split: only the lighter state groups fetch the emission rows (CV_EM_LIGHT)
     int bt_split = 1;              // backtrace with four lanes per sequence (backtrace_split_kernel) where it applies (CV_BT_SPLIT)
     int uneven_chunks = 1;         // streamed host path, automatic chunking: 10/25/25/20/12/8 % with the last chunk's long sequences promoted (CV_UNEVEN_CHUNKS)
+    int long_pct = 0;              // long-sequence split: limit in % of the tile-steps per resident CTA, 0 = automatic (70 / 45) (CV_LONG_PCT)
     int prefilter = 0;             // forward tile kernel with the f32 pre-filter (decode_prefilter.cuh) when the model allows it (CV_PREFILTER)
     int long_split = 1;            // very long sequences of a short batch go to the warp-per-sequence kernel (CV_LONG_SPLIT)
     int debug = 0;                 // print launch shapes                                         (CV_DEBUG)
