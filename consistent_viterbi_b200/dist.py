@@ -82,9 +82,8 @@ class ShardedDecoder:
             narrow_paths = on_gpu and hmm.nstates() <= 64
         self.narrow_paths = bool(narrow_paths)
         P, S = max(max(self.n_el), 1), max(max(self.n_sq), 1)
-        # rows padded to 512 bytes (scores and paths each): every rank's row then starts on a 512-byte boundary of the
-        # gather buffer -- with rows that were only 16-byte multiples the same all-gather took 0.24-0.28 ms at 4 GPUs
-        # against 0.07 ms for 256-byte-aligned rows of the same size (tools/allgather_probe.py)
+        # rows padded to 512 bytes (scores and paths each): every rank's row starts on a 512-byte boundary of the gather
+        # buffer
         P, S = (P + 511) // 512 * 512, (S + 63) // 64 * 64
         self.off_l = torch.from_numpy(off_l.copy()).to(self.dev)
         self.obs_l = torch.zeros(max(self.n_el[self.rank], 1), dtype=torch.int32, device=self.dev)
